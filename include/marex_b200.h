@@ -1,0 +1,168 @@
+/*
+ * marex_b200.h -- C-ABI of libmarex_b200.so: the B200 (sm_100a) implementation of the
+ * marEx `preprocess_data` detection hot path.
+ *
+ * The reference (wienkers/marEx) is pure Python and has no FFI layer; its boundary for this
+ * path is the Python signature `marEx.preprocess_data` (marEx/detect.py:287-313).  Each entry
+ * point below replaces one arithmetic stage that the reference expresses as an
+ * xarray/dask/flox/numpy graph; the stage it replaces is cited as detect.py:<lines>.
+ * `marex_b200/detect.py` (the Python mirror of the reference API) binds these with ctypes;
+ * INTEGRATION.md shows the stub a marEx maintainer would add.
+ *
+ * Conventions
+ * -----------
+ *  - Every pointer is CALLER-OWNED DEVICE memory (cudaMalloc / torch allocation) unless the
+ *    comment says "host".  The library allocates nothing that outlives a call.
+ *  - Fields are time-major: element (t, c) of a [T, N] field lives at base[t * pitch + c],
+ *    pitch >= N in ELEMENTS.  Gridded fields flatten (lat, lon) row-major: c = iy * nx + ix.
+ *  - Calls are asynchronous on `stream` (a cudaStream_t passed as void*; NULL = legacy stream).
+ *  - Return value: MAREX_OK or a negative MAREX_ERR_* code; marex_last_error() returns the
+ *    thread-local message of the last failure on the calling thread.
+ *  - Day-of-year thresholds are produced and consumed DOY-MAJOR: thr[(doy-1) * N + c].
+ *
+ * Calendar tables (built on the host from the time coordinate, see marex_b200/calendar.py;
+ * reference: `.dt.year` / `.dt.dayofyear`, detect.py:1605-1606) and uploaded by the caller:
+ *  - doy[T]      int16  day of year 1..366 of every row
+ *  - year_val[n_years] int32 ascending distinct calendar years present
+ *  - tidx[n_years*366] int32 row index of (year i, doy d) at [i*366 + d-1], or -1
+ *  - out_row[T]  int32  output row of input row t, or -1 when the row is trimmed
+ *  - doy_ptr[367], doy_rows[doy_ptr[366]] int32  CSR list of the rows of each day of year
+ */
+#ifndef MAREX_B200_H
+#define MAREX_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MAREX_OK 0
+#define MAREX_ERR_INVALID_ARG (-1)
+#define MAREX_ERR_CUDA (-2)
+#define MAREX_ERR_UNSUPPORTED (-3)
+
+#define MAREX_NDOY 366
+
+/* Library version (major*10000 + minor*100 + patch). */
+int marex_version(void);
+/* Message of the last error on this thread ("" if none). */
+const char* marex_last_error(void);
+/* Number of kernel launches issued by this process so far (bench.py's gpu_launches). */
+long long marex_launch_count(void);
+
+/* ---- (a) shifting baseline ------------------------------------------------------------
+ * smoothed_rolling_climatology + anomaly + trim (detect.py:1511-1688, 1691-1816, 1819-1850,
+ * 615-641) and the per-cell numbers _validate_data_values needs (detect.py:205-279).
+ *   s[t]     = centred S-day mean of x (NaN unless the full window is valid)
+ *   clim     = nanmean of s over the (year, doy) samples of the previous W calendar years
+ *   anom     = x - clim for rows with out_row[t] >= 0   (anom row = out_row[t])
+ *   mask0[c] = isfinite(x[0, c]);  nonfinite[c] = number of non-finite x[:, c]
+ * mode 0 writes the anomaly, mode 1 writes clim itself (marEx.rolling_climatology /
+ * smoothed_rolling_climatology, detect.py:1511, 1691); rows of non-target years are not
+ * written.  Requires at most one row per (year, doy) (daily data, gaps allowed).  W, S <= 1023. */
+int marex_shift_anomaly_f32(const float* x, int64_t T, int64_t N, int64_t pitch,
+                            const int32_t* tidx, const int32_t* year_val, int32_t n_years,
+                            int32_t W, int32_t S, const int32_t* out_row, int32_t mode,
+                            float* anom, int64_t anom_pitch,
+                            uint8_t* mask0, int32_t* nonfinite, void* stream);
+
+/* ---- (a') fixed baseline ---------------------------------------------------------------
+ * Per-day-of-year nanmean (flox nanmean, detect.py:2365-2373) over the rows listed in the CSR
+ * (doy_ptr, doy_rows) -- all rows, or only the reference_period's rows (detect.py:2334-2361).
+ * If `shift` is non-NULL the averaged value is f32(x - shift[c]) (used after detrending with
+ * force_zero_mean).  clim[366, N] float32, NaN for days of year without a valid sample. */
+int marex_doy_climatology_f32(const float* x, int64_t T, int64_t N, int64_t pitch,
+                              const int32_t* doy_ptr, const int32_t* doy_rows,
+                              const float* shift, float* clim, void* stream);
+/* anom[t] = f32(f32(x[t] - shift) - clim[doy[t]])  (groupby subtraction, detect.py:2377-2379);
+ * mask0 = isfinite of the first shifted row (detect.py:2391).  `nonfinite` (optional) counts
+ * non-finite x per cell.  x and anom may alias (in-place). */
+int marex_sub_doy_climatology_f32(const float* x, int64_t T, int64_t N, int64_t pitch,
+                                  const int16_t* doy, const float* shift, const float* clim,
+                                  float* anom, int64_t anom_pitch,
+                                  uint8_t* mask0, int32_t* nonfinite, void* stream);
+
+/* ---- (a'') polynomial detrend ----------------------------------------------------------
+ * coef[K, N] = P^T x  with P[T, K] = pinv(model) (detect.py:2169, 2206), float64 accumulate.
+ * Also the raw-input validation numbers (mask0, nonfinite) as in (a). */
+int marex_detrend_coef_f64(const float* x, int64_t T, int64_t N, int64_t pitch,
+                           const double* P, int32_t K, double* coef,
+                           uint8_t* mask0, int32_t* nonfinite, void* stream);
+/* xd[t] = x[t] - f32(sum_k M[k, t] * coef[k])  (detect.py:2220); if `mean` is non-NULL it
+ * receives f32(nanmean_t xd) (the force_zero_mean term, detect.py:2223-2224). */
+int marex_detrend_apply_f32(const float* x, int64_t T, int64_t N, int64_t pitch,
+                            const double* M, int32_t K, const double* coef,
+                            float* xd, int64_t xd_pitch, float* mean, void* stream);
+
+/* ---- (b) thresholds --------------------------------------------------------------------
+ * np.digitize(a, edges) - 1 as uint16 (detect.py:2622-2631): NaN and a >= edges[n_edges-1]
+ * give n_edges-1 (dropped).  edges[0] must be -inf. */
+int marex_digitize_f32(const float* a, int64_t T, int64_t N, int64_t pitch,
+                       const float* edges, int32_t n_edges,
+                       uint16_t* bins, int64_t bins_pitch, void* stream);
+
+/* Approximate Hobday thresholds: (doy x bin) counts, ws x ws spatial pooling (periodic in x,
+ * truncated in y), +-w/2 doy window (wrap 366), count-space interpolated quantile, NaN mask
+ * from anom_row0, clamp to lower_bound (_compute_histogram_quantile_2d detect.py:2562-2734,
+ * _rolling_histogram_quantile detect.py:2465-2559).  Unstructured: ny = 1, nx = N, ws = 1.
+ * thr[366, ny*nx] float32 doy-major.  stats[2] receives {min, max} of the thresholds before
+ * the clamp, ignoring NaN (for the reference's two UserWarnings).  w odd, 3 <= w <= 365. */
+int marex_hobday_thresholds_hist(const uint16_t* bins, int64_t T, int64_t ny, int64_t nx,
+                                 int64_t pitch, const int32_t* doy_ptr, const int32_t* doy_rows,
+                                 int32_t max_window_rows, const float* centers, int32_t nb,
+                                 int32_t w, int32_t ws, double q, const float* anom_row0,
+                                 float lower_bound, float* thr, float* stats, void* stream);
+
+/* Exact Hobday thresholds: np.nanpercentile (float32 'linear') over the +-w/2 doy window
+ * (detect.py:1921-1956).  thr[366, N] doy-major, NaN where the window holds no valid sample. */
+int marex_hobday_thresholds_exact_f32(const float* anom, int64_t T, int64_t N, int64_t pitch,
+                                      const int32_t* doy_ptr, const int32_t* doy_rows,
+                                      int32_t max_window_rows, int32_t w, float percentile,
+                                      float* thr, void* stream);
+
+/* Global (constant in time) thresholds, approximate: per-cell histogram with float64 edges
+ * (last bin right-closed), pdf/cdf in float64 in the reference's order
+ * (_compute_histogram_quantile_1d detect.py:2737-2865).  thr[N] float64. */
+int marex_global_threshold_hist_f64(const float* anom, int64_t T, int64_t N, int64_t pitch,
+                                    const double* edges, const double* centers, int32_t nb,
+                                    double q, double lower_bound, double* thr, double* stats,
+                                    void* stream);
+/* Global thresholds, exact: np.nanquantile(a, q) with a float64 q ('linear'), float64 result
+ * (xarray .quantile, detect.py:2899). */
+int marex_global_threshold_exact_f64(const float* anom, int64_t T, int64_t N, int64_t pitch,
+                                     double q, double* thr, void* stream);
+
+/* ---- (c) compare ------------------------------------------------------------------------
+ * events[t, c] = anom[t, c] >= thr  (NaN on either side -> 0).  hobday: thr[366, N] float32
+ * selected by doy[t] (detect.py:2001-2004); global: thr[N] float64, compared in float64
+ * (detect.py:2915).  Either output may be NULL: `events` is one byte per gridpoint-day (the
+ * bool array the reference returns), `bits` is the bit-packed mask, row t at
+ * bits[t * bits_pitch ...], bit (c & 31) of word (c >> 5).  `count` (optional, device
+ * uint64, accumulated into) receives the number of extreme gridpoint-days. */
+int marex_compare_hobday(const float* anom, int64_t T, int64_t N, int64_t pitch,
+                         const int16_t* doy, const float* thr,
+                         uint8_t* events, int64_t events_pitch,
+                         uint32_t* bits, int64_t bits_pitch,
+                         unsigned long long* count, void* stream);
+int marex_compare_global(const float* anom, int64_t T, int64_t N, int64_t pitch,
+                         const double* thr,
+                         uint8_t* events, int64_t events_pitch,
+                         uint32_t* bits, int64_t bits_pitch,
+                         unsigned long long* count, void* stream);
+
+/* ---- utilities --------------------------------------------------------------------------
+ * out[c, r] = in[r, c] : doy-major thr[366, N] -> the reference's (..space, dayofyear) layout. */
+int marex_transpose_f32(const float* in, int64_t rows, int64_t cols, float* out, void* stream);
+
+/* Deterministic synthetic SST: seasonal cycle + trend + AR(1) noise, with
+ * all-NaN "land" blobs; counter-based so any shard [c0, c0+N) of a global grid of
+ * `n_global` cells regenerates identically.  doy_frac[T] = decimal year (float32) host-built. */
+int marex_synth_sst_f32(float* x, int64_t T, int64_t N, int64_t pitch, int64_t c0,
+                        int64_t ny_global, int64_t nx_global, const float* dec_year,
+                        uint64_t seed, float land_fraction, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MAREX_B200_H */

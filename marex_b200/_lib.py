@@ -1,0 +1,66 @@
+"""ctypes binding of libmarex_b200.so (include/marex_b200.h).  There is NO fallback: if the
+library is missing or a call fails, the caller gets an exception."""
+import ctypes
+import os
+from ctypes import c_char_p, c_double, c_float, c_int32, c_int64, c_longlong, c_uint64, c_void_p
+
+from .exceptions import ProcessingError
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libmarex_b200.so")
+
+_P = c_void_p
+_SIGNATURES = {
+    "marex_version": ([], ctypes.c_int),
+    "marex_last_error": ([], c_char_p),
+    "marex_launch_count": ([], c_longlong),
+    "marex_shift_anomaly_f32": ([_P, c_int64, c_int64, c_int64, _P, _P, c_int32, c_int32, c_int32, _P, c_int32, _P, c_int64, _P, _P, _P], ctypes.c_int),
+    "marex_doy_climatology_f32": ([_P, c_int64, c_int64, c_int64, _P, _P, _P, _P, _P], ctypes.c_int),
+    "marex_sub_doy_climatology_f32": ([_P, c_int64, c_int64, c_int64, _P, _P, _P, _P, c_int64, _P, _P, _P], ctypes.c_int),
+    "marex_detrend_coef_f64": ([_P, c_int64, c_int64, c_int64, _P, c_int32, _P, _P, _P, _P], ctypes.c_int),
+    "marex_detrend_apply_f32": ([_P, c_int64, c_int64, c_int64, _P, c_int32, _P, _P, c_int64, _P, _P], ctypes.c_int),
+    "marex_digitize_f32": ([_P, c_int64, c_int64, c_int64, _P, c_int32, _P, c_int64, _P], ctypes.c_int),
+    "marex_hobday_thresholds_hist": ([_P, c_int64, c_int64, c_int64, c_int64, _P, _P, c_int32, _P, c_int32, c_int32, c_int32, c_double, _P, c_float, _P, _P, _P], ctypes.c_int),
+    "marex_hobday_thresholds_exact_f32": ([_P, c_int64, c_int64, c_int64, _P, _P, c_int32, c_int32, c_float, _P, _P], ctypes.c_int),
+    "marex_global_threshold_hist_f64": ([_P, c_int64, c_int64, c_int64, _P, _P, c_int32, c_double, c_double, _P, _P, _P], ctypes.c_int),
+    "marex_global_threshold_exact_f64": ([_P, c_int64, c_int64, c_int64, c_double, _P, _P], ctypes.c_int),
+    "marex_compare_hobday": ([_P, c_int64, c_int64, c_int64, _P, _P, _P, c_int64, _P, c_int64, _P, _P], ctypes.c_int),
+    "marex_compare_global": ([_P, c_int64, c_int64, c_int64, _P, _P, c_int64, _P, c_int64, _P, _P], ctypes.c_int),
+    "marex_transpose_f32": ([_P, c_int64, c_int64, _P, _P], ctypes.c_int),
+    "marex_synth_sst_f32": ([_P, c_int64, c_int64, c_int64, c_int64, c_int64, c_int64, _P, c_uint64, c_float, _P], ctypes.c_int),
+}
+EXPORTED = tuple(_SIGNATURES)
+
+_lib = None
+
+
+def load() -> ctypes.CDLL:
+    """Load the shared library (once).  Raises if it has not been built: no CPU fallback exists."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise ProcessingError(
+                "libmarex_b200.so is not built",
+                details=f"expected {LIB_PATH}",
+                suggestions=["run `python -c 'import __graft_entry__ as g; g.build()'` or `python marex_b200/_build.py`"],
+            )
+        lib = ctypes.CDLL(LIB_PATH)
+        for name, (argtypes, restype) in _SIGNATURES.items():
+            fn = getattr(lib, name)
+            fn.argtypes = argtypes
+            fn.restype = restype
+        _lib = lib
+    return _lib
+
+
+def call(name: str, *args) -> None:
+    """Call an int-returning entry point and raise ProcessingError on a non-zero code."""
+    lib = load()
+    rc = getattr(lib, name)(*args)
+    if rc != 0:
+        msg = lib.marex_last_error().decode("utf-8", "replace")
+        raise ProcessingError(f"{name} failed (code {rc})", details=msg)
+
+
+def launch_count() -> int:
+    return int(load().marex_launch_count())

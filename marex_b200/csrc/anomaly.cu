@@ -1,0 +1,371 @@
+// Anomaly kernels: shifting baseline (a), fixed baseline (a'), polynomial detrend (a'').
+// Layout: time-major fields, a warp's 32 lanes own 32 adjacent gridpoints, so every row
+// access is one coalesced 128-byte segment.
+#include "common.cuh"
+
+namespace marex {
+
+// =======================================================================================
+// (a) shifting baseline  -- reference: detect.py:1511-1688, 1691-1816, 1819-1850
+//
+// Thread = (gridpoint c, strip of R consecutive days of year).  The thread sweeps the
+// calendar years in order.  For its R days it keeps, per day,
+//   * a ring of the last W smoothed values s[year, doy] in shared memory (slot = year % W),
+//   * the running float64 sum of the finite ring entries and a packed valid/inf counter,
+// so clim[year, doy] = sum / count is available without re-reading any earlier year.
+// The S-day centred window sum slides along the strip (2 loads per day after the first
+// window); neighbouring strips share their halo rows through L1/L2.
+// =======================================================================================
+template <int R>
+__global__ void __launch_bounds__(256) shift_anomaly_kernel(
+    const float* __restrict__ x, int64_t T, int64_t N, int64_t pitch,
+    const int32_t* __restrict__ tidx, const int32_t* __restrict__ year_val, int n_years, int W, int S,
+    const int32_t* __restrict__ out_row, float* __restrict__ anom, int64_t anom_pitch,
+    uint8_t* __restrict__ mask0, int32_t* __restrict__ nonfinite, int n_strips, int spb, int mode) {
+  extern __shared__ float ring[];  // [W][R][spb][32]
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int64_t c = (int64_t)blockIdx.x * 32 + lane;
+  const int strip = blockIdx.y * spb + warp;
+  if (strip >= n_strips) return;  // whole warp leaves together
+  const bool live = c < N;
+  const int64_t cc = live ? c : N - 1;  // clamp: dead lanes read a valid column, never write
+  const int d0 = strip * R;
+  const int off = S / 2;
+  const int first_target = year_val[0] + W;
+
+  double sum[R];
+  uint32_t cnt[R];  // bits 0..9 valid (non-NaN) count, 10..19 +inf, 20..29 -inf
+#pragma unroll
+  for (int r = 0; r < R; ++r) { sum[r] = 0.0; cnt[r] = 0u; }
+  int bad = 0;
+
+  auto ring_at = [&](int slot, int r) -> float& { return ring[((slot * R + r) * spb + warp) * 32 + lane]; };
+  auto ring_update = [&](float s, int r, int sign) {
+    if (s == s) {  // NaN contributes nothing to a nanmean
+      const bool fin = is_finite_f(s);
+      if (fin) sum[r] += sign * (double)s;
+      const uint32_t code = fin ? 1u : (1u + ((s > 0.f) ? (1u << 10) : (1u << 20)));
+      cnt[r] += sign > 0 ? code : (0u - code);
+    }
+  };
+
+  if (strip == 0 && live) mask0[c] = is_finite_f(x[c]) ? 1 : 0;
+
+  int rm = 0;  // oldest year index still in the ring
+  for (int i = 0; i < n_years; ++i) {
+    const int Ty = year_val[i];
+    // (1) expire years older than Ty - W: they do not contribute to target year Ty
+    while (rm < i && year_val[rm] < Ty - W) {
+#pragma unroll
+      for (int r = 0; r < R; ++r) ring_update(ring_at(rm % W, r), r, -1);
+      ++rm;
+    }
+    const bool is_target = Ty >= first_target;
+    // sliding S-day window state (float64 sum of finite samples + packed non-finite counts)
+    double ws = 0.0;
+    uint32_t wnf = 0u;
+    int64_t wlo = -(1LL << 40);
+    bool wvalid = false;
+    float snew[R];
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+      const int d = d0 + r;
+      const int u = (d < NDOY) ? __ldg(&tidx[i * NDOY + d]) : -1;
+      float s = CUDART_NAN_F;
+      if (u >= 0) {
+        const float xu = __ldg(&x[(int64_t)u * pitch + cc]);
+        if (!is_finite_f(xu)) ++bad;
+        // (2) anomaly of a target-year sample against the W previous years
+        if (is_target) {
+          const int orow = __ldg(&out_row[u]);
+          if (orow >= 0) {
+            const uint32_t n = cnt[r] & 1023u;
+            float clim;
+            if (n == 0u) clim = CUDART_NAN_F;
+            else if (cnt[r] >> 10) clim = nonfinite_result(cnt[r] & ~1023u);
+            else clim = (float)(sum[r] / (double)n);
+            if (live) st_stream(&anom[(int64_t)orow * anom_pitch + c], mode ? clim : xu - clim);
+          }
+        }
+        // smoothed value of this sample: window rows [u - off, u - off + S - 1]
+        const int64_t lo = (int64_t)u - off;
+        if (lo >= 0 && lo + S <= T) {
+          if (wvalid && lo == wlo + 1) {
+            const float vo = __ldg(&x[wlo * pitch + cc]);
+            const float vn = __ldg(&x[(wlo + S) * pitch + cc]);
+            if (is_finite_f(vo)) ws -= (double)vo; else wnf -= nonfinite_code(vo);
+            if (is_finite_f(vn)) ws += (double)vn; else wnf += nonfinite_code(vn);
+          } else if (!(wvalid && lo == wlo)) {
+            ws = 0.0;
+            wnf = 0u;
+#pragma unroll 7
+            for (int k = 0; k < S; ++k) {
+              const float v = __ldg(&x[(lo + k) * pitch + cc]);
+              if (is_finite_f(v)) ws += (double)v; else wnf += nonfinite_code(v);
+            }
+          }
+          wlo = lo;
+          wvalid = true;
+          s = wnf ? nonfinite_result(wnf) : (float)(ws / (double)S);
+        }
+      }
+      snew[r] = s;
+    }
+    // (3) expire year Ty - W (it contributed to Ty but not to any later year) ...
+    while (rm < i && year_val[rm] < Ty + 1 - W) {
+#pragma unroll
+      for (int r = 0; r < R; ++r) ring_update(ring_at(rm % W, r), r, -1);
+      ++rm;
+    }
+    // (4) ... and enter year i for the targets to come
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+      ring_at(i % W, r) = snew[r];
+      ring_update(snew[r], r, +1);
+    }
+  }
+  if (live && bad) atomicAdd(&nonfinite[c], bad);
+}
+
+// =======================================================================================
+// (a') fixed baseline -- reference: detect.py:2299-2397
+// =======================================================================================
+// clim[d, c] = nanmean over the rows of day-of-year d (CSR list).  Thread = gridpoint,
+// blockIdx.y strides over days of year.
+__global__ void __launch_bounds__(256) doy_climatology_kernel(
+    const float* __restrict__ x, int64_t N, int64_t pitch, const int32_t* __restrict__ doy_ptr,
+    const int32_t* __restrict__ doy_rows, const float* __restrict__ shift, float* __restrict__ clim) {
+  const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= N) return;
+  const float sh = shift ? shift[c] : 0.f;
+  for (int d = blockIdx.y; d < NDOY; d += gridDim.y) {
+    const int b = __ldg(&doy_ptr[d]), e = __ldg(&doy_ptr[d + 1]);
+    double sum = 0.0;
+    uint32_t n = 0u, nf = 0u;
+#pragma unroll 4
+    for (int j = b; j < e; ++j) {
+      float v = ld_stream(&x[(int64_t)__ldg(&doy_rows[j]) * pitch + c]);
+      if (shift) v = v - sh;
+      if (v == v) {
+        ++n;
+        if (is_finite_f(v)) sum += (double)v; else nf |= nonfinite_code(v);
+      }
+    }
+    float m;
+    if (n == 0u) m = CUDART_NAN_F;
+    else if (nf) m = nonfinite_result(nf);
+    else m = (float)(sum / (double)n);
+    clim[(int64_t)d * N + c] = m;
+  }
+}
+
+// anom[t, c] = f32(f32(x - shift) - clim[doy[t], c]); thread = gridpoint, blockIdx.y = row chunk.
+__global__ void __launch_bounds__(256) sub_doy_climatology_kernel(
+    const float* x, int64_t T, int64_t N, int64_t pitch, const int16_t* __restrict__ doy,
+    const float* __restrict__ shift, const float* __restrict__ clim, float* anom, int64_t anom_pitch,
+    uint8_t* __restrict__ mask0, int32_t* __restrict__ nonfinite, int rows_per_block) {
+  const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= N) return;
+  const float sh = shift ? shift[c] : 0.f;
+  const int64_t t0 = (int64_t)blockIdx.y * rows_per_block;
+  const int64_t t1 = min(T, t0 + rows_per_block);
+  int bad = 0;
+#pragma unroll 4
+  for (int64_t t = t0; t < t1; ++t) {
+    float v = ld_stream(&x[t * pitch + c]);
+    if (!is_finite_f(v)) ++bad;
+    if (shift) v = v - sh;
+    if (t == 0 && mask0) mask0[c] = is_finite_f(v) ? 1 : 0;
+    const int d = __ldg(&doy[t]) - 1;
+    st_stream(&anom[t * anom_pitch + c], v - __ldg(&clim[(int64_t)d * N + c]));
+  }
+  if (nonfinite && bad) atomicAdd(&nonfinite[c], bad);
+}
+
+// =======================================================================================
+// (a'') polynomial detrend -- reference: detect.py:2061-2296 (remove_harmonics=False)
+// =======================================================================================
+
+// coef[k, c] = sum_t P[t, k] * x[t, c], float64 accumulate, sequential in t (deterministic).
+template <int K>
+__global__ void __launch_bounds__(256) detrend_coef_kernel(
+    const float* __restrict__ x, int64_t T, int64_t N, int64_t pitch, const double* __restrict__ P,
+    double* __restrict__ coef, uint8_t* __restrict__ mask0, int32_t* __restrict__ nonfinite) {
+  const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= N) return;
+  double acc[K];
+#pragma unroll
+  for (int k = 0; k < K; ++k) acc[k] = 0.0;
+  int bad = 0;
+#pragma unroll 4
+  for (int64_t t = 0; t < T; ++t) {
+    const float v = ld_stream(&x[t * pitch + c]);
+    if (!is_finite_f(v)) ++bad;
+    if (t == 0 && mask0) mask0[c] = is_finite_f(v) ? 1 : 0;
+    const double dv = (double)v;
+#pragma unroll
+    for (int k = 0; k < K; ++k) acc[k] = fma(__ldg(&P[t * K + k]), dv, acc[k]);
+  }
+#pragma unroll
+  for (int k = 0; k < K; ++k) coef[(int64_t)k * N + c] = acc[k];
+  if (nonfinite) nonfinite[c] = bad;
+}
+
+// xd[t, c] = x[t, c] - f32(sum_k M[k, t] * coef[k, c]);  mean[c] = f32(nanmean_t xd).
+template <int K>
+__global__ void __launch_bounds__(256) detrend_apply_kernel(
+    const float* x, int64_t T, int64_t N, int64_t pitch, const double* __restrict__ M,
+    const double* __restrict__ coef, float* xd, int64_t xd_pitch, float* __restrict__ mean) {
+  const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= N) return;
+  double cf[K];
+#pragma unroll
+  for (int k = 0; k < K; ++k) cf[k] = coef[(int64_t)k * N + c];
+  double sum = 0.0;
+  int64_t cnt = 0;
+  uint32_t nf = 0u;
+#pragma unroll 4
+  for (int64_t t = 0; t < T; ++t) {
+    const float v = ld_stream(&x[t * pitch + c]);
+    double fit = 0.0;
+#pragma unroll
+    for (int k = 0; k < K; ++k) fit = fma(__ldg(&M[(int64_t)k * T + t]), cf[k], fit);
+    const float r = v - (float)fit;
+    st_stream(&xd[t * xd_pitch + c], r);
+    if (r == r) {
+      ++cnt;
+      if (is_finite_f(r)) sum += (double)r; else nf |= nonfinite_code(r);
+    }
+  }
+  if (mean) {
+    float m;
+    if (cnt == 0) m = CUDART_NAN_F;
+    else if (nf) m = nonfinite_result(nf);
+    else m = (float)(sum / (double)cnt);
+    mean[c] = m;
+  }
+}
+
+}  // namespace marex
+
+using namespace marex;
+
+extern "C" int marex_shift_anomaly_f32(const float* x, int64_t T, int64_t N, int64_t pitch, const int32_t* tidx,
+                                       const int32_t* year_val, int32_t n_years, int32_t W, int32_t S,
+                                       const int32_t* out_row, int32_t mode, float* anom, int64_t anom_pitch,
+                                       uint8_t* mask0, int32_t* nonfinite, void* stream) {
+  MAREX_REQUIRE(x && tidx && year_val && out_row && anom && mask0 && nonfinite, "null pointer");
+  MAREX_REQUIRE(T > 0 && N > 0 && pitch >= N && anom_pitch >= N && n_years > 0, "bad shape");
+  MAREX_REQUIRE(W >= 1 && W <= 1023 && S >= 1 && S <= 1023, "W and S must be in 1..1023");
+  cudaStream_t st = (cudaStream_t)stream;
+  MAREX_CUDA(cudaMemsetAsync(nonfinite, 0, sizeof(int32_t) * N, st));
+  const size_t smem_budget = 96 * 1024;  // two CTAs per SM
+  const int64_t nblk_x = (N + 31) / 32;
+  auto launch = [&](auto kern, int R) -> int {
+    const size_t per_warp = (size_t)W * R * 32 * sizeof(float);
+    if (per_warp > 200 * 1024) return MAREX_ERR_UNSUPPORTED;
+    int spb = (int)(smem_budget / per_warp);
+    if (spb < 1) spb = 1;
+    if (spb > 8) spb = 8;
+    const int n_strips = (NDOY + R - 1) / R;
+    if (spb > n_strips) spb = n_strips;
+    const size_t smem = per_warp * spb;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(shift_anomaly)");
+    dim3 grid((unsigned)nblk_x, (unsigned)((n_strips + spb - 1) / spb));
+    kern<<<grid, spb * 32, smem, st>>>(x, T, N, pitch, tidx, year_val, n_years, W, S, out_row, anom, anom_pitch,
+                                       mask0, nonfinite, n_strips, spb, mode);
+    MAREX_LAUNCH_CHECK("shift_anomaly_kernel");
+    return MAREX_OK;
+  };
+  int rc = launch(shift_anomaly_kernel<8>, 8);
+  if (rc == MAREX_ERR_UNSUPPORTED) rc = launch(shift_anomaly_kernel<2>, 2);
+  if (rc == MAREX_ERR_UNSUPPORTED) rc = launch(shift_anomaly_kernel<1>, 1);
+  if (rc == MAREX_ERR_UNSUPPORTED) return fail(rc, "window_year_baseline too large for the shared-memory ring");
+  return rc;
+}
+
+extern "C" int marex_doy_climatology_f32(const float* x, int64_t T, int64_t N, int64_t pitch, const int32_t* doy_ptr,
+                                         const int32_t* doy_rows, const float* shift, float* clim, void* stream) {
+  MAREX_REQUIRE(x && doy_ptr && doy_rows && clim, "null pointer");
+  MAREX_REQUIRE(T > 0 && N > 0 && pitch >= N, "bad shape");
+  const int threads = 128;
+  const int64_t bx = (N + threads - 1) / threads;
+  int by = (int)((4LL * sm_count() * 4 + bx - 1) / bx);  // enough CTAs to fill the chip for small N
+  by = by < 1 ? 1 : (by > NDOY ? NDOY : by);
+  doy_climatology_kernel<<<dim3((unsigned)bx, by), threads, 0, (cudaStream_t)stream>>>(x, N, pitch, doy_ptr, doy_rows,
+                                                                                        shift, clim);
+  MAREX_LAUNCH_CHECK("doy_climatology_kernel");
+  return MAREX_OK;
+}
+
+extern "C" int marex_sub_doy_climatology_f32(const float* x, int64_t T, int64_t N, int64_t pitch, const int16_t* doy,
+                                             const float* shift, const float* clim, float* anom, int64_t anom_pitch,
+                                             uint8_t* mask0, int32_t* nonfinite, void* stream) {
+  MAREX_REQUIRE(x && doy && clim && anom, "null pointer");
+  MAREX_REQUIRE(T > 0 && N > 0 && pitch >= N && anom_pitch >= N, "bad shape");
+  cudaStream_t st = (cudaStream_t)stream;
+  if (nonfinite) MAREX_CUDA(cudaMemsetAsync(nonfinite, 0, sizeof(int32_t) * N, st));
+  const int threads = 128;
+  const int64_t bx = (N + threads - 1) / threads;
+  int64_t by = (8LL * sm_count() + bx - 1) / bx;
+  if (by < 1) by = 1;
+  if (by > T) by = T;
+  if (by > 65535) by = 65535;
+  const int rows_per_block = (int)((T + by - 1) / by);
+  by = (T + rows_per_block - 1) / rows_per_block;
+  sub_doy_climatology_kernel<<<dim3((unsigned)bx, (unsigned)by), threads, 0, st>>>(
+      x, T, N, pitch, doy, shift, clim, anom, anom_pitch, mask0, nonfinite, rows_per_block);
+  MAREX_LAUNCH_CHECK("sub_doy_climatology_kernel");
+  return MAREX_OK;
+}
+
+template <int K>
+static int launch_detrend_coef(const float* x, int64_t T, int64_t N, int64_t pitch, const double* P, double* coef,
+                               uint8_t* mask0, int32_t* nonfinite, cudaStream_t st) {
+  const int threads = 128;
+  detrend_coef_kernel<K><<<(unsigned)((N + threads - 1) / threads), threads, 0, st>>>(x, T, N, pitch, P, coef, mask0,
+                                                                                      nonfinite);
+  MAREX_LAUNCH_CHECK("detrend_coef_kernel");
+  return MAREX_OK;
+}
+template <int K>
+static int launch_detrend_apply(const float* x, int64_t T, int64_t N, int64_t pitch, const double* M,
+                                const double* coef, float* xd, int64_t xd_pitch, float* mean, cudaStream_t st) {
+  const int threads = 128;
+  detrend_apply_kernel<K><<<(unsigned)((N + threads - 1) / threads), threads, 0, st>>>(x, T, N, pitch, M, coef, xd,
+                                                                                       xd_pitch, mean);
+  MAREX_LAUNCH_CHECK("detrend_apply_kernel");
+  return MAREX_OK;
+}
+
+#define MAREX_K_DISPATCH(fn, ...)                                                 \
+  switch (K) {                                                                    \
+    case 1: return fn<1>(__VA_ARGS__);                                            \
+    case 2: return fn<2>(__VA_ARGS__);                                            \
+    case 3: return fn<3>(__VA_ARGS__);                                            \
+    case 4: return fn<4>(__VA_ARGS__);                                            \
+    case 5: return fn<5>(__VA_ARGS__);                                            \
+    case 6: return fn<6>(__VA_ARGS__);                                            \
+    case 7: return fn<7>(__VA_ARGS__);                                            \
+    case 8: return fn<8>(__VA_ARGS__);                                            \
+    case 9: return fn<9>(__VA_ARGS__);                                            \
+    case 10: return fn<10>(__VA_ARGS__);                                          \
+    case 11: return fn<11>(__VA_ARGS__);                                          \
+    case 12: return fn<12>(__VA_ARGS__);                                          \
+    default: return fail(MAREX_ERR_UNSUPPORTED, "K (model columns) must be 1..12"); \
+  }
+
+extern "C" int marex_detrend_coef_f64(const float* x, int64_t T, int64_t N, int64_t pitch, const double* P, int32_t K,
+                                      double* coef, uint8_t* mask0, int32_t* nonfinite, void* stream) {
+  MAREX_REQUIRE(x && P && coef, "null pointer");
+  MAREX_REQUIRE(T > 0 && N > 0 && pitch >= N, "bad shape");
+  MAREX_K_DISPATCH(launch_detrend_coef, x, T, N, pitch, P, coef, mask0, nonfinite, (cudaStream_t)stream);
+}
+
+extern "C" int marex_detrend_apply_f32(const float* x, int64_t T, int64_t N, int64_t pitch, const double* M, int32_t K,
+                                       const double* coef, float* xd, int64_t xd_pitch, float* mean, void* stream) {
+  MAREX_REQUIRE(x && M && coef && xd, "null pointer");
+  MAREX_REQUIRE(T > 0 && N > 0 && pitch >= N && xd_pitch >= N, "bad shape");
+  MAREX_K_DISPATCH(launch_detrend_apply, x, T, N, pitch, M, coef, xd, xd_pitch, mean, (cudaStream_t)stream);
+}

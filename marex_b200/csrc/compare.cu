@@ -1,0 +1,167 @@
+// (c) fused compare -> bool bytes and/or bit-packed extreme mask; utilities (transpose,
+// synthetic SST generator, library globals).
+#include "common.cuh"
+
+namespace marex {
+
+thread_local std::string g_last_error;
+std::atomic<long long> g_launches{0};
+
+// events[t, c] = anom[t, c] >= thr.  A warp covers 32 consecutive gridpoints of one row, so the
+// packed word is one __ballot_sync (bit = lane = c & 31).  THR_GLOBAL: thr is float64[N] and the
+// comparison is done in float64 (detect.py:2915); otherwise thr is float32[366, N] selected by
+// doy[t] (detect.py:2001-2004).  NaN on either side compares false.
+template <bool THR_GLOBAL>
+__global__ void __launch_bounds__(256) compare_kernel(const float* __restrict__ anom, int64_t T, int64_t N,
+                                                      int64_t pitch, const int16_t* __restrict__ doy,
+                                                      const void* __restrict__ thr_v, uint8_t* __restrict__ events,
+                                                      int64_t events_pitch, uint32_t* __restrict__ bits,
+                                                      int64_t bits_pitch, unsigned long long* __restrict__ count,
+                                                      int rows_per_block) {
+  const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;  // blockDim.x multiple of 32
+  const bool live = c < N;
+  const int64_t cc = live ? c : N - 1;
+  const int64_t t0 = (int64_t)blockIdx.y * rows_per_block, t1 = min(T, t0 + rows_per_block);
+  double thr_g = 0.0;
+  if (THR_GLOBAL) thr_g = reinterpret_cast<const double*>(thr_v)[cc];
+  const float* thr_f = reinterpret_cast<const float*>(thr_v);
+  unsigned int local = 0;
+#pragma unroll 4
+  for (int64_t t = t0; t < t1; ++t) {
+    const float a = ld_stream(&anom[t * pitch + cc]);
+    bool e;
+    if (THR_GLOBAL) e = (double)a >= thr_g;
+    else e = a >= __ldg(&thr_f[(int64_t)(__ldg(&doy[t]) - 1) * N + cc]);
+    e = e && live;
+    if (events && live) events[t * events_pitch + c] = e ? 1 : 0;
+    const unsigned int word = __ballot_sync(0xffffffffu, e);
+    if (bits && (threadIdx.x & 31) == 0 && (c >> 5) < bits_pitch) bits[t * bits_pitch + (c >> 5)] = word;
+    local += e ? 1u : 0u;
+  }
+  if (count) {
+    for (int o = 16; o; o >>= 1) local += __shfl_xor_sync(0xffffffffu, local, o);
+    if ((threadIdx.x & 31) == 0 && local) atomicAdd(count, (unsigned long long)local);
+  }
+}
+
+__global__ void transpose_kernel(const float* __restrict__ in, int64_t rows, int64_t cols, float* __restrict__ out) {
+  __shared__ float tile[32][33];
+  const int64_t c0 = (int64_t)blockIdx.x * 32, r0 = (int64_t)blockIdx.y * 32;
+  for (int j = threadIdx.y; j < 32; j += blockDim.y) {
+    const int64_t r = r0 + j, c = c0 + threadIdx.x;
+    if (r < rows && c < cols) tile[j][threadIdx.x] = in[r * cols + c];
+  }
+  __syncthreads();
+  for (int j = threadIdx.y; j < 32; j += blockDim.y) {
+    const int64_t c = c0 + j, r = r0 + threadIdx.x;
+    if (r < rows && c < cols) out[c * rows + r] = tile[threadIdx.x][j];
+  }
+}
+
+// ---- synthetic SST ------------------------------------------------------
+__device__ __forceinline__ uint64_t splitmix64(uint64_t z) {
+  z += 0x9E3779B97F4A7C15ull;
+  z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+  z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+  return z ^ (z >> 31);
+}
+__device__ __forceinline__ float u01(uint64_t h) { return (float)((h >> 40) + 1) * (1.0f / 16777217.0f); }  // (0, 1)
+
+__global__ void __launch_bounds__(128) synth_sst_kernel(float* __restrict__ x, int64_t T, int64_t N, int64_t pitch,
+                                                        int64_t c0, int64_t ny_g, int64_t nx_g,
+                                                        const float* __restrict__ dec_year, uint64_t seed,
+                                                        float land_fraction) {
+  const int64_t cl = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (cl >= N) return;
+  const int64_t cg = c0 + cl;
+  const int64_t iy = cg / nx_g, ix = cg % nx_g;
+  // land: 8 x 8-cell blobs chosen by a hash of the coarse block
+  const uint64_t hb = splitmix64(seed ^ (uint64_t)((iy >> 3) * 1315423911ull + (ix >> 3)));
+  const bool land = u01(hb) < land_fraction;
+  const uint64_t hc = splitmix64(seed * 0x5851F42D4C957F2Dull + (uint64_t)cg);
+  const float latf = ny_g > 1 ? (float)iy / (float)(ny_g - 1) : 0.5f;  // 0 south .. 1 north
+  const float mu = -1.8f + 31.8f * (1.f - fabsf(2.f * latf - 1.f));     // [-1.8, 30]
+  const float amp = 0.5f + 5.5f * u01(hc);
+  const float phase = u01(splitmix64(hc));
+  const float rho = 0.9f, sig = 0.6f * sqrtf(1.f - rho * rho);
+  float ar = 0.f;
+  uint64_t state = splitmix64(hc ^ 0xD1B54A32D192ED03ull);
+  const float y0 = dec_year[0];
+  for (int64_t t = 0; t < T; ++t) {
+    state = splitmix64(state);
+    const float u1 = u01(state), u2 = u01(state * 0x9E3779B97F4A7C15ull + 1);
+    const float z = sqrtf(-2.f * __logf(u1)) * __cosf(6.2831853f * u2);
+    ar = rho * ar + sig * z;
+    const float dy = dec_year[t];
+    const float v = mu + amp * __cosf(6.2831853f * (dy - floorf(dy) - phase)) + 0.02f * (dy - y0) + ar;
+    x[t * pitch + cl] = land ? CUDART_NAN_F : v;
+  }
+}
+
+}  // namespace marex
+
+using namespace marex;
+
+extern "C" int marex_version(void) { return 100; }
+extern "C" const char* marex_last_error(void) { return g_last_error.c_str(); }
+extern "C" long long marex_launch_count(void) { return g_launches.load(); }
+
+template <bool G>
+static int launch_compare(const float* anom, int64_t T, int64_t N, int64_t pitch, const int16_t* doy, const void* thr,
+                          uint8_t* events, int64_t events_pitch, uint32_t* bits, int64_t bits_pitch,
+                          unsigned long long* count, cudaStream_t st) {
+  const int threads = 128;
+  const int64_t bx = (N + threads - 1) / threads;
+  int64_t by = (8LL * sm_count() + bx - 1) / bx;
+  by = by < 1 ? 1 : (by > T ? T : by);
+  if (by > 65535) by = 65535;
+  const int rows_per_block = (int)((T + by - 1) / by);
+  by = (T + rows_per_block - 1) / rows_per_block;
+  compare_kernel<G><<<dim3((unsigned)bx, (unsigned)by), threads, 0, st>>>(anom, T, N, pitch, doy, thr, events,
+                                                                          events_pitch, bits, bits_pitch, count,
+                                                                          rows_per_block);
+  MAREX_LAUNCH_CHECK("compare_kernel");
+  return MAREX_OK;
+}
+
+extern "C" int marex_compare_hobday(const float* anom, int64_t T, int64_t N, int64_t pitch, const int16_t* doy,
+                                    const float* thr, uint8_t* events, int64_t events_pitch, uint32_t* bits,
+                                    int64_t bits_pitch, unsigned long long* count, void* stream) {
+  MAREX_REQUIRE(anom && doy && thr && (events || bits || count), "null pointer");
+  MAREX_REQUIRE(T > 0 && N > 0 && pitch >= N, "bad shape");
+  MAREX_REQUIRE(!events || events_pitch >= N, "events_pitch < N");
+  MAREX_REQUIRE(!bits || bits_pitch >= (N + 31) / 32, "bits_pitch < ceil(N/32)");
+  return launch_compare<false>(anom, T, N, pitch, doy, thr, events, events_pitch, bits, bits_pitch, count,
+                               (cudaStream_t)stream);
+}
+
+extern "C" int marex_compare_global(const float* anom, int64_t T, int64_t N, int64_t pitch, const double* thr,
+                                    uint8_t* events, int64_t events_pitch, uint32_t* bits, int64_t bits_pitch,
+                                    unsigned long long* count, void* stream) {
+  MAREX_REQUIRE(anom && thr && (events || bits || count), "null pointer");
+  MAREX_REQUIRE(T > 0 && N > 0 && pitch >= N, "bad shape");
+  MAREX_REQUIRE(!events || events_pitch >= N, "events_pitch < N");
+  MAREX_REQUIRE(!bits || bits_pitch >= (N + 31) / 32, "bits_pitch < ceil(N/32)");
+  return launch_compare<true>(anom, T, N, pitch, nullptr, thr, events, events_pitch, bits, bits_pitch, count,
+                              (cudaStream_t)stream);
+}
+
+extern "C" int marex_transpose_f32(const float* in, int64_t rows, int64_t cols, float* out, void* stream) {
+  MAREX_REQUIRE(in && out && rows > 0 && cols > 0, "bad argument");
+  dim3 grid((unsigned)((cols + 31) / 32), (unsigned)((rows + 31) / 32));
+  MAREX_REQUIRE(grid.y <= 65535, "too many rows for transpose grid");
+  transpose_kernel<<<grid, dim3(32, 8), 0, (cudaStream_t)stream>>>(in, rows, cols, out);
+  MAREX_LAUNCH_CHECK("transpose_kernel");
+  return MAREX_OK;
+}
+
+extern "C" int marex_synth_sst_f32(float* x, int64_t T, int64_t N, int64_t pitch, int64_t c0, int64_t ny_global,
+                                   int64_t nx_global, const float* dec_year, uint64_t seed, float land_fraction,
+                                   void* stream) {
+  MAREX_REQUIRE(x && dec_year && T > 0 && N > 0 && pitch >= N && ny_global > 0 && nx_global > 0, "bad argument");
+  synth_sst_kernel<<<(unsigned)((N + 127) / 128), 128, 0, (cudaStream_t)stream>>>(x, T, N, pitch, c0, ny_global,
+                                                                                  nx_global, dec_year, seed,
+                                                                                  land_fraction);
+  MAREX_LAUNCH_CHECK("synth_sst_kernel");
+  return MAREX_OK;
+}

@@ -1,0 +1,607 @@
+// Threshold kernels: digitize, Hobday histogram quantile (own-cell and ws x ws pooled),
+// exact Hobday / global percentiles, global histogram quantile.
+//
+// Common shape: one warp per CTA, lane = gridpoint, a private histogram per lane laid out
+// hist[bin][lane] in shared memory (bank = lane, conflict-free up to the 16-bit pairing).
+// Counts are integers, so everything up to the final interpolation is bit-exact.
+#include "common.cuh"
+
+namespace marex {
+
+// ---------------------------------------------------------------------------------------
+// np.digitize(a, edges) - 1  (detect.py:2622-2631).  `edges` (shared memory) is ascending
+// with edges[0] = -inf; the near-uniform spacing gives a first guess that the two loops fix
+// up against the REAL float32 edge table, so counts match numpy bit for bit.
+// ---------------------------------------------------------------------------------------
+__device__ __forceinline__ int digitize_f32(float a, const float* __restrict__ edges, int n_edges, float e1,
+                                            float inv_step) {
+  if (a != a) return n_edges - 1;
+  float g = floorf((a - e1) * inv_step) + 1.f;
+  g = fminf(fmaxf(g, 0.f), (float)(n_edges - 1));
+  int i = (int)g;
+  while (i > 0 && a < edges[i]) --i;
+  while (i < n_edges - 1 && a >= edges[i + 1]) ++i;
+  return i;
+}
+
+__global__ void __launch_bounds__(256) digitize_kernel(const float* __restrict__ a, int64_t T, int64_t N,
+                                                       int64_t pitch, const float* __restrict__ edges, int n_edges,
+                                                       uint16_t* __restrict__ bins, int64_t bins_pitch,
+                                                       int rows_per_block) {
+  extern __shared__ float s_edges[];
+  for (int i = threadIdx.x; i < n_edges; i += blockDim.x) s_edges[i] = edges[i];
+  __syncthreads();
+  const float e1 = s_edges[1];
+  const float inv_step = (n_edges > 2) ? 1.f / (s_edges[2] - s_edges[1]) : 1.f;
+  const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= N) return;
+  const int64_t t0 = (int64_t)blockIdx.y * rows_per_block, t1 = min(T, t0 + rows_per_block);
+#pragma unroll 4
+  for (int64_t t = t0; t < t1; ++t)
+    bins[t * bins_pitch + c] = (uint16_t)digitize_f32(ld_stream(&a[t * pitch + c]), s_edges, n_edges, e1, inv_step);
+}
+
+// ---------------------------------------------------------------------------------------
+// Approximate Hobday thresholds (detect.py:2562-2734 + 2465-2559).
+//
+// One lane = one target gridpoint.  The lane owns the histogram of ALL samples that feed its
+// threshold: rows of the +-w/2 day-of-year window x the ws x ws neighbourhood (periodic in x,
+// truncated in y).  Advancing the day of year removes one day's rows and adds another's, so the
+// histogram, the total N and the running rank state (iu, cl = #samples in bins < iu) are all
+// updated incrementally; the quantile bin is re-found by walking iu a few bins.
+// ---------------------------------------------------------------------------------------
+template <typename CT, bool POOLED>
+__global__ void __launch_bounds__(32) hobday_hist_kernel(
+    const uint16_t* __restrict__ bins, int64_t ny, int64_t nx, int64_t pitch, const int32_t* __restrict__ doy_ptr,
+    const int32_t* __restrict__ doy_rows, const float* __restrict__ centers, int nb, int w, int ws, double q,
+    const float* __restrict__ anom_row0, float lower_bound, float* __restrict__ thr, float* __restrict__ stats) {
+  extern __shared__ unsigned char smem_raw[];
+  CT* hist = reinterpret_cast<CT*>(smem_raw);  // [nb][32]
+  const int lane = threadIdx.x;
+  const int64_t xg = (int64_t)blockIdx.x * 32 + lane;
+  const int64_t y = blockIdx.y;
+  const bool live = xg < nx;
+  const int64_t xx = live ? xg : nx - 1;
+  const int64_t N = ny * nx;
+  for (int b = 0; b < nb; ++b) hist[b * 32 + lane] = 0;
+  __syncwarp();
+  const int half = w / 2, p = ws / 2;
+  int ntot = 0, iu = 0, cl = 0;
+
+  auto apply_doy = [&](int d, int sign) {
+    const int b0 = __ldg(&doy_ptr[d]), b1 = __ldg(&doy_ptr[d + 1]);
+    for (int j = b0; j < b1; ++j) {
+      const uint16_t* row = bins + (int64_t)__ldg(&doy_rows[j]) * pitch;
+      if (POOLED) {
+        for (int dy = -p; dy <= p; ++dy) {
+          const int64_t yy = y + dy;
+          if (yy < 0 || yy >= ny) continue;
+          const uint16_t* rowy = row + yy * nx;
+          for (int dx = -p; dx <= p; ++dx) {
+            int64_t xn = (xx + dx) % nx;
+            if (xn < 0) xn += nx;
+            const int v = rowy[xn];
+            if (v < nb) {
+              hist[v * 32 + lane] += (CT)sign;
+              ntot += sign;
+              if (v < iu) cl += sign;
+            }
+          }
+        }
+      } else {
+        const int v = row[y * nx + xx];
+        if (v < nb) {
+          hist[v * 32 + lane] += (CT)sign;
+          ntot += sign;
+          if (v < iu) cl += sign;
+        }
+      }
+    }
+  };
+
+  for (int k = -half; k <= half; ++k) apply_doy(((k % NDOY) + NDOY) % NDOY, +1);
+  const bool masked = live ? (anom_row0[y * nx + xx] != anom_row0[y * nx + xx]) : true;
+  float vmin = CUDART_INF_F, vmax = -CUDART_INF_F;
+
+  for (int d = 0; d < NDOY; ++d) {
+    if (d > 0) {
+      apply_doy((d - 1 - half + 2 * NDOY) % NDOY, -1);
+      apply_doy((d + half) % NDOY, +1);
+    }
+    float res = CUDART_NAN_F;
+    if (ntot > 0) {
+      const double pos = q * (double)ntot;             // detect.py:2516
+      const int kk = (int)floor(pos);                  // cum > pos  <=>  cum >= kk + 1
+      while (cl > kk) { --iu; cl -= (int)hist[iu * 32 + lane]; }
+      while (iu < nb - 1 && cl + (int)hist[iu * 32 + lane] <= kk) { cl += (int)hist[iu * 32 + lane]; ++iu; }
+      if (iu == 0) {
+        res = __ldg(&centers[0]);                      // detect.py:2557
+      } else {
+        const int h = (int)hist[iu * 32 + lane];
+        const float bl = __ldg(&centers[iu - 1]), bu = __ldg(&centers[iu]);
+        const double frac = (h > 0) ? (pos - (double)cl) / (double)h : 0.5;  // detect.py:2545-2547
+        res = (float)((double)bl + frac * (double)__fsub_rn(bu, bl));       // detect.py:2550
+      }
+    }
+    if (masked) res = CUDART_NAN_F;                    // detect.py:2704-2705
+    if (res == res) { vmin = fminf(vmin, res); vmax = fmaxf(vmax, res); }
+    if (res < lower_bound) res = lower_bound;          // detect.py:2722-2732
+    if (live) thr[(int64_t)d * N + y * nx + xg] = res;
+  }
+  vmin = warp_min(vmin);
+  vmax = warp_max(vmax);
+  if (lane == 0 && stats) {
+    if (vmin != CUDART_INF_F) atomic_min_f(&stats[0], vmin);
+    if (vmax != -CUDART_INF_F) atomic_max_f(&stats[1], vmax);
+  }
+}
+
+// ---------------------------------------------------------------------------------------
+// Exact order statistics.  A per-lane uniform histogram over [min, max] of the lane's own
+// series localises the bin that holds the wanted rank; the few samples of that bin are then
+// gathered and ordered exactly.  `SampleIter` abstracts "all samples of the current window".
+// ---------------------------------------------------------------------------------------
+constexpr int NBX = 512;  // bins of the localising histogram
+constexpr int CAND = 8;   // in-bin candidates handled by the fast path
+
+struct BinMap {
+  float mn, scale;
+  __device__ __forceinline__ int operator()(float v) const {  // monotone non-decreasing in v; NaN excluded by caller
+    if (v == CUDART_INF_F) return NBX - 1;
+    if (v == -CUDART_INF_F) return 0;
+    const float f = (v - mn) * scale;
+    const int b = (int)f;
+    return b < 0 ? 0 : (b > NBX - 1 ? NBX - 1 : b);
+  }
+};
+
+// Order statistics of ranks r0 and r1 (r1 == r0 or r0 + 1) among the window's valid samples,
+// given that bin `ib` holds rank r0, `cl` samples lie in lower bins and `h` in bin ib.
+template <typename ForEach>
+__device__ __forceinline__ void select_pair(ForEach&& for_each, const BinMap& bm, int ib, int cl, int h, int r0,
+                                            int r1, float& a, float& b) {
+  const int j0 = r0 - cl;  // rank inside the bin
+  float nextmin = CUDART_INF_F;  // smallest sample in a higher bin
+  if (h <= CAND) {
+    float cand[CAND] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    int m = 0;
+    for_each([&](float v) {
+      const int bi = bm(v);
+      if (bi == ib) {
+        int k = m++;
+        while (k > 0 && cand[k - 1] > v) { cand[k] = cand[k - 1]; --k; }
+        cand[k] = v;
+      } else if (bi > ib) {
+        nextmin = fminf(nextmin, v);
+      }
+    });
+    a = cand[j0];
+    b = (r1 == r0) ? a : ((j0 + 1 < m) ? cand[j0 + 1] : nextmin);
+    return;
+  }
+  // Crowded bin (constant or heavily tied series): walk the distinct values upwards.
+  float cur = -CUDART_INF_F;
+  bool first = true;
+  int seen = 0;
+  a = CUDART_NAN_F;
+  b = CUDART_NAN_F;
+  bool have_a = false;
+  while (true) {
+    float nxt = CUDART_INF_F;
+    int mult = 0;
+    bool any = false;
+    for_each([&](float v) {
+      const int bi = bm(v);
+      if (bi == ib) {
+        if (first ? true : (v > cur)) {
+          if (!any || v < nxt) { nxt = v; mult = 1; any = true; }
+          else if (v == nxt) ++mult;
+        }
+      } else if (bi > ib) {
+        nextmin = fminf(nextmin, v);
+      }
+    });
+    if (!any) {  // ran out of the bin: rank r1 lives in a higher bin
+      if (!have_a) a = nextmin;
+      b = nextmin;
+      return;
+    }
+    first = false;
+    cur = nxt;
+    if (!have_a && j0 < seen + mult) {
+      a = nxt;
+      have_a = true;
+      if (r1 == r0 || j0 + 1 < seen + mult) { b = nxt; return; }
+    } else if (have_a) {
+      b = nxt;
+      return;
+    }
+    seen += mult;
+  }
+}
+
+// numpy 'linear' quantile in float32 (numpy/lib/_function_base_impl.py _quantile/_lerp), as
+// np.nanpercentile(float32 data, python scalar) computes it (detect.py:1941).
+__device__ __forceinline__ void f32_rank(int n, float qf, int& r0, int& r1, float& g) {
+  const float vi = __fmul_rn((float)(n - 1), qf);
+  if (vi >= (float)(n - 1)) { r0 = r1 = n - 1; g = 0.f; return; }
+  if (vi < 0.f) { r0 = r1 = 0; g = 0.f; return; }
+  const float lo = floorf(vi);
+  r0 = (int)lo;
+  r1 = r0 + 1;
+  g = __fsub_rn(vi, lo);
+}
+__device__ __forceinline__ float f32_lerp(float a, float b, float g) {
+  const float diff = __fsub_rn(b, a);
+  float r = __fadd_rn(a, __fmul_rn(diff, g));
+  if (g >= 0.5f) r = __fsub_rn(b, __fmul_rn(diff, __fsub_rn(1.f, g)));
+  return r;
+}
+
+template <typename CT>
+__global__ void __launch_bounds__(32) hobday_exact_kernel(const float* __restrict__ anom, int64_t T, int64_t N,
+                                                          int64_t pitch, const int32_t* __restrict__ doy_ptr,
+                                                          const int32_t* __restrict__ doy_rows, int w, float qf,
+                                                          float* __restrict__ thr) {
+  extern __shared__ unsigned char smem_raw[];
+  CT* hist = reinterpret_cast<CT*>(smem_raw);  // [NBX][32]
+  const int lane = threadIdx.x;
+  const int64_t c = (int64_t)blockIdx.x * 32 + lane;
+  const bool live = c < N;
+  const int64_t cc = live ? c : N - 1;
+  for (int b = 0; b < NBX; ++b) hist[b * 32 + lane] = 0;
+  // value range of the lane's series
+  float mn = CUDART_INF_F, mx = -CUDART_INF_F;
+#pragma unroll 4
+  for (int64_t t = 0; t < T; ++t) {
+    const float v = __ldg(&anom[t * pitch + cc]);
+    if (is_finite_f(v)) { mn = fminf(mn, v); mx = fmaxf(mx, v); }
+  }
+  BinMap bm;
+  bm.mn = (mn <= mx) ? mn : 0.f;
+  bm.scale = (mx > mn) ? ((float)NBX / (mx - mn)) : 0.f;
+  if (!is_finite_f(bm.scale)) bm.scale = 0.f;
+  const int half = w / 2;
+  int n = 0, ib = 0, cl = 0;
+
+  auto apply_doy = [&](int d, int sign) {
+    const int b0 = __ldg(&doy_ptr[d]), b1 = __ldg(&doy_ptr[d + 1]);
+    for (int j = b0; j < b1; ++j) {
+      const float v = __ldg(&anom[(int64_t)__ldg(&doy_rows[j]) * pitch + cc]);
+      if (v == v) {
+        const int bi = bm(v);
+        hist[bi * 32 + lane] += (CT)sign;
+        n += sign;
+        if (bi < ib) cl += sign;
+      }
+    }
+  };
+  for (int k = -half; k <= half; ++k) apply_doy(((k % NDOY) + NDOY) % NDOY, +1);
+
+  for (int d = 0; d < NDOY; ++d) {
+    if (d > 0) {
+      apply_doy((d - 1 - half + 2 * NDOY) % NDOY, -1);
+      apply_doy((d + half) % NDOY, +1);
+    }
+    float res = CUDART_NAN_F;
+    if (n > 0) {
+      int r0, r1;
+      float g;
+      f32_rank(n, qf, r0, r1, g);
+      while (cl > r0) { --ib; cl -= (int)hist[ib * 32 + lane]; }
+      while (ib < NBX - 1 && cl + (int)hist[ib * 32 + lane] <= r0) { cl += (int)hist[ib * 32 + lane]; ++ib; }
+      const int h = (int)hist[ib * 32 + lane];
+      auto for_each = [&](auto&& fn) {
+        for (int k = -half; k <= half; ++k) {
+          const int dd = (d + k + NDOY) % NDOY;
+          const int b0 = __ldg(&doy_ptr[dd]), b1 = __ldg(&doy_ptr[dd + 1]);
+          for (int j = b0; j < b1; ++j) {
+            const float v = __ldg(&anom[(int64_t)__ldg(&doy_rows[j]) * pitch + cc]);
+            if (v == v) fn(v);
+          }
+        }
+      };
+      float a, b;
+      select_pair(for_each, bm, ib, cl, h, r0, r1, a, b);
+      res = f32_lerp(a, b, g);
+    }
+    if (live) thr[(int64_t)d * N + c] = res;
+  }
+}
+
+// np.nanquantile(a, float64 q) 'linear' (xarray .quantile, detect.py:2899): float64 virtual
+// index and lerp, the difference (b - a) still taken in float32.
+template <typename CT>
+__global__ void __launch_bounds__(32) global_exact_kernel(const float* __restrict__ anom, int64_t T, int64_t N,
+                                                          int64_t pitch, double q, double* __restrict__ thr) {
+  extern __shared__ unsigned char smem_raw[];
+  CT* hist = reinterpret_cast<CT*>(smem_raw);
+  const int lane = threadIdx.x;
+  const int64_t c = (int64_t)blockIdx.x * 32 + lane;
+  const bool live = c < N;
+  const int64_t cc = live ? c : N - 1;
+  for (int b = 0; b < NBX; ++b) hist[b * 32 + lane] = 0;
+  float mn = CUDART_INF_F, mx = -CUDART_INF_F;
+#pragma unroll 4
+  for (int64_t t = 0; t < T; ++t) {
+    const float v = __ldg(&anom[t * pitch + cc]);
+    if (is_finite_f(v)) { mn = fminf(mn, v); mx = fmaxf(mx, v); }
+  }
+  BinMap bm;
+  bm.mn = (mn <= mx) ? mn : 0.f;
+  bm.scale = (mx > mn) ? ((float)NBX / (mx - mn)) : 0.f;
+  if (!is_finite_f(bm.scale)) bm.scale = 0.f;
+  int n = 0;
+#pragma unroll 4
+  for (int64_t t = 0; t < T; ++t) {
+    const float v = __ldg(&anom[t * pitch + cc]);
+    if (v == v) { hist[bm(v) * 32 + lane] += 1; ++n; }
+  }
+  double res = CUDART_NAN;
+  if (n > 0) {
+    const double vi = (double)(n - 1) * q;
+    int r0, r1;
+    double g;
+    if (vi >= (double)(n - 1)) { r0 = r1 = n - 1; g = 0.0; }
+    else if (vi < 0.0) { r0 = r1 = 0; g = 0.0; }
+    else { const double lo = floor(vi); r0 = (int)lo; r1 = r0 + 1; g = vi - lo; }
+    int ib = 0, cl = 0;
+    while (ib < NBX - 1 && cl + (int)hist[ib * 32 + lane] <= r0) { cl += (int)hist[ib * 32 + lane]; ++ib; }
+    const int h = (int)hist[ib * 32 + lane];
+    auto for_each = [&](auto&& fn) {
+      for (int64_t t = 0; t < T; ++t) {
+        const float v = __ldg(&anom[t * pitch + cc]);
+        if (v == v) fn(v);
+      }
+    };
+    float a, b;
+    select_pair(for_each, bm, ib, cl, h, r0, r1, a, b);
+    const double diff = (double)__fsub_rn(b, a);
+    res = __dadd_rn((double)a, __dmul_rn(diff, g));
+    if (g >= 0.5) res = __dsub_rn((double)b, __dmul_rn(diff, __dsub_rn(1.0, g)));
+  }
+  if (live) thr[c] = res;
+}
+
+// ---------------------------------------------------------------------------------------
+// Global approximate threshold (_compute_histogram_quantile_1d, detect.py:2737-2865).
+// float64 edges, last bin right-closed; pdf = hist / (sum + 1e-10); cdf = sequential cumsum.
+// ---------------------------------------------------------------------------------------
+template <typename CT>
+__global__ void __launch_bounds__(32) global_hist_kernel(const float* __restrict__ anom, int64_t T, int64_t N,
+                                                         int64_t pitch, const double* __restrict__ edges,
+                                                         const double* __restrict__ centers, int nb, double q,
+                                                         double lower_bound, double* __restrict__ thr,
+                                                         double* __restrict__ stats) {
+  extern __shared__ unsigned char smem_raw[];
+  CT* hist = reinterpret_cast<CT*>(smem_raw);                         // [nb][32]
+  double* s_edges = reinterpret_cast<double*>(smem_raw + (((size_t)nb * 32 * sizeof(CT) + 15) & ~(size_t)15));  // [nb+1]
+  const int lane = threadIdx.x;
+  const int64_t c = (int64_t)blockIdx.x * 32 + lane;
+  const bool live = c < N;
+  const int64_t cc = live ? c : N - 1;
+  for (int b = 0; b < nb; ++b) hist[b * 32 + lane] = 0;
+  for (int i = lane; i <= nb; i += 32) s_edges[i] = edges[i];
+  __syncwarp();
+  const double e1 = s_edges[1];
+  const double inv_step = (nb > 1) ? 1.0 / (s_edges[2] - s_edges[1]) : 1.0;
+  const double e_last = s_edges[nb];
+  bool has_nan = false;
+  long long total = 0;
+#pragma unroll 2
+  for (int64_t t = 0; t < T; ++t) {
+    const float vf = ld_stream(&anom[t * pitch + cc]);
+    if (vf != vf) { has_nan = true; continue; }
+    const double v = (double)vf;
+    if (v > e_last) continue;  // out of range (xhistogram drops it)
+    // largest i in [0, nb-1] with edges[i] <= v  (v == edges[nb] falls in the last bin)
+    double g = floor((v - e1) * inv_step) + 1.0;
+    g = fmin(fmax(g, 0.0), (double)(nb - 1));
+    int i = (int)g;
+    while (i > 0 && v < s_edges[i]) --i;
+    while (i < nb - 1 && v >= s_edges[i + 1]) ++i;
+    hist[i * 32 + lane] += 1;
+    ++total;
+  }
+  const double eps = 1e-10;
+  const double hist_sum = (double)total + 1e-10;      // detect.py:2778
+  // sweep 1: iu = first bin with cdf >= q - eps (0 if none); cdf_target = cdf[max(iu - 1, 0)]
+  int iu = 0;
+  {
+    double cdf = 0.0;
+    bool found = false;
+    for (int b = 0; b < nb && !found; ++b) {
+      const int h = (int)hist[b * 32 + lane];
+      if (h) cdf = __dadd_rn(cdf, __ddiv_rn((double)h, hist_sum));
+      if (cdf >= q - eps) { iu = b; found = true; }
+    }
+  }
+  auto cdf_at = [&](int idx) {
+    double cdf = 0.0;
+    for (int b = 0; b <= idx; ++b) {
+      const int h = (int)hist[b * 32 + lane];
+      if (h) cdf = __dadd_rn(cdf, __ddiv_rn((double)h, hist_sum));
+    }
+    return cdf;
+  };
+  const int ibefore = (iu - 1 > 0) ? iu - 1 : 0;      // detect.py:2793
+  const double cdf_target = cdf_at(ibefore);
+  int il = 0;                                          // first bin with cdf > cdf_target (0 if none)
+  {
+    double cdf = 0.0;
+    bool found = false;
+    for (int b = 0; b < nb && !found; ++b) {
+      const int h = (int)hist[b * 32 + lane];
+      if (h) cdf = __dadd_rn(cdf, __ddiv_rn((double)h, hist_sum));
+      if (cdf > cdf_target) { il = b; found = true; }
+    }
+  }
+  il = il < 0 ? 0 : (il > nb - 2 ? nb - 2 : il);      // detect.py:2804-2805
+  iu = iu < 1 ? 1 : (iu > nb - 1 ? nb - 1 : iu);
+  const double cdl = cdf_at(il), cdu = cdf_at(iu);
+  const double bl = centers[il], bu = centers[iu];
+  const double denom = __dsub_rn(cdu, cdl);
+  const bool exact = fabs(__dsub_rn(cdl, q)) < eps;
+  const bool zero = fabs(denom) <= eps;
+  const double frac = __ddiv_rn(__dsub_rn(q, cdl), (fabs(denom) > eps) ? denom : 1.0);
+  double res = __dadd_rn(bl, __dmul_rn(frac, __dsub_rn(bu, bl)));
+  if (exact) res = bl;
+  if (zero && !exact) res = __ddiv_rn(__dadd_rn(bl, bu), 2.0);
+  if (has_nan) res = CUDART_NAN;                       // detect.py:2835-2836
+  double vmin = CUDART_INF, vmax = -CUDART_INF;
+  if (live && res == res) { vmin = res; vmax = res; }
+  if (res < lower_bound) res = lower_bound;            // detect.py:2853-2863
+  if (live) thr[c] = res;
+  vmin = warp_min(vmin);
+  vmax = warp_max(vmax);
+  if (lane == 0 && stats) {
+    if (vmin != CUDART_INF) atomic_min_d(&stats[0], vmin);
+    if (vmax != -CUDART_INF) atomic_max_d(&stats[1], vmax);
+  }
+}
+
+template <typename F>
+__global__ void init_stats_kernel(F* stats) {
+  stats[0] = (F)CUDART_INF;
+  stats[1] = (F)-CUDART_INF;
+}
+
+}  // namespace marex
+
+using namespace marex;
+
+extern "C" int marex_digitize_f32(const float* a, int64_t T, int64_t N, int64_t pitch, const float* edges,
+                                  int32_t n_edges, uint16_t* bins, int64_t bins_pitch, void* stream) {
+  MAREX_REQUIRE(a && edges && bins, "null pointer");
+  MAREX_REQUIRE(T > 0 && N > 0 && pitch >= N && bins_pitch >= N, "bad shape");
+  MAREX_REQUIRE(n_edges >= 3 && n_edges <= 65535, "n_edges must be in 3..65535");
+  const int threads = 256;
+  const int64_t bx = (N + threads - 1) / threads;
+  int64_t by = (8LL * sm_count() + bx - 1) / bx;
+  by = by < 1 ? 1 : (by > T ? T : by);
+  if (by > 65535) by = 65535;
+  const int rows_per_block = (int)((T + by - 1) / by);
+  by = (T + rows_per_block - 1) / rows_per_block;
+  digitize_kernel<<<dim3((unsigned)bx, (unsigned)by), threads, n_edges * sizeof(float), (cudaStream_t)stream>>>(
+      a, T, N, pitch, edges, n_edges, bins, bins_pitch, rows_per_block);
+  MAREX_LAUNCH_CHECK("digitize_kernel");
+  return MAREX_OK;
+}
+
+template <typename K>
+static int set_smem(K kern, size_t smem) {
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute");
+  return MAREX_OK;
+}
+
+extern "C" int marex_hobday_thresholds_hist(const uint16_t* bins, int64_t T, int64_t ny, int64_t nx, int64_t pitch,
+                                            const int32_t* doy_ptr, const int32_t* doy_rows, int32_t max_window_rows,
+                                            const float* centers, int32_t nb, int32_t w, int32_t ws, double q,
+                                            const float* anom_row0, float lower_bound, float* thr, float* stats,
+                                            void* stream) {
+  MAREX_REQUIRE(bins && doy_ptr && doy_rows && centers && anom_row0 && thr, "null pointer");
+  MAREX_REQUIRE(T > 0 && ny > 0 && nx > 0 && pitch >= ny * nx, "bad shape");
+  MAREX_REQUIRE(nb >= 2 && nb <= 1700, "nb must be in 2..1700 (shared-memory histogram)");
+  MAREX_REQUIRE(w >= 3 && w <= 365 && (w & 1), "window_days_hobday must be odd and in 3..365");
+  MAREX_REQUIRE(ws >= 1 && (ws & 1), "window_spatial_hobday must be odd");
+  MAREX_REQUIRE(ny <= 65535, "ny too large for grid.y");
+  cudaStream_t st = (cudaStream_t)stream;
+  if (stats) {
+    init_stats_kernel<float><<<1, 1, 0, st>>>(stats);
+    MAREX_LAUNCH_CHECK("init_stats_kernel");
+  }
+  const long long max_count = (long long)max_window_rows * ws * ws;
+  const bool wide = max_count > 65535;
+  const size_t smem = (size_t)nb * 32 * (wide ? 4 : 2);
+  MAREX_REQUIRE(smem <= 220 * 1024, "histogram does not fit shared memory");
+  dim3 grid((unsigned)((nx + 31) / 32), (unsigned)ny);
+#define MAREX_HH(CT, P)                                                                                           \
+  do {                                                                                                            \
+    int rc = set_smem(hobday_hist_kernel<CT, P>, smem);                                                           \
+    if (rc) return rc;                                                                                            \
+    hobday_hist_kernel<CT, P><<<grid, 32, smem, st>>>(bins, ny, nx, pitch, doy_ptr, doy_rows, centers, nb, w, ws, \
+                                                      q, anom_row0, lower_bound, thr, stats);                     \
+  } while (0)
+  if (ws > 1) { if (wide) MAREX_HH(uint32_t, true); else MAREX_HH(uint16_t, true); }
+  else        { if (wide) MAREX_HH(uint32_t, false); else MAREX_HH(uint16_t, false); }
+#undef MAREX_HH
+  MAREX_LAUNCH_CHECK("hobday_hist_kernel");
+  return MAREX_OK;
+}
+
+extern "C" int marex_hobday_thresholds_exact_f32(const float* anom, int64_t T, int64_t N, int64_t pitch,
+                                                 const int32_t* doy_ptr, const int32_t* doy_rows,
+                                                 int32_t max_window_rows, int32_t w, float percentile, float* thr,
+                                                 void* stream) {
+  MAREX_REQUIRE(anom && doy_ptr && doy_rows && thr, "null pointer");
+  MAREX_REQUIRE(T > 0 && N > 0 && pitch >= N, "bad shape");
+  MAREX_REQUIRE(w >= 1 && w <= 365 && (w & 1), "window_days_hobday must be odd and in 1..365");
+  const float qf = percentile / 100.0f;  // np.true_divide(q, float32(100)) in float32
+  const bool wide = max_window_rows > 65535;
+  const size_t smem = (size_t)NBX * 32 * (wide ? 4 : 2);
+  const unsigned grid = (unsigned)((N + 31) / 32);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (wide) {
+    int rc = set_smem(hobday_exact_kernel<uint32_t>, smem);
+    if (rc) return rc;
+    hobday_exact_kernel<uint32_t><<<grid, 32, smem, st>>>(anom, T, N, pitch, doy_ptr, doy_rows, w, qf, thr);
+  } else {
+    int rc = set_smem(hobday_exact_kernel<uint16_t>, smem);
+    if (rc) return rc;
+    hobday_exact_kernel<uint16_t><<<grid, 32, smem, st>>>(anom, T, N, pitch, doy_ptr, doy_rows, w, qf, thr);
+  }
+  MAREX_LAUNCH_CHECK("hobday_exact_kernel");
+  return MAREX_OK;
+}
+
+extern "C" int marex_global_threshold_exact_f64(const float* anom, int64_t T, int64_t N, int64_t pitch, double q,
+                                                double* thr, void* stream) {
+  MAREX_REQUIRE(anom && thr, "null pointer");
+  MAREX_REQUIRE(T > 0 && N > 0 && pitch >= N, "bad shape");
+  const bool wide = T > 65535;
+  const size_t smem = (size_t)NBX * 32 * (wide ? 4 : 2);
+  const unsigned grid = (unsigned)((N + 31) / 32);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (wide) {
+    int rc = set_smem(global_exact_kernel<uint32_t>, smem);
+    if (rc) return rc;
+    global_exact_kernel<uint32_t><<<grid, 32, smem, st>>>(anom, T, N, pitch, q, thr);
+  } else {
+    int rc = set_smem(global_exact_kernel<uint16_t>, smem);
+    if (rc) return rc;
+    global_exact_kernel<uint16_t><<<grid, 32, smem, st>>>(anom, T, N, pitch, q, thr);
+  }
+  MAREX_LAUNCH_CHECK("global_exact_kernel");
+  return MAREX_OK;
+}
+
+extern "C" int marex_global_threshold_hist_f64(const float* anom, int64_t T, int64_t N, int64_t pitch,
+                                               const double* edges, const double* centers, int32_t nb, double q,
+                                               double lower_bound, double* thr, double* stats, void* stream) {
+  MAREX_REQUIRE(anom && edges && centers && thr, "null pointer");
+  MAREX_REQUIRE(T > 0 && N > 0 && pitch >= N, "bad shape");
+  MAREX_REQUIRE(nb >= 3 && nb <= 1600, "nb must be in 3..1600 (shared-memory histogram)");
+  cudaStream_t st = (cudaStream_t)stream;
+  if (stats) {
+    init_stats_kernel<double><<<1, 1, 0, st>>>(stats);
+    MAREX_LAUNCH_CHECK("init_stats_kernel");
+  }
+  const bool wide = T > 65535;
+  const size_t smem = (((size_t)nb * 32 * (wide ? 4 : 2) + 15) & ~(size_t)15) + (size_t)(nb + 1) * sizeof(double);
+  MAREX_REQUIRE(smem <= 220 * 1024, "histogram does not fit shared memory");
+  const unsigned grid = (unsigned)((N + 31) / 32);
+  if (wide) {
+    int rc = set_smem(global_hist_kernel<uint32_t>, smem);
+    if (rc) return rc;
+    global_hist_kernel<uint32_t><<<grid, 32, smem, st>>>(anom, T, N, pitch, edges, centers, nb, q, lower_bound, thr,
+                                                         stats);
+  } else {
+    int rc = set_smem(global_hist_kernel<uint16_t>, smem);
+    if (rc) return rc;
+    global_hist_kernel<uint16_t><<<grid, 32, smem, st>>>(anom, T, N, pitch, edges, centers, nb, q, lower_bound, thr,
+                                                         stats);
+  }
+  MAREX_LAUNCH_CHECK("global_hist_kernel");
+  return MAREX_OK;
+}

@@ -1,0 +1,829 @@
+"""
+Host-side mirror of ``marEx/detect.py`` for the detection hot path, driving the sm_100a kernels
+of ``libmarex_b200.so`` through ctypes.  PyTorch is used only for device buffers, streams and
+host<->device copies.  There is no CPU fallback: without a CUDA device or without the built
+library every entry point raises.
+
+Two levels:
+
+* array level (``preprocess_arrays``, ``compute_normalised_anomaly_arrays``,
+  ``identify_extremes_arrays``, ``rolling_climatology_arrays``): time-major numpy / torch arrays
+  plus a ``datetime64`` time axis.  This is the boundary the parity tests exercise.
+* xarray level (``preprocess_data`` ... in ``marex_b200/xr_api.py``): the reference's public
+  signatures (detect.py:287-313, 891-907, 1119-1133, 1511-1517, 1691-1698), DataArray in and
+  Dataset out.
+
+Validation rules, defaults and messages follow the reference line by line; each block cites it.
+"""
+from __future__ import annotations
+
+import ctypes
+import logging
+import warnings
+from typing import Any, Dict, List, Optional, Sequence, Tuple
+
+import numpy as np
+import torch
+
+from . import _lib
+from .calendar import NDOY, Calendar, build_calendar, decimal_year, doy_csr, max_window_rows, shifting_out_rows
+from .exceptions import ConfigurationError, create_data_validation_error
+
+logger = logging.getLogger("marex_b200")
+
+VALID_ANOMALY = ("shifting_baseline", "fixed_baseline", "detrend_fixed_baseline")
+VALID_EXTREME = ("global_extreme", "hobday_extreme")
+
+
+# --------------------------------------------------------------------------------------
+# small plumbing helpers
+# --------------------------------------------------------------------------------------
+def _p(t: Optional[torch.Tensor]):
+    return ctypes.c_void_p(t.data_ptr()) if t is not None else None
+
+
+def _stream():
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _device(device=None) -> torch.device:
+    if not torch.cuda.is_available():
+        raise RuntimeError("marex_b200 needs a CUDA device (B200, sm_100a); there is no CPU fallback")
+    if device is None:
+        return torch.device("cuda", torch.cuda.current_device())
+    return torch.device(device)
+
+
+def _up(a: np.ndarray, dtype, device) -> torch.Tensor:
+    return torch.from_numpy(np.ascontiguousarray(a, dtype=dtype)).to(device)
+
+
+def _to_device_field(x, device) -> Tuple[torch.Tensor, Tuple[int, ...]]:
+    """Any (T, ...space) array -> contiguous float32 CUDA tensor (T, N) + the space shape.
+    ``da.astype(np.float32)`` of detect.py:600."""
+    if isinstance(x, torch.Tensor):
+        t = x
+    else:
+        t = torch.from_numpy(np.ascontiguousarray(x))
+    space = tuple(int(s) for s in t.shape[1:])
+    t = t.to(device=device, dtype=torch.float32, non_blocking=True).reshape(t.shape[0], -1).contiguous()
+    return t, space
+
+
+# --------------------------------------------------------------------------------------
+# configuration validation (messages follow the reference; tests match on them)
+# --------------------------------------------------------------------------------------
+def validate_reference_period_method(reference_period, method_anomaly: str) -> None:
+    """detect.py:571-579 / 1069-1077."""
+    if reference_period is not None and method_anomaly not in ("fixed_baseline", "detrend_fixed_baseline"):
+        raise ConfigurationError(
+            f"reference_period is not supported for method_anomaly='{method_anomaly}'",
+            details="reference_period is only applicable to 'fixed_baseline' and 'detrend_fixed_baseline' methods",
+            suggestions=[
+                "Remove the reference_period parameter, or",
+                "Use method_anomaly='fixed_baseline' or 'detrend_fixed_baseline'",
+            ],
+        )
+
+
+def validate_anomaly_method(method_anomaly: str) -> None:
+    """detect.py:1100-1116.  ``detrend_harmonic`` exists upstream but is outside this
+    library's hot-path scope: it is reported as such, not silently approximated."""
+    if method_anomaly == "detrend_harmonic":
+        raise NotImplementedError(
+            "method_anomaly='detrend_harmonic' is outside the B200 hot path "
+            "(shifting_baseline, fixed_baseline, detrend_fixed_baseline)"
+        )
+    if method_anomaly not in VALID_ANOMALY:
+        raise ConfigurationError(
+            f"Unknown anomaly method '{method_anomaly}'",
+            details="Invalid method_anomaly parameter",
+            suggestions=[
+                "Use 'detrend_harmonic' for efficient processing with trend and harmonic removal",
+                "Use 'shifting_baseline' for accurate climatology (requires more data)",
+                "Use 'fixed_baseline' to remove a single daily climatology across all years "
+                "(keeps any long-term trend in the anomaly)",
+                "Use 'detrend_fixed_baseline' for trend removal followed by fixed climatology",
+            ],
+            context={
+                "provided_method": method_anomaly,
+                "valid_methods": ["detrend_harmonic", "shifting_baseline", "fixed_baseline", "detrend_fixed_baseline"],
+            },
+        )
+
+
+def validate_detrend_orders(detrend_orders: Sequence[int]) -> None:
+    """detect.py:2104-2126."""
+    if not detrend_orders:
+        raise ConfigurationError(
+            "detrend_orders cannot be empty",
+            details="At least one polynomial order must be specified for detrending",
+            suggestions=[
+                "Use detrend_orders=[1] for linear detrending",
+                "Use detrend_orders=[1, 2] for linear + quadratic detrending",
+                "Remove detrend_orders optional parameter to use default [1]",
+            ],
+        )
+    if any(order < 1 for order in detrend_orders):
+        invalid = [order for order in detrend_orders if order < 1]
+        raise ConfigurationError(
+            f"Invalid polynomial orders: {invalid}",
+            details="Polynomial orders must be positive integers (≥ 1)",
+            suggestions=[
+                "Use only positive integers for polynomial orders",
+                "Common values: [1] for linear, [1,2] for linear+quadratic",
+                f"Remove invalid orders: {invalid}",
+            ],
+        )
+
+
+def validate_reference_period(reference_period, year: np.ndarray) -> np.ndarray:
+    """detect.py:2334-2355: returns the row indices of the reference period."""
+    start_year, end_year = reference_period
+    if start_year > end_year:
+        raise ConfigurationError(
+            f"Invalid reference_period: start year ({start_year}) must be <= end year ({end_year})",
+            details="The reference_period tuple must be (start_year, end_year) with start_year <= end_year",
+            suggestions=[f"Swap the order: use reference_period=({end_year}, {start_year})"],
+        )
+    rows = np.nonzero((year >= start_year) & (year <= end_year))[0]
+    if rows.size == 0:
+        lo, hi = int(year.min()), int(year.max())
+        raise ConfigurationError(
+            f"No data found in reference_period ({start_year}, {end_year})",
+            details=f"Dataset spans {lo}-{hi} but no timesteps fall within the specified period",
+            suggestions=[
+                f"Adjust reference_period to overlap with data range ({lo}-{hi})",
+                "Set reference_period=None to use the full time series",
+            ],
+        )
+    return rows
+
+
+def resolve_extreme_config(
+    method_extreme: str,
+    threshold_percentile: float,
+    window_days_hobday: Optional[int],
+    window_spatial_hobday: Optional[int],
+    method_percentile: str,
+    precision: float,
+    max_anomaly: float,
+    gridded: bool,
+    dimensions: Optional[Dict[str, str]] = None,
+    available_dims: Optional[List[str]] = None,
+) -> Optional[int]:
+    """The configuration rules of ``identify_extremes`` (detect.py:1277-1503), in the reference's
+    order.  Returns the effective ``window_spatial_hobday`` (5 by default on gridded data,
+    detect.py:1450-1452)."""
+    valid_methods = ["exact", "approximate"]
+    if method_percentile not in valid_methods:
+        raise ConfigurationError(
+            f"Unknown method_percentile '{method_percentile}'",
+            details="Invalid method_percentile parameter",
+            suggestions=[
+                "Use 'exact' for precise percentile computation (memory intensive)",
+                "Use 'approximate' for efficient histogram-based computation (default)",
+            ],
+            context={"provided_method": method_percentile, "valid_methods": valid_methods},
+        )
+    if method_percentile == "exact":
+        if precision != 0.01:
+            raise ConfigurationError(
+                "Parameter 'precision' cannot be used with method_percentile='exact'",
+                details=(
+                    f"The precision parameter (precision={precision}) is only used by the approximate "
+                    "histogram method and is ignored when using exact percentile computation"
+                ),
+                suggestions=[
+                    "Remove the 'precision' parameter when using method_percentile='exact'",
+                    "Use method_percentile='approximate' if you want to control histogram precision",
+                ],
+                context={"method_percentile": method_percentile, "provided_precision": precision, "default_precision": 0.01},
+            )
+        if max_anomaly != 5.0:
+            raise ConfigurationError(
+                "Parameter 'max_anomaly' cannot be used with method_percentile='exact'",
+                details=(
+                    f"The max_anomaly parameter (max_anomaly={max_anomaly}) is only used by the approximate "
+                    "histogram method and is ignored when using exact percentile computation"
+                ),
+                suggestions=[
+                    "Remove the 'max_anomaly' parameter when using method_percentile='exact'",
+                    "Use method_percentile='approximate' if you want to control histogram binning range",
+                ],
+                context={
+                    "method_percentile": method_percentile,
+                    "provided_max_anomaly": max_anomaly,
+                    "default_max_anomaly": 5.0,
+                },
+            )
+    if threshold_percentile < 60 and method_percentile == "approximate":
+        raise ConfigurationError(
+            f"Percentile threshold {threshold_percentile}% is not supported with method_percentile='approximate'",
+            details=(
+                "Low percentile thresholds (<60%) produce undefined and unsupported behaviour "
+                "when using approximate histogram methods"
+            ),
+            suggestions=[
+                "Use method_percentile='exact' for percentiles below 60%",
+                "Use a higher percentile threshold (≥60%) with method_percentile='approximate'",
+                "Consider if such low percentiles are appropriate for extreme event identification",
+            ],
+            context={
+                "threshold_percentile": threshold_percentile,
+                "method_percentile": method_percentile,
+                "min_supported_percentile": 60,
+            },
+        )
+    if window_spatial_hobday is not None:
+        if not gridded:
+            raise ConfigurationError(
+                "window_spatial_hobday is not supported for unstructured grids",
+                details=(
+                    "Spatial smoothing with window_spatial_hobday requires structured grids with both x and y dimensions. "
+                    "Unstructured grids do not support spatial window operations due to computational and memory "
+                    "limitations of the algorithms."
+                ),
+                suggestions=[
+                    "Remove the window_spatial_hobday parameter for unstructured grids",
+                    "Use structured grid data if spatial smoothing is required",
+                    "Set window_spatial_hobday=None to use default behavior",
+                ],
+                context={
+                    "grid_type": "unstructured",
+                    "window_spatial_hobday": window_spatial_hobday,
+                    "dimensions": dimensions,
+                    "available_dims": available_dims,
+                },
+            )
+        if method_extreme != "hobday_extreme":
+            raise ConfigurationError(
+                "window_spatial_hobday can only be used with method_extreme='hobday_extreme'",
+                details=(
+                    "The window_spatial_hobday parameter is only implemented for the Hobday extreme method. "
+                    "Other extreme methods do not support spatial smoothing due to computational and memory "
+                    "limitations of the algorithms."
+                ),
+                suggestions=[
+                    "Remove the window_spatial_hobday parameter when using method_extreme='global_extreme'",
+                    "Use method_extreme='hobday_extreme' if spatial smoothing is required",
+                    "Set window_spatial_hobday=None to use default behavior",
+                ],
+                context={
+                    "method_extreme": method_extreme,
+                    "window_spatial_hobday": window_spatial_hobday,
+                    "compatible_methods": ["hobday_extreme"],
+                },
+            )
+        if method_percentile == "exact":
+            raise ConfigurationError(
+                "window_spatial_hobday is not supported with method_percentile='exact'",
+                details=(
+                    "The window_spatial_hobday parameter is only implemented for the approximate percentile method. "
+                    "Exact percentile computation does not support spatial smoothing due to computational and memory "
+                    "limitations of the algorithms."
+                ),
+                suggestions=[
+                    "Remove the window_spatial_hobday parameter when using method_percentile='exact'",
+                    "Use method_percentile='approximate' if spatial smoothing is required",
+                    "Set window_spatial_hobday=None to use default behavior",
+                ],
+                context={
+                    "method_percentile": method_percentile,
+                    "window_spatial_hobday": window_spatial_hobday,
+                    "compatible_methods": ["approximate"],
+                },
+            )
+    if method_extreme == "hobday_extreme" and window_days_hobday is not None and window_days_hobday % 2 == 0:
+        raise ConfigurationError(
+            "window_days_hobday must be an odd number",
+            details=(
+                f"Window parameters require odd numbers to ensure symmetric windows around a central point. "
+                f"window_days_hobday={window_days_hobday} is even, which would create asymmetric temporal windows."
+            ),
+            suggestions=[f"Use window_days_hobday={window_days_hobday + 1} or {window_days_hobday - 1}", "Choose an odd number"],
+            context={"window_days_hobday": window_days_hobday, "is_odd": False},
+        )
+    if method_extreme == "hobday_extreme" and window_spatial_hobday is None and gridded:
+        window_spatial_hobday = 5  # detect.py:1451-1452
+    if method_extreme == "hobday_extreme" and window_spatial_hobday is not None and window_spatial_hobday % 2 == 0:
+        raise ConfigurationError(
+            "window_spatial_hobday must be an odd number",
+            details=(
+                f"Window parameters require odd numbers to ensure symmetric windows around a central point. "
+                f"window_spatial_hobday={window_spatial_hobday} is even, which would create asymmetric spatial windows."
+            ),
+            suggestions=[f"Use window_days_hobday={window_days_hobday + 1} or {window_days_hobday - 1}", "Choose an odd number."],
+            context={"window_spatial_hobday": window_spatial_hobday, "is_odd": False},
+        )
+    if method_extreme not in VALID_EXTREME:
+        raise ConfigurationError(
+            f"Unknown extreme method '{method_extreme}'",
+            details="Invalid method_extreme parameter",
+            suggestions=[
+                "Use 'global_extreme' for efficient constant percentile threshold",
+                "Use 'hobday_extreme' for day-of-year specific thresholds",
+            ],
+            context={"provided_method": method_extreme, "valid_methods": ["global_extreme", "hobday_extreme"]},
+        )
+    return window_spatial_hobday
+
+
+def get_preprocessing_steps(
+    method_anomaly: str,
+    method_extreme: str,
+    std_normalise: bool,
+    detrend_orders: List[int],
+    window_year_baseline: int,
+    smooth_days_baseline: int,
+    window_days_hobday: int,
+    window_spatial_hobday: Optional[int],
+    reference_period: Optional[Tuple[int, int]] = None,
+) -> List[str]:
+    """``_get_preprocessing_steps`` (detect.py:844-888): the attrs strings, pinned by
+    tests/golden/ref_preprocessing_steps.json."""
+    steps = []
+    if method_anomaly == "detrend_harmonic":
+        steps.append(f"Removed polynomial trend orders={detrend_orders} & seasonal cycle")
+        if std_normalise:
+            steps.append("Normalised by 30-day rolling STD")
+    elif method_anomaly == "shifting_baseline":
+        steps.append(f"Rolling climatology using {window_year_baseline} years")
+        steps.append(f"Smoothed with {smooth_days_baseline}-day window")
+    elif method_anomaly == "fixed_baseline":
+        if reference_period is not None:
+            steps.append(f"Daily climatology computed from {reference_period[0]}-{reference_period[1]}")
+        else:
+            steps.append("Daily climatology computed from full time series")
+    elif method_anomaly == "detrend_fixed_baseline":
+        steps.append(f"Removed polynomial trend orders={detrend_orders}")
+        if reference_period is not None:
+            steps.append(f"Daily climatology computed from detrended data ({reference_period[0]}-{reference_period[1]})")
+        else:
+            steps.append("Daily climatology computed from detrended data")
+    if method_extreme == "global_extreme":
+        steps.append("Global percentile threshold applied to all days")
+    elif method_extreme == "hobday_extreme":
+        if window_spatial_hobday is not None:
+            steps.append(
+                f"Day-of-year thresholds with {window_days_hobday} day window & {window_spatial_hobday} spatial neighbours"
+            )
+        else:
+            steps.append(f"Day-of-year thresholds with {window_days_hobday} day window")
+    return steps
+
+
+def check_data_values(mask0: torch.Tensor, nonfinite: torch.Tensor, T: int, total_values: int) -> None:
+    """``_validate_data_values`` (detect.py:205-279) from the per-cell numbers the first anomaly
+    kernel produced in the same pass that read the data."""
+    m = mask0.bool()
+    if not bool(m.any()):
+        raise create_data_validation_error(
+            "Dataset contains no valid (finite) data",
+            details="All values in the first time step are NaN or infinite",
+            suggestions=[
+                "Check your input data for data quality issues",
+                "Verify the data was loaded correctly",
+                "Check for issues in data preprocessing steps",
+            ],
+            data_info={"total_values": int(total_values), "total_spatial_locations": int(m.numel())},
+        )
+    inv = torch.where(m, nonfinite, torch.zeros_like(nonfinite))
+    max_invalid = int(inv.max())
+    if max_invalid > 0:
+        total_invalid = int(inv.sum())
+        affected = int((inv > 0).sum())
+        ocean = int(m.sum())
+        raise create_data_validation_error(
+            f"Dataset contains {total_invalid} invalid values in {affected} ocean locations",
+            details=(
+                f"Found invalid data across time series. Worst location has {max_invalid} "
+                f"invalid time steps out of {T}."
+            ),
+            suggestions=[
+                "Remove or interpolate NaN/infinite values before preprocessing",
+                "Check data quality and loading procedures",
+                "Consider using data.fillna() or data.interpolate_na() methods",
+                "Verify coordinate/dimension alignment in your dataset",
+                "For ocean data, ensure land mask is properly applied before preprocessing",
+            ],
+            data_info={
+                "total_invalid_values_in_ocean": total_invalid,
+                "locations_affected": affected,
+                "total_ocean_locations": ocean,
+                "max_invalid_at_one_location": max_invalid,
+                "total_time_steps": int(T),
+                "percentage_affected": f"{100.0 * affected / ocean:.2f}%",
+            },
+        )
+
+
+def check_sufficient_years(cal: Calendar, W: int) -> None:
+    """detect.py:615-636."""
+    min_year, max_year = int(cal.year_val[0]), int(cal.year_val[-1])
+    total_years = max_year - min_year + 1
+    if total_years < W:
+        raise create_data_validation_error(
+            "Insufficient data for shifting_baseline method",
+            details=f"Dataset spans {total_years} years but requires at least {W} years",
+            suggestions=[
+                "Use more years of data to meet minimum requirement",
+                f"Reduce window_year_baseline parameter (currently {W})",
+                "Consider using detrend_fixed_baseline or detrend_harmonic method instead",
+            ],
+            data_info={"available_years": int(total_years), "required_years": int(W)},
+        )
+
+
+# --------------------------------------------------------------------------------------
+# (a) anomalies
+# --------------------------------------------------------------------------------------
+def detrend_model(time, detrend_orders: Sequence[int]) -> Tuple[np.ndarray, np.ndarray]:
+    """Design matrix (K, T) and its pseudo-inverse (T, K), float64 (detect.py:2139-2169),
+    polynomial terms only (``remove_harmonics=False``, detect.py:2450)."""
+    dy = decimal_year(time)
+    comps = [np.ones(len(dy))]
+    centered = dy - np.mean(dy)
+    for order in detrend_orders:
+        comps.append(centered**order)
+    model = np.array(comps)
+    for i in range(1, model.shape[0]):
+        model[i] = model[i] - np.mean(model[i]) * model[0]
+    return model, np.linalg.pinv(model)
+
+
+def rolling_climatology_arrays(x, time, window_year_baseline: int = 15, smooth_days_baseline: int = 1, device=None):
+    """``rolling_climatology`` (S = 1, detect.py:1511-1688) / ``smoothed_rolling_climatology``
+    (detect.py:1691-1816) at array level: the per-time-step climatology, NaN for the first
+    ``window_year_baseline`` years.  Returns a float32 CUDA tensor shaped like ``x``."""
+    dev = _device(device)
+    cal = build_calendar(time)
+    xd, space = _to_device_field(x, dev)
+    T, N = xd.shape
+    out = torch.full((T, N), float("nan"), dtype=torch.float32, device=dev)
+    mask0 = torch.empty(N, dtype=torch.uint8, device=dev)
+    nonfinite = torch.empty(N, dtype=torch.int32, device=dev)
+    out_row = _up(np.arange(T), np.int32, dev)
+    _lib.call(
+        "marex_shift_anomaly_f32", _p(xd), T, N, N, _p(_up(cal.tidx, np.int32, dev)), _p(_up(cal.year_val, np.int32, dev)),
+        cal.n_years, int(window_year_baseline), int(smooth_days_baseline), _p(out_row), 1, _p(out), N, _p(mask0),
+        _p(nonfinite), _stream(),
+    )  # fmt: skip
+    return out.reshape((T,) + space)
+
+
+def compute_normalised_anomaly_arrays(
+    x_dev: torch.Tensor,
+    cal: Calendar,
+    method_anomaly: str = "shifting_baseline",
+    window_year_baseline: int = 15,
+    smooth_days_baseline: int = 21,
+    detrend_orders: Optional[Sequence[int]] = None,
+    force_zero_mean: bool = True,
+    reference_period: Optional[Tuple[int, int]] = None,
+    validate: bool = True,
+    in_place: bool = False,
+) -> Dict[str, Any]:
+    """Array-level ``compute_normalised_anomaly`` (detect.py:891-1116) for the three hot-path
+    methods.  ``x_dev`` is a float32 CUDA tensor (T, N).  Returns ``dat_anomaly`` (T_out, N)
+    (already trimmed for shifting_baseline, detect.py:638-641), ``mask`` (N,) bool, the kept
+    rows and, when ``validate``, runs ``_validate_data_values`` on the numbers of the same pass.
+    ``in_place`` lets the fixed/detrend methods overwrite ``x_dev``."""
+    if detrend_orders is None:
+        detrend_orders = [1]
+    validate_reference_period_method(reference_period, method_anomaly)
+    validate_anomaly_method(method_anomaly)
+    dev = x_dev.device
+    T, N = x_dev.shape
+    assert T == cal.T
+    mask0 = torch.empty(N, dtype=torch.uint8, device=dev)
+    nonfinite = torch.empty(N, dtype=torch.int32, device=dev)
+    st = _stream()
+
+    if method_anomaly == "shifting_baseline":
+        W, S = int(window_year_baseline), int(smooth_days_baseline)
+        check_sufficient_years(cal, W)
+        out_row, keep = shifting_out_rows(cal, W)
+        T_out = int(keep.sum())
+        if T_out == 0:
+            raise IndexError("shifting_baseline: no time steps remain after removing the first window_year_baseline years")
+        anom = torch.empty((T_out, N), dtype=torch.float32, device=dev)
+        _lib.call(
+            "marex_shift_anomaly_f32", _p(x_dev), T, N, N, _p(_up(cal.tidx, np.int32, dev)),
+            _p(_up(cal.year_val, np.int32, dev)), cal.n_years, W, S, _p(_up(out_row, np.int32, dev)), 0,
+            _p(anom), N, _p(mask0), _p(nonfinite), st,
+        )  # fmt: skip
+        if validate:
+            check_data_values(mask0, nonfinite, T, T * N)
+        return {"dat_anomaly": anom, "mask": mask0.bool(), "keep": keep, "mask_raw": mask0.bool()}
+
+    keep = np.ones(T, dtype=bool)
+    rows = None
+    if reference_period is not None:
+        rows = validate_reference_period(reference_period, cal.year)
+    ptr, drows = doy_csr(cal.doy, rows)
+    ptr_d, rows_d = _up(ptr, np.int32, dev), _up(drows, np.int32, dev)
+    doy_d = _up(cal.doy, np.int16, dev)
+    clim = torch.empty((NDOY, N), dtype=torch.float32, device=dev)
+
+    if method_anomaly == "fixed_baseline":
+        _lib.call("marex_doy_climatology_f32", _p(x_dev), T, N, N, _p(ptr_d), _p(rows_d), None, _p(clim), st)
+        anom = x_dev if in_place else torch.empty_like(x_dev)
+        _lib.call(
+            "marex_sub_doy_climatology_f32", _p(x_dev), T, N, N, _p(doy_d), None, _p(clim), _p(anom), N, _p(mask0),
+            _p(nonfinite), st,
+        )  # fmt: skip
+        if validate:
+            check_data_values(mask0, nonfinite, T, T * N)
+        return {"dat_anomaly": anom, "mask": mask0.bool(), "keep": keep, "mask_raw": mask0.bool(), "climatology": clim}
+
+    # detrend_fixed_baseline (detect.py:2400-2462)
+    validate_detrend_orders(detrend_orders)
+    if 1 not in detrend_orders and len(detrend_orders) > 1:
+        print("Warning: Higher-order detrending without linear term may be unstable")  # detect.py:2135-2136
+    model, pmodel = detrend_model(cal.time, list(detrend_orders))
+    K = model.shape[0]
+    coef = torch.empty((K, N), dtype=torch.float64, device=dev)
+    _lib.call(
+        "marex_detrend_coef_f64", _p(x_dev), T, N, N, _p(_up(pmodel, np.float64, dev)), K, _p(coef), _p(mask0),
+        _p(nonfinite), st,
+    )  # fmt: skip
+    mask_raw = mask0.bool()
+    if validate:
+        check_data_values(mask0, nonfinite, T, T * N)
+    xd = x_dev if in_place else torch.empty_like(x_dev)
+    mean = torch.empty(N, dtype=torch.float32, device=dev) if force_zero_mean else None
+    _lib.call(
+        "marex_detrend_apply_f32", _p(x_dev), T, N, N, _p(_up(model, np.float64, dev)), K, _p(coef), _p(xd), N,
+        _p(mean), st,
+    )  # fmt: skip
+    _lib.call("marex_doy_climatology_f32", _p(xd), T, N, N, _p(ptr_d), _p(rows_d), _p(mean), _p(clim), st)
+    mask1 = torch.empty(N, dtype=torch.uint8, device=dev)
+    _lib.call(
+        "marex_sub_doy_climatology_f32", _p(xd), T, N, N, _p(doy_d), _p(mean), _p(clim), _p(xd), N, _p(mask1), None, st
+    )
+    return {"dat_anomaly": xd, "mask": mask1.bool(), "keep": keep, "mask_raw": mask_raw, "climatology": clim}
+
+
+# --------------------------------------------------------------------------------------
+# (b) + (c) thresholds and compare
+# --------------------------------------------------------------------------------------
+def hobday_bins(precision: float = 0.01, max_anomaly: float = 5.0) -> Tuple[np.ndarray, np.ndarray]:
+    """The reference's float32 edge/centre expression, verbatim (detect.py:2601-2608): the kernels
+    take these tables from the host so that counts match numpy bit for bit."""
+    edges = np.concatenate(
+        [[-np.inf], np.arange(-precision, max_anomaly + precision, precision, dtype=np.float32)], dtype=np.float32
+    )
+    centers = (edges[1:] + edges[:-1]) / 2
+    centers[0] = 0.0
+    return edges, centers.astype(np.float32)
+
+
+def global_bins(precision: float = 0.01, max_anomaly: float = 5.0) -> Tuple[np.ndarray, np.ndarray]:
+    """float64 edges/centres of the 1-D path (detect.py:2770-2784)."""
+    edges = np.concatenate([[-np.inf], np.arange(-precision, max_anomaly + precision, precision)])
+    centers = (edges[1:] + edges[:-1]) / 2
+    centers[0] = 0.0
+    return edges, centers
+
+
+def _warn_threshold_range(vmin: float, vmax: float, upper: float, lower: float, max_anomaly: float) -> None:
+    """The two UserWarnings of detect.py:2711-2730 / 2842-2861."""
+    if np.isfinite(vmax) and vmax > upper:
+        warnings.warn(
+            f"Quantile values exceed expected range: max={vmax:.4f} > {upper:.4f}. "
+            f"Consider increasing max_anomaly parameter (currently {max_anomaly:.2f}) or using a lower percentile threshold.",
+            UserWarning,
+            stacklevel=3,
+        )
+    if np.isfinite(vmin) and vmin < lower:
+        warnings.warn(
+            f"Quantile values below expected range in some locations: min={vmin:.4f} < {lower:.4f}. "
+            "This is likely due to a constant anomaly in certain (e.g. due to sea ice). "
+            "Double check the computed threshold values are correct.",
+            UserWarning,
+            stacklevel=3,
+        )
+
+
+def identify_extremes_arrays(
+    anom: torch.Tensor,
+    doy: np.ndarray,
+    grid: Optional[Tuple[int, int]] = None,
+    method_extreme: str = "hobday_extreme",
+    threshold_percentile: float = 95,
+    window_days_hobday: int = 11,
+    window_spatial_hobday: Optional[int] = None,
+    method_percentile: str = "approximate",
+    precision: float = 0.01,
+    max_anomaly: float = 5.0,
+    want_events: bool = True,
+    want_bits: bool = False,
+    n_years: Optional[int] = None,
+) -> Dict[str, Any]:
+    """Array-level ``identify_extremes`` (detect.py:1119-1503).  ``anom`` float32 CUDA (T, N);
+    ``grid=(ny, nx)`` for gridded data (enables the default 5x5 pooling), ``None`` for
+    unstructured.  Returns the doy-major thresholds (``thresholds_dm``), the thresholds in the
+    reference's layout (``thresholds``), ``extreme_events`` (bool) and/or ``bits``."""
+    gridded = grid is not None
+    ws = resolve_extreme_config(
+        method_extreme, threshold_percentile, window_days_hobday, window_spatial_hobday, method_percentile, precision,
+        max_anomaly, gridded,
+    )  # fmt: skip
+    dev = anom.device
+    T, N = anom.shape
+    st = _stream()
+    doy = np.asarray(doy).astype(np.int16)
+    out: Dict[str, Any] = {"window_spatial_hobday": ws}
+    q = threshold_percentile / 100.0
+
+    if method_extreme == "hobday_extreme":
+        w = int(window_days_hobday)
+        if n_years is not None:  # detect.py:1905-1915
+            n_above = n_years * w * (ws if ws is not None else 1) ** 2 * (1.0 - threshold_percentile / 100.0)
+            if n_above < 50:
+                logger.warning(
+                    f"Not enough samples for accurate extreme detection: {n_above} < 50. "
+                    "Consider using a lower threshold_percentile, increasing your time-series size, "
+                    "increasing the window_days_hobday, or using a larger window_spatial_hobday."
+                    "If your time-series is very short, consider using method_percentile='exact'."
+                )
+        ptr, rows = doy_csr(doy)
+        mwr = max_window_rows(ptr, w)
+        ptr_d, rows_d = _up(ptr, np.int32, dev), _up(rows, np.int32, dev)
+        thr = torch.empty((NDOY, N), dtype=torch.float32, device=dev)
+        if method_percentile == "exact":
+            _lib.call(
+                "marex_hobday_thresholds_exact_f32", _p(anom), T, N, N, _p(ptr_d), _p(rows_d), mwr, w,
+                float(threshold_percentile), _p(thr), st,
+            )  # fmt: skip
+            out["thresholds"] = thr if not gridded else thr.reshape((NDOY,) + tuple(grid))
+            out["thresholds_layout"] = "doy_first"
+        else:
+            if w < 3:
+                raise ConfigurationError(
+                    "window_days_hobday must be at least 3 with method_percentile='approximate'",
+                    details="The reference's wrap padding is undefined for a 1-day window (detect.py:2495-2496)",
+                )
+            edges, centers = hobday_bins(precision, max_anomaly)
+            nb = len(centers)
+            bins = torch.empty((T, N), dtype=torch.uint16, device=dev)
+            _lib.call("marex_digitize_f32", _p(anom), T, N, N, _p(_up(edges, np.float32, dev)), len(edges), _p(bins), N, st)
+            ny, nx = (grid if gridded else (1, N))
+            stats = torch.empty(2, dtype=torch.float32, device=dev)
+            _lib.call(
+                "marex_hobday_thresholds_hist", _p(bins), T, ny, nx, N, _p(ptr_d), _p(rows_d), mwr,
+                _p(_up(centers, np.float32, dev)), nb, w, int(ws) if (gridded and ws) else 1, float(q), _p(anom),
+                float(edges[3]), _p(thr), _p(stats), st,
+            )  # fmt: skip
+            del bins
+            vmin, vmax = (float(v) for v in stats.cpu())
+            _warn_threshold_range(vmin, vmax, float(edges[-2]), float(edges[3]), max_anomaly)
+            thr_cm = torch.empty((N, NDOY), dtype=torch.float32, device=dev)
+            _lib.call("marex_transpose_f32", _p(thr), NDOY, N, _p(thr_cm), st)
+            out["thresholds"] = thr_cm if not gridded else thr_cm.reshape(tuple(grid) + (NDOY,))
+            out["thresholds_layout"] = "doy_last"
+        out["thresholds_dm"] = thr
+    else:  # global_extreme (detect.py:2873-2923)
+        thr = torch.empty(N, dtype=torch.float64, device=dev)
+        if method_percentile == "exact":
+            _lib.call("marex_global_threshold_exact_f64", _p(anom), T, N, N, float(q), _p(thr), st)
+        else:
+            edges, centers = global_bins(precision, max_anomaly)
+            stats = torch.empty(2, dtype=torch.float64, device=dev)
+            _lib.call(
+                "marex_global_threshold_hist_f64", _p(anom), T, N, N, _p(_up(edges, np.float64, dev)),
+                _p(_up(centers, np.float64, dev)), len(centers), float(q), float(edges[3]), _p(thr), _p(stats), st,
+            )  # fmt: skip
+            vmin, vmax = (float(v) for v in stats.cpu())
+            _warn_threshold_range(vmin, vmax, float(edges[-2]), float(edges[3]), max_anomaly)
+        out["thresholds"] = thr if not gridded else thr.reshape(tuple(grid))
+        out["thresholds_layout"] = "space"
+        out["thresholds_dm"] = thr
+
+    events = torch.empty((T, N), dtype=torch.uint8, device=dev) if want_events else None
+    nw = (N + 31) // 32
+    bits = torch.empty((T, nw), dtype=torch.int32, device=dev) if want_bits else None
+    count = torch.zeros(1, dtype=torch.int64, device=dev)
+    if method_extreme == "hobday_extreme":
+        _lib.call(
+            "marex_compare_hobday", _p(anom), T, N, N, _p(_up(doy, np.int16, dev)), _p(out["thresholds_dm"]), _p(events),
+            N, _p(bits), nw, _p(count), st,
+        )  # fmt: skip
+    else:
+        _lib.call(
+            "marex_compare_global", _p(anom), T, N, N, _p(out["thresholds_dm"]), _p(events), N, _p(bits), nw, _p(count), st
+        )
+    if events is not None:
+        out["extreme_events"] = events.view(torch.bool)
+    if bits is not None:
+        out["bits"] = bits
+    out["count"] = count
+    return out
+
+
+# --------------------------------------------------------------------------------------
+# full pipeline at array level
+# --------------------------------------------------------------------------------------
+def preprocess_arrays(
+    x,
+    time,
+    method_anomaly: str = "shifting_baseline",
+    method_extreme: str = "hobday_extreme",
+    threshold_percentile: float = 95,
+    window_year_baseline: int = 15,
+    smooth_days_baseline: int = 21,
+    window_days_hobday: int = 11,
+    window_spatial_hobday: Optional[int] = None,
+    std_normalise: bool = False,
+    detrend_orders: Optional[Sequence[int]] = None,
+    force_zero_mean: bool = True,
+    reference_period: Optional[Tuple[int, int]] = None,
+    method_percentile: str = "approximate",
+    precision: float = 0.01,
+    max_anomaly: float = 5.0,
+    device=None,
+    output: str = "numpy",
+    want_events: bool = True,
+    want_bits: bool = False,
+    gridded: Optional[bool] = None,
+) -> Dict[str, Any]:
+    """``preprocess_data`` (detect.py:287-841) on arrays: ``x`` is ``(time, lat, lon)`` (gridded)
+    or ``(time, ncells)`` (unstructured), numpy or torch, host or device; ``time`` a datetime64
+    axis.  Returns ``dat_anomaly`` (T_out, ..space) float32, ``mask`` (..space) bool,
+    ``thresholds`` in the reference's layout and dtype, ``extreme_events`` (T_out, ..space) bool,
+    ``time`` (trimmed), ``attrs`` (the Dataset attrs, detect.py:731-783) -- numpy arrays
+    (``output="numpy"``) or CUDA tensors (``output="torch"``)."""
+    if detrend_orders is None:
+        detrend_orders = [1]
+    if std_normalise:
+        raise NotImplementedError("std_normalise is only defined for detrend_harmonic, outside the B200 hot path")
+    dev = _device(device)
+    validate_reference_period_method(reference_period, method_anomaly)
+    validate_anomaly_method(method_anomaly)
+    cal = build_calendar(time)
+    owns_input = not (isinstance(x, torch.Tensor) and x.is_cuda and x.dtype == torch.float32)
+    x_dev, space = _to_device_field(x, dev)
+    if gridded is None:
+        gridded = len(space) == 2
+    grid = tuple(space) if gridded else None
+    if x_dev.shape[0] != cal.T:
+        raise ValueError("time axis length does not match the data")
+
+    res = compute_normalised_anomaly_arrays(
+        x_dev, cal, method_anomaly, window_year_baseline, smooth_days_baseline, detrend_orders, force_zero_mean,
+        reference_period, validate=True, in_place=owns_input and method_anomaly != "shifting_baseline",
+    )  # fmt: skip
+    anom, keep = res["dat_anomaly"], res["keep"]
+    if owns_input and method_anomaly == "shifting_baseline":
+        del x_dev
+    doy_out = cal.doy[keep]
+    ext = identify_extremes_arrays(
+        anom, doy_out, grid, method_extreme, threshold_percentile, window_days_hobday, window_spatial_hobday,
+        method_percentile, precision, max_anomaly, want_events=want_events, want_bits=want_bits,
+        n_years=int(np.unique(cal.year[keep]).size),
+    )  # fmt: skip
+
+    attrs: Dict[str, Any] = {
+        "method_anomaly": method_anomaly,
+        "method_extreme": method_extreme,
+        "threshold_percentile": threshold_percentile,
+        "preprocessing_steps": get_preprocessing_steps(
+            method_anomaly, method_extreme, std_normalise, list(detrend_orders), window_year_baseline,
+            smooth_days_baseline, window_days_hobday, window_spatial_hobday, reference_period,
+        ),
+    }  # fmt: skip
+    if method_anomaly == "shifting_baseline":
+        attrs.update({"window_year_baseline": window_year_baseline, "smooth_days_baseline": smooth_days_baseline})
+    elif method_anomaly == "fixed_baseline":
+        if reference_period is not None:
+            attrs["reference_period"] = list(reference_period)
+    elif method_anomaly == "detrend_fixed_baseline":
+        attrs.update({"detrend_orders": list(detrend_orders), "force_zero_mean": force_zero_mean})
+        if reference_period is not None:
+            attrs["reference_period"] = list(reference_period)
+    if method_extreme == "hobday_extreme":
+        attrs["window_days_hobday"] = window_days_hobday
+    attrs.update({"method_percentile": method_percentile, "precision": precision, "max_anomaly": max_anomaly})
+
+    T_out = anom.shape[0]
+    out: Dict[str, Any] = {
+        "dat_anomaly": anom.reshape((T_out,) + space),
+        "mask": res["mask"].reshape(space),
+        "thresholds": ext["thresholds"],
+        "thresholds_layout": ext["thresholds_layout"],
+        "time": cal.time[keep],
+        "attrs": attrs,
+        "extreme_count": ext["count"],
+    }
+    if want_events:
+        out["extreme_events"] = ext["extreme_events"].reshape((T_out,) + space)
+    if want_bits:
+        out["bits"] = ext["bits"]
+    logger.info("Preprocessing completed successfully - %d extreme events identified", int(ext["count"]))
+    if output == "numpy":
+        for k in ("dat_anomaly", "mask", "thresholds", "extreme_events", "bits"):
+            if k in out:
+                out[k] = out[k].cpu().numpy()
+        out["extreme_count"] = int(out["extreme_count"])
+    return out

@@ -1,0 +1,393 @@
+"""GPU parity tests: every stage of the CUDA path, called through the C-ABI (ctypes binding in
+marex_b200/_lib.py), against the numpy oracle on the same seeded inputs.
+
+Bars (north_star): histogram counts / masks / thresholds-from-identical-anomalies BIT-EXACT;
+anomalies and end-to-end thresholds within 1e-5 relative of the field scale in float32.
+"""
+import os
+import warnings
+
+import numpy as np
+import pytest
+
+torch = pytest.importorskip("torch")
+pytestmark = pytest.mark.gpu
+
+from oracle import marex_oracle as mo  # noqa: E402
+
+
+def _cuda():
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    import marex_b200
+
+    return marex_b200
+
+
+def _field(T0="1990-01-01", T1="2006-01-01", ny=7, nx=37, seed=0, kelvin=False):
+    rng = np.random.default_rng(seed)
+    time = np.arange(np.datetime64(T0), np.datetime64(T1))
+    T = len(time)
+    frac = (time - time.astype("datetime64[Y]")).astype(float) / 365.25
+    amp = rng.uniform(0.5, 6, (ny, nx))
+    ph = rng.uniform(0, 1, (ny, nx))
+    x = 15 + amp * np.cos(2 * np.pi * (frac[:, None, None] - ph)) + 0.02 * np.arange(T)[:, None, None] / 365.25
+    ar = np.zeros((ny, nx))
+    noise = np.empty((T, ny, nx))
+    for t in range(T):
+        ar = 0.9 * ar + 0.26 * rng.standard_normal((ny, nx))
+        noise[t] = ar
+    x = (x + noise + (273.15 if kelvin else 0)).astype(np.float32)
+    x[:, 1, 1] = np.nan  # land column (reference tests inject one)
+    x[:, 3, 5] = np.float32(2.5)  # constant cell -> anomaly exactly 0 -> clamp rule
+    return x, time
+
+
+def _ulp_equal(a, b):
+    np.testing.assert_array_equal(np.asarray(a).view(np.uint32), np.asarray(b).view(np.uint32))
+
+
+# ---------------------------------------------------------------- (a) anomalies
+@pytest.mark.parametrize("W,S", [(5, 11), (3, 1), (4, 6), (15, 21)])
+def test_shifting_baseline_anomaly(W, S):
+    mb = _cuda()
+    x, time = _field(T1="2010-03-05" if W == 15 else "2001-07-01")
+    if W == 15:
+        time = np.arange(np.datetime64("1982-01-01"), np.datetime64("1982-01-01") + len(time))
+    year, doy = mo.calendar_tables(time)
+    ref, mask, keep = mo.anomaly_shifting_baseline(x, year, doy, W, S)
+    cal = mb.detect.build_calendar(time)
+    xd, space = mb.detect._to_device_field(x, "cuda")
+    res = mb.compute_normalised_anomaly_arrays(xd, cal, "shifting_baseline", W, S)
+    got = res["dat_anomaly"].cpu().numpy().reshape(ref.shape)
+    np.testing.assert_array_equal(res["keep"], keep)
+    np.testing.assert_array_equal(res["mask"].cpu().numpy().reshape(mask.shape), mask)
+    np.testing.assert_array_equal(np.isnan(got), np.isnan(ref))
+    # tolerance: 1e-5 relative to the field scale (|x| ~ 30) -> 3e-4; in practice both sides round one
+    # float64 result to float32, so they agree to the last bit almost everywhere.
+    np.testing.assert_allclose(got, ref, rtol=0, atol=1e-5 * 30, equal_nan=True)
+    assert (got.view(np.uint32) != ref.view(np.uint32)).mean() < 1e-3
+
+
+def test_shifting_baseline_nonfinite_and_gaps():
+    """NaN / inf bookkeeping in the running sums, missing days and a missing year."""
+    mb = _cuda()
+    x, time = _field(T1="2002-01-01", ny=3, nx=33, seed=3)
+    x[100:140, 0, 2] = np.nan
+    x[2000, 0, 3] = np.inf
+    x[2500, 0, 4] = -np.inf
+    x[0, 0, 6] = np.nan  # masked cell with later finite data
+    sel = np.ones(len(time), bool)
+    sel[400:430] = False  # a gap of days
+    sel[(time >= np.datetime64("1995-01-01")) & (time < np.datetime64("1996-01-01"))] = False  # a missing year
+    x, time = x[sel], time[sel]
+    year, doy = mo.calendar_tables(time)
+    W, S = 4, 7
+    ref, mask, keep = mo.anomaly_shifting_baseline(x, year, doy, W, S)
+    cal = mb.detect.build_calendar(time)
+    xd, _ = mb.detect._to_device_field(x, "cuda")
+    res = mb.compute_normalised_anomaly_arrays(xd, cal, "shifting_baseline", W, S, validate=False)
+    got = res["dat_anomaly"].cpu().numpy().reshape(ref.shape)
+    np.testing.assert_array_equal(res["keep"], keep)
+    np.testing.assert_array_equal(np.isnan(got), np.isnan(ref))
+    np.testing.assert_array_equal(np.isinf(got), np.isinf(ref))
+    fin = np.isfinite(ref)
+    np.testing.assert_allclose(got[fin], ref[fin], rtol=0, atol=3e-4)
+
+
+def test_rolling_climatology_modes():
+    mb = _cuda()
+    x, time = _field(T1="1999-01-01", ny=2, nx=33)
+    year, doy = mo.calendar_tables(time)
+    for W, S in [(3, 1), (3, 9)]:
+        ref = mo.rolling_climatology(mo.smooth_centered(x, S), year, doy, W)
+        got = mb.rolling_climatology_arrays(x, time, W, S).cpu().numpy()
+        np.testing.assert_array_equal(np.isnan(got), np.isnan(ref))
+        np.testing.assert_allclose(got, ref, rtol=0, atol=3e-4, equal_nan=True)
+
+
+@pytest.mark.parametrize("period", [None, (1992, 1997)])
+def test_fixed_baseline_anomaly(period):
+    mb = _cuda()
+    x, time = _field(T1="2000-01-01")
+    year, doy = mo.calendar_tables(time)
+    ref, mask = mo.anomaly_fixed_baseline(x, year, doy, period)
+    cal = mb.detect.build_calendar(time)
+    xd, _ = mb.detect._to_device_field(x, "cuda")
+    res = mb.compute_normalised_anomaly_arrays(xd, cal, "fixed_baseline", reference_period=period)
+    got = res["dat_anomaly"].cpu().numpy().reshape(ref.shape)
+    np.testing.assert_array_equal(res["mask"].cpu().numpy().reshape(mask.shape), mask)
+    np.testing.assert_allclose(got, ref, rtol=0, atol=3e-4, equal_nan=True)
+    assert (got.view(np.uint32) != ref.view(np.uint32)).mean() < 1e-3
+
+
+@pytest.mark.parametrize("orders,fzm,period", [([1], True, None), ([1, 2], False, None), ([1, 2, 3], True, (1991, 1995))])
+def test_detrend_fixed_baseline_anomaly(orders, fzm, period):
+    mb = _cuda()
+    x, time = _field(T1="1999-06-01")
+    year, doy = mo.calendar_tables(time)
+    ref, mask = mo.anomaly_detrend_fixed_baseline(x, time, year, doy, orders, fzm, period)
+    cal = mb.detect.build_calendar(time)
+    xd, _ = mb.detect._to_device_field(x, "cuda")
+    res = mb.compute_normalised_anomaly_arrays(
+        xd, cal, "detrend_fixed_baseline", detrend_orders=orders, force_zero_mean=fzm, reference_period=period
+    )
+    got = res["dat_anomaly"].cpu().numpy().reshape(ref.shape)
+    np.testing.assert_array_equal(res["mask"].cpu().numpy().reshape(mask.shape), mask)
+    np.testing.assert_array_equal(np.isnan(got), np.isnan(ref))
+    np.testing.assert_allclose(got, ref, rtol=0, atol=3e-4, equal_nan=True)
+
+
+# ---------------------------------------------------------------- (b) thresholds on identical anomalies
+def _anoms(seed=1, ny=6, nx=35, T1="2003-01-01", scale=1.0):
+    rng = np.random.default_rng(seed)
+    time = np.arange(np.datetime64("1990-01-01"), np.datetime64(T1))
+    a = (rng.standard_normal((len(time), ny, nx)) * rng.uniform(0.2, 2.0, (ny, nx)) * scale).astype(np.float32)
+    f = a.reshape(len(time), -1)  # view: special cells by flat index (works for any ny)
+    f[:, 0] = np.nan
+    f[:, 9] = 0.0  # constant zero -> threshold clamped to edges[3]
+    f[:, 10] = -1.0  # all negative -> bin 0
+    f[::3, 20] = 7.0  # values above max_anomaly are dropped
+    f[5:9, 30] = np.nan  # NaNs after the first step: dropped from counts, no mask
+    return a, time
+
+
+def test_digitize_bit_exact():
+    mb = _cuda()
+    edges, _ = mo.hobday_bins()
+    rng = np.random.default_rng(5)
+    v = np.concatenate(
+        [
+            edges[1:].astype(np.float32),
+            np.nextafter(edges[1:], np.float32(np.inf)),
+            np.nextafter(edges[1:], np.float32(-np.inf)),
+            rng.uniform(-1, 6, 20000).astype(np.float32),
+            np.array([np.nan, np.inf, -np.inf, 0.0, -0.0, 5.0, 4.9999995], np.float32),
+        ]
+    ).astype(np.float32)
+    N = 33
+    v = np.resize(v, (len(v) // N + 1, N)).astype(np.float32)
+    a = torch.from_numpy(v).cuda()
+    bins = torch.empty(v.shape, dtype=torch.uint16, device="cuda")
+    D = mb.detect
+    mb._lib.call("marex_digitize_f32", D._p(a), v.shape[0], N, N, D._p(D._up(edges, np.float32, a.device)), len(edges), D._p(bins), N, D._stream())
+    np.testing.assert_array_equal(bins.cpu().numpy(), mo.digitize(v, edges))
+
+
+@pytest.mark.parametrize("ws,w,p", [(None, 11, 95), (1, 5, 90), (5, 11, 95), (3, 31, 99), (5, 3, 60)])
+def test_hobday_approx_thresholds_bit_exact(ws, w, p):
+    mb = _cuda()
+    a, time = _anoms()
+    _, doy = mo.calendar_tables(time)
+    ny, nx = a.shape[1:]
+    a2 = a.reshape(len(time), -1)
+    eff_ws = 5 if ws is None else ws
+    ref = mo.hobday_thresholds_approx(a2, doy, p / 100.0, w, eff_ws, (ny, nx))
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        res = mb.identify_extremes_arrays(torch.from_numpy(a2).cuda(), doy, (ny, nx), "hobday_extreme", p, w, ws)
+    got = res["thresholds"].cpu().numpy().reshape(-1, 366)
+    _ulp_equal(got, ref)
+    ev = mo.compare_hobday(a2, doy, np.ascontiguousarray(ref.T))
+    np.testing.assert_array_equal(res["extreme_events"].cpu().numpy(), ev)
+    assert int(res["count"]) == int(ev.sum())
+
+
+def test_hobday_approx_unstructured_bit_exact():
+    mb = _cuda()
+    a, time = _anoms(ny=1, nx=70)
+    _, doy = mo.calendar_tables(time)
+    a2 = a.reshape(len(time), -1)
+    ref = mo.hobday_thresholds_approx(a2, doy, 0.95, 11, None, None)
+    with pytest.warns(UserWarning):
+        res = mb.identify_extremes_arrays(torch.from_numpy(a2).cuda(), doy, None, "hobday_extreme", 95, 11, None, want_bits=True)
+    _ulp_equal(res["thresholds"].cpu().numpy(), ref)
+    ev = mo.compare_hobday(a2, doy, np.ascontiguousarray(ref.T))
+    np.testing.assert_array_equal(res["bits"].cpu().numpy().view(np.uint32), mo.pack_bits_time_major(ev))
+
+
+@pytest.mark.parametrize("w,p", [(11, 95), (5, 99.5), (1, 50), (11, 10)])
+def test_hobday_exact_thresholds_bit_exact(w, p):
+    mb = _cuda()
+    a, time = _anoms(T1="2001-01-01")
+    a[:, 3, 3] = np.round(a[:, 3, 3], 1)  # heavy ties
+    a[10, 3, 4] = np.inf
+    a[20, 3, 5] = -np.inf
+    _, doy = mo.calendar_tables(time)
+    a2 = a.reshape(len(time), -1)
+    ref = mo.hobday_thresholds_exact(a2, doy, p, w)
+    res = mb.identify_extremes_arrays(
+        torch.from_numpy(a2).cuda(), doy, a.shape[1:], "hobday_extreme", p, w, None, method_percentile="exact"
+    )
+    got = res["thresholds"].cpu().numpy().reshape(366, -1)
+    _ulp_equal(got, ref)
+    np.testing.assert_array_equal(res["extreme_events"].cpu().numpy(), mo.compare_hobday(a2, doy, ref))
+
+
+def test_hobday_exact_matches_reference_golden(golden_dir):
+    """Against outputs of the reference's own _doy_percentiles (detect.py:1936-1942)."""
+    mb = _cuda()
+    g = np.load(os.path.join(golden_dir, "ref_doy_percentiles.npz"))
+    data, doy = g["data"], g["doy"]
+    a = torch.from_numpy(np.ascontiguousarray(data.T)).cuda()
+    for i, key in enumerate(g["keys"]):
+        w, p = str(key).split("|")
+        res = mb.identify_extremes_arrays(a, doy, None, "hobday_extreme", float(p), int(w), None, method_percentile="exact")
+        _ulp_equal(res["thresholds"].cpu().numpy().T, g[f"out_{i}"])
+
+
+@pytest.mark.parametrize("p", [95, 60, 99])
+def test_global_approx_thresholds_bit_exact(p):
+    mb = _cuda()
+    a, time = _anoms()
+    _, doy = mo.calendar_tables(time)
+    a2 = a.reshape(len(time), -1)
+    ref = mo.global_threshold_approx(a2, p / 100.0)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        res = mb.identify_extremes_arrays(torch.from_numpy(a2).cuda(), doy, a.shape[1:], "global_extreme", p)
+    got = res["thresholds"].cpu().numpy().reshape(-1)
+    np.testing.assert_array_equal(got.view(np.uint64), ref.view(np.uint64))
+    np.testing.assert_array_equal(res["extreme_events"].cpu().numpy(), mo.compare_global(a2, ref))
+
+
+@pytest.mark.parametrize("p", [95, 50, 99.9])
+def test_global_exact_thresholds_bit_exact(p):
+    mb = _cuda()
+    a, time = _anoms()
+    a[:, 3, 3] = np.round(a[:, 3, 3], 1)
+    _, doy = mo.calendar_tables(time)
+    a2 = a.reshape(len(time), -1)
+    ref = mo.global_threshold_exact(a2, p)
+    res = mb.identify_extremes_arrays(
+        torch.from_numpy(a2).cuda(), doy, a.shape[1:], "global_extreme", p, method_percentile="exact"
+    )
+    got = res["thresholds"].cpu().numpy().reshape(-1)
+    np.testing.assert_array_equal(got.view(np.uint64), ref.view(np.uint64))
+
+
+def test_rolling_histogram_quantile_reference_golden(golden_dir):
+    """Feed per-cell (366 x 502) histograms of the reference golden set through the CUDA kernel by
+    synthesising a bins array that realises exactly those counts, and compare with the outputs of
+    the reference's own _rolling_histogram_quantile (detect.py:2465-2559)."""
+    mb = _cuda()
+    g = np.load(os.path.join(golden_dir, "ref_rolling_hist_quantile.npz"))
+    names = [n for n in g["hist_names"] if not str(n).startswith("pooled")]
+    hists = [g[f"hist_{n}"].astype(np.int64) for n in names]
+    nb = hists[0].shape[1]
+    n_rows = max(int(h.sum(axis=1).max()) for h in hists)
+    N = len(hists)
+    # row r of doy d holds, for cell c, the r-th sample of that (cell, doy) or the "dropped" bin nb
+    bins = np.full((n_rows * 366, N), nb, dtype=np.uint16)
+    doy = np.repeat(np.arange(1, 367), n_rows).astype(np.int16)
+    for c, h in enumerate(hists):
+        for d in range(366):
+            vals = np.repeat(np.arange(nb), h[d])
+            bins[d * n_rows : d * n_rows + len(vals), c] = vals
+    D = mb.detect
+    dev = torch.device("cuda")
+    ptr, rows = D.doy_csr(doy)
+    _, centers = mo.hobday_bins()
+    bins_d = torch.from_numpy(bins.view(np.int16)).cuda()
+    row0 = torch.zeros(N, dtype=torch.float32, device=dev)
+    for w in (3, 11, 31):
+        for q in (0.6, 0.9, 0.95, 0.99):
+            thr = torch.empty((366, N), dtype=torch.float32, device=dev)
+            stats = torch.empty(2, dtype=torch.float32, device=dev)
+            mb._lib.call(
+                "marex_hobday_thresholds_hist", D._p(bins_d), bins.shape[0], 1, N, N, D._p(D._up(ptr, np.int32, dev)),
+                D._p(D._up(rows, np.int32, dev)), D.max_window_rows(ptr, w), D._p(D._up(centers, np.float32, dev)), nb, w, 1,
+                float(q), D._p(row0), float("-inf"), D._p(thr), D._p(stats), D._stream(),
+            )  # fmt: skip
+            got = thr.cpu().numpy()
+            keys = list(g["case_keys"])
+            for c, n in enumerate(names):
+                ref = g[f"out_{keys.index(f'{n}|{w}|{q}')}"]
+                _ulp_equal(got[:, c], ref)
+
+
+# ---------------------------------------------------------------- end to end
+@pytest.mark.parametrize(
+    "kw",
+    [
+        dict(),
+        dict(method_percentile="exact"),
+        dict(method_anomaly="detrend_fixed_baseline", method_extreme="global_extreme"),
+        dict(method_anomaly="fixed_baseline", method_extreme="hobday_extreme", window_spatial_hobday=3),
+        dict(method_anomaly="fixed_baseline", method_extreme="global_extreme", method_percentile="exact"),
+    ],
+)
+def test_preprocess_real_data_gridded(golden_dir, kw):
+    """The reference's own OSTIA fixture subset (Kelvin SST, 40 years) end to end."""
+    mb = _cuda()
+    g = np.load(os.path.join(golden_dir, "sst_gridded_subset.npz"))
+    x, time = g["sst"], g["time"]
+    ref = mo.preprocess(x, time, **kw)
+    got = mb.preprocess_arrays(x, time, **kw)
+    assert got["dat_anomaly"].dtype == np.float32 and got["extreme_events"].dtype == bool
+    assert got["thresholds"].dtype == ref["thresholds"].dtype and got["thresholds"].shape == ref["thresholds"].shape
+    np.testing.assert_array_equal(got["time"], ref["time"])
+    np.testing.assert_array_equal(got["mask"], ref["mask"])
+    # anomalies: 1e-5 relative to the field scale (|SST| ~ 300 K -> 3e-3)
+    np.testing.assert_allclose(got["dat_anomaly"], ref["dat_anomaly"], rtol=0, atol=1e-5 * 300, equal_nan=True)
+    # thresholds: one count moved across a 0.01 bin edge shifts an interpolated threshold by <= ~1 bin
+    np.testing.assert_allclose(got["thresholds"], ref["thresholds"], rtol=0, atol=0.011, equal_nan=True)
+    # masks may differ only where |anomaly - threshold| is within the float tolerance
+    diff = got["extreme_events"] != ref["extreme_events"]
+    assert diff.mean() < 2e-3
+    m = got["mask"]
+    freq = got["extreme_events"][:, m].mean()
+    assert 0.04 < freq < 0.06  # assert_percentile_frequency of the reference tests (5% +- 20%)
+
+
+def test_preprocess_real_data_unstructured(golden_dir):
+    mb = _cuda()
+    g = np.load(os.path.join(golden_dir, "sst_unstructured_subset.npz"))
+    x, time = g["sst"], g["time"]
+    for kw in (dict(), dict(method_anomaly="detrend_fixed_baseline", method_extreme="global_extreme")):
+        ref = mo.preprocess(x, time, **kw)
+        got = mb.preprocess_arrays(x, time, **kw)
+        np.testing.assert_array_equal(got["mask"], ref["mask"])
+        np.testing.assert_allclose(got["dat_anomaly"], ref["dat_anomaly"], rtol=0, atol=3e-4, equal_nan=True)
+        np.testing.assert_allclose(got["thresholds"], ref["thresholds"], rtol=0, atol=0.011, equal_nan=True)
+        assert (got["extreme_events"] != ref["extreme_events"]).mean() < 2e-3
+
+
+def test_stagewise_exact_from_gpu_anomalies(golden_dir):
+    """Counts/masks are bit-exact when both sides start from the SAME anomalies."""
+    mb = _cuda()
+    g = np.load(os.path.join(golden_dir, "sst_gridded_subset.npz"))
+    x, time = g["sst"], g["time"]
+    got = mb.preprocess_arrays(x, time)
+    a = got["dat_anomaly"]
+    _, doy = mo.calendar_tables(got["time"])
+    thr = mo.hobday_thresholds_approx(a.reshape(a.shape[0], -1), doy, 0.95, 11, 5, a.shape[1:])
+    _ulp_equal(got["thresholds"].reshape(-1, 366), thr)
+    ev = mo.compare_hobday(a.reshape(a.shape[0], -1), doy, np.ascontiguousarray(thr.T))
+    np.testing.assert_array_equal(got["extreme_events"].reshape(a.shape[0], -1), ev)
+
+
+def test_threshold_range_warnings():
+    """UserWarnings of detect.py:2711-2730: constant-zero cell -> below range; huge anomalies -> above."""
+    mb = _cuda()
+    a, time = _anoms(ny=1, nx=40)
+    _, doy = mo.calendar_tables(time)
+    a2 = a.reshape(len(time), -1)
+    with pytest.warns(UserWarning, match="below expected range"):
+        mb.identify_extremes_arrays(torch.from_numpy(a2).cuda(), doy, None, "hobday_extreme", 95, 11, None)
+    big = (a2 * 0 + 4.995).astype(np.float32)
+    with pytest.warns(UserWarning, match="exceed expected range"):
+        mb.identify_extremes_arrays(torch.from_numpy(big).cuda(), doy, None, "hobday_extreme", 95, 11, None)
+
+
+def test_data_validation_errors():
+    mb = _cuda()
+    x, time = _field(T1="1998-01-01", ny=2, nx=33)
+    bad = x.copy()
+    bad[500:510, 0, 4] = np.nan
+    with pytest.raises(mb.DataValidationError, match=r"Dataset contains 10 invalid values in 1 ocean locations"):
+        mb.preprocess_arrays(bad, time, window_year_baseline=3)
+    with pytest.raises(mb.DataValidationError, match="no valid"):
+        mb.preprocess_arrays(np.full_like(x, np.nan), time, window_year_baseline=3)
+    with pytest.raises(mb.DataValidationError, match="Insufficient data for shifting_baseline"):
+        mb.preprocess_arrays(x, time, window_year_baseline=15)
