@@ -1,0 +1,439 @@
+#!/usr/bin/env python
+"""
+bench.py -- gridpoint-days/s of the full preprocess_data pipeline on B200.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload NAME] [--impl reference]
+
+A "step" is one pass of the whole hot path (validation numbers + shifting-baseline anomalies +
+approximate 5x5-pooled Hobday thresholds + compare) over one synthetic field that is already
+resident in HBM.  Default workload: BASELINE.json configs[1], 0.25 deg global daily SST
+(1440 x 720, 1982-2021, T = 14610), shifting_baseline + hobday_extreme p95, approximate.
+N > 1 (torchrun): weak scaling, every rank owns one such field as a latitude band of a global
+(720*N) x 1440 grid, loads its 2-row pooling halo, and the small outputs (thresholds, mask,
+count) are gathered with NCCL.  One JSON line is printed by rank 0.
+
+`--impl reference` times the CPU restatement of the reference (oracle/marex_oracle.py -- the
+reference itself needs xarray/dask/flox/xhistogram, none of which is installed) on all host
+cores, on a bounded sample of the same workload.
+"""
+import argparse
+import json
+import multiprocessing as mp
+import os
+import subprocess
+import sys
+import tempfile
+import threading
+import time as _time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    # name: (ny, nx, start, end, kwargs)
+    "0.25deg_40yr_shifting_hobday_approx": (720, 1440, "1982-01-01", "2022-01-01", dict()),
+    "0.25deg_40yr_shifting_hobday_exact": (720, 1440, "1982-01-01", "2022-01-01", dict(method_percentile="exact")),
+    "1deg_40yr_shifting_hobday_approx": (180, 360, "1982-01-01", "2022-01-01", dict()),
+    "smoke_0.5deg_20yr": (90, 180, "2000-01-01", "2020-01-01", dict(window_year_baseline=5)),
+}
+PUBLISHED_PER_CORE = 3.1e4  # gridpoint-days/s/core, docs/modules/detect.rst:729-732
+
+
+def algorithmic_bytes_per_cell(T, T_out):
+    """read x once, write dat_anomaly f32 + extreme_events bool + thresholds + mask."""
+    return 4 * T + 4 * T_out + 1 * T_out + 4 * 366 + 1
+
+
+# per-kernel algorithmic bytes per gridpoint (what that launch must read + write at minimum)
+def kernel_bytes_per_cell(T, T_out):
+    return {
+        "marex_shift_anomaly_f32": 4 * T + 4 * T_out + 1 + 4,
+        "marex_digitize_f32": 4 * T_out + 2 * T_out,
+        "marex_hobday_thresholds_hist": 2 * T_out + 4 * 366 + 4,
+        "marex_hobday_thresholds_exact_f32": 4 * T_out + 4 * 366,
+        "marex_transpose_f32": 2 * 4 * 366,
+        "marex_compare_hobday": 4 * T_out + T_out + 4 * 366,
+    }
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+# ------------------------------------------------------------------------------------------
+# CPU side: oracle on a bounded sample, one tile per process
+# ------------------------------------------------------------------------------------------
+def _oracle_tile(args):
+    x, time, kw = args
+    from oracle import marex_oracle as mo
+
+    r = mo.preprocess(x, time, **kw)
+    return int(r["extreme_events"].sum())
+
+
+def cpu_oracle_run(tiles, time, kw, cores):
+    t0 = _time.perf_counter()
+    with mp.get_context("fork").Pool(cores) as pool:
+        pool.map(_oracle_tile, [(t, time, kw) for t in tiles])
+    return _time.perf_counter() - t0
+
+
+def synth_host_tiles(time, n_tiles, tile=(6, 8), seed=2):
+    """numpy twin of the synthetic field's statistics for the CPU arms (the CPU baseline does not
+    need bit-identical inputs to be timed; the GPU arm's own tiles are used when available)."""
+    rng = np.random.default_rng(seed)
+    T = len(time)
+    frac = (time - time.astype("datetime64[Y]")).astype(float) / 365.25
+    tiles = []
+    for _ in range(n_tiles):
+        ny, nx = tile
+        amp = rng.uniform(0.5, 6, (ny, nx))
+        ph = rng.uniform(0, 1, (ny, nx))
+        x = 15 + amp * np.cos(2 * np.pi * (frac[:, None, None] - ph)) + 0.02 * np.arange(T)[:, None, None] / 365.25
+        ar = np.zeros((ny, nx))
+        for t in range(T):
+            ar = 0.9 * ar + 0.26 * rng.standard_normal((ny, nx))
+            x[t] += ar
+        tiles.append(x.astype(np.float32))
+    return tiles
+
+
+# ------------------------------------------------------------------------------------------
+# clocks
+# ------------------------------------------------------------------------------------------
+class ClockSampler:
+    FIELDS = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, uuid):
+        self.uuid, self.proc, self.path = uuid, None, None
+
+    def start(self):
+        try:
+            fd, self.path = tempfile.mkstemp(suffix=".csv")
+            os.close(fd)
+            cmd = ["nvidia-smi", f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits", "-lms", "100"]
+            if self.uuid:
+                cmd += ["-i", self.uuid]
+            self.proc = subprocess.Popen(cmd, stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        if self.proc is None:
+            return out
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, reasons, mx = [], set(), None
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in open(self.path):
+            parts = [p.strip() for p in line.split(",")]
+            if len(parts) < 7:
+                continue
+            try:
+                sm.append(float(parts[0]))
+                mx = float(parts[1])
+            except ValueError:
+                continue
+            for n, v in zip(names, parts[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        os.unlink(self.path)
+        if sm:
+            out.update(sm_mhz=float(np.median(sm)), sm_max_mhz=mx, reasons=sorted(reasons), samples=len(sm))
+        return out
+
+
+# ------------------------------------------------------------------------------------------
+def run_reference(args, rank, world):
+    """Reference arm: the CPU restatement of marEx.preprocess_data on all host cores."""
+    if rank != 0:
+        return
+    ny, nx, start, end, kw = WORKLOADS[args.workload]
+    time = np.arange(np.datetime64(start), np.datetime64(end))
+    cores = os.cpu_count() or 1
+    tiles = synth_host_tiles(time, cores, tile=(6, 8))  # one 48-cell tile per core and step (~3 s each)
+    cells = sum(t.shape[1] * t.shape[2] for t in tiles)
+    for _ in range(args.warmup):
+        cpu_oracle_run(tiles[: max(1, cores // 4)], time, kw, cores)
+    t0 = _time.perf_counter()
+    for _ in range(args.steps):
+        cpu_oracle_run(tiles, time, kw, cores)
+    dt = (_time.perf_counter() - t0) / args.steps
+    value = cells * len(time) / dt
+    sample = f"{len(tiles)} tiles of 6x8 cells x {len(time)} days per step (each tile its own periodic domain)"
+    print(
+        json.dumps(
+            {
+                "impl": "reference",
+                "metric": "gridpoint-days/s",
+                "value": value,
+                "unit": "gridpoint-days/s",
+                "n_gpus": args.gpus,
+                "steps": args.steps,
+                "warmup": args.warmup,
+                "ms_per_step": dt * 1e3,
+                "higher_is_better": True,
+                "scaling": "weak",
+                "vs_baseline": None,
+                "dtype": "f32",
+                "data": "synthetic",
+                "config": {"workload": args.workload, "grid": [ny, nx], "days": len(time), **kw},
+                "cpu_baseline": {
+                    "value": value,
+                    "unit": "gridpoint-days/s",
+                    "cores": cores,
+                    "kind": "port",
+                    "sample": sample,
+                    "note": "numpy oracle, not the dask reference (xarray/dask/flox/xhistogram not installed)",
+                    "published_per_core": PUBLISHED_PER_CORE,
+                },
+                "e2e": {"value": value, "unit": "gridpoint-days/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            }
+        ),
+        flush=True,
+    )
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--workload", default="0.25deg_40yr_shifting_hobday_approx", choices=sorted(WORKLOADS))
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        return run_reference(args, rank, world)
+
+    import torch
+    import torch.distributed as dist
+
+    import marex_b200
+    from marex_b200 import _lib, sharding, synthetic
+
+    assert torch.cuda.is_available(), "bench.py needs a CUDA device"
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+    ny, nx, start, end, kw = WORKLOADS[args.workload]
+    time = np.arange(np.datetime64(start), np.datetime64(end))
+    T = len(time)
+    W = kw.get("window_year_baseline", 15)
+    cal = marex_b200.detect.build_calendar(time)
+    T_out = int((cal.year >= cal.year_val[0] + W).sum())
+
+    # this rank's latitude band of the global (ny * world) x nx grid, with its pooling halo
+    halo = sharding.effective_halo("hobday_extreme", kw.get("method_percentile", "approximate"), None, True)
+    ny_g = ny * world
+    own_lo, own_hi, lo, hi = sharding.lat_band(ny_g, world, rank, halo)
+    x = synthetic.synth_sst(time, (ny_g, nx), rows=(lo, hi), seed=2, device=dev)
+    torch.cuda.synchronize()
+    n_own = (own_hi - own_lo) * nx
+
+    marks = []
+    _lib.TRACE = lambda name: marks.append((name, _ev(torch)))
+
+    def step():
+        res = marex_b200.preprocess_arrays(x, time, output="torch", **kw)
+        out = sharding.crop_owned(res, (own_lo, own_hi), (lo, hi))
+        if world > 1:
+            lay = out["thresholds_layout"]
+            out["thresholds_global"] = sharding.dist_gather(out["thresholds"], 1 if lay == "doy_first" else 0)
+            out["mask_global"] = sharding.dist_gather(out["mask"], 0)
+            dist.all_reduce(out["extreme_count"])
+        return out
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(args.warmup, 3)):
+        r = step()
+        del r
+    barrier()
+    launches0 = _lib.launch_count()
+    marks.clear()
+    uuid = None
+    try:
+        uuid = "GPU-" + str(torch.cuda.get_device_properties(local).uuid)
+    except Exception:
+        pass
+    clocks = ClockSampler(uuid)
+    if rank == 0:
+        clocks.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    stage_marks = []
+    for _ in range(args.steps):
+        marks.append(("step_begin", _ev(torch)))
+        r = step()
+        n_events = int(r["extreme_count"])
+        del r
+        stage_marks.append(list(marks))
+        marks.clear()
+    e1.record()
+    barrier()
+    clk = clocks.stop() if rank == 0 else None
+    launches = _lib.launch_count() - launches0
+    ms = e0.elapsed_time(e1) / args.steps
+    if world > 1:
+        t = torch.tensor([ms], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t)
+    value = n_own * world * T / (ms * 1e-3)
+
+    # per-stage device time (CUDA events recorded right after each C-ABI call, same stream)
+    stage_ms = {}
+    for sm_ in stage_marks:
+        for (n0, a), (n1, b) in zip(sm_[:-1], sm_[1:]):
+            stage_ms[n1] = stage_ms.get(n1, 0.0) + a.elapsed_time(b) / args.steps
+    n_load = (hi - lo) * nx
+    kb = kernel_bytes_per_cell(T, T_out)
+    peak, peak_src = measured_peaks()
+    dom = max((k for k in stage_ms if k in kb), key=lambda k: stage_ms[k])
+    achieved = kb[dom] * n_load / (stage_ms[dom] * 1e-3) / 1e9
+    roofline = {
+        "kernel": dom,
+        "bound": "hbm",
+        "achieved": achieved,
+        "peak": peak,
+        "unit": "GB/s",
+        "frac": achieved / peak,
+        "traffic": None,
+        "peak_source": peak_src,
+        "ms_per_launch": stage_ms[dom],
+    }
+    B = algorithmic_bytes_per_cell(T, T_out)
+    pipe_gbs = B * n_own / (ms * 1e-3) / 1e9
+    stages = {k: {"ms": v, "GBps": (kb[k] * n_load / (v * 1e-3) / 1e9) if k in kb and v > 0 else None} for k, v in stage_ms.items()}
+
+    # ---- end to end: host (pinned) buffers in, host buffers out, through the public array API ----
+    e2e = None
+    if not args.no_e2e:
+        _lib.TRACE = None
+        xh = torch.empty(x.shape, dtype=torch.float32, pin_memory=True)
+        xh.copy_(x)
+        torch.cuda.synchronize()
+        del x
+        torch.cuda.empty_cache()
+        e2e_steps = min(args.steps, 2)
+        d2h = 0
+        for i in range(1 + e2e_steps):
+            if i == 1:
+                barrier()
+                t0 = _time.perf_counter()
+            res = marex_b200.preprocess_arrays(xh, time, output="pinned", **kw)
+            d2h = sum(res[k].nbytes for k in ("dat_anomaly", "mask", "thresholds", "extreme_events"))
+            del res
+        barrier()
+        dt = (_time.perf_counter() - t0) / e2e_steps
+        if world > 1:
+            t = torch.tensor([dt], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            dt = float(t)
+        e2e = {
+            "value": n_own * world * T / dt,
+            "unit": "gridpoint-days/s",
+            "h2d_bytes_per_step": int(xh.numel() * 4),
+            "d2h_bytes_per_step": int(d2h),
+            "steps": e2e_steps,
+            "warmup": 1,
+            "ms_per_step": dt * 1e3,
+            "timer": "host perf_counter around the public call (copies + kernels + sync), max over ranks",
+        }
+        x_sample_src = xh
+    else:
+        x_sample_src = x
+
+    # ---- CPU baseline on rank 0, N = 1 only: oracle on a bounded sample of this very field ----
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu:
+        cores = os.cpu_count() or 1
+        th, tw = 6, 8
+        tiles = []
+        r0 = (x_sample_src.shape[1] // 2) // th * th
+        for i in range(cores):
+            c0 = (i * 5 * tw) % (nx - tw)
+            tiles.append(np.ascontiguousarray(x_sample_src[:, r0 : r0 + th, c0 : c0 + tw].cpu().numpy()))
+        dtc = cpu_oracle_run(tiles, time, kw, cores)
+        cells = len(tiles) * th * tw
+        cpu = {
+            "value": cells * T / dtc,
+            "unit": "gridpoint-days/s",
+            "cores": cores,
+            "kind": "port",
+            "sample": f"{len(tiles)} tiles of {th}x{tw} cells x {T} days cut from the benchmark field (each tile its own periodic domain), {dtc:.1f} s",
+            "note": "numpy oracle, not the dask reference (xarray/dask/flox/xhistogram not installed)",
+            "published_per_core": PUBLISHED_PER_CORE,
+        }
+
+    if rank == 0:
+        line = {
+            "metric": "gridpoint-days/s",
+            "value": value,
+            "unit": "gridpoint-days/s",
+            "n_gpus": world,
+            "steps": args.steps,
+            "warmup": max(args.warmup, 3),
+            "ms_per_step": ms,
+            "higher_is_better": True,
+            "scaling": "weak",
+            "vs_baseline": None,
+            "dtype": "f32",
+            "data": "synthetic",
+            "config": {
+                "workload": args.workload,
+                "per_gpu_grid": [ny, nx],
+                "days": T,
+                "days_out": T_out,
+                "halo_rows": halo,
+                "l2": "inputs (60 GB per GPU at 0.25 deg) are far larger than L2; no flush needed",
+                **kw,
+            },
+            "roofline": roofline,
+            "pipeline_roofline": {
+                "bytes_per_gridpoint": B,
+                "achieved": pipe_gbs,
+                "peak": peak,
+                "unit": "GB/s",
+                "frac": pipe_gbs / peak,
+                "peak_source": peak_src,
+            },
+            "stages": stages,
+            "cpu_baseline": cpu,
+            "e2e": e2e,
+            "gpu_launches": int(launches),
+            "extreme_events": n_events,
+            "clocks": clk,
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def _ev(torch):
+    e = torch.cuda.Event(enable_timing=True)
+    e.record()
+    return e
+
+
+if __name__ == "__main__":
+    main()

@@ -32,6 +32,7 @@ _SIGNATURES = {
 EXPORTED = tuple(_SIGNATURES)
 
 _lib = None
+TRACE = None  # optional callable(name) invoked after every kernel-launching call (bench.py stage timing)
 
 
 def load() -> ctypes.CDLL:
@@ -60,6 +61,8 @@ def call(name: str, *args) -> None:
     if rc != 0:
         msg = lib.marex_last_error().decode("utf-8", "replace")
         raise ProcessingError(f"{name} failed (code {rc})", details=msg)
+    if TRACE is not None:
+        TRACE(name)
 
 
 def launch_count() -> int:

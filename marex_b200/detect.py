@@ -58,6 +58,34 @@ def _up(a: np.ndarray, dtype, device) -> torch.Tensor:
     return torch.from_numpy(np.ascontiguousarray(a, dtype=dtype)).to(device)
 
 
+_PINNED: Dict[Any, torch.Tensor] = {}
+
+
+def _to_host(t: torch.Tensor, key: str, pinned: bool):
+    """Device -> host.  ``pinned`` reuses a cached page-locked buffer per (key, shape, dtype) so a
+    repeated pipeline call pays the PCIe transfer, not cudaHostAlloc."""
+    if not pinned:
+        return t.cpu()
+    k = (key, tuple(t.shape), t.dtype)
+    buf = _PINNED.get(k)
+    if buf is None:
+        buf = torch.empty(t.shape, dtype=t.dtype, pin_memory=True)
+        _PINNED[k] = buf
+    buf.copy_(t, non_blocking=True)
+    return buf
+
+
+class _Hold(list):
+    """Keeps uploaded table tensors alive until the call that uses them has been enqueued: a
+    temporary freed right after ``data_ptr()`` could be handed out again by the caching
+    allocator to the NEXT upload and be overwritten before the kernel launches."""
+
+    def up(self, a: np.ndarray, dtype, device):
+        t = _up(a, dtype, device)
+        self.append(t)
+        return _p(t)
+
+
 def _to_device_field(x, device) -> Tuple[torch.Tensor, Tuple[int, ...]]:
     """Any (T, ...space) array -> contiguous float32 CUDA tensor (T, N) + the space shape.
     ``da.astype(np.float32)`` of detect.py:600."""
@@ -457,6 +485,7 @@ def rolling_climatology_arrays(x, time, window_year_baseline: int = 15, smooth_d
     (detect.py:1691-1816) at array level: the per-time-step climatology, NaN for the first
     ``window_year_baseline`` years.  Returns a float32 CUDA tensor shaped like ``x``."""
     dev = _device(device)
+    h = _Hold()
     cal = build_calendar(time)
     xd, space = _to_device_field(x, dev)
     T, N = xd.shape
@@ -465,7 +494,7 @@ def rolling_climatology_arrays(x, time, window_year_baseline: int = 15, smooth_d
     nonfinite = torch.empty(N, dtype=torch.int32, device=dev)
     out_row = _up(np.arange(T), np.int32, dev)
     _lib.call(
-        "marex_shift_anomaly_f32", _p(xd), T, N, N, _p(_up(cal.tidx, np.int32, dev)), _p(_up(cal.year_val, np.int32, dev)),
+        "marex_shift_anomaly_f32", _p(xd), T, N, N, h.up(cal.tidx, np.int32, dev), h.up(cal.year_val, np.int32, dev),
         cal.n_years, int(window_year_baseline), int(smooth_days_baseline), _p(out_row), 1, _p(out), N, _p(mask0),
         _p(nonfinite), _stream(),
     )  # fmt: skip
@@ -494,6 +523,7 @@ def compute_normalised_anomaly_arrays(
     validate_reference_period_method(reference_period, method_anomaly)
     validate_anomaly_method(method_anomaly)
     dev = x_dev.device
+    h = _Hold()
     T, N = x_dev.shape
     assert T == cal.T
     mask0 = torch.empty(N, dtype=torch.uint8, device=dev)
@@ -509,8 +539,8 @@ def compute_normalised_anomaly_arrays(
             raise IndexError("shifting_baseline: no time steps remain after removing the first window_year_baseline years")
         anom = torch.empty((T_out, N), dtype=torch.float32, device=dev)
         _lib.call(
-            "marex_shift_anomaly_f32", _p(x_dev), T, N, N, _p(_up(cal.tidx, np.int32, dev)),
-            _p(_up(cal.year_val, np.int32, dev)), cal.n_years, W, S, _p(_up(out_row, np.int32, dev)), 0,
+            "marex_shift_anomaly_f32", _p(x_dev), T, N, N, h.up(cal.tidx, np.int32, dev),
+            h.up(cal.year_val, np.int32, dev), cal.n_years, W, S, h.up(out_row, np.int32, dev), 0,
             _p(anom), N, _p(mask0), _p(nonfinite), st,
         )  # fmt: skip
         if validate:
@@ -545,7 +575,7 @@ def compute_normalised_anomaly_arrays(
     K = model.shape[0]
     coef = torch.empty((K, N), dtype=torch.float64, device=dev)
     _lib.call(
-        "marex_detrend_coef_f64", _p(x_dev), T, N, N, _p(_up(pmodel, np.float64, dev)), K, _p(coef), _p(mask0),
+        "marex_detrend_coef_f64", _p(x_dev), T, N, N, h.up(pmodel, np.float64, dev), K, _p(coef), _p(mask0),
         _p(nonfinite), st,
     )  # fmt: skip
     mask_raw = mask0.bool()
@@ -554,7 +584,7 @@ def compute_normalised_anomaly_arrays(
     xd = x_dev if in_place else torch.empty_like(x_dev)
     mean = torch.empty(N, dtype=torch.float32, device=dev) if force_zero_mean else None
     _lib.call(
-        "marex_detrend_apply_f32", _p(x_dev), T, N, N, _p(_up(model, np.float64, dev)), K, _p(coef), _p(xd), N,
+        "marex_detrend_apply_f32", _p(x_dev), T, N, N, h.up(model, np.float64, dev), K, _p(coef), _p(xd), N,
         _p(mean), st,
     )  # fmt: skip
     _lib.call("marex_doy_climatology_f32", _p(xd), T, N, N, _p(ptr_d), _p(rows_d), _p(mean), _p(clim), st)
@@ -631,6 +661,7 @@ def identify_extremes_arrays(
         max_anomaly, gridded,
     )  # fmt: skip
     dev = anom.device
+    h = _Hold()
     T, N = anom.shape
     st = _stream()
     doy = np.asarray(doy).astype(np.int16)
@@ -668,12 +699,12 @@ def identify_extremes_arrays(
             edges, centers = hobday_bins(precision, max_anomaly)
             nb = len(centers)
             bins = torch.empty((T, N), dtype=torch.uint16, device=dev)
-            _lib.call("marex_digitize_f32", _p(anom), T, N, N, _p(_up(edges, np.float32, dev)), len(edges), _p(bins), N, st)
+            _lib.call("marex_digitize_f32", _p(anom), T, N, N, h.up(edges, np.float32, dev), len(edges), _p(bins), N, st)
             ny, nx = (grid if gridded else (1, N))
             stats = torch.empty(2, dtype=torch.float32, device=dev)
             _lib.call(
                 "marex_hobday_thresholds_hist", _p(bins), T, ny, nx, N, _p(ptr_d), _p(rows_d), mwr,
-                _p(_up(centers, np.float32, dev)), nb, w, int(ws) if (gridded and ws) else 1, float(q), _p(anom),
+                h.up(centers, np.float32, dev), nb, w, int(ws) if (gridded and ws) else 1, float(q), _p(anom),
                 float(edges[3]), _p(thr), _p(stats), st,
             )  # fmt: skip
             del bins
@@ -692,8 +723,8 @@ def identify_extremes_arrays(
             edges, centers = global_bins(precision, max_anomaly)
             stats = torch.empty(2, dtype=torch.float64, device=dev)
             _lib.call(
-                "marex_global_threshold_hist_f64", _p(anom), T, N, N, _p(_up(edges, np.float64, dev)),
-                _p(_up(centers, np.float64, dev)), len(centers), float(q), float(edges[3]), _p(thr), _p(stats), st,
+                "marex_global_threshold_hist_f64", _p(anom), T, N, N, h.up(edges, np.float64, dev),
+                h.up(centers, np.float64, dev), len(centers), float(q), float(edges[3]), _p(thr), _p(stats), st,
             )  # fmt: skip
             vmin, vmax = (float(v) for v in stats.cpu())
             _warn_threshold_range(vmin, vmax, float(edges[-2]), float(edges[3]), max_anomaly)
@@ -707,7 +738,7 @@ def identify_extremes_arrays(
     count = torch.zeros(1, dtype=torch.int64, device=dev)
     if method_extreme == "hobday_extreme":
         _lib.call(
-            "marex_compare_hobday", _p(anom), T, N, N, _p(_up(doy, np.int16, dev)), _p(out["thresholds_dm"]), _p(events),
+            "marex_compare_hobday", _p(anom), T, N, N, h.up(doy, np.int16, dev), _p(out["thresholds_dm"]), _p(events),
             N, _p(bits), nw, _p(count), st,
         )  # fmt: skip
     else:
@@ -753,7 +784,8 @@ def preprocess_arrays(
     axis.  Returns ``dat_anomaly`` (T_out, ..space) float32, ``mask`` (..space) bool,
     ``thresholds`` in the reference's layout and dtype, ``extreme_events`` (T_out, ..space) bool,
     ``time`` (trimmed), ``attrs`` (the Dataset attrs, detect.py:731-783) -- numpy arrays
-    (``output="numpy"``) or CUDA tensors (``output="torch"``)."""
+    (``output="numpy"``), numpy views of cached page-locked buffers that the next call overwrites
+    (``output="pinned"``) or CUDA tensors (``output="torch"``)."""
     if detrend_orders is None:
         detrend_orders = [1]
     if std_normalise:
@@ -821,9 +853,9 @@ def preprocess_arrays(
     if want_bits:
         out["bits"] = ext["bits"]
     logger.info("Preprocessing completed successfully - %d extreme events identified", int(ext["count"]))
-    if output == "numpy":
-        for k in ("dat_anomaly", "mask", "thresholds", "extreme_events", "bits"):
-            if k in out:
-                out[k] = out[k].cpu().numpy()
-        out["extreme_count"] = int(out["extreme_count"])
+    if output in ("numpy", "pinned"):
+        host = {k: _to_host(out[k], k, output == "pinned") for k in ("dat_anomaly", "mask", "thresholds", "extreme_events", "bits") if k in out}
+        out["extreme_count"] = int(out["extreme_count"])  # synchronises the stream: the copies above are complete
+        for k, v in host.items():
+            out[k] = v.numpy()
     return out

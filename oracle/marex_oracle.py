@@ -454,9 +454,17 @@ def global_threshold_approx(anom, q: float, precision: float = 0.01, max_anomaly
 def global_threshold_exact(anom, percentile: float) -> np.ndarray:
     """``da.quantile(p/100, dim=time)`` (detect.py:2899): nanquantile with a float64 q -> float64."""
     a2, _ = _flat(np.asarray(anom, dtype=np.float32))
-    with warnings.catch_warnings():
-        warnings.simplefilter("ignore", RuntimeWarning)
-        return np.nanquantile(a2, np.asarray([percentile / 100.0]), axis=0)[0].astype(np.float64)
+    # numpy quirk: np.nanquantile(..., axis) goes through apply_along_axis, whose output dtype is
+    # taken from the FIRST slice; an all-NaN first cell returns a float32 NaN and silently demotes
+    # every other cell's float64 result to float32.  The clean float64 semantics are restated here
+    # by keeping all-NaN cells out of the call.
+    valid = ~np.isnan(a2).all(axis=0)
+    out = np.full(a2.shape[1], np.nan, dtype=np.float64)
+    if valid.any():
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore", RuntimeWarning)
+            out[valid] = np.nanquantile(a2[:, valid], np.asarray([percentile / 100.0]), axis=0)[0]
+    return out
 
 
 # --------------------------------------------------------------------------- #

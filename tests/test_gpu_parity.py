@@ -38,13 +38,28 @@ def _field(T0="1990-01-01", T1="2006-01-01", ny=7, nx=37, seed=0, kelvin=False):
         ar = 0.9 * ar + 0.26 * rng.standard_normal((ny, nx))
         noise[t] = ar
     x = (x + noise + (273.15 if kelvin else 0)).astype(np.float32)
-    x[:, 1, 1] = np.nan  # land column (reference tests inject one)
-    x[:, 3, 5] = np.float32(2.5)  # constant cell -> anomaly exactly 0 -> clamp rule
+    f = x.reshape(T, -1)  # view
+    f[:, nx + 1 if ny > 1 else 1] = np.nan  # land column (reference tests inject one)
+    f[:, 7] = np.float32(2.5)  # constant cell -> anomaly exactly 0 -> clamp rule
     return x, time
 
 
+def _canon(a):
+    """Bit pattern with every NaN mapped to one canonical payload (CUDA's NaN is 0x7fffffff, numpy's 0x7fc00000)."""
+    a = np.ascontiguousarray(a)
+    u = a.view(np.uint32 if a.dtype == np.float32 else np.uint64).copy()
+    u[np.isnan(a)] = 0
+    u[a == 0] = 0  # -0.0 == +0.0: which of two tied zeros a selection returns is unspecified in numpy too
+    return u
+
+
 def _ulp_equal(a, b):
-    np.testing.assert_array_equal(np.asarray(a).view(np.uint32), np.asarray(b).view(np.uint32))
+    np.testing.assert_array_equal(np.isnan(a), np.isnan(b))
+    np.testing.assert_array_equal(_canon(a), _canon(b))
+
+
+def _frac_bits_differ(a, b):
+    return (_canon(a) != _canon(b)).mean()
 
 
 # ---------------------------------------------------------------- (a) anomalies
@@ -66,7 +81,7 @@ def test_shifting_baseline_anomaly(W, S):
     # tolerance: 1e-5 relative to the field scale (|x| ~ 30) -> 3e-4; in practice both sides round one
     # float64 result to float32, so they agree to the last bit almost everywhere.
     np.testing.assert_allclose(got, ref, rtol=0, atol=1e-5 * 30, equal_nan=True)
-    assert (got.view(np.uint32) != ref.view(np.uint32)).mean() < 1e-3
+    assert _frac_bits_differ(got, ref) < 1e-3
 
 
 def test_shifting_baseline_nonfinite_and_gaps():
@@ -118,7 +133,7 @@ def test_fixed_baseline_anomaly(period):
     got = res["dat_anomaly"].cpu().numpy().reshape(ref.shape)
     np.testing.assert_array_equal(res["mask"].cpu().numpy().reshape(mask.shape), mask)
     np.testing.assert_allclose(got, ref, rtol=0, atol=3e-4, equal_nan=True)
-    assert (got.view(np.uint32) != ref.view(np.uint32)).mean() < 1e-3
+    assert _frac_bits_differ(got, ref) < 1e-3
 
 
 @pytest.mark.parametrize("orders,fzm,period", [([1], True, None), ([1, 2], False, None), ([1, 2, 3], True, (1991, 1995))])
@@ -170,7 +185,8 @@ def test_digitize_bit_exact():
     a = torch.from_numpy(v).cuda()
     bins = torch.empty(v.shape, dtype=torch.uint16, device="cuda")
     D = mb.detect
-    mb._lib.call("marex_digitize_f32", D._p(a), v.shape[0], N, N, D._p(D._up(edges, np.float32, a.device)), len(edges), D._p(bins), N, D._stream())
+    e_d = D._up(edges, np.float32, a.device)
+    mb._lib.call("marex_digitize_f32", D._p(a), v.shape[0], N, N, D._p(e_d), len(edges), D._p(bins), N, D._stream())
     np.testing.assert_array_equal(bins.cpu().numpy(), mo.digitize(v, edges))
 
 
@@ -247,7 +263,7 @@ def test_global_approx_thresholds_bit_exact(p):
         warnings.simplefilter("ignore")
         res = mb.identify_extremes_arrays(torch.from_numpy(a2).cuda(), doy, a.shape[1:], "global_extreme", p)
     got = res["thresholds"].cpu().numpy().reshape(-1)
-    np.testing.assert_array_equal(got.view(np.uint64), ref.view(np.uint64))
+    _ulp_equal(got, ref)
     np.testing.assert_array_equal(res["extreme_events"].cpu().numpy(), mo.compare_global(a2, ref))
 
 
@@ -263,7 +279,7 @@ def test_global_exact_thresholds_bit_exact(p):
         torch.from_numpy(a2).cuda(), doy, a.shape[1:], "global_extreme", p, method_percentile="exact"
     )
     got = res["thresholds"].cpu().numpy().reshape(-1)
-    np.testing.assert_array_equal(got.view(np.uint64), ref.view(np.uint64))
+    _ulp_equal(got, ref)
 
 
 def test_rolling_histogram_quantile_reference_golden(golden_dir):
@@ -290,13 +306,14 @@ def test_rolling_histogram_quantile_reference_golden(golden_dir):
     _, centers = mo.hobday_bins()
     bins_d = torch.from_numpy(bins.view(np.int16)).cuda()
     row0 = torch.zeros(N, dtype=torch.float32, device=dev)
+    ptr_d, rows_d, cen_d = D._up(ptr, np.int32, dev), D._up(rows, np.int32, dev), D._up(centers, np.float32, dev)
     for w in (3, 11, 31):
         for q in (0.6, 0.9, 0.95, 0.99):
             thr = torch.empty((366, N), dtype=torch.float32, device=dev)
             stats = torch.empty(2, dtype=torch.float32, device=dev)
             mb._lib.call(
-                "marex_hobday_thresholds_hist", D._p(bins_d), bins.shape[0], 1, N, N, D._p(D._up(ptr, np.int32, dev)),
-                D._p(D._up(rows, np.int32, dev)), D.max_window_rows(ptr, w), D._p(D._up(centers, np.float32, dev)), nb, w, 1,
+                "marex_hobday_thresholds_hist", D._p(bins_d), bins.shape[0], 1, N, N, D._p(ptr_d),
+                D._p(rows_d), D.max_window_rows(ptr, w), D._p(cen_d), nb, w, 1,
                 float(q), D._p(row0), float("-inf"), D._p(thr), D._p(stats), D._stream(),
             )  # fmt: skip
             got = thr.cpu().numpy()
