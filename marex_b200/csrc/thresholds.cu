@@ -4,6 +4,8 @@
 // Common shape: one warp per CTA, lane = gridpoint, a private histogram per lane laid out
 // hist[bin][lane] in shared memory (bank = lane, conflict-free up to the 16-bit pairing).
 // Counts are integers, so everything up to the final interpolation is bit-exact.
+#include <cstdlib>
+
 #include "common.cuh"
 
 namespace marex {
@@ -110,7 +112,7 @@ __global__ void __launch_bounds__(32) hobday_hist_kernel(
     }
     float res = CUDART_NAN_F;
     if (ntot > 0) {
-      const double pos = q * (double)ntot;             // detect.py:2516
+      const double pos = __dmul_rn(q, (double)ntot);   // detect.py:2516
       const int kk = (int)floor(pos);                  // cum > pos  <=>  cum >= kk + 1
       while (cl > kk) { --iu; cl -= (int)hist[iu * 32 + lane]; }
       while (iu < nb - 1 && cl + (int)hist[iu * 32 + lane] <= kk) { cl += (int)hist[iu * 32 + lane]; ++iu; }
@@ -119,8 +121,8 @@ __global__ void __launch_bounds__(32) hobday_hist_kernel(
       } else {
         const int h = (int)hist[iu * 32 + lane];
         const float bl = __ldg(&centers[iu - 1]), bu = __ldg(&centers[iu]);
-        const double frac = (h > 0) ? (pos - (double)cl) / (double)h : 0.5;  // detect.py:2545-2547
-        res = (float)((double)bl + frac * (double)__fsub_rn(bu, bl));       // detect.py:2550
+        const double frac = (h > 0) ? __ddiv_rn(pos - (double)cl, (double)h) : 0.5;               // detect.py:2545-2547
+        res = (float)__dadd_rn((double)bl, __dmul_rn(frac, (double)__fsub_rn(bu, bl)));           // detect.py:2550 (no FMA)
       }
     }
     if (masked) res = CUDART_NAN_F;                    // detect.py:2704-2705
@@ -131,6 +133,230 @@ __global__ void __launch_bounds__(32) hobday_hist_kernel(
   vmin = warp_min(vmin);
   vmax = warp_max(vmax);
   if (lane == 0 && stats) {
+    if (vmin != CUDART_INF_F) atomic_min_f(&stats[0], vmin);
+    if (vmax != -CUDART_INF_F) atomic_max_f(&stats[1], vmax);
+  }
+}
+
+// ---------------------------------------------------------------------------------------
+// Pooled (ws x ws) approximate Hobday thresholds, tiled.
+//
+// The per-lane version above re-reads every sample ws*ws times.  Here a CTA owns an OY x OX tile
+// of gridpoints ("own" cells = targets + a ws/2 halo).  Each own cell keeps the histogram of ITS
+// OWN +-w/2 day-of-year window in shared memory, updated incrementally by ONE thread per own
+// cell (private 16-bit counters, no atomics; every sample is touched exactly twice: entering
+// and leaving the window), at three resolutions: L0 = bins, L1 = blocks of 8 bins, L2 = groups
+// of 64 bins.  A target's pooled cumulative count below bin B is the sum over its ws*ws
+// neighbours of (B>>6) group + ((B>>3)&7) block + (B&7) bin counters: ~10 counter rows, each
+// summed over the neighbours with compile-time offsets, two threads per target.  The quantile
+// bin is tracked from the previous day of year and walked.  All counts are integers: bit-exact.
+//
+// Event phase detail: a leaving and an entering sample are applied as a PAIR -- if they fall in
+// the same bin (block, group) the two updates cancel and nothing is touched, otherwise the two
+// read-modify-writes hit different addresses and are issued back to back, which halves the
+// dependent shared-memory latency chain.
+// ---------------------------------------------------------------------------------------
+template <int P>
+__global__ void __launch_bounds__(768) hobday_pool_tile_kernel(
+    const uint16_t* __restrict__ bins, int64_t ny, int64_t nx, int64_t pitch, const int32_t* __restrict__ doy_ptr,
+    const int32_t* __restrict__ doy_rows, const float* __restrict__ centers, int nb, int w, double q,
+    const float* __restrict__ anom_row0, float lower_bound, float* __restrict__ thr, float* __restrict__ stats,
+    int OY, int OX, int CS, int CR, int LPT) {
+  constexpr int WS = 2 * P + 1, NN = WS * WS;
+  constexpr int CAP = 32;   // slots of the staged per-step row table
+  constexpr int MAXQ = (NN + 3) / 4;  // neighbours per query lane when LPT = 4 (LPT = 8 uses fewer)
+  extern __shared__ unsigned char smem_raw[];
+  const int C = OY * OX;   // own cells; counter rows have stride CS > C, column C is a permanently-zero dummy
+  const int nb1 = (nb + 7) >> 3, nb2 = (nb + 63) >> 6;
+  uint16_t* L0 = reinterpret_cast<uint16_t*>(smem_raw);  // [nb][CS]  bins >= 1 (bin 0 lives in Z0)
+  uint16_t* L1 = L0 + (size_t)nb * CS;                    // [nb1][CS] blocks of 8 bins (block 0 without bin 0)
+  uint16_t* L2 = L1 + (size_t)nb1 * CS;                   // [nb2][CS] groups of 64 bins (group 0 without bin 0)
+  uint16_t* NT = L2 + (size_t)nb2 * CS;                   // [CS] samples in the own-cell window
+  uint16_t* Z0 = NT + CS;                                 // [CS] of which in bin 0
+  const int total16 = (nb + nb1 + nb2 + 2) * CS;
+  for (int i = threadIdx.x; i < total16; i += blockDim.x) L0[i] = 0;
+
+  const int TY = OY - 2 * P, TX = OX - 2 * P;             // targets per tile
+  const int64_t y0 = (int64_t)blockIdx.y * TY, x0 = (int64_t)blockIdx.x * TX;
+  const int64_t N = ny * nx;
+  const int half = w / 2;
+
+  // ---- event roles: three threads per own cell, one per counter level (disjoint arrays, no
+  //      atomics, three short dependent chains instead of one long one, 3x the warps) ----
+  const int role = threadIdx.x / CR;  // warp-uniform: CR is a multiple of 32
+  const int oc = threadIdx.x % CR;
+  const bool own_thread = role < 3 && oc < C;
+  const int oy = own_thread ? oc / OX : 0, ox = own_thread ? oc % OX : 0;
+  const int64_t gy = y0 - P + oy;
+  int64_t gx = (x0 - P + ox) % nx;
+  if (gx < 0) gx += nx;
+  const bool own_valid = own_thread && gy >= 0 && gy < ny;
+  const uint16_t* col = bins + (own_valid ? gy * nx + gx : 0);
+  const int sh = 3 * role;                                 // key = bin >> sh
+  uint16_t* colp = (role == 0 ? L0 : role == 1 ? L1 : L2) + (own_thread ? oc : C);
+  int ntot_own = 0, n0_own = 0;                            // maintained by role 0
+
+  // Bin 0 (every anomaly below -precision: about half of all samples) is only counted in Z0.
+  auto apply = [&](int vl, int ve) {  // vl leaves the window, ve enters it (0xFFFF = none)
+    if (role == 0) {
+      ntot_own += (int)(ve < nb) - (int)(vl < nb);
+      n0_own += (int)(ve == 0) - (int)(vl == 0);
+    }
+    const bool al = vl < nb && vl != 0, ae = ve < nb && ve != 0;
+    const int kl = vl >> sh, ke = ve >> sh;
+    if (al && ae) {
+      if (kl != ke) {  // same counter: the two updates cancel
+        const int a = colp[kl * CS], b = colp[ke * CS];
+        colp[kl * CS] = (uint16_t)(a - 1);
+        colp[ke * CS] = (uint16_t)(b + 1);
+      }
+    } else if (al) {
+      colp[kl * CS] = (uint16_t)(colp[kl * CS] - 1);
+    } else if (ae) {
+      colp[ke * CS] = (uint16_t)(colp[ke * CS] + 1);
+    }
+  };
+  auto load_bin = [&](int j) -> int { return col[(int64_t)__ldg(&doy_rows[j]) * pitch]; };
+  // The CTA's shared memory is all counters, so there is no L1: the row lists of the next step
+  // are staged into a tiny shared table (one global load per thread) instead of being chased
+  // through doy_rows by every thread.
+  __shared__ int s_rows[2][2][CAP];   // [step parity][leave / enter][slot] row index or -1
+  __shared__ int s_cnt[2][2][2];      // [step parity][leave / enter][begin, end) in doy_rows
+  auto stage = [&](int step) {        // rows leaving / entering the window at `step` (1..365)
+    const int par = step & 1;
+    const int d_leave = (step - 1 - half + 2 * NDOY) % NDOY, d_enter = (step + half) % NDOY;
+    if (threadIdx.x < 2 * CAP) {
+      const int which = threadIdx.x / CAP, u = threadIdx.x % CAP;
+      const int dd = which ? d_enter : d_leave;
+      const int b0 = __ldg(&doy_ptr[dd]), b1 = __ldg(&doy_ptr[dd + 1]);
+      s_rows[par][which][u] = (b0 + u < b1) ? __ldg(&doy_rows[b0 + u]) : -1;
+      if (u == 0) { s_cnt[par][which][0] = b0; s_cnt[par][which][1] = b1; }
+    }
+  };
+  auto publish = [&]() {
+    if (role == 0) {
+      NT[oc] = (uint16_t)ntot_own;
+      Z0[oc] = (uint16_t)n0_own;
+    }
+  };
+  auto warm_l2 = [&](int step) {  // pull the samples entering at `step` into L2 while the queries run
+    if (role != 0 || !own_valid) return;
+    const int par = step & 1;
+#pragma unroll 4
+    for (int u = 0; u < CAP; ++u) {
+      const int re = s_rows[par][1][u];
+      if (re >= 0) asm volatile("prefetch.global.L2 [%0];" ::"l"(col + (int64_t)re * pitch));
+    }
+  };
+  auto advance = [&](int step) {  // needs stage(step) + a barrier before it
+    if (!own_valid) return;
+    const int par = step & 1;
+    const int nl = s_cnt[par][0][1] - s_cnt[par][0][0], ne = s_cnt[par][1][1] - s_cnt[par][1][0];
+    const int npair = min(CAP, max(nl, ne));
+    constexpr int BATCH = 14;
+    for (int u0 = 0; u0 < npair; u0 += BATCH) {
+      int vl[BATCH], ve[BATCH];
+#pragma unroll
+      for (int u = 0; u < BATCH; ++u) {  // all loads first ...
+        const int rl = (u0 + u < CAP) ? s_rows[par][0][u0 + u] : -1, re = (u0 + u < CAP) ? s_rows[par][1][u0 + u] : -1;
+        vl[u] = (rl >= 0) ? (int)col[(int64_t)rl * pitch] : 0xFFFF;
+        ve[u] = (re >= 0) ? (int)col[(int64_t)re * pitch] : 0xFFFF;
+      }
+#pragma unroll
+      for (int u = 0; u < BATCH; ++u) apply(vl[u], ve[u]);  // ... then the shared-memory updates
+    }
+    for (int a = s_cnt[par][0][0] + CAP; a < s_cnt[par][0][1]; ++a) apply(load_bin(a), 0xFFFF);  // lists longer than CAP
+    for (int b = s_cnt[par][1][0] + CAP; b < s_cnt[par][1][1]; ++b) apply(0xFFFF, load_bin(b));
+    publish();
+  };
+
+  // ---- query role: LPT lanes per target (LPT = 4 or 8), neighbours dealt round-robin ----
+  const int nt = TY * TX;
+  const int tq = threadIdx.x / LPT, hq = threadIdx.x % LPT;
+  const bool q_thread = tq < nt;
+  const int tt = q_thread ? tq : 0;
+  const int ty = tt / TX, tx = tt % TX;
+  const int64_t ty_g = y0 + ty, tx_g = x0 + tx;
+  const bool target_live = q_thread && ty_g < ny && tx_g < nx;
+  const int center = (ty + P) * OX + (tx + P);
+  int off[MAXQ];  // this lane's neighbours; unused slots -> dummy zero cell
+#pragma unroll
+  for (int i = 0; i < MAXQ; ++i) {
+    const int n = LPT * i + hq;
+    off[i] = (n < NN) ? center + (n / WS - P) * OX + (n % WS - P) : C;
+  }
+  const unsigned grp_mask = ((LPT == 8) ? 0xFFu : 0xFu) << (threadIdx.x & 31 & ~(LPT - 1));
+  auto grp_sum = [&](int v) {
+    v += __shfl_xor_sync(grp_mask, v, 1);
+    v += __shfl_xor_sync(grp_mask, v, 2);
+    if (LPT == 8) v += __shfl_xor_sync(grp_mask, v, 4);
+    return v;
+  };
+  auto row_sum = [&](const uint16_t* row) {
+    int s = 0;
+#pragma unroll
+    for (int i = 0; i < MAXQ; ++i) s += row[off[i]];
+    return s;
+  };
+  auto pooled_cum = [&](int B) {  // pooled samples with bin < B  (B >= 1)
+    int s = row_sum(Z0);
+    for (int g = 0; g < (B >> 6); ++g) s += row_sum(L2 + g * CS);
+    for (int k = (B >> 6) << 3; k < (B >> 3); ++k) s += row_sum(L1 + k * CS);
+    for (int b = max(1, (B >> 3) << 3); b < B; ++b) s += row_sum(L0 + b * CS);
+    return grp_sum(s);
+  };
+  auto pooled_bin = [&](int b) { return grp_sum(row_sum(b ? L0 + b * CS : Z0)); };
+
+  __syncthreads();
+  if (own_valid) {
+    for (int k = -half; k <= half; ++k) {
+      const int d = ((k % NDOY) + NDOY) % NDOY;
+      const int b0 = __ldg(&doy_ptr[d]), b1 = __ldg(&doy_ptr[d + 1]);
+      for (int j = b0; j < b1; ++j) apply(0xFFFF, load_bin(j));
+    }
+    publish();
+  }
+  stage(1);
+  __syncthreads();
+
+  const bool masked = target_live ? (anom_row0[ty_g * nx + tx_g] != anom_row0[ty_g * nx + tx_g]) : true;
+  float vmin = CUDART_INF_F, vmax = -CUDART_INF_F;
+  int iu = 1;
+  for (int d = 0; d < NDOY; ++d) {
+    if (d > 0) {
+      if (d + 1 < NDOY) stage(d + 1);
+      advance(d);
+      __syncthreads();
+      if (d + 1 < NDOY) warm_l2(d + 1);
+    }
+    if (q_thread) {
+      float res = CUDART_NAN_F;
+      const int ntot = grp_sum(row_sum(NT));
+      if (ntot > 0) {
+        const double pos = __dmul_rn(q, (double)ntot);
+        const int kk = (int)floor(pos);
+        int cl = (iu > 0) ? pooled_cum(iu) : 0;
+        int h = pooled_bin(iu);
+        while (cl > kk) { --iu; h = pooled_bin(iu); cl -= h; }
+        while (iu < nb - 1 && cl + h <= kk) { cl += h; ++iu; h = pooled_bin(iu); }
+        if (iu == 0) {
+          res = __ldg(&centers[0]);
+        } else {
+          const float bl = __ldg(&centers[iu - 1]), bu = __ldg(&centers[iu]);
+          const double frac = (h > 0) ? __ddiv_rn(pos - (double)cl, (double)h) : 0.5;
+          res = (float)__dadd_rn((double)bl, __dmul_rn(frac, (double)__fsub_rn(bu, bl)));  // numpy: mul then add, no FMA
+        }
+      }
+      if (masked) res = CUDART_NAN_F;
+      if (res == res) { vmin = fminf(vmin, res); vmax = fmaxf(vmax, res); }
+      if (res < lower_bound) res = lower_bound;
+      if (target_live && hq == 0) thr[(int64_t)d * N + ty_g * nx + tx_g] = res;
+    }
+    __syncthreads();  // queries done before the next day's updates touch the counters
+  }
+  vmin = warp_min(vmin);
+  vmax = warp_max(vmax);
+  if ((threadIdx.x & 31) == 0 && stats) {
     if (vmin != CUDART_INF_F) atomic_min_f(&stats[0], vmin);
     if (vmax != -CUDART_INF_F) atomic_max_f(&stats[1], vmax);
   }
@@ -510,6 +736,46 @@ extern "C" int marex_hobday_thresholds_hist(const uint16_t* bins, int64_t T, int
   if (stats) {
     init_stats_kernel<float><<<1, 1, 0, st>>>(stats);
     MAREX_LAUNCH_CHECK("init_stats_kernel");
+  }
+  if (ws > 1 && ws <= 7 && max_window_rows <= 65535 && !getenv("MAREX_POOL_V1")) {
+    // tiled kernel: pick the own-cell tile OY x OX that fits shared memory
+    const int p = ws / 2;
+    const int nb1 = (nb + 7) >> 3, nb2 = (nb + 63) >> 6;
+    const size_t per_col = (size_t)(nb + nb1 + nb2 + 2) * 2;  // bytes per counter column (own cell or dummy)
+    int cs_max = (int)((227 * 1024 - 1024) / per_col);
+    if (cs_max > 257) cs_max = 257;
+    const int c_max = ((cs_max - 1) | 1) - 1;  // odd column stride spreads a row's cells over all banks
+    int best_oy = 0, best_ox = 0, best_t = 0;
+    for (int oy = 2 * p + 1; oy <= 64; ++oy)
+      for (int ox = 2 * p + 1; ox <= 64; ++ox) {
+        if (oy * ox > c_max) continue;
+        const int t = (oy - 2 * p) * (ox - 2 * p);
+        if (t > best_t || (t == best_t && ox > best_ox)) { best_t = t; best_oy = oy; best_ox = ox; }
+      }
+    if (best_t > 0) {
+      const int C = best_oy * best_ox;
+      const int CS = (C + 1) | 1;
+      const size_t smem_t = per_col * CS;
+      const int TY = best_oy - 2 * p, TX = best_ox - 2 * p;
+      const int CR = ((C + 31) / 32) * 32;
+      int threads = 3 * CR;                       // three event roles
+      const int LPT = (8 * TY * TX <= threads) ? 8 : 4;
+      if (LPT * TY * TX > threads) threads = ((LPT * TY * TX + 31) / 32) * 32;
+      if (threads > 768) return fail(MAREX_ERR_UNSUPPORTED, "pooled tile needs more than 768 threads");
+      dim3 grid_t((unsigned)((nx + TX - 1) / TX), (unsigned)((ny + TY - 1) / TY));
+#define MAREX_POOL(PP)                                                                                             \
+  do {                                                                                                             \
+    int rc = set_smem(hobday_pool_tile_kernel<PP>, smem_t);                                                        \
+    if (rc) return rc;                                                                                             \
+    hobday_pool_tile_kernel<PP><<<grid_t, threads, smem_t, st>>>(bins, ny, nx, pitch, doy_ptr, doy_rows, centers,  \
+                                                                 nb, w, q, anom_row0, lower_bound, thr, stats,    \
+                                                                 best_oy, best_ox, CS, CR, LPT);                   \
+  } while (0)
+      if (p == 1) MAREX_POOL(1); else if (p == 2) MAREX_POOL(2); else MAREX_POOL(3);
+#undef MAREX_POOL
+      MAREX_LAUNCH_CHECK("hobday_pool_tile_kernel");
+      return MAREX_OK;
+    }
   }
   const long long max_count = (long long)max_window_rows * ws * ws;
   const bool wide = max_count > 65535;
