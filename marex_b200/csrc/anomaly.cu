@@ -21,17 +21,26 @@ __global__ void __launch_bounds__(256) shift_anomaly_kernel(
     const float* __restrict__ x, int64_t T, int64_t N, int64_t pitch,
     const int32_t* __restrict__ tidx, const int32_t* __restrict__ year_val, int n_years, int W, int S,
     const int32_t* __restrict__ out_row, float* __restrict__ anom, int64_t anom_pitch,
-    uint8_t* __restrict__ mask0, int32_t* __restrict__ nonfinite, int n_strips, int spb, int mode) {
+    uint8_t* __restrict__ mask0, int32_t* __restrict__ nonfinite, int n_strips, int spb, int mode,
+    const int32_t* __restrict__ cell_list, const int32_t* __restrict__ n_list) {
   extern __shared__ float ring[];  // [W][R][spb][32]
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int64_t c = (int64_t)blockIdx.x * 32 + lane;
   const int strip = blockIdx.y * spb + warp;
   if (strip >= n_strips) return;  // whole warp leaves together
-  const bool live = c < N;
-  const int64_t cc = live ? c : N - 1;  // clamp: dead lanes read a valid column, never write
+  // Cell groups: all of 0..N-1, or (fix-up pass of the daily kernel) the cells of `cell_list`,
+  // walked grid-stride so the launch does not need the list length on the host.
+  const int64_t n_cells = cell_list ? (int64_t)__ldg(n_list) : N;
+  const int64_t n_groups = (n_cells + 31) / 32;
   const int d0 = strip * R;
   const int off = S / 2;
   const int first_target = year_val[0] + W;
+  auto ring_at = [&](int slot, int r) -> float& { return ring[((slot * R + r) * spb + warp) * 32 + lane]; };
+
+  for (int64_t g = blockIdx.x; g < n_groups; g += gridDim.x) {
+  const int64_t idx = g * 32 + lane;
+  const bool live = idx < n_cells;
+  const int64_t c = cell_list ? (int64_t)__ldg(&cell_list[live ? idx : n_cells - 1]) : (live ? idx : N - 1);
+  const int64_t cc = c;  // dead lanes read a valid column, never write
 
   double sum[R];
   uint32_t cnt[R];  // bits 0..9 valid (non-NaN) count, 10..19 +inf, 20..29 -inf
@@ -39,7 +48,6 @@ __global__ void __launch_bounds__(256) shift_anomaly_kernel(
   for (int r = 0; r < R; ++r) { sum[r] = 0.0; cnt[r] = 0u; }
   int bad = 0;
 
-  auto ring_at = [&](int slot, int r) -> float& { return ring[((slot * R + r) * spb + warp) * 32 + lane]; };
   auto ring_update = [&](float s, int r, int sign) {
     if (s == s) {  // NaN contributes nothing to a nanmean
       const bool fin = is_finite_f(s);
@@ -125,6 +133,7 @@ __global__ void __launch_bounds__(256) shift_anomaly_kernel(
     }
   }
   if (live && bad) atomicAdd(&nonfinite[c], bad);
+  }
 }
 
 // =======================================================================================
@@ -250,17 +259,15 @@ __global__ void __launch_bounds__(256) detrend_apply_kernel(
 
 using namespace marex;
 
-extern "C" int marex_shift_anomaly_f32(const float* x, int64_t T, int64_t N, int64_t pitch, const int32_t* tidx,
-                                       const int32_t* year_val, int32_t n_years, int32_t W, int32_t S,
-                                       const int32_t* out_row, int32_t mode, float* anom, int64_t anom_pitch,
-                                       uint8_t* mask0, int32_t* nonfinite, void* stream) {
-  MAREX_REQUIRE(x && tidx && year_val && out_row && anom && mask0 && nonfinite, "null pointer");
-  MAREX_REQUIRE(T > 0 && N > 0 && pitch >= N && anom_pitch >= N && n_years > 0, "bad shape");
-  MAREX_REQUIRE(W >= 1 && W <= 1023 && S >= 1 && S <= 1023, "W and S must be in 1..1023");
-  cudaStream_t st = (cudaStream_t)stream;
-  MAREX_CUDA(cudaMemsetAsync(nonfinite, 0, sizeof(int32_t) * N, st));
+// Launches the generic kernel over all N cells (cell_list == nullptr) or, grid-stride, over the
+// cells listed in cell_list[0 .. *n_list) (device memory), with `list_ctas` CTAs per strip row.
+namespace marex {
+int launch_shift_generic(const float* x, int64_t T, int64_t N, int64_t pitch, const int32_t* tidx,
+                         const int32_t* year_val, int32_t n_years, int32_t W, int32_t S, const int32_t* out_row,
+                         int32_t mode, float* anom, int64_t anom_pitch, uint8_t* mask0, int32_t* nonfinite,
+                         const int32_t* cell_list, const int32_t* n_list, int list_ctas, cudaStream_t st) {
   const size_t smem_budget = 96 * 1024;  // two CTAs per SM
-  const int64_t nblk_x = (N + 31) / 32;
+  const int64_t nblk_x = cell_list ? list_ctas : (N + 31) / 32;
   auto launch = [&](auto kern, int R) -> int {
     const size_t per_warp = (size_t)W * R * 32 * sizeof(float);
     if (per_warp > 200 * 1024) return MAREX_ERR_UNSUPPORTED;
@@ -274,7 +281,7 @@ extern "C" int marex_shift_anomaly_f32(const float* x, int64_t T, int64_t N, int
     if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(shift_anomaly)");
     dim3 grid((unsigned)nblk_x, (unsigned)((n_strips + spb - 1) / spb));
     kern<<<grid, spb * 32, smem, st>>>(x, T, N, pitch, tidx, year_val, n_years, W, S, out_row, anom, anom_pitch,
-                                       mask0, nonfinite, n_strips, spb, mode);
+                                       mask0, nonfinite, n_strips, spb, mode, cell_list, n_list);
     MAREX_LAUNCH_CHECK("shift_anomaly_kernel");
     return MAREX_OK;
   };
@@ -283,6 +290,20 @@ extern "C" int marex_shift_anomaly_f32(const float* x, int64_t T, int64_t N, int
   if (rc == MAREX_ERR_UNSUPPORTED) rc = launch(shift_anomaly_kernel<1>, 1);
   if (rc == MAREX_ERR_UNSUPPORTED) return fail(rc, "window_year_baseline too large for the shared-memory ring");
   return rc;
+}
+}  // namespace marex
+
+extern "C" int marex_shift_anomaly_f32(const float* x, int64_t T, int64_t N, int64_t pitch, const int32_t* tidx,
+                                       const int32_t* year_val, int32_t n_years, int32_t W, int32_t S,
+                                       const int32_t* out_row, int32_t mode, float* anom, int64_t anom_pitch,
+                                       uint8_t* mask0, int32_t* nonfinite, void* stream) {
+  MAREX_REQUIRE(x && tidx && year_val && out_row && anom && mask0 && nonfinite, "null pointer");
+  MAREX_REQUIRE(T > 0 && N > 0 && pitch >= N && anom_pitch >= N && n_years > 0, "bad shape");
+  MAREX_REQUIRE(W >= 1 && W <= 1023 && S >= 1 && S <= 1023, "W and S must be in 1..1023");
+  cudaStream_t st = (cudaStream_t)stream;
+  MAREX_CUDA(cudaMemsetAsync(nonfinite, 0, sizeof(int32_t) * N, st));
+  return launch_shift_generic(x, T, N, pitch, tidx, year_val, n_years, W, S, out_row, mode, anom, anom_pitch, mask0,
+                              nonfinite, nullptr, nullptr, 0, st);
 }
 
 extern "C" int marex_doy_climatology_f32(const float* x, int64_t T, int64_t N, int64_t pitch, const int32_t* doy_ptr,

@@ -100,6 +100,12 @@ __device__ __forceinline__ void atomic_max_d(double* addr, double v) {
   else atomicMin(reinterpret_cast<unsigned long long*>(addr), (unsigned long long)__double_as_longlong(v));
 }
 
+// anomaly.cu: generic shifting-baseline kernel over all cells or over a device-side cell list.
+int launch_shift_generic(const float* x, int64_t T, int64_t N, int64_t pitch, const int32_t* tidx,
+                         const int32_t* year_val, int32_t n_years, int32_t W, int32_t S, const int32_t* out_row,
+                         int32_t mode, float* anom, int64_t anom_pitch, uint8_t* mask0, int32_t* nonfinite,
+                         const int32_t* cell_list, const int32_t* n_list, int list_ctas, cudaStream_t st);
+
 inline int sm_count() {
   static int n = 0;
   if (!n) {
