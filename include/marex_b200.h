@@ -67,6 +67,25 @@ int marex_shift_anomaly_f32(const float* x, int64_t T, int64_t N, int64_t pitch,
                             float* anom, int64_t anom_pitch,
                             uint8_t* mask0, int32_t* nonfinite, void* stream);
 
+/* Same stage, fast path for a GAP-FREE DAILY proleptic-Gregorian time axis whose row 0 is day
+ * `doy0` (1..366) of calendar year `year0` (the kernel derives every calendar table itself).
+ * One TMA box load per (32 gridpoints, day-of-year strip, year) stages the rows in shared
+ * memory; requires x 16-byte aligned and pitch % 4 == 0.  Exact for gridpoints whose series is
+ * all finite or all NaN; `nonfinite` receives the per-gridpoint count of non-finite inputs and
+ * marex_shift_anomaly_fixup_f32 must follow to recompute gridpoints with 0 < count < T.
+ * Output row of input row t is t - (first row of year0 + W) for mode 0, t for mode 1. */
+int marex_shift_anomaly_daily_f32(const float* x, int64_t T, int64_t N, int64_t pitch,
+                                  int32_t year0, int32_t doy0, int32_t W, int32_t S, int32_t mode,
+                                  float* out, int64_t out_pitch,
+                                  uint8_t* mask0, int32_t* nonfinite, void* stream);
+/* Recomputes, with the generic kernel of marex_shift_anomaly_f32 (same tables), the gridpoints
+ * whose `nonfinite` count is strictly between 0 and T.  `work`: device scratch of N + 1 int32. */
+int marex_shift_anomaly_fixup_f32(const float* x, int64_t T, int64_t N, int64_t pitch,
+                                  const int32_t* tidx, const int32_t* year_val, int32_t n_years,
+                                  int32_t W, int32_t S, const int32_t* out_row, int32_t mode,
+                                  float* anom, int64_t anom_pitch,
+                                  uint8_t* mask0, int32_t* nonfinite, int32_t* work, void* stream);
+
 /* ---- (a') fixed baseline ---------------------------------------------------------------
  * Per-day-of-year nanmean (flox nanmean, detect.py:2365-2373) over the rows listed in the CSR
  * (doy_ptr, doy_rows) -- all rows, or only the reference_period's rows (detect.py:2334-2361).

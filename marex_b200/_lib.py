@@ -15,6 +15,8 @@ _SIGNATURES = {
     "marex_last_error": ([], c_char_p),
     "marex_launch_count": ([], c_longlong),
     "marex_shift_anomaly_f32": ([_P, c_int64, c_int64, c_int64, _P, _P, c_int32, c_int32, c_int32, _P, c_int32, _P, c_int64, _P, _P, _P], ctypes.c_int),
+    "marex_shift_anomaly_daily_f32": ([_P, c_int64, c_int64, c_int64, c_int32, c_int32, c_int32, c_int32, c_int32, _P, c_int64, _P, _P, _P], ctypes.c_int),
+    "marex_shift_anomaly_fixup_f32": ([_P, c_int64, c_int64, c_int64, _P, _P, c_int32, c_int32, c_int32, _P, c_int32, _P, c_int64, _P, _P, _P, _P], ctypes.c_int),
     "marex_doy_climatology_f32": ([_P, c_int64, c_int64, c_int64, _P, _P, _P, _P, _P], ctypes.c_int),
     "marex_sub_doy_climatology_f32": ([_P, c_int64, c_int64, c_int64, _P, _P, _P, _P, c_int64, _P, _P, _P], ctypes.c_int),
     "marex_detrend_coef_f64": ([_P, c_int64, c_int64, c_int64, _P, c_int32, _P, _P, _P, _P], ctypes.c_int),

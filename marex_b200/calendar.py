@@ -24,6 +24,12 @@ class Calendar:
     def n_years(self) -> int:
         return int(self.year_val.shape[0])
 
+    @property
+    def is_daily(self) -> bool:
+        """Gap-free daily axis: every row is the day after the previous one (what the TMA-staged
+        shifting-baseline kernel assumes; anything else takes the generic table-driven kernel)."""
+        return bool(np.all(np.diff(self.time.astype("datetime64[D]").astype(np.int64)) == 1))
+
 
 def year_doy(time) -> Tuple[np.ndarray, np.ndarray]:
     t = np.asarray(time).astype("datetime64[D]")

@@ -57,7 +57,7 @@ __global__ void __launch_bounds__(256) shift_anomaly_kernel(
     }
   };
 
-  if (strip == 0 && live) mask0[c] = is_finite_f(x[c]) ? 1 : 0;
+  if (strip == 0 && live && !cell_list) mask0[c] = is_finite_f(x[c]) ? 1 : 0;
 
   int rm = 0;  // oldest year index still in the ring
   for (int i = 0; i < n_years; ++i) {
@@ -132,7 +132,7 @@ __global__ void __launch_bounds__(256) shift_anomaly_kernel(
       ring_update(snew[r], r, +1);
     }
   }
-  if (live && bad) atomicAdd(&nonfinite[c], bad);
+  if (live && bad && !cell_list) atomicAdd(&nonfinite[c], bad);  // the fix-up pass keeps the first count
   }
 }
 

@@ -480,6 +480,33 @@ def detrend_model(time, detrend_orders: Sequence[int]) -> Tuple[np.ndarray, np.n
     return model, np.linalg.pinv(model)
 
 
+def _shift_anomaly_call(h: "_Hold", xd: torch.Tensor, cal: Calendar, W: int, S: int, out_row: np.ndarray, mode: int,
+                        out: torch.Tensor, mask0: torch.Tensor, nonfinite: torch.Tensor) -> None:
+    """Dispatch of kernel (a): the TMA-staged daily kernel + fix-up of gridpoints with mixed
+    finite / non-finite series when the time axis is gap-free daily, else the generic
+    table-driven kernel (sub-sampled or gappy axes)."""
+    dev = xd.device
+    T, N = xd.shape
+    st = _stream()
+    tidx, yv, orow = h.up(cal.tidx, np.int32, dev), h.up(cal.year_val, np.int32, dev), h.up(out_row, np.int32, dev)
+    if cal.is_daily and N % 4 == 0 and xd.data_ptr() % 16 == 0:
+        _lib.call(
+            "marex_shift_anomaly_daily_f32", _p(xd), T, N, N, int(cal.year[0]), int(cal.doy[0]), W, S, mode, _p(out), N,
+            _p(mask0), _p(nonfinite), st,
+        )  # fmt: skip
+        work = torch.empty(N + 1, dtype=torch.int32, device=dev)
+        h.append(work)
+        _lib.call(
+            "marex_shift_anomaly_fixup_f32", _p(xd), T, N, N, tidx, yv, cal.n_years, W, S, orow, mode, _p(out), N,
+            _p(mask0), _p(nonfinite), _p(work), st,
+        )  # fmt: skip
+    else:
+        _lib.call(
+            "marex_shift_anomaly_f32", _p(xd), T, N, N, tidx, yv, cal.n_years, W, S, orow, mode, _p(out), N, _p(mask0),
+            _p(nonfinite), st,
+        )  # fmt: skip
+
+
 def rolling_climatology_arrays(x, time, window_year_baseline: int = 15, smooth_days_baseline: int = 1, device=None):
     """``rolling_climatology`` (S = 1, detect.py:1511-1688) / ``smoothed_rolling_climatology``
     (detect.py:1691-1816) at array level: the per-time-step climatology, NaN for the first
@@ -492,12 +519,7 @@ def rolling_climatology_arrays(x, time, window_year_baseline: int = 15, smooth_d
     out = torch.full((T, N), float("nan"), dtype=torch.float32, device=dev)
     mask0 = torch.empty(N, dtype=torch.uint8, device=dev)
     nonfinite = torch.empty(N, dtype=torch.int32, device=dev)
-    out_row = _up(np.arange(T), np.int32, dev)
-    _lib.call(
-        "marex_shift_anomaly_f32", _p(xd), T, N, N, h.up(cal.tidx, np.int32, dev), h.up(cal.year_val, np.int32, dev),
-        cal.n_years, int(window_year_baseline), int(smooth_days_baseline), _p(out_row), 1, _p(out), N, _p(mask0),
-        _p(nonfinite), _stream(),
-    )  # fmt: skip
+    _shift_anomaly_call(h, xd, cal, int(window_year_baseline), int(smooth_days_baseline), np.arange(T), 1, out, mask0, nonfinite)
     return out.reshape((T,) + space)
 
 
@@ -538,11 +560,7 @@ def compute_normalised_anomaly_arrays(
         if T_out == 0:
             raise IndexError("shifting_baseline: no time steps remain after removing the first window_year_baseline years")
         anom = torch.empty((T_out, N), dtype=torch.float32, device=dev)
-        _lib.call(
-            "marex_shift_anomaly_f32", _p(x_dev), T, N, N, h.up(cal.tidx, np.int32, dev),
-            h.up(cal.year_val, np.int32, dev), cal.n_years, W, S, h.up(out_row, np.int32, dev), 0,
-            _p(anom), N, _p(mask0), _p(nonfinite), st,
-        )  # fmt: skip
+        _shift_anomaly_call(h, x_dev, cal, W, S, out_row, 0, anom, mask0, nonfinite)
         if validate:
             check_data_values(mask0, nonfinite, T, T * N)
         return {"dat_anomaly": anom, "mask": mask0.bool(), "keep": keep, "mask_raw": mask0.bool()}
