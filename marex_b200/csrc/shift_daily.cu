@@ -18,6 +18,8 @@
 // series is all finite or all NaN (land).  It counts the non-finite inputs per gridpoint (the
 // same numbers _validate_data_values needs, detect.py:205-279); marex_shift_anomaly_fixup_f32
 // then recomputes the few gridpoints with 0 < count < T with the generic kernel (anomaly.cu).
+#include <cstdlib>
+
 #include "tma.cuh"
 
 namespace marex {
@@ -25,7 +27,7 @@ namespace marex {
 struct DailyParams {
   int64_t T, N, out_pitch, out_off;  // output row of input row t is t - out_off
   int year0, doy0;                   // calendar year and 0-based day of year of row 0
-  int n_years, W, S, D, rows_box, mode;
+  int n_years, W, S, D, rows_box, n_strips;
   float* out;
   uint8_t* mask0;
   int32_t* nonfinite;
@@ -33,22 +35,27 @@ struct DailyParams {
 
 __host__ __device__ __forceinline__ bool is_leap(int y) { return (y % 4 == 0 && y % 100 != 0) || (y % 400 == 0); }
 
-template <int R, int NST>
-__global__ void __launch_bounds__(512) shift_daily_kernel(const __grid_constant__ CUtensorMap tmap, const DailyParams p) {
+template <int R, int NST, int MODE>
+__global__ void __launch_bounds__(R >= 12 ? 256 : 512) shift_daily_kernel(const __grid_constant__ CUtensorMap tmap,
+                                                                         const DailyParams p) {
   extern __shared__ __align__(1024) unsigned char smem_raw[];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int D = p.D, W = p.W, S = p.S, off = p.S / 2;
   // shared memory carve-up (all offsets multiples of 128 bytes)
   uint64_t* bar = reinterpret_cast<uint64_t*>(smem_raw);                         // [NST]
-  double* invtab = reinterpret_cast<double*>(smem_raw + 128);                    // [W + 1]
+  double* invtab = reinterpret_cast<double*>(smem_raw + 128);                    // [W + 1], invtab[0] = NaN
   const size_t inv_bytes = (((size_t)(W + 1) * 8 + 127) / 128) * 128;
   float* xs = reinterpret_cast<float*>(smem_raw + 128 + inv_bytes);              // [NST][rows_box][32]
-  float* ring = xs + (size_t)NST * p.rows_box * 32;                              // [W][D][32]
+  const int stage_elems = p.rows_box * 32;
+  float* ring = xs + (size_t)NST * stage_elems;                                  // [W][D][32]
 
-  const int64_t c0 = (int64_t)blockIdx.x * 32;
+  // strips of one 32-gridpoint group are adjacent CTAs: they run at the same time and at the
+  // same pace, so the S - 1 halo rows a strip shares with its neighbour are L2 hits
+  const int strip = blockIdx.x % p.n_strips;
+  const int64_t c0 = (int64_t)(blockIdx.x / p.n_strips) * 32;
   const int64_t c = c0 + lane;
   const bool live = c < p.N;
-  const int d0 = blockIdx.y * D;
+  const int d0 = strip * D;
   const int rbase = warp * R;
   const uint32_t box_bytes = (uint32_t)p.rows_box * 128u;
 
@@ -56,22 +63,22 @@ __global__ void __launch_bounds__(512) shift_daily_kernel(const __grid_constant_
     for (int s = 0; s < NST; ++s) mbar_init(&bar[s], 1);
     mbar_fence_init();
   }
-  for (int i = threadIdx.x; i <= W; i += blockDim.x) invtab[i] = i ? 1.0 / (double)i : 0.0;
+  for (int i = threadIdx.x; i <= W; i += blockDim.x) invtab[i] = i ? 1.0 / (double)i : (double)CUDART_NAN;
   for (int i = threadIdx.x; i < W * D * 32; i += blockDim.x) ring[i] = CUDART_NAN_F;
   __syncthreads();
 
   // producer state (thread 0): first row of the box of the next year to issue
-  int issue_year = 0;
+  int issue_year = 0, issue_st = 0;
   int64_t issue_base = -(int64_t)p.doy0;  // row index of day-of-year 0 of year `issue_year`
   auto issue = [&]() {  // a box that lies entirely outside the series is neither loaded nor waited for
-    const int st = issue_year % NST;
     const int64_t tb = issue_base + d0 - off;
     if (tb < p.T && tb + p.rows_box > 0) {
-      mbar_expect_tx(&bar[st], box_bytes);
-      tma_load_2d(xs + (size_t)st * p.rows_box * 32, &tmap, (int)c0, (int)tb, &bar[st]);
+      mbar_expect_tx(&bar[issue_st], box_bytes);
+      tma_load_2d(xs + (size_t)issue_st * stage_elems, &tmap, (int)c0, (int)tb, &bar[issue_st]);
     }
     issue_base += is_leap(p.year0 + issue_year) ? 366 : 365;
     ++issue_year;
+    if (++issue_st == NST) issue_st = 0;
   };
   if (threadIdx.x == 0) {
     tma_prefetch_desc(&tmap);
@@ -86,12 +93,15 @@ __global__ void __launch_bounds__(512) shift_daily_kernel(const __grid_constant_
   const double invS = 1.0 / (double)S;
   int64_t base = -(int64_t)p.doy0;
   uint32_t phase = 0;  // bit st = parity of the next completion of stage st
+  int st = 0, slot = 0;
+  const float* Xst = xs + rbase * 32 + lane;          // this thread's first window row in stage 0
+  float* ringp = ring + (size_t)rbase * 32 + lane;    // this thread's first day in ring slot 0
+  float* const outc = p.out + c;                      // column of this gridpoint (dead lanes never store)
 
   for (int i = 0; i < p.n_years; ++i) {
     const int ylen = is_leap(p.year0 + i) ? 366 : 365;
-    const int st = i % NST;
-    const float* X = xs + (size_t)st * p.rows_box * 32 + lane;  // X[j * 32]: row j of the box, this lane's column
-    float* ringslot = ring + ((size_t)(i % W) * D + rbase) * 32 + lane;
+    const float* X = Xst + st * stage_elems;          // X[j * 32]: row rbase + j of the box
+    float* ringslot = ringp + slot * (D * 32);
     const int nd = min(D, ylen - d0);                 // days of this strip that exist in year i
     const int64_t t0 = base + d0 + rbase;             // input row of this thread's first day
     const bool target = i >= W;
@@ -102,36 +112,51 @@ __global__ void __launch_bounds__(512) shift_daily_kernel(const __grid_constant_
         phase ^= 1u << st;
       }
     }
+    float* outp = outc + (t0 - p.out_off) * p.out_pitch;  // only dereferenced for target years
 
-    auto finish_day = [&](int r, int64_t t, float xv, float s) {
-      // anomaly of a target-year day against the W previous years, then ring turnover
-      if (!is_finite_f(xv)) ++bad;
-      if (target) {
-        const float clim = cnt[r] ? (float)(sum[r] * invtab[cnt[r]]) : CUDART_NAN_F;
-        if (live) st_stream(&p.out[(t - p.out_off) * p.out_pitch + c], p.mode ? clim : xv - clim);
-      }
+    // ring turnover of one (day, gridpoint): year i - W leaves, year i enters
+    auto turnover = [&](int r, float s) {
       const float old = ringslot[r * 32];
       if (old == old) { sum[r] -= (double)old; --cnt[r]; }
       ringslot[r * 32] = s;
       if (s == s) { sum[r] += (double)s; ++cnt[r]; }
     };
-    auto expire_only = [&](int r) {  // (year, day) without a sample: year i - W still has to leave the ring
-      const float old = ringslot[r * 32];
-      if (old == old) { sum[r] -= (double)old; --cnt[r]; ringslot[r * 32] = CUDART_NAN_F; }
+    auto emit = [&](int r, float xv) {  // anomaly (or climatology) of a target-year day
+      const float clim = (float)(sum[r] * invtab[cnt[r]]);
+      if (live) st_stream(outp, MODE ? clim : xv - clim);
     };
 
     if (rbase + R <= nd && t0 - off >= 0 && t0 + (R - 1) - off + S <= p.T) {
       // ---- whole sub-strip inside the year and the series: no per-day checks ----
-      if (t0 <= 0 && live) {  // only reachable when S == 1
-        if (t0 == 0) p.mask0[c] = is_finite_f(X[(rbase + off) * 32]) ? 1 : 0;
+      if (t0 == 0 && live) p.mask0[c] = is_finite_f(X[off * 32]) ? 1 : 0;  // only reachable when S == 1
+      const float* Xhi = X + (S - 1) * 32;
+      const float* Xc = X + off * 32;
+      double wa = 0.0, wb = 0.0, wc = 0.0;  // three chains: the sum is exact, so its order is free
+      int k = 0;
+      for (; k + 3 <= S; k += 3) {
+        wa += (double)X[k * 32];
+        wb += (double)X[(k + 1) * 32];
+        wc += (double)X[(k + 2) * 32];
       }
-      double ws = 0.0;
-#pragma unroll 7
-      for (int k = 0; k < S; ++k) ws += (double)X[(rbase + k) * 32];
+      for (; k < S; ++k) wa += (double)X[k * 32];
+      double ws = (wa + wb) + wc;
+      if (target) {
 #pragma unroll
-      for (int r = 0; r < R; ++r) {
-        if (r > 0) ws += (double)X[(rbase + r + S - 1) * 32] - (double)X[(rbase + r - 1) * 32];
-        finish_day(r, t0 + r, X[(rbase + r + off) * 32], (float)(ws * invS));
+        for (int r = 0; r < R; ++r) {
+          if (r > 0) ws += (double)Xhi[r * 32] - (double)X[(r - 1) * 32];
+          const float xv = Xc[r * 32];
+          bad += is_finite_f(xv) ? 0 : 1;
+          emit(r, xv);
+          outp += p.out_pitch;
+          turnover(r, (float)(ws * invS));
+        }
+      } else {
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+          if (r > 0) ws += (double)Xhi[r * 32] - (double)X[(r - 1) * 32];
+          bad += is_finite_f(Xc[r * 32]) ? 0 : 1;
+          turnover(r, (float)(ws * invS));
+        }
       }
     } else {
       // ---- series edges / last days of the year: checked path ----
@@ -141,26 +166,30 @@ __global__ void __launch_bounds__(512) shift_daily_kernel(const __grid_constant_
       for (int r = 0; r < R; ++r) {
         const int64_t t = t0 + r;
         if (rbase + r < nd && t >= 0 && t < p.T) {
-          const float xv = X[(rbase + r + off) * 32];
+          const float xv = X[(r + off) * 32];
           if (t == 0 && live) p.mask0[c] = is_finite_f(xv) ? 1 : 0;
           float s = CUDART_NAN_F;
           if (t - off >= 0 && t - off + S <= p.T) {  // full window inside the series (min_periods = S)
             if (have) {
-              ws += (double)X[(rbase + r + S - 1) * 32] - (double)X[(rbase + r - 1) * 32];
+              ws += (double)X[(r + S - 1) * 32] - (double)X[(r - 1) * 32];
             } else {
               ws = 0.0;
-              for (int k = 0; k < S; ++k) ws += (double)X[(rbase + r + k) * 32];
+              for (int k = 0; k < S; ++k) ws += (double)X[(r + k) * 32];
               have = true;
             }
             s = (float)(ws * invS);
           } else {
             have = false;
           }
-          finish_day(r, t, xv, s);
+          bad += is_finite_f(xv) ? 0 : 1;
+          if (target) emit(r, xv);
+          turnover(r, s);
         } else {
-          have = false;
-          expire_only(r);
+          have = false;  // (year, day) without a sample: year i - W still has to leave the ring
+          const float old = ringslot[r * 32];
+          if (old == old) { sum[r] -= (double)old; --cnt[r]; ringslot[r * 32] = CUDART_NAN_F; }
         }
+        outp += p.out_pitch;
       }
     }
     __syncthreads();  // everyone is done with stage `st`
@@ -169,6 +198,8 @@ __global__ void __launch_bounds__(512) shift_daily_kernel(const __grid_constant_
       issue();
     }
     base += ylen;
+    if (++st == NST) st = 0;
+    if (++slot == W) slot = 0;
   }
   if (live && bad) atomicAdd(&p.nonfinite[c], bad);
 }
@@ -198,7 +229,7 @@ extern "C" int marex_shift_anomaly_daily_f32(const float* x, int64_t T, int64_t 
   DailyParams p;
   p.T = T; p.N = N; p.out_pitch = out_pitch;
   p.year0 = year0; p.doy0 = doy0 - 1;
-  p.W = W; p.S = S; p.mode = mode;
+  p.W = W; p.S = S;
   p.out = out; p.mask0 = mask0; p.nonfinite = nonfinite;
   // years covered by T daily rows starting at (year0, doy0); row of Jan 1 of year index W
   int64_t base = -(int64_t)(doy0 - 1), base_w = -1;
@@ -212,43 +243,59 @@ extern "C" int marex_shift_anomaly_daily_f32(const float* x, int64_t T, int64_t 
   p.out_off = mode ? 0 : (base_w >= 0 ? base_w : T);
   MAREX_CUDA(cudaMemsetAsync(nonfinite, 0, sizeof(int32_t) * N, st));
 
-  constexpr int NST = 2;
-  const size_t budget = 225 * 1024;
-  auto plan = [&](int R, int& NW, size_t& smem) -> bool {  // largest NW (<= 16) whose strip fits shared memory
-    const size_t fixed = 128 + (((size_t)(W + 1) * 8 + 127) / 128) * 128;
-    for (NW = 16; NW >= 1; --NW) {
+  // Strip length D = R * NW days.  Shared memory = ring (W * D rows) + NST staged boxes (D + S - 1
+  // rows each) of 128 bytes per row; CTAS_PER_SM co-resident CTAs split the 227 KB.
+  const int env_r = getenv("MAREX_SHIFT_R") ? atoi(getenv("MAREX_SHIFT_R")) : 0;
+  const int env_nw = getenv("MAREX_SHIFT_NW") ? atoi(getenv("MAREX_SHIFT_NW")) : 0;
+  const int env_nst = getenv("MAREX_SHIFT_NST") ? atoi(getenv("MAREX_SHIFT_NST")) : 0;
+  const int env_cps = getenv("MAREX_SHIFT_CPS") ? atoi(getenv("MAREX_SHIFT_CPS")) : 0;
+  const size_t fixed = 128 + (((size_t)(W + 1) * 8 + 127) / 128) * 128;
+  auto smem_of = [&](int D, int nst) { return fixed + (size_t)nst * (D + S - 1) * 128 + (size_t)W * D * 128; };
+  auto launch = [&](auto kern, int R, int nst, int cps) -> int {
+    const size_t budget = (size_t)(227 * 1024) / cps - (cps > 1 ? 1024 : 0);
+    const int nw_max = R >= 12 ? 8 : 16;
+    int NW = env_nw ? env_nw : nw_max;
+    for (; NW >= 1; --NW) {
       const int D = R * NW;
-      const int rows = D + S - 1;
-      if (rows > 256) continue;
-      if (D > NDOY + R) continue;
-      smem = fixed + (size_t)NST * rows * 128 + (size_t)W * D * 128;
-      if (smem <= budget) return true;
+      if (D + S - 1 <= 256 && D <= NDOY + R && smem_of(D, nst) <= budget) break;
     }
-    return false;
-  };
-  auto launch = [&](auto kern, int R) -> int {
-    int NW;
-    size_t smem;
-    if (!plan(R, NW, smem)) return MAREX_ERR_UNSUPPORTED;
+    if (NW < 1) return MAREX_ERR_UNSUPPORTED;
     // even out the strips: the fewest strips this R allows, then the smallest NW that still gives that count
     const int n_strips = (NDOY + R * NW - 1) / (R * NW);
-    while (NW > 1 && (NDOY + R * (NW - 1) - 1) / (R * (NW - 1)) == n_strips) --NW;
+    while (!env_nw && NW > 1 && (NDOY + R * (NW - 1) - 1) / (R * (NW - 1)) == n_strips) --NW;
     p.D = R * NW;
     p.rows_box = p.D + S - 1;
-    smem = 128 + (((size_t)(W + 1) * 8 + 127) / 128) * 128 + (size_t)NST * p.rows_box * 128 + (size_t)W * p.D * 128;
+    p.n_strips = n_strips;
+    const size_t smem = smem_of(p.D, nst);
     CUtensorMap tmap;
     int rc = make_tmap_2d(&tmap, x, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, T, N, pitch, p.rows_box, 32);
     if (rc) return rc;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(shift_daily)");
-    dim3 grid((unsigned)((N + 31) / 32), (unsigned)n_strips);
-    kern<<<grid, NW * 32, smem, st>>>(tmap, p);
+    const int64_t n_cta = ((N + 31) / 32) * n_strips;
+    if (n_cta >= (1LL << 31)) return fail(MAREX_ERR_UNSUPPORTED, "grid too large");
+    kern<<<(unsigned)n_cta, NW * 32, smem, st>>>(tmap, p);
     MAREX_LAUNCH_CHECK("shift_daily_kernel");
     return MAREX_OK;
   };
-  int rc = launch(shift_daily_kernel<12, NST>, 12);
-  if (rc == MAREX_ERR_UNSUPPORTED) rc = launch(shift_daily_kernel<4, NST>, 4);
-  if (rc == MAREX_ERR_UNSUPPORTED) rc = launch(shift_daily_kernel<1, NST>, 1);
+#define MAREX_SD(R_, NST_, CPS_)                                                          \
+  (mode ? launch(shift_daily_kernel<R_, NST_, 1>, R_, NST_, CPS_) : launch(shift_daily_kernel<R_, NST_, 0>, R_, NST_, CPS_))
+  int rc = MAREX_ERR_UNSUPPORTED;
+  if (env_r) {  // tuning knobs (MAREX_SHIFT_R / _NW / _NST / _CPS), not part of the API
+    const int nst = env_nst ? env_nst : 2, cps = env_cps ? env_cps : 1;
+    if (env_r == 12) rc = nst == 3 ? MAREX_SD(12, 3, cps) : MAREX_SD(12, 2, cps);
+    else if (env_r == 6) rc = nst == 3 ? MAREX_SD(6, 3, cps) : MAREX_SD(6, 2, cps);
+    else if (env_r == 4) rc = MAREX_SD(4, 2, cps);
+    else rc = MAREX_SD(1, 2, cps);
+  } else {
+    // measured on B200 (0.25 deg, W=15, S=21): two co-resident CTAs of 8 warps x 6 days beat one CTA
+    // of 8 x 12 (57.6 vs 78.8 ms): the arithmetic is latency-bound, the staging is not
+    rc = MAREX_SD(6, 2, 2);
+    if (rc == MAREX_ERR_UNSUPPORTED) rc = MAREX_SD(12, 2, 1);
+    if (rc == MAREX_ERR_UNSUPPORTED) rc = MAREX_SD(4, 2, 1);
+    if (rc == MAREX_ERR_UNSUPPORTED) rc = MAREX_SD(1, 2, 1);
+  }
+#undef MAREX_SD
   if (rc == MAREX_ERR_UNSUPPORTED)
     return fail(rc, "window_year_baseline / smooth_days_baseline too large for the shared-memory ring");
   return rc;
