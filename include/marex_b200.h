@@ -133,6 +133,20 @@ int marex_hobday_thresholds_hist(const uint16_t* bins, int64_t T, int64_t ny, in
                                  int32_t w, int32_t ws, double q, const float* anom_row0,
                                  float lower_bound, float* thr, float* stats, void* stream);
 
+/* Same computation for gridded data with ws in {3, 5, 7}, straight from the float32 anomalies:
+ * digitizes into `workspace` (edges[nb + 1] float32, edges[0] = -inf) and runs the banded
+ * warp-cooperative kernel (pool_band.cu); tiles whose thresholds do not fit one band are
+ * recomputed with full-range counters.  Requires nx >= 32, nb <= 1024.  `workspace`: device
+ * scratch of at least marex_hobday_pooled_workspace_bytes(T, ny, nx) bytes.  The NaN mask is
+ * taken from row 0 of `anom` (detect.py:2704-2705). */
+int64_t marex_hobday_pooled_workspace_bytes(int64_t T, int64_t ny, int64_t nx);
+int marex_hobday_thresholds_pooled_f32(const float* anom, int64_t T, int64_t ny, int64_t nx,
+                                       int64_t pitch, const int32_t* doy_ptr, const int32_t* doy_rows,
+                                       int32_t max_window_rows, const float* edges, const float* centers,
+                                       int32_t nb, int32_t w, int32_t ws, double q, float lower_bound,
+                                       float* thr, float* stats, void* workspace, int64_t workspace_bytes,
+                                       void* stream);
+
 /* Exact Hobday thresholds: np.nanpercentile (float32 'linear') over the +-w/2 doy window
  * (detect.py:1921-1956).  thr[366, N] doy-major, NaN where the window holds no valid sample. */
 int marex_hobday_thresholds_exact_f32(const float* anom, int64_t T, int64_t N, int64_t pitch,

@@ -1,0 +1,500 @@
+// Approximate Hobday thresholds with ws x ws spatial pooling -- banded, warp-cooperative kernel.
+// Reference: _compute_histogram_quantile_2d (detect.py:2562-2734: digitize, (doy x bin) counts,
+// pooling :2651-2668) and _rolling_histogram_quantile (detect.py:2465-2559).
+//
+// Tile = OY x 32 "own" gridpoints (warp = own row, lane = own column), of which the inner
+// (OY - 2P) x (32 - 2P) are targets.  Each own gridpoint keeps the histogram of ITS OWN +-w/2
+// day-of-year window in shared memory, but only for a BAND of K bins [Blo, Blo + K) that brackets
+// the tile's thresholds: a p95 threshold is decided by the top few percent of the samples, so
+//   * a sample below the band only counts in NT (valid samples) - no shared-memory traffic,
+//   * a sample inside the band is a read-modify-write of one bin counter and one 8-bin block
+//     counter of its own gridpoint (private to one thread: no atomics),
+//   * a sample above the band only counts in TB (samples >= Blo).
+// Per day-of-year step every thread first scans its entering / leaving samples (2 instructions
+// for a below-band sample) and compacts the few that matter into a small shared list, then
+// applies the list - so the divergent read-modify-write code runs for ~10 % of the samples only.
+//
+// A target's pooled cumulative count is  sum over its ws x ws neighbours of
+// (NT - TB) + blocks below + bins below.  Pooling is separable, and the 32 lanes of a warp are 32
+// adjacent own columns of one target row, so one counter row is pooled for the whole warp by
+// 2P+1 shared loads (column sum) + 2P shuffles (row sum).  The warp scans block rows, then the
+// bin rows of the blocks that hold its lanes' quantiles; each lane keeps what it needs.  All
+// counts are integers: the result is bit-exact against the reference's arithmetic.
+//
+// If a threshold leaves the band the tile rebuilds its counters around the new position (a
+// coarse full-range pass over the current window picks the band).  A tile whose thresholds do
+// not fit one band is appended to `fail_list` and recomputed by the full-range tile kernel
+// (thresholds.cu), so exactness never depends on the band heuristic.
+#include <cstdlib>
+
+#include "common.cuh"
+
+namespace marex {
+
+constexpr int BAND_LCAP = 16;  // slots of the per-thread compacted event list
+constexpr int BAND_CAP = 32;   // staged row indices per step and direction
+
+struct BandParams {
+  const uint16_t* bins;  // [T][ny*nx], 0xFFFF = invalid (NaN or >= last edge)
+  int64_t ny, nx, pitch;
+  const int32_t* doy_ptr;
+  const int32_t* doy_rows;
+  const float* centers;
+  int nb, w, margin;
+  double q;
+  const float* anom_row0;
+  float lower_bound;
+  float* thr;
+  float* stats;
+  int32_t* fail_list;  // [0] = count, then (y0, x0) pairs
+  int force_fail;
+};
+
+template <int P>
+__device__ __forceinline__ int pooled_row(const uint16_t* __restrict__ p, int lane) {
+  int v = 0;
+#pragma unroll
+  for (int dy = 0; dy <= 2 * P; ++dy) v += p[dy * 32];
+  int s = v;
+#pragma unroll
+  for (int k = 1; k <= P; ++k) s += __shfl_sync(0xffffffffu, v, lane + k) + __shfl_sync(0xffffffffu, v, lane - k);
+  return s;
+}
+
+template <int P, int K>
+__global__ void __launch_bounds__(512) hobday_band_kernel(const BandParams p) {
+  constexpr int KB = K / 8;  // blocks in the band
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int OY = blockDim.x >> 5, TY = OY - 2 * P, TX = 32 - 2 * P;
+  const int CS = OY * 32, tid = threadIdx.x;
+  uint16_t* L0 = reinterpret_cast<uint16_t*>(smem_raw);  // [K][CS]; the coarse pass reuses it as [nblk][CS]
+  uint16_t* L1 = L0 + (size_t)K * CS;                     // [KB][CS]
+  uint16_t* NTr = L1 + (size_t)KB * CS;                   // [CS] valid samples in the own window
+  uint16_t* TBr = NTr + CS;                               // [CS] of which >= Blo
+  uint16_t* EV = TBr + CS;                                // [BAND_LCAP][CS]
+  int* s_rows = reinterpret_cast<int*>(EV + (size_t)BAND_LCAP * CS);  // [2 parity][2 leave/enter][BAND_CAP]
+  int* s_cnt = s_rows + 4 * BAND_CAP;                                  // [2][2][2] begin, end in doy_rows
+  int* s_misc = s_cnt + 8;                                             // [0] violation flag, [1] min blk, [2] max blk
+
+  const int nb = p.nb, half = p.w / 2;
+  const int nblk = (nb + 7) >> 3;
+  const int64_t nx = p.nx, ny = p.ny, N = nx * ny;
+  const int64_t y0 = (int64_t)blockIdx.y * TY, x0 = (int64_t)blockIdx.x * TX;
+
+  // ---- own gridpoint of this thread (update role) ----
+  const int64_t gy = y0 - P + warp;
+  int64_t gx = (x0 - P + lane) % nx;
+  if (gx < 0) gx += nx;
+  const bool own_valid = gy >= 0 && gy < ny;
+  const uint16_t* col = p.bins + (own_valid ? gy * nx + gx : 0);
+  uint16_t* myL0 = L0 + tid;
+  uint16_t* myL1 = L1 + tid;
+  int NT = 0, TB = 0, Blo = 0;
+
+  // ---- target of this lane (query role: warps 0..TY-1, lanes P..31-P) ----
+  const int64_t ty_g = y0 + warp, tx_g = x0 + lane - P;
+  const bool target_live = warp < TY && lane >= P && lane < 32 - P && ty_g < ny && tx_g < nx;
+  bool masked = true;
+  if (target_live) {
+    const float a0 = p.anom_row0[ty_g * nx + tx_g];
+    masked = a0 != a0;  // detect.py:2704-2705
+  }
+  float vmin = CUDART_INF_F, vmax = -CUDART_INF_F;
+
+  auto stage = [&](int step) {  // rows leaving / entering the window at `step` (1..365)
+    const int par = step & 1;
+    const int d_leave = (step - 1 - half + 2 * NDOY) % NDOY, d_enter = (step + half) % NDOY;
+    if (tid < 2 * BAND_CAP) {
+      const int which = tid / BAND_CAP, u = tid % BAND_CAP;
+      const int dd = which ? d_enter : d_leave;
+      const int b0 = __ldg(&p.doy_ptr[dd]), b1 = __ldg(&p.doy_ptr[dd + 1]);
+      s_rows[(par * 2 + which) * BAND_CAP + u] = (b0 + u < b1) ? __ldg(&p.doy_rows[b0 + u]) : -1;
+      if (u == 0) { s_cnt[(par * 2 + which) * 2] = b0; s_cnt[(par * 2 + which) * 2 + 1] = b1; }
+    }
+  };
+
+  // Apply one sample to the band counters (sign = +1 / -1); v is a valid bin >= Blo.
+  auto band_apply = [&](int s, int sign) {
+    TB += sign;
+    if (s < K) {
+      myL0[s * CS] = (uint16_t)(myL0[s * CS] + sign);
+      myL1[(s >> 3) * CS] = (uint16_t)(myL1[(s >> 3) * CS] + sign);
+    }
+  };
+
+  // ---- (re)build the counters of the window centred on day-of-year index d ----
+  // returns false when the tile's thresholds do not fit one band (tile goes to the fail list)
+  auto for_window = [&](int d, auto&& fn) {
+    for (int k = -half; k <= half; ++k) {
+      const int dd = ((d + k) % NDOY + NDOY) % NDOY;
+      const int b0 = __ldg(&p.doy_ptr[dd]), b1 = __ldg(&p.doy_ptr[dd + 1]);
+      for (int j = b0; j < b1; j += 8) {
+        int v[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) v[u] = (j + u < b1) ? (int)col[(int64_t)__ldg(&p.doy_rows[j + u]) * p.pitch] : 0xFFFF;
+#pragma unroll
+        for (int u = 0; u < 8; ++u) if (v[u] != 0xFFFF) fn(v[u]);
+      }
+    }
+  };
+  auto rebuild = [&](int d) -> bool {
+    // 1. coarse pass: 8-bin block counts over the full range, own window
+    for (int i = tid; i < (K + KB) * CS; i += blockDim.x) L0[i] = 0;  // L0 and L1 are contiguous
+    if (tid < 3) s_misc[tid] = tid == 1 ? 0x7fffffff : (tid == 2 ? -1 : 0);
+    __syncthreads();
+    NT = 0;
+    if (own_valid) for_window(d, [&](int v) { ++NT; if (K < 8 * nblk) { myL0[(v >> 3) * CS] = (uint16_t)(myL0[(v >> 3) * CS] + 1); } });
+    NTr[tid] = (uint16_t)NT;
+    __syncthreads();
+    if (K >= 8 * nblk) {
+      Blo = 0;  // the band covers every bin: no coarse pass, no violation possible
+    } else {
+      if (warp < TY) {
+        const int ntot = pooled_row<P>(NTr + warp * 32 + lane, lane);
+        const bool livet = target_live && !masked && ntot > 0;
+        const int kk = (int)floor(__dmul_rn(p.q, (double)ntot));
+        int run = 0, jb = -1;
+        for (int j = 0; j < nblk; ++j) {
+          const int pj = pooled_row<P>(L0 + (size_t)j * CS + warp * 32 + lane, lane);
+          if (jb < 0) { if (run + pj > kk) jb = j; else run += pj; }
+          if (__all_sync(0xffffffffu, jb >= 0 || !livet)) break;
+        }
+        if (livet) {
+          if (jb < 0) jb = nblk + K;  // rank beyond the last bin (q = 1): not representable in a band
+          atomicMin(&s_misc[1], jb);
+          atomicMax(&s_misc[2], jb);
+        }
+      }
+      __syncthreads();
+      const int jmin = s_misc[1], jmax = s_misc[2];
+      if (jmax >= 0) {
+        int lo = 8 * jmin - p.margin;
+        lo = lo < 0 ? 0 : (lo & ~7);
+        if (8 * jmax + 7 >= lo + K || p.force_fail) return false;
+        Blo = lo;
+      } else {
+        Blo = 0;
+        if (p.force_fail) return false;
+      }
+      __syncthreads();
+      for (int i = tid; i < (K + KB) * CS; i += blockDim.x) L0[i] = 0;
+      __syncthreads();
+    }
+    // 2. band counters
+    TB = 0;
+    if (own_valid) for_window(d, [&](int v) { if (v >= Blo) band_apply(v - Blo, +1); });
+    TBr[tid] = (uint16_t)TB;
+    __syncthreads();
+    return true;
+  };
+
+  // ---- advance the own window by one day of year (needs stage(step) + a barrier before) ----
+  auto advance = [&](int step) {
+    if (!own_valid) return;
+    const int par = step & 1;
+    const int* rl = s_rows + (par * 2 + 0) * BAND_CAP;
+    const int* re = s_rows + (par * 2 + 1) * BAND_CAP;
+    const int bl0 = s_cnt[(par * 2 + 0) * 2], bl1 = s_cnt[(par * 2 + 0) * 2 + 1];
+    const int be0 = s_cnt[(par * 2 + 1) * 2], be1 = s_cnt[(par * 2 + 1) * 2 + 1];
+    const int nl = bl1 - bl0, ne = be1 - be0;
+    int len = 0, inval = 0;
+    uint16_t* ev = EV + tid;
+    auto scan = [&](int v, int sign01) {  // sign01: 0 = entering (+1), 1 = leaving (-1)
+      const int s = (int)(int16_t)v - Blo;  // invalid (0xFFFF) is -1 - Blo < 0
+      inval += (v >> 15) ? (1 - 2 * sign01) : 0;
+      if (s >= 0) {
+        if (len < BAND_LCAP) ev[len * CS] = (uint16_t)((s << 1) | sign01);
+        else band_apply(s, 1 - 2 * sign01);  // list full: apply in place (rare)
+        ++len;
+      }
+    };
+    constexpr int BATCH = 13;
+    const int npair = min(BAND_CAP, max(nl, ne));
+    for (int u0 = 0; u0 < npair; u0 += BATCH) {
+      int vl[BATCH], ve[BATCH];
+#pragma unroll
+      for (int u = 0; u < BATCH; ++u) {  // all loads first ...
+        const int a = (u0 + u < BAND_CAP) ? rl[u0 + u] : -1, b = (u0 + u < BAND_CAP) ? re[u0 + u] : -1;
+        vl[u] = (a >= 0) ? (int)col[(int64_t)a * p.pitch] : -1;
+        ve[u] = (b >= 0) ? (int)col[(int64_t)b * p.pitch] : -1;
+      }
+#pragma unroll
+      for (int u = 0; u < BATCH; ++u) {  // ... then the scan (a slot without a row is skipped)
+        if (vl[u] >= 0) scan(vl[u], 1);
+        if (ve[u] >= 0) scan(ve[u], 0);
+      }
+    }
+    for (int a = bl0 + BAND_CAP; a < bl1; ++a) scan((int)col[(int64_t)__ldg(&p.doy_rows[a]) * p.pitch], 1);  // long lists
+    for (int b = be0 + BAND_CAP; b < be1; ++b) scan((int)col[(int64_t)__ldg(&p.doy_rows[b]) * p.pitch], 0);
+    NT += (ne - nl) - inval;
+    const int m = min(len, BAND_LCAP);
+    for (int j = 0; j < m; ++j) {
+      const int e = ev[j * CS];
+      band_apply(e >> 1, 1 - 2 * (e & 1));
+    }
+    NTr[tid] = (uint16_t)NT;
+    TBr[tid] = (uint16_t)TB;
+  };
+  auto warm_l2 = [&](int step) {  // pull the samples of `step` into L2 while the queries run
+    if (!own_valid) return;
+    const int par = step & 1;
+#pragma unroll 4
+    for (int u = 0; u < BAND_CAP; ++u) {
+      const int re = s_rows[(par * 2 + 1) * BAND_CAP + u];
+      if (re >= 0) asm volatile("prefetch.global.L2 [%0];" ::"l"(col + (int64_t)re * p.pitch));
+    }
+  };
+
+  // ---- query of one day of year: returns false for the warp's lanes that left the band ----
+  auto query = [&](int d) {
+    const uint16_t* base = nullptr;
+    const int rowoff = warp * 32 + lane;
+    const int ntot = pooled_row<P>(NTr + rowoff, lane);
+    const int tb = pooled_row<P>(TBr + rowoff, lane);
+    const bool livet = target_live && !masked && ntot > 0;
+    const double pos = __dmul_rn(p.q, (double)ntot);  // detect.py:2516
+    const int kk = (int)floor(pos);                   // cum > pos  <=>  cum >= kk + 1
+    const int below = ntot - tb;
+    bool viol = livet && below > kk;                  // quantile bin lies below the band
+    (void)base;
+    // block scan
+    int run = below, jb = -1;
+    bool done = !livet || viol;
+    for (int j = 0; j < KB; ++j) {
+      if (__all_sync(0xffffffffu, done)) break;
+      const int pj = pooled_row<P>(L1 + (size_t)j * CS + rowoff, lane);
+      if (!done) {
+        if (run + pj > kk) { jb = j; done = true; }
+        else run += pj;
+      }
+    }
+    int iu = -1, cl = 0, h = 0;
+    if (livet && !viol && jb < 0) {
+      // not found inside the band: either the band is too low, or (band = full range) the rank lies
+      // beyond the last bin and the reference clips iu to nb - 1 (detect.py:2530-2532)
+      if (K >= 8 * nblk) { iu = nb - 1; }
+      else viol = true;
+    }
+    // bin scan inside the blocks that hold a lane's quantile
+    const unsigned want = __ballot_sync(0xffffffffu, jb >= 0);
+    if (want) {
+      int jlo = jb >= 0 ? jb : KB, jhi = jb;
+      for (int o = 16; o; o >>= 1) {
+        jlo = min(jlo, __shfl_xor_sync(0xffffffffu, jlo, o));
+        jhi = max(jhi, __shfl_xor_sync(0xffffffffu, jhi, o));
+      }
+      for (int j = jlo; j <= jhi; ++j) {
+        if (!__any_sync(0xffffffffu, jb == j)) continue;
+#pragma unroll
+        for (int b = 0; b < 8; ++b) {
+          const int pb = pooled_row<P>(L0 + (size_t)(8 * j + b) * CS + rowoff, lane);
+          if (jb == j && iu < 0) {
+            if (run + pb > kk) { iu = Blo + 8 * j + b; cl = run; h = pb; }
+            else run += pb;
+          }
+        }
+      }
+    }
+    if (iu == nb - 1 && jb < 0 && livet && !viol) {  // clipped rank (q = 1): cl = cum[nb - 2], h = hist[nb - 1]
+      h = pooled_row<P>(L0 + (size_t)(nb - 1 - Blo) * CS + rowoff, lane);
+      cl = ntot - h;
+    }
+    if (__any_sync(0xffffffffu, viol)) {
+      if (lane == 0) s_misc[0] = 1;
+      return;
+    }
+    float res = CUDART_NAN_F;
+    if (livet) {
+      if (iu == 0) {
+        res = __ldg(&p.centers[0]);  // detect.py:2557
+      } else {
+        const float bl = __ldg(&p.centers[iu - 1]), bu = __ldg(&p.centers[iu]);
+        const double frac = (h > 0) ? __ddiv_rn(pos - (double)cl, (double)h) : 0.5;       // detect.py:2545-2547
+        res = (float)__dadd_rn((double)bl, __dmul_rn(frac, (double)__fsub_rn(bu, bl)));   // detect.py:2550 (no FMA)
+      }
+      vmin = fminf(vmin, res);
+      vmax = fmaxf(vmax, res);
+      if (res < p.lower_bound) res = p.lower_bound;  // detect.py:2722-2732
+    }
+    if (target_live) p.thr[(int64_t)d * N + ty_g * nx + tx_g] = res;
+  };
+
+  auto give_up = [&]() {
+    if (tid == 0) {
+      const int i = atomicAdd(&p.fail_list[0], 1);
+      p.fail_list[1 + 2 * i] = (int)y0;
+      p.fail_list[2 + 2 * i] = (int)x0;
+    }
+  };
+
+  if (!rebuild(0)) { give_up(); return; }
+  stage(1);
+  __syncthreads();
+  for (int d = 0; d < NDOY; ++d) {
+    if (d > 0) {
+      if (d + 1 < NDOY) stage(d + 1);
+      advance(d);
+      __syncthreads();
+      if (d + 1 < NDOY) warm_l2(d + 1);
+    }
+    if (warp < TY) query(d);
+    __syncthreads();
+    if (s_misc[0]) {  // a threshold left the band: re-centre the band on the current window and redo the day
+      __syncthreads();
+      if (!rebuild(d)) { give_up(); return; }
+      if (warp < TY) query(d);
+      __syncthreads();
+      if (s_misc[0]) { give_up(); return; }
+    }
+  }
+  if (warp < TY && p.stats) {
+    vmin = warp_min(vmin);
+    vmax = warp_max(vmax);
+    if (lane == 0) {
+      if (vmin != CUDART_INF_F) atomic_min_f(&p.stats[0], vmin);
+      if (vmax != -CUDART_INF_F) atomic_max_f(&p.stats[1], vmax);
+    }
+  }
+}
+
+// np.digitize(a, edges) - 1 with the invalid class (NaN or a >= last edge) coded 0xFFFF, so that
+// "below the band" and "invalid" are one signed comparison in the kernel above.
+__global__ void __launch_bounds__(256) digitize_ffff_kernel(const float* __restrict__ a, int64_t T, int64_t N,
+                                                            int64_t pitch, const float* __restrict__ edges, int n_edges,
+                                                            uint16_t* __restrict__ bins, int64_t bins_pitch,
+                                                            int rows_per_block) {
+  extern __shared__ float s_edges[];
+  for (int i = threadIdx.x; i < n_edges; i += blockDim.x) s_edges[i] = edges[i];
+  __syncthreads();
+  const float e1 = s_edges[1];
+  const float inv_step = (n_edges > 2) ? 1.f / (s_edges[2] - s_edges[1]) : 1.f;
+  const int64_t c = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * 2;  // two gridpoints per thread
+  if (c >= N) return;
+  const bool pair = c + 1 < N && ((pitch | bins_pitch) & 1) == 0;
+  const int64_t t0 = (int64_t)blockIdx.y * rows_per_block, t1 = min(T, t0 + rows_per_block);
+  auto dig = [&](float v) -> uint32_t {
+    if (v != v) return 0xFFFFu;
+    float g = floorf((v - e1) * inv_step) + 1.f;
+    g = fminf(fmaxf(g, 0.f), (float)(n_edges - 1));
+    int i = (int)g;
+    while (i > 0 && v < s_edges[i]) --i;
+    while (i < n_edges - 1 && v >= s_edges[i + 1]) ++i;
+    return i >= n_edges - 1 ? 0xFFFFu : (uint32_t)i;
+  };
+  if (pair) {
+#pragma unroll 4
+    for (int64_t t = t0; t < t1; ++t) {
+      const float2 v = __ldcs(reinterpret_cast<const float2*>(a + t * pitch + c));
+      *reinterpret_cast<uint32_t*>(bins + t * bins_pitch + c) = dig(v.x) | (dig(v.y) << 16);
+    }
+  } else {
+    for (int64_t t = t0; t < t1; ++t) {
+      bins[t * bins_pitch + c] = (uint16_t)dig(a[t * pitch + c]);
+      if (c + 1 < N) bins[t * bins_pitch + c + 1] = (uint16_t)dig(a[t * pitch + c + 1]);
+    }
+  }
+}
+
+// defined in thresholds.cu: the full-range tile kernel over a list of failed band tiles
+int launch_pool_tile_list(const uint16_t* bins, int64_t ny, int64_t nx, int64_t pitch, const int32_t* doy_ptr,
+                          const int32_t* doy_rows, const float* centers, int nb, int w, int ws, double q,
+                          const float* anom_row0, float lower_bound, float* thr, float* stats,
+                          const int32_t* fail_list, int max_tiles, int band_ty, int band_tx, cudaStream_t st);
+
+__global__ void init_band_kernel(float* stats, int32_t* fail_list) {
+  if (stats) { stats[0] = CUDART_INF_F; stats[1] = -CUDART_INF_F; }
+  fail_list[0] = 0;
+}
+
+}  // namespace marex
+
+using namespace marex;
+
+extern "C" int64_t marex_hobday_pooled_workspace_bytes(int64_t T, int64_t ny, int64_t nx) {
+  // bins (uint16 [T][ny*nx], rows padded to an even count) + fail list
+  const int64_t N = ny * nx, pitch = (N + 1) & ~1LL;
+  const int64_t tiles = ((ny + 0) / 1 + 1) * ((nx + 27) / 28 + 1);  // generous upper bound on band tiles
+  return T * pitch * 2 + (2 * tiles + 8) * 4 + 256;
+}
+
+extern "C" int marex_hobday_thresholds_pooled_f32(const float* anom, int64_t T, int64_t ny, int64_t nx, int64_t pitch,
+                                                  const int32_t* doy_ptr, const int32_t* doy_rows,
+                                                  int32_t max_window_rows, const float* edges, const float* centers,
+                                                  int32_t nb, int32_t w, int32_t ws, double q, float lower_bound,
+                                                  float* thr, float* stats, void* workspace, int64_t workspace_bytes,
+                                                  void* stream) {
+  MAREX_REQUIRE(anom && doy_ptr && doy_rows && edges && centers && thr && workspace, "null pointer");
+  MAREX_REQUIRE(T > 0 && ny > 0 && nx > 0 && pitch >= ny * nx, "bad shape");
+  MAREX_REQUIRE(nb >= 2 && nb <= 1024, "nb must be in 2..1024");
+  MAREX_REQUIRE(w >= 3 && w <= 365 && (w & 1), "window_days_hobday must be odd and in 3..365");
+  MAREX_REQUIRE(ws == 3 || ws == 5 || ws == 7, "window_spatial_hobday must be 3, 5 or 7 for the pooled kernel");
+  MAREX_REQUIRE(max_window_rows <= 65535, "too many rows per day-of-year window for 16-bit counters");
+  MAREX_REQUIRE(nx >= 32 && ny <= 65535 * 4, "grid too small or too tall for the band tiles");
+  MAREX_REQUIRE(workspace_bytes >= marex_hobday_pooled_workspace_bytes(T, ny, nx), "workspace too small");
+  cudaStream_t st = (cudaStream_t)stream;
+  const int64_t N = ny * nx, bpitch = (N + 1) & ~1LL;
+  uint16_t* bins = reinterpret_cast<uint16_t*>(workspace);
+  int32_t* fail_list = reinterpret_cast<int32_t*>(reinterpret_cast<unsigned char*>(workspace) +
+                                                  (((size_t)T * bpitch * 2 + 255) & ~(size_t)255));
+  {  // digitize (detect.py:2622-2631)
+    const int threads = 256;
+    const int64_t bx = ((N + 1) / 2 + threads - 1) / threads;
+    int64_t by = (8LL * sm_count() + bx - 1) / bx;
+    by = by < 1 ? 1 : (by > T ? T : by);
+    if (by > 65535) by = 65535;
+    const int rows_per_block = (int)((T + by - 1) / by);
+    by = (T + rows_per_block - 1) / rows_per_block;
+    digitize_ffff_kernel<<<dim3((unsigned)bx, (unsigned)by), threads, (nb + 1) * sizeof(float), st>>>(
+        anom, T, N, pitch, edges, nb + 1, bins, bpitch, rows_per_block);
+    MAREX_LAUNCH_CHECK("digitize_ffff_kernel");
+  }
+  init_band_kernel<<<1, 1, 0, st>>>(stats, fail_list);
+  MAREX_LAUNCH_CHECK("init_band_kernel");
+
+  const int P = ws / 2;
+  const int env_k = getenv("MAREX_POOL_K") ? atoi(getenv("MAREX_POOL_K")) : 0;
+  const int env_ty = getenv("MAREX_POOL_TY") ? atoi(getenv("MAREX_POOL_TY")) : 0;
+  BandParams bp;
+  bp.bins = bins; bp.ny = ny; bp.nx = nx; bp.pitch = bpitch;
+  bp.doy_ptr = doy_ptr; bp.doy_rows = doy_rows; bp.centers = centers;
+  bp.nb = nb; bp.w = w; bp.q = q;
+  bp.margin = getenv("MAREX_POOL_MARGIN") ? atoi(getenv("MAREX_POOL_MARGIN")) : 16;
+  bp.anom_row0 = anom; bp.lower_bound = lower_bound; bp.thr = thr; bp.stats = stats;
+  bp.fail_list = fail_list;
+  bp.force_fail = getenv("MAREX_POOL_FORCE_FAIL") ? atoi(getenv("MAREX_POOL_FORCE_FAIL")) : 0;
+  const int K = env_k ? env_k : 128;
+  MAREX_REQUIRE(K == 64 || K == 128 || K == 256, "MAREX_POOL_K must be 64, 128 or 256");
+  MAREX_REQUIRE(nb <= 8 * K, "nb too large for the coarse pass of this band width");
+  auto smem_of = [&](int oy) {
+    const size_t cs = (size_t)oy * 32;
+    return (size_t)(K + K / 8 + 2 + BAND_LCAP) * cs * 2 + (4 * BAND_CAP + 8 + 4) * sizeof(int);
+  };
+  int TY = env_ty ? env_ty : 8;
+  while (TY > 1 && (smem_of(TY + 2 * P) > 220 * 1024 || (TY + 2 * P) * 32 > 512)) --TY;
+  MAREX_REQUIRE(smem_of(TY + 2 * P) <= 220 * 1024, "band tile does not fit shared memory");
+  const int OY = TY + 2 * P, TX = 32 - 2 * P;
+  const size_t smem = smem_of(OY);
+  dim3 grid((unsigned)((nx + TX - 1) / TX), (unsigned)((ny + TY - 1) / TY));
+  const int max_tiles = (int)(grid.x * grid.y);
+#define MAREX_BAND(PP, KK)                                                                                  \
+  do {                                                                                                      \
+    cudaError_t e = cudaFuncSetAttribute(hobday_band_kernel<PP, KK>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+                                         (int)smem);                                                        \
+    if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(hobday_band)");                         \
+    hobday_band_kernel<PP, KK><<<grid, OY * 32, smem, st>>>(bp);                                            \
+  } while (0)
+#define MAREX_BAND_K(PP)                                        \
+  do {                                                          \
+    if (K == 64) MAREX_BAND(PP, 64);                            \
+    else if (K == 128) MAREX_BAND(PP, 128);                     \
+    else MAREX_BAND(PP, 256);                                   \
+  } while (0)
+  if (P == 1) MAREX_BAND_K(1); else if (P == 2) MAREX_BAND_K(2); else MAREX_BAND_K(3);
+#undef MAREX_BAND_K
+#undef MAREX_BAND
+  MAREX_LAUNCH_CHECK("hobday_band_kernel");
+  // tiles whose thresholds did not fit one band: full-range counters
+  return launch_pool_tile_list(bins, ny, nx, bpitch, doy_ptr, doy_rows, centers, nb, w, ws, q, anom, lower_bound, thr,
+                               stats, fail_list, max_tiles, TY, TX, st);
+}

@@ -161,8 +161,12 @@ __global__ void __launch_bounds__(768) hobday_pool_tile_kernel(
     const uint16_t* __restrict__ bins, int64_t ny, int64_t nx, int64_t pitch, const int32_t* __restrict__ doy_ptr,
     const int32_t* __restrict__ doy_rows, const float* __restrict__ centers, int nb, int w, double q,
     const float* __restrict__ anom_row0, float lower_bound, float* __restrict__ thr, float* __restrict__ stats,
-    int OY, int OX, int CS, int CR, int LPT) {
+    int OY, int OX, int CS, int CR, int LPT, const int32_t* __restrict__ fail_list, int sub_x, int sub_n, int band_ty,
+    int band_tx) {
   constexpr int WS = 2 * P + 1, NN = WS * WS;
+  // List mode (fail_list != nullptr): the grid is 1-D, sub_n CTAs per failed band tile (pool_band.cu);
+  // CTA k recomputes sub-tile k % sub_n of band tile k / sub_n, whose origin is read from the list.
+  if (fail_list && (int)(blockIdx.x / sub_n) >= __ldg(&fail_list[0])) return;
   constexpr int CAP = 32;   // slots of the staged per-step row table
   constexpr int MAXQ = (NN + 3) / 4;  // neighbours per query lane when LPT = 4 (LPT = 8 uses fewer)
   extern __shared__ unsigned char smem_raw[];
@@ -177,7 +181,16 @@ __global__ void __launch_bounds__(768) hobday_pool_tile_kernel(
   for (int i = threadIdx.x; i < total16; i += blockDim.x) L0[i] = 0;
 
   const int TY = OY - 2 * P, TX = OX - 2 * P;             // targets per tile
-  const int64_t y0 = (int64_t)blockIdx.y * TY, x0 = (int64_t)blockIdx.x * TX;
+  int64_t y0 = (int64_t)blockIdx.y * TY, x0 = (int64_t)blockIdx.x * TX;
+  int64_t y_end = ny, x_end = nx;                         // targets live below these
+  if (fail_list) {
+    const int it = blockIdx.x / sub_n, sub = blockIdx.x % sub_n;
+    const int64_t fy = __ldg(&fail_list[1 + 2 * it]), fx = __ldg(&fail_list[2 + 2 * it]);
+    y0 = fy + (int64_t)(sub / sub_x) * TY;
+    x0 = fx + (int64_t)(sub % sub_x) * TX;
+    y_end = min(ny, fy + band_ty);
+    x_end = min(nx, fx + band_tx);
+  }
   const int64_t N = ny * nx;
   const int half = w / 2;
 
@@ -277,7 +290,7 @@ __global__ void __launch_bounds__(768) hobday_pool_tile_kernel(
   const int tt = q_thread ? tq : 0;
   const int ty = tt / TX, tx = tt % TX;
   const int64_t ty_g = y0 + ty, tx_g = x0 + tx;
-  const bool target_live = q_thread && ty_g < ny && tx_g < nx;
+  const bool target_live = q_thread && ty_g < y_end && tx_g < x_end;
   const int center = (ty + P) * OX + (tx + P);
   int off[MAXQ];  // this lane's neighbours; unused slots -> dummy zero cell
 #pragma unroll
@@ -721,6 +734,71 @@ static int set_smem(K kern, size_t smem) {
   return MAREX_OK;
 }
 
+// Full-range tiled pooled kernel over the whole grid (fail_list == nullptr) or over the band tiles
+// listed in fail_list (band_ty x band_tx targets each; pool_band.cu).  MAREX_ERR_UNSUPPORTED when
+// no tile fits shared memory.
+static int launch_pool_tile(const uint16_t* bins, int64_t ny, int64_t nx, int64_t pitch, const int32_t* doy_ptr,
+                            const int32_t* doy_rows, const float* centers, int nb, int w, int ws, double q,
+                            const float* anom_row0, float lower_bound, float* thr, float* stats,
+                            const int32_t* fail_list, int max_tiles, int band_ty, int band_tx, cudaStream_t st) {
+  // pick the own-cell tile OY x OX that fits shared memory
+  const int p = ws / 2;
+  const int nb1 = (nb + 7) >> 3, nb2 = (nb + 63) >> 6;
+  const size_t per_col = (size_t)(nb + nb1 + nb2 + 2) * 2;  // bytes per counter column (own cell or dummy)
+  int cs_max = (int)((227 * 1024 - 1024) / per_col);
+  if (cs_max > 257) cs_max = 257;
+  const int c_max = ((cs_max - 1) | 1) - 1;  // odd column stride spreads a row's cells over all banks
+  int best_oy = 0, best_ox = 0, best_t = 0;
+  for (int oy = 2 * p + 1; oy <= 64; ++oy)
+    for (int ox = 2 * p + 1; ox <= 64; ++ox) {
+      if (oy * ox > c_max) continue;
+      const int t = (oy - 2 * p) * (ox - 2 * p);
+      if (t > best_t || (t == best_t && ox > best_ox)) { best_t = t; best_oy = oy; best_ox = ox; }
+    }
+  if (best_t <= 0) return MAREX_ERR_UNSUPPORTED;
+  const int C = best_oy * best_ox;
+  const int CS = (C + 1) | 1;
+  const size_t smem_t = per_col * CS;
+  const int TY = best_oy - 2 * p, TX = best_ox - 2 * p;
+  const int CR = ((C + 31) / 32) * 32;
+  int threads = 3 * CR;                       // three event roles
+  const int LPT = (8 * TY * TX <= threads) ? 8 : 4;
+  if (LPT * TY * TX > threads) threads = ((LPT * TY * TX + 31) / 32) * 32;
+  if (threads > 768) return fail(MAREX_ERR_UNSUPPORTED, "pooled tile needs more than 768 threads");
+  dim3 grid_t((unsigned)((nx + TX - 1) / TX), (unsigned)((ny + TY - 1) / TY));
+  int sub_x = 1, sub_n = 1;
+  if (fail_list) {
+    sub_x = (band_tx + TX - 1) / TX;
+    sub_n = sub_x * ((band_ty + TY - 1) / TY);
+    grid_t = dim3((unsigned)((int64_t)max_tiles * sub_n), 1);
+  }
+#define MAREX_POOL(PP)                                                                                             \
+  do {                                                                                                             \
+    int rc = set_smem(hobday_pool_tile_kernel<PP>, smem_t);                                                        \
+    if (rc) return rc;                                                                                             \
+    hobday_pool_tile_kernel<PP><<<grid_t, threads, smem_t, st>>>(bins, ny, nx, pitch, doy_ptr, doy_rows, centers,  \
+                                                                 nb, w, q, anom_row0, lower_bound, thr, stats,    \
+                                                                 best_oy, best_ox, CS, CR, LPT, fail_list, sub_x, \
+                                                                 sub_n, band_ty, band_tx);                        \
+  } while (0)
+  if (p == 1) MAREX_POOL(1); else if (p == 2) MAREX_POOL(2); else MAREX_POOL(3);
+#undef MAREX_POOL
+  MAREX_LAUNCH_CHECK("hobday_pool_tile_kernel");
+  return MAREX_OK;
+}
+
+namespace marex {
+int launch_pool_tile_list(const uint16_t* bins, int64_t ny, int64_t nx, int64_t pitch, const int32_t* doy_ptr,
+                          const int32_t* doy_rows, const float* centers, int nb, int w, int ws, double q,
+                          const float* anom_row0, float lower_bound, float* thr, float* stats,
+                          const int32_t* fail_list, int max_tiles, int band_ty, int band_tx, cudaStream_t st) {
+  const int rc = launch_pool_tile(bins, ny, nx, pitch, doy_ptr, doy_rows, centers, nb, w, ws, q, anom_row0, lower_bound,
+                                  thr, stats, fail_list, max_tiles, band_ty, band_tx, st);
+  if (rc == MAREX_ERR_UNSUPPORTED) return fail(rc, "no full-range tile fits shared memory for the band fallback");
+  return rc;
+}
+}  // namespace marex
+
 extern "C" int marex_hobday_thresholds_hist(const uint16_t* bins, int64_t T, int64_t ny, int64_t nx, int64_t pitch,
                                             const int32_t* doy_ptr, const int32_t* doy_rows, int32_t max_window_rows,
                                             const float* centers, int32_t nb, int32_t w, int32_t ws, double q,
@@ -738,44 +816,9 @@ extern "C" int marex_hobday_thresholds_hist(const uint16_t* bins, int64_t T, int
     MAREX_LAUNCH_CHECK("init_stats_kernel");
   }
   if (ws > 1 && ws <= 7 && max_window_rows <= 65535 && !getenv("MAREX_POOL_V1")) {
-    // tiled kernel: pick the own-cell tile OY x OX that fits shared memory
-    const int p = ws / 2;
-    const int nb1 = (nb + 7) >> 3, nb2 = (nb + 63) >> 6;
-    const size_t per_col = (size_t)(nb + nb1 + nb2 + 2) * 2;  // bytes per counter column (own cell or dummy)
-    int cs_max = (int)((227 * 1024 - 1024) / per_col);
-    if (cs_max > 257) cs_max = 257;
-    const int c_max = ((cs_max - 1) | 1) - 1;  // odd column stride spreads a row's cells over all banks
-    int best_oy = 0, best_ox = 0, best_t = 0;
-    for (int oy = 2 * p + 1; oy <= 64; ++oy)
-      for (int ox = 2 * p + 1; ox <= 64; ++ox) {
-        if (oy * ox > c_max) continue;
-        const int t = (oy - 2 * p) * (ox - 2 * p);
-        if (t > best_t || (t == best_t && ox > best_ox)) { best_t = t; best_oy = oy; best_ox = ox; }
-      }
-    if (best_t > 0) {
-      const int C = best_oy * best_ox;
-      const int CS = (C + 1) | 1;
-      const size_t smem_t = per_col * CS;
-      const int TY = best_oy - 2 * p, TX = best_ox - 2 * p;
-      const int CR = ((C + 31) / 32) * 32;
-      int threads = 3 * CR;                       // three event roles
-      const int LPT = (8 * TY * TX <= threads) ? 8 : 4;
-      if (LPT * TY * TX > threads) threads = ((LPT * TY * TX + 31) / 32) * 32;
-      if (threads > 768) return fail(MAREX_ERR_UNSUPPORTED, "pooled tile needs more than 768 threads");
-      dim3 grid_t((unsigned)((nx + TX - 1) / TX), (unsigned)((ny + TY - 1) / TY));
-#define MAREX_POOL(PP)                                                                                             \
-  do {                                                                                                             \
-    int rc = set_smem(hobday_pool_tile_kernel<PP>, smem_t);                                                        \
-    if (rc) return rc;                                                                                             \
-    hobday_pool_tile_kernel<PP><<<grid_t, threads, smem_t, st>>>(bins, ny, nx, pitch, doy_ptr, doy_rows, centers,  \
-                                                                 nb, w, q, anom_row0, lower_bound, thr, stats,    \
-                                                                 best_oy, best_ox, CS, CR, LPT);                   \
-  } while (0)
-      if (p == 1) MAREX_POOL(1); else if (p == 2) MAREX_POOL(2); else MAREX_POOL(3);
-#undef MAREX_POOL
-      MAREX_LAUNCH_CHECK("hobday_pool_tile_kernel");
-      return MAREX_OK;
-    }
+    const int rc = launch_pool_tile(bins, ny, nx, pitch, doy_ptr, doy_rows, centers, nb, w, ws, q, anom_row0,
+                                    lower_bound, thr, stats, nullptr, 0, 0, 0, st);
+    if (rc != MAREX_ERR_UNSUPPORTED) return rc;
   }
   const long long max_count = (long long)max_window_rows * ws * ws;
   const bool wide = max_count > 65535;

@@ -716,16 +716,28 @@ def identify_extremes_arrays(
                 )
             edges, centers = hobday_bins(precision, max_anomaly)
             nb = len(centers)
-            bins = torch.empty((T, N), dtype=torch.uint16, device=dev)
-            _lib.call("marex_digitize_f32", _p(anom), T, N, N, h.up(edges, np.float32, dev), len(edges), _p(bins), N, st)
             ny, nx = (grid if gridded else (1, N))
+            ws_eff = int(ws) if (gridded and ws) else 1
             stats = torch.empty(2, dtype=torch.float32, device=dev)
-            _lib.call(
-                "marex_hobday_thresholds_hist", _p(bins), T, ny, nx, N, _p(ptr_d), _p(rows_d), mwr,
-                h.up(centers, np.float32, dev), nb, w, int(ws) if (gridded and ws) else 1, float(q), _p(anom),
-                float(edges[3]), _p(thr), _p(stats), st,
-            )  # fmt: skip
-            del bins
+            if ws_eff in (3, 5, 7) and nx >= 32 and nb <= 1024 and mwr <= 65535:
+                # banded warp-cooperative kernel (digitizes into its own workspace)
+                wbytes = int(_lib.load().marex_hobday_pooled_workspace_bytes(T, ny, nx))
+                work = torch.empty(wbytes, dtype=torch.uint8, device=dev)
+                _lib.call(
+                    "marex_hobday_thresholds_pooled_f32", _p(anom), T, ny, nx, N, _p(ptr_d), _p(rows_d), mwr,
+                    h.up(edges, np.float32, dev), h.up(centers, np.float32, dev), nb, w, ws_eff, float(q),
+                    float(edges[3]), _p(thr), _p(stats), _p(work), wbytes, st,
+                )  # fmt: skip
+                del work
+            else:
+                bins = torch.empty((T, N), dtype=torch.uint16, device=dev)
+                _lib.call("marex_digitize_f32", _p(anom), T, N, N, h.up(edges, np.float32, dev), len(edges), _p(bins), N, st)
+                _lib.call(
+                    "marex_hobday_thresholds_hist", _p(bins), T, ny, nx, N, _p(ptr_d), _p(rows_d), mwr,
+                    h.up(centers, np.float32, dev), nb, w, ws_eff, float(q), _p(anom),
+                    float(edges[3]), _p(thr), _p(stats), st,
+                )  # fmt: skip
+                del bins
             vmin, vmax = (float(v) for v in stats.cpu())
             _warn_threshold_range(vmin, vmax, float(edges[-2]), float(edges[3]), max_anomaly)
             thr_cm = torch.empty((N, NDOY), dtype=torch.float32, device=dev)

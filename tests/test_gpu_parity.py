@@ -408,3 +408,75 @@ def test_data_validation_errors():
         mb.preprocess_arrays(np.full_like(x, np.nan), time, window_year_baseline=3)
     with pytest.raises(mb.DataValidationError, match="Insufficient data for shifting_baseline"):
         mb.preprocess_arrays(x, time, window_year_baseline=15)
+
+
+# ---------------------------------------------------------------- banded pooled kernel: rebuilds, fall-back, edges
+def _hetero_anoms(ny=21, nx=70, T1="2001-01-01", seed=11):
+    """Anomalies whose spread varies strongly with season and position, so that the thresholds of a
+    tile drift through (and beyond) one band: exercises re-centring and the full-range fall-back."""
+    rng = np.random.default_rng(seed)
+    time = np.arange(np.datetime64("1990-01-01"), np.datetime64(T1))
+    T = len(time)
+    _, doy = mo.calendar_tables(time)
+    season = 0.25 + 1.0 * (1 + np.cos(2 * np.pi * doy / 366.0))  # 0.25 .. 2.25
+    space = np.linspace(0.3, 2.2, nx)[None, :] * np.linspace(1.0, 1.6, ny)[:, None]
+    a = rng.standard_normal((T, ny, nx)) * season[:, None, None] * space[None]
+    a = a.astype(np.float32)
+    f = a.reshape(T, -1)
+    f[:, 3] = np.nan
+    f[:, nx * 5 + 9] = np.nan
+    f[:, nx * 2 + 4] = 0.0  # constant cell -> clamp
+    f[::3, nx * 7 + 20] = 9.0  # values beyond the last edge are dropped
+    f[0, nx * 9 + 30] = np.nan  # NaN on the first day -> masked threshold, but later samples still pool
+    return a, time, doy
+
+
+@pytest.mark.parametrize(
+    "env,ws,w,p",
+    [
+        ({}, 5, 11, 95),
+        ({"MAREX_POOL_K": "64"}, 5, 11, 95),
+        ({"MAREX_POOL_K": "64", "MAREX_POOL_MARGIN": "0"}, 3, 5, 90),
+        ({"MAREX_POOL_K": "256", "MAREX_POOL_TY": "3"}, 7, 11, 99),
+        ({"MAREX_POOL_FORCE_FAIL": "1"}, 5, 11, 95),
+        ({"MAREX_POOL_TY": "1"}, 5, 31, 80),
+    ],
+)
+def test_banded_pooled_kernel_bit_exact(monkeypatch, env, ws, w, p):
+    mb = _cuda()
+    for k in ("MAREX_POOL_K", "MAREX_POOL_MARGIN", "MAREX_POOL_TY", "MAREX_POOL_FORCE_FAIL"):
+        monkeypatch.delenv(k, raising=False)
+    for k, v in env.items():
+        monkeypatch.setenv(k, v)
+    a, time, doy = _hetero_anoms()
+    ny, nx = a.shape[1:]
+    ref = mo.hobday_thresholds_approx(a.reshape(len(time), -1), doy, p / 100.0, w, ws, (ny, nx))
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        res = mb.identify_extremes_arrays(
+            torch.from_numpy(a.reshape(len(time), -1)).cuda(), doy, (ny, nx), "hobday_extreme", p, w, ws
+        )
+    got = res["thresholds"].cpu().numpy().reshape(-1, 366)
+    _ulp_equal(got, ref)
+    np.testing.assert_array_equal(
+        res["extreme_events"].cpu().numpy(), mo.compare_hobday(a.reshape(len(time), -1), doy, np.ascontiguousarray(ref.T))
+    )
+
+
+def test_digitize_ffff_matches_numpy_digitize():
+    """The pooled path digitizes internally (invalid class coded 0xFFFF); its counts feed the same
+    thresholds as np.digitize - checked here through a band wide enough that nothing is pooled away."""
+    mb = _cuda()
+    rng = np.random.default_rng(3)
+    time = np.arange(np.datetime64("1995-01-01"), np.datetime64("2001-01-01"))
+    _, doy = mo.calendar_tables(time)
+    a = (rng.standard_normal((len(time), 6, 33)) * 2.5).astype(np.float32)  # odd N: scalar digitize path
+    edges, _ = mo.hobday_bins()
+    a[5, 2, 7] = edges[200]  # exactly on an edge
+    a[6, 2, 7] = np.nextafter(edges[200], np.float32(-np.inf))
+    a[7, 2, 7] = edges[-1]
+    a[8, 2, 7] = np.inf
+    a[9, 2, 7] = -np.inf
+    ref = mo.hobday_thresholds_approx(a.reshape(len(time), -1), doy, 0.9, 5, 3, (6, 33))
+    res = mb.identify_extremes_arrays(torch.from_numpy(a.reshape(len(time), -1)).cuda(), doy, (6, 33), "hobday_extreme", 90, 5, 3)
+    _ulp_equal(res["thresholds"].cpu().numpy().reshape(-1, 366), ref)
