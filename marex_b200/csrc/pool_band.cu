@@ -35,7 +35,7 @@ constexpr int BAND_LCAP = 16;  // slots of the per-thread compacted event list
 constexpr int BAND_CAP = 32;   // staged row indices per step and direction
 
 struct BandParams {
-  const uint16_t* bins;  // [T][ny*nx], 0xFFFF = invalid (NaN or >= last edge)
+  const uint16_t* bins;  // [T][ny*nx], 0x7FFF = invalid (NaN or >= last edge)
   int64_t ny, nx, pitch;
   const int32_t* doy_ptr;
   const int32_t* doy_rows;
@@ -61,21 +61,23 @@ __device__ __forceinline__ int pooled_row(const uint16_t* __restrict__ p, int la
   return s;
 }
 
-template <int P, int K>
-__global__ void __launch_bounds__(512) hobday_band_kernel(const BandParams p) {
+constexpr int BAND_INV = 0x7FFF;  // bin code of an invalid sample (NaN or >= last edge)
+constexpr int BAND_PRE = 26;       // entering samples prefetched into registers per step
+
+template <int P, int K, int OY>
+__global__ void __launch_bounds__(OY * 32) hobday_band_kernel(const BandParams p) {
   constexpr int KB = K / 8;  // blocks in the band
+  constexpr int TY = OY - 2 * P, TX = 32 - 2 * P, CS = OY * 32;
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int OY = blockDim.x >> 5, TY = OY - 2 * P, TX = 32 - 2 * P;
-  const int CS = OY * 32, tid = threadIdx.x;
-  uint16_t* L0 = reinterpret_cast<uint16_t*>(smem_raw);  // [K][CS]; the coarse pass reuses it as [nblk][CS]
-  uint16_t* L1 = L0 + (size_t)K * CS;                     // [KB][CS]
-  uint16_t* NTr = L1 + (size_t)KB * CS;                   // [CS] valid samples in the own window
-  uint16_t* TBr = NTr + CS;                               // [CS] of which >= Blo
-  uint16_t* EV = TBr + CS;                                // [BAND_LCAP][CS]
-  int* s_rows = reinterpret_cast<int*>(EV + (size_t)BAND_LCAP * CS);  // [2 parity][2 leave/enter][BAND_CAP]
-  int* s_cnt = s_rows + 4 * BAND_CAP;                                  // [2][2][2] begin, end in doy_rows
-  int* s_misc = s_cnt + 8;                                             // [0] violation flag, [1] min blk, [2] max blk
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, tid = threadIdx.x;
+  uint16_t* const L0 = reinterpret_cast<uint16_t*>(smem_raw);  // [K][CS]; the coarse pass reuses it as [nblk][CS]
+  uint16_t* const L1 = L0 + K * CS;                             // [KB][CS]
+  uint16_t* const NTr = L1 + KB * CS;                           // [CS] valid samples in the own window
+  uint16_t* const TBr = NTr + CS;                               // [CS] of which >= Blo
+  uint16_t* const EV = TBr + CS;                                // [BAND_LCAP][CS]
+  long long* const s_off = reinterpret_cast<long long*>(EV + BAND_LCAP * CS);  // [2 parity][2 leave/enter][BAND_CAP]
+  int* const s_cnt = reinterpret_cast<int*>(s_off + 4 * BAND_CAP);             // [2][2][2] begin, end in doy_rows
+  int* const s_misc = s_cnt + 8;                                               // [0] violation flag, [1] min blk, [2] max blk
 
   const int nb = p.nb, half = p.w / 2;
   const int nblk = (nb + 7) >> 3;
@@ -87,10 +89,14 @@ __global__ void __launch_bounds__(512) hobday_band_kernel(const BandParams p) {
   int64_t gx = (x0 - P + lane) % nx;
   if (gx < 0) gx += nx;
   const bool own_valid = gy >= 0 && gy < ny;
-  const uint16_t* col = p.bins + (own_valid ? gy * nx + gx : 0);
-  uint16_t* myL0 = L0 + tid;
-  uint16_t* myL1 = L1 + tid;
+  const uint16_t* const col = p.bins + (own_valid ? gy * nx + gx : 0);
+  const char* const colb = reinterpret_cast<const char*>(col);
+  uint16_t* const myL0 = L0 + tid;
+  uint16_t* const myL1 = L1 + tid;
+  uint16_t* const ev = EV + tid;
   int NT = 0, TB = 0, Blo = 0;
+  bool dead = !own_valid;  // no valid sample in the own window: nothing to keep up to date
+  int pre[BAND_PRE];       // entering samples of the next step
 
   // ---- target of this lane (query role: warps 0..TY-1, lanes P..31-P) ----
   const int64_t ty_g = y0 + warp, tx_g = x0 + lane - P;
@@ -102,20 +108,23 @@ __global__ void __launch_bounds__(512) hobday_band_kernel(const BandParams p) {
   }
   float vmin = CUDART_INF_F, vmax = -CUDART_INF_F;
 
-  auto stage = [&](int step) {  // rows leaving / entering the window at `step` (1..365)
+  auto stage = [&](int step) {  // byte offsets of the rows leaving / entering the window at `step` (1..365)
     const int par = step & 1;
     const int d_leave = (step - 1 - half + 2 * NDOY) % NDOY, d_enter = (step + half) % NDOY;
     if (tid < 2 * BAND_CAP) {
       const int which = tid / BAND_CAP, u = tid % BAND_CAP;
       const int dd = which ? d_enter : d_leave;
       const int b0 = __ldg(&p.doy_ptr[dd]), b1 = __ldg(&p.doy_ptr[dd + 1]);
-      s_rows[(par * 2 + which) * BAND_CAP + u] = (b0 + u < b1) ? __ldg(&p.doy_rows[b0 + u]) : -1;
+      s_off[(par * 2 + which) * BAND_CAP + u] = (b0 + u < b1) ? (long long)__ldg(&p.doy_rows[b0 + u]) * p.pitch * 2 : 0;
       if (u == 0) { s_cnt[(par * 2 + which) * 2] = b0; s_cnt[(par * 2 + which) * 2 + 1] = b1; }
     }
   };
+  auto load_at = [&](long long off) -> int { return (int)*reinterpret_cast<const uint16_t*>(colb + off); };
+  auto load_row = [&](int j) -> int { return (int)col[(int64_t)__ldg(&p.doy_rows[j]) * p.pitch]; };
 
-  // Apply one sample to the band counters (sign = +1 / -1); v is a valid bin >= Blo.
+  // One sample (relative bin s = v - Blo >= 0, sign +1 / -1) applied to the own counters.
   auto band_apply = [&](int s, int sign) {
+    if (s >= BAND_INV - Blo) { NT -= sign; return; }  // invalid sample: only the valid count is corrected
     TB += sign;
     if (s < K) {
       myL0[s * CS] = (uint16_t)(myL0[s * CS] + sign);
@@ -132,19 +141,20 @@ __global__ void __launch_bounds__(512) hobday_band_kernel(const BandParams p) {
       for (int j = b0; j < b1; j += 8) {
         int v[8];
 #pragma unroll
-        for (int u = 0; u < 8; ++u) v[u] = (j + u < b1) ? (int)col[(int64_t)__ldg(&p.doy_rows[j + u]) * p.pitch] : 0xFFFF;
+        for (int u = 0; u < 8; ++u) v[u] = (j + u < b1) ? load_row(j + u) : BAND_INV;
 #pragma unroll
-        for (int u = 0; u < 8; ++u) if (v[u] != 0xFFFF) fn(v[u]);
+        for (int u = 0; u < 8; ++u) if (v[u] != BAND_INV) fn(v[u]);
       }
     }
   };
   auto rebuild = [&](int d) -> bool {
     // 1. coarse pass: 8-bin block counts over the full range, own window
-    for (int i = tid; i < (K + KB) * CS; i += blockDim.x) L0[i] = 0;  // L0 and L1 are contiguous
+    for (int i = tid; i < (K + KB) * CS; i += OY * 32) L0[i] = 0;  // L0 and L1 are contiguous
     if (tid < 3) s_misc[tid] = tid == 1 ? 0x7fffffff : (tid == 2 ? -1 : 0);
     __syncthreads();
     NT = 0;
     if (own_valid) for_window(d, [&](int v) { ++NT; if (K < 8 * nblk) { myL0[(v >> 3) * CS] = (uint16_t)(myL0[(v >> 3) * CS] + 1); } });
+    dead = NT == 0;
     NTr[tid] = (uint16_t)NT;
     __syncthreads();
     if (K >= 8 * nblk) {
@@ -156,7 +166,7 @@ __global__ void __launch_bounds__(512) hobday_band_kernel(const BandParams p) {
         const int kk = (int)floor(__dmul_rn(p.q, (double)ntot));
         int run = 0, jb = -1;
         for (int j = 0; j < nblk; ++j) {
-          const int pj = pooled_row<P>(L0 + (size_t)j * CS + warp * 32 + lane, lane);
+          const int pj = pooled_row<P>(L0 + j * CS + warp * 32 + lane, lane);
           if (jb < 0) { if (run + pj > kk) jb = j; else run += pj; }
           if (__all_sync(0xffffffffu, jb >= 0 || !livet)) break;
         }
@@ -177,79 +187,86 @@ __global__ void __launch_bounds__(512) hobday_band_kernel(const BandParams p) {
         Blo = 0;
         if (p.force_fail) return false;
       }
-      __syncthreads();
-      for (int i = tid; i < (K + KB) * CS; i += blockDim.x) L0[i] = 0;
+      for (int i = tid; i < (K + KB) * CS; i += OY * 32) L0[i] = 0;
       __syncthreads();
     }
     // 2. band counters
     TB = 0;
-    if (own_valid) for_window(d, [&](int v) { if (v >= Blo) band_apply(v - Blo, +1); });
+    if (!dead) for_window(d, [&](int v) { if (v >= Blo) { const int n0 = NT; band_apply(v - Blo, +1); NT = n0; } });
     TBr[tid] = (uint16_t)TB;
     __syncthreads();
     return true;
   };
 
-  // ---- advance the own window by one day of year (needs stage(step) + a barrier before) ----
+  // ---- entering samples of `step` into registers (needs stage(step) + a barrier before) ----
+  auto prefetch = [&](int step) {
+    if (!own_valid) return;
+    const long long* oe = s_off + ((step & 1) * 2 + 1) * BAND_CAP;
+    const int ne = s_cnt[((step & 1) * 2 + 1) * 2 + 1] - s_cnt[((step & 1) * 2 + 1) * 2];
+#pragma unroll
+    for (int u = 0; u < BAND_PRE; ++u) pre[u] = (u < ne) ? load_at(oe[u]) : -1;
+  };
+
+  // ---- advance the own window by one day of year (needs prefetch(step) before) ----
   auto advance = [&](int step) {
     if (!own_valid) return;
     const int par = step & 1;
-    const int* rl = s_rows + (par * 2 + 0) * BAND_CAP;
-    const int* re = s_rows + (par * 2 + 1) * BAND_CAP;
+    const long long* ol = s_off + (par * 2 + 0) * BAND_CAP;
     const int bl0 = s_cnt[(par * 2 + 0) * 2], bl1 = s_cnt[(par * 2 + 0) * 2 + 1];
     const int be0 = s_cnt[(par * 2 + 1) * 2], be1 = s_cnt[(par * 2 + 1) * 2 + 1];
     const int nl = bl1 - bl0, ne = be1 - be0;
-    int len = 0, inval = 0;
-    uint16_t* ev = EV + tid;
-    auto scan = [&](int v, int sign01) {  // sign01: 0 = entering (+1), 1 = leaving (-1)
-      const int s = (int)(int16_t)v - Blo;  // invalid (0xFFFF) is -1 - Blo < 0
-      inval += (v >> 15) ? (1 - 2 * sign01) : 0;
-      if (s >= 0) {
-        if (len < BAND_LCAP) ev[len * CS] = (uint16_t)((s << 1) | sign01);
-        else band_apply(s, 1 - 2 * sign01);  // list full: apply in place (rare)
-        ++len;
-      }
+    uint16_t* evp = ev;
+    uint16_t* const ev_full = ev + (BAND_LCAP - 13) * CS;  // a batch of 13 still fits below this fill level
+    auto flush = [&]() {
+      for (uint16_t* q = ev; q < evp; q += CS) { const int e = *q; band_apply(e >> 1, 1 - 2 * (e & 1)); }
+      evp = ev;
     };
-    constexpr int BATCH = 13;
-    const int npair = min(BAND_CAP, max(nl, ne));
-    for (int u0 = 0; u0 < npair; u0 += BATCH) {
-      int vl[BATCH], ve[BATCH];
+    // a sample that matters (inside / above the band, or invalid) goes to the list; sign01: 0 enters, 1 leaves
+    auto scan = [&](int v, int sign01) {
+      const int s = v - Blo;
+      if (s >= 0) { *evp = (uint16_t)(s * 2 + sign01); evp += CS; }
+    };
+    bool skip_leaving = false;
+    if (dead) {  // window without a valid sample: stays so unless a valid sample enters
+      int all = BAND_INV;
 #pragma unroll
-      for (int u = 0; u < BATCH; ++u) {  // all loads first ...
-        const int a = (u0 + u < BAND_CAP) ? rl[u0 + u] : -1, b = (u0 + u < BAND_CAP) ? re[u0 + u] : -1;
-        vl[u] = (a >= 0) ? (int)col[(int64_t)a * p.pitch] : -1;
-        ve[u] = (b >= 0) ? (int)col[(int64_t)b * p.pitch] : -1;
-      }
+      for (int u = 0; u < BAND_PRE; ++u) all &= pre[u];  // missing slots are -1: neutral
+      for (int b = be0 + BAND_PRE; b < be1; ++b) all &= load_row(b);
+      if (all == BAND_INV) return;
+      dead = false;
+      skip_leaving = true;  // every leaving sample is invalid: the valid count does not change
+    }
+    // entering samples (prefetched)
 #pragma unroll
-      for (int u = 0; u < BATCH; ++u) {  // ... then the scan (a slot without a row is skipped)
-        if (vl[u] >= 0) scan(vl[u], 1);
-        if (ve[u] >= 0) scan(ve[u], 0);
+    for (int u = 0; u < BAND_PRE; ++u) {
+      if (u == 13 && evp > ev_full) flush();
+      if (pre[u] >= 0) scan(pre[u], 0);
+    }
+    for (int b = be0 + BAND_PRE; b < be1; ++b) { if (evp > ev_full) flush(); scan(load_row(b), 0); }
+    NT += ne;
+    if (!skip_leaving) {
+      NT -= nl;
+      constexpr int BATCH = 13;
+      const int nlc = min(nl, BAND_CAP);
+      for (int u0 = 0; u0 < nlc; u0 += BATCH) {
+        int vl[BATCH];
+#pragma unroll
+        for (int u = 0; u < BATCH; ++u) vl[u] = (u0 + u < nlc) ? load_at(ol[u0 + u]) : -1;
+        if (evp > ev_full) flush();
+#pragma unroll
+        for (int u = 0; u < BATCH; ++u) if (vl[u] >= 0) scan(vl[u], 1);
       }
+      for (int a = bl0 + BAND_CAP; a < bl1; ++a) { if (evp > ev_full) flush(); scan(load_row(a), 1); }
     }
-    for (int a = bl0 + BAND_CAP; a < bl1; ++a) scan((int)col[(int64_t)__ldg(&p.doy_rows[a]) * p.pitch], 1);  // long lists
-    for (int b = be0 + BAND_CAP; b < be1; ++b) scan((int)col[(int64_t)__ldg(&p.doy_rows[b]) * p.pitch], 0);
-    NT += (ne - nl) - inval;
-    const int m = min(len, BAND_LCAP);
-    for (int j = 0; j < m; ++j) {
-      const int e = ev[j * CS];
-      band_apply(e >> 1, 1 - 2 * (e & 1));
-    }
+    flush();
     NTr[tid] = (uint16_t)NT;
     TBr[tid] = (uint16_t)TB;
   };
-  auto warm_l2 = [&](int step) {  // pull the samples of `step` into L2 while the queries run
-    if (!own_valid) return;
-    const int par = step & 1;
-#pragma unroll 4
-    for (int u = 0; u < BAND_CAP; ++u) {
-      const int re = s_rows[(par * 2 + 1) * BAND_CAP + u];
-      if (re >= 0) asm volatile("prefetch.global.L2 [%0];" ::"l"(col + (int64_t)re * p.pitch));
-    }
-  };
 
-  // ---- query of one day of year: returns false for the warp's lanes that left the band ----
+  // ---- query of one day of year ----
   auto query = [&](int d) {
-    const uint16_t* base = nullptr;
-    const int rowoff = warp * 32 + lane;
+    constexpr int rowbase = 0;
+    const int rowoff = warp * 32 + lane + rowbase;
     const int ntot = pooled_row<P>(NTr + rowoff, lane);
     const int tb = pooled_row<P>(TBr + rowoff, lane);
     const bool livet = target_live && !masked && ntot > 0;
@@ -257,13 +274,12 @@ __global__ void __launch_bounds__(512) hobday_band_kernel(const BandParams p) {
     const int kk = (int)floor(pos);                   // cum > pos  <=>  cum >= kk + 1
     const int below = ntot - tb;
     bool viol = livet && below > kk;                  // quantile bin lies below the band
-    (void)base;
     // block scan
     int run = below, jb = -1;
     bool done = !livet || viol;
     for (int j = 0; j < KB; ++j) {
       if (__all_sync(0xffffffffu, done)) break;
-      const int pj = pooled_row<P>(L1 + (size_t)j * CS + rowoff, lane);
+      const int pj = pooled_row<P>(L1 + j * CS + rowoff, lane);
       if (!done) {
         if (run + pj > kk) { jb = j; done = true; }
         else run += pj;
@@ -288,7 +304,7 @@ __global__ void __launch_bounds__(512) hobday_band_kernel(const BandParams p) {
         if (!__any_sync(0xffffffffu, jb == j)) continue;
 #pragma unroll
         for (int b = 0; b < 8; ++b) {
-          const int pb = pooled_row<P>(L0 + (size_t)(8 * j + b) * CS + rowoff, lane);
+          const int pb = pooled_row<P>(L0 + (8 * j + b) * CS + rowoff, lane);
           if (jb == j && iu < 0) {
             if (run + pb > kk) { iu = Blo + 8 * j + b; cl = run; h = pb; }
             else run += pb;
@@ -297,7 +313,7 @@ __global__ void __launch_bounds__(512) hobday_band_kernel(const BandParams p) {
       }
     }
     if (iu == nb - 1 && jb < 0 && livet && !viol) {  // clipped rank (q = 1): cl = cum[nb - 2], h = hist[nb - 1]
-      h = pooled_row<P>(L0 + (size_t)(nb - 1 - Blo) * CS + rowoff, lane);
+      h = pooled_row<P>(L0 + (nb - 1 - Blo) * CS + rowoff, lane);
       cl = ntot - h;
     }
     if (__any_sync(0xffffffffu, viol)) {
@@ -331,12 +347,13 @@ __global__ void __launch_bounds__(512) hobday_band_kernel(const BandParams p) {
   if (!rebuild(0)) { give_up(); return; }
   stage(1);
   __syncthreads();
+  prefetch(1);
   for (int d = 0; d < NDOY; ++d) {
     if (d > 0) {
       if (d + 1 < NDOY) stage(d + 1);
       advance(d);
       __syncthreads();
-      if (d + 1 < NDOY) warm_l2(d + 1);
+      if (d + 1 < NDOY) prefetch(d + 1);  // in flight while the queries run
     }
     if (warp < TY) query(d);
     __syncthreads();
@@ -358,8 +375,8 @@ __global__ void __launch_bounds__(512) hobday_band_kernel(const BandParams p) {
   }
 }
 
-// np.digitize(a, edges) - 1 with the invalid class (NaN or a >= last edge) coded 0xFFFF, so that
-// "below the band" and "invalid" are one signed comparison in the kernel above.
+// np.digitize(a, edges) - 1 with the invalid class (NaN or a >= last edge) coded BAND_INV, which sorts
+// above every band: invalid samples travel through the event list like any sample that matters.
 __global__ void __launch_bounds__(256) digitize_ffff_kernel(const float* __restrict__ a, int64_t T, int64_t N,
                                                             int64_t pitch, const float* __restrict__ edges, int n_edges,
                                                             uint16_t* __restrict__ bins, int64_t bins_pitch,
@@ -374,13 +391,13 @@ __global__ void __launch_bounds__(256) digitize_ffff_kernel(const float* __restr
   const bool pair = c + 1 < N && ((pitch | bins_pitch) & 1) == 0;
   const int64_t t0 = (int64_t)blockIdx.y * rows_per_block, t1 = min(T, t0 + rows_per_block);
   auto dig = [&](float v) -> uint32_t {
-    if (v != v) return 0xFFFFu;
+    if (v != v) return (uint32_t)BAND_INV;
     float g = floorf((v - e1) * inv_step) + 1.f;
     g = fminf(fmaxf(g, 0.f), (float)(n_edges - 1));
     int i = (int)g;
     while (i > 0 && v < s_edges[i]) --i;
     while (i < n_edges - 1 && v >= s_edges[i + 1]) ++i;
-    return i >= n_edges - 1 ? 0xFFFFu : (uint32_t)i;
+    return i >= n_edges - 1 ? (uint32_t)BAND_INV : (uint32_t)i;
   };
   if (pair) {
 #pragma unroll 4
@@ -464,31 +481,25 @@ extern "C" int marex_hobday_thresholds_pooled_f32(const float* anom, int64_t T, 
   bp.fail_list = fail_list;
   bp.force_fail = getenv("MAREX_POOL_FORCE_FAIL") ? atoi(getenv("MAREX_POOL_FORCE_FAIL")) : 0;
   const int K = env_k ? env_k : 128;
-  MAREX_REQUIRE(K == 64 || K == 128 || K == 256, "MAREX_POOL_K must be 64, 128 or 256");
+  MAREX_REQUIRE(K == 64 || K == 128, "MAREX_POOL_K must be 64 or 128");
   MAREX_REQUIRE(nb <= 8 * K, "nb too large for the coarse pass of this band width");
-  auto smem_of = [&](int oy) {
-    const size_t cs = (size_t)oy * 32;
-    return (size_t)(K + K / 8 + 2 + BAND_LCAP) * cs * 2 + (4 * BAND_CAP + 8 + 4) * sizeof(int);
-  };
-  int TY = env_ty ? env_ty : 8;
-  while (TY > 1 && (smem_of(TY + 2 * P) > 220 * 1024 || (TY + 2 * P) * 32 > 512)) --TY;
-  MAREX_REQUIRE(smem_of(TY + 2 * P) <= 220 * 1024, "band tile does not fit shared memory");
+  const int TY = (env_ty && env_ty < 8) ? 3 : 8;  // 3: small tiles, exercised by the tests
   const int OY = TY + 2 * P, TX = 32 - 2 * P;
-  const size_t smem = smem_of(OY);
+  const size_t smem = (size_t)(K + K / 8 + 2 + BAND_LCAP) * OY * 32 * 2 + 4 * BAND_CAP * 8 + (8 + 4) * sizeof(int);
+  MAREX_REQUIRE(smem <= 227 * 1024, "band tile does not fit shared memory");
   dim3 grid((unsigned)((nx + TX - 1) / TX), (unsigned)((ny + TY - 1) / TY));
   const int max_tiles = (int)(grid.x * grid.y);
-#define MAREX_BAND(PP, KK)                                                                                  \
-  do {                                                                                                      \
-    cudaError_t e = cudaFuncSetAttribute(hobday_band_kernel<PP, KK>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
-                                         (int)smem);                                                        \
-    if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(hobday_band)");                         \
-    hobday_band_kernel<PP, KK><<<grid, OY * 32, smem, st>>>(bp);                                            \
+#define MAREX_BAND(PP, KK, TT)                                                                                 \
+  do {                                                                                                         \
+    cudaError_t e = cudaFuncSetAttribute(hobday_band_kernel<PP, KK, TT + 2 * PP>,                              \
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);              \
+    if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(hobday_band)");                            \
+    hobday_band_kernel<PP, KK, TT + 2 * PP><<<grid, (TT + 2 * PP) * 32, smem, st>>>(bp);                       \
   } while (0)
-#define MAREX_BAND_K(PP)                                        \
-  do {                                                          \
-    if (K == 64) MAREX_BAND(PP, 64);                            \
-    else if (K == 128) MAREX_BAND(PP, 128);                     \
-    else MAREX_BAND(PP, 256);                                   \
+#define MAREX_BAND_K(PP)                                                    \
+  do {                                                                      \
+    if (K == 64) { if (TY == 8) MAREX_BAND(PP, 64, 8); else MAREX_BAND(PP, 64, 3); }     \
+    else { if (TY == 8) MAREX_BAND(PP, 128, 8); else MAREX_BAND(PP, 128, 3); }           \
   } while (0)
   if (P == 1) MAREX_BAND_K(1); else if (P == 2) MAREX_BAND_K(2); else MAREX_BAND_K(3);
 #undef MAREX_BAND_K

@@ -411,7 +411,7 @@ def test_data_validation_errors():
 
 
 # ---------------------------------------------------------------- banded pooled kernel: rebuilds, fall-back, edges
-def _hetero_anoms(ny=21, nx=70, T1="2001-01-01", seed=11):
+def _hetero_anoms(ny=13, nx=70, T1="2001-01-01", seed=11):
     """Anomalies whose spread varies strongly with season and position, so that the thresholds of a
     tile drift through (and beyond) one band: exercises re-centring and the full-range fall-back."""
     rng = np.random.default_rng(seed)
@@ -437,7 +437,7 @@ def _hetero_anoms(ny=21, nx=70, T1="2001-01-01", seed=11):
         ({}, 5, 11, 95),
         ({"MAREX_POOL_K": "64"}, 5, 11, 95),
         ({"MAREX_POOL_K": "64", "MAREX_POOL_MARGIN": "0"}, 3, 5, 90),
-        ({"MAREX_POOL_K": "256", "MAREX_POOL_TY": "3"}, 7, 11, 99),
+        ({"MAREX_POOL_K": "128", "MAREX_POOL_TY": "3"}, 7, 11, 99),
         ({"MAREX_POOL_FORCE_FAIL": "1"}, 5, 11, 95),
         ({"MAREX_POOL_TY": "1"}, 5, 31, 80),
     ],
@@ -464,7 +464,7 @@ def test_banded_pooled_kernel_bit_exact(monkeypatch, env, ws, w, p):
 
 
 def test_digitize_ffff_matches_numpy_digitize():
-    """The pooled path digitizes internally (invalid class coded 0xFFFF); its counts feed the same
+    """The pooled path digitizes internally (invalid class coded 0x7FFF); its counts feed the same
     thresholds as np.digitize - checked here through a band wide enough that nothing is pooled away."""
     mb = _cuda()
     rng = np.random.default_rng(3)
