@@ -172,9 +172,12 @@ int marex_global_threshold_exact_f64(const float* anom, int64_t T, int64_t N, in
  * (detect.py:2915).  Either output may be NULL: `events` is one byte per gridpoint-day (the
  * bool array the reference returns), `bits` is the bit-packed mask, row t at
  * bits[t * bits_pitch ...], bit (c & 31) of word (c >> 5).  `count` (optional, device
- * uint64, accumulated into) receives the number of extreme gridpoint-days. */
+ * uint64, accumulated into) receives the number of extreme gridpoint-days.  When the optional CSR
+ * (doy_ptr, doy_rows) of the rows of each day of year is given and N % 4 == 0, the hobday compare
+ * runs day-of-year major (each threshold row is read once, 16-byte loads). */
 int marex_compare_hobday(const float* anom, int64_t T, int64_t N, int64_t pitch,
-                         const int16_t* doy, const float* thr,
+                         const int16_t* doy, const int32_t* doy_ptr, const int32_t* doy_rows,
+                         const float* thr,
                          uint8_t* events, int64_t events_pitch,
                          uint32_t* bits, int64_t bits_pitch,
                          unsigned long long* count, void* stream);

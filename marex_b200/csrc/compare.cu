@@ -44,6 +44,55 @@ __global__ void __launch_bounds__(256) compare_kernel(const float* __restrict__ 
   }
 }
 
+// Hobday compare organised by day of year: a CTA owns (512 gridpoints, one day of year), keeps that
+// day's thresholds in registers and walks the rows (one per year) of the day.  The threshold field
+// is read once instead of once per row, loads are 16 bytes and stores 4 bytes per thread.
+__global__ void __launch_bounds__(128) compare_doy_kernel(const float* __restrict__ anom, int64_t N, int64_t pitch,
+                                                          const int32_t* __restrict__ doy_ptr,
+                                                          const int32_t* __restrict__ doy_rows,
+                                                          const float* __restrict__ thr, uint8_t* __restrict__ events,
+                                                          int64_t events_pitch, uint32_t* __restrict__ bits,
+                                                          int64_t bits_pitch, unsigned long long* __restrict__ count) {
+  const int d = blockIdx.y;
+  const int64_t c = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * 4;  // N % 4 == 0: all four live or none
+  const bool live = c < N;
+  const int64_t cc = live ? c : 0;
+  const int b0 = __ldg(&doy_ptr[d]), b1 = __ldg(&doy_ptr[d + 1]);
+  const float4 th = __ldg(reinterpret_cast<const float4*>(thr + (int64_t)d * N + cc));
+  const int lane = threadIdx.x & 31;
+  unsigned int local = 0;
+  for (int j0 = b0; j0 < b1; j0 += 5) {
+    float4 a[5];
+    int64_t row[5];
+#pragma unroll
+    for (int u = 0; u < 5; ++u) {
+      row[u] = (j0 + u < b1) ? (int64_t)__ldg(&doy_rows[j0 + u]) : -1;
+      if (row[u] >= 0) a[u] = __ldcs(reinterpret_cast<const float4*>(anom + row[u] * pitch + cc));
+    }
+#pragma unroll
+    for (int u = 0; u < 5; ++u) {
+      if (row[u] < 0) continue;
+      const unsigned e0 = (a[u].x >= th.x) && live, e1 = (a[u].y >= th.y) && live, e2 = (a[u].z >= th.z) && live,
+                     e3 = (a[u].w >= th.w) && live;
+      const unsigned nib = e0 | (e1 << 1) | (e2 << 2) | (e3 << 3);
+      local += __popc(nib);
+      if (events && live)
+        __stcs(reinterpret_cast<unsigned int*>(events + row[u] * events_pitch + c), e0 | (e1 << 8) | (e2 << 16) | (e3 << 24));
+      if (bits) {  // 8 lanes x 4 gridpoints = one 32-bit word
+        unsigned w = nib << ((lane & 7) * 4);
+        w |= __shfl_xor_sync(0xffffffffu, w, 1);
+        w |= __shfl_xor_sync(0xffffffffu, w, 2);
+        w |= __shfl_xor_sync(0xffffffffu, w, 4);
+        if ((lane & 7) == 0 && live) bits[row[u] * bits_pitch + (c >> 5)] = w;
+      }
+    }
+  }
+  if (count) {
+    for (int o = 16; o; o >>= 1) local += __shfl_xor_sync(0xffffffffu, local, o);
+    if (lane == 0 && local) atomicAdd(count, (unsigned long long)local);
+  }
+}
+
 __global__ void transpose_kernel(const float* __restrict__ in, int64_t rows, int64_t cols, float* __restrict__ out) {
   __shared__ float tile[32][33];
   const int64_t c0 = (int64_t)blockIdx.x * 32, r0 = (int64_t)blockIdx.y * 32;
@@ -125,12 +174,24 @@ static int launch_compare(const float* anom, int64_t T, int64_t N, int64_t pitch
 }
 
 extern "C" int marex_compare_hobday(const float* anom, int64_t T, int64_t N, int64_t pitch, const int16_t* doy,
-                                    const float* thr, uint8_t* events, int64_t events_pitch, uint32_t* bits,
-                                    int64_t bits_pitch, unsigned long long* count, void* stream) {
+                                    const int32_t* doy_ptr, const int32_t* doy_rows, const float* thr,
+                                    uint8_t* events, int64_t events_pitch, uint32_t* bits, int64_t bits_pitch,
+                                    unsigned long long* count, void* stream) {
   MAREX_REQUIRE(anom && doy && thr && (events || bits || count), "null pointer");
   MAREX_REQUIRE(T > 0 && N > 0 && pitch >= N, "bad shape");
   MAREX_REQUIRE(!events || events_pitch >= N, "events_pitch < N");
   MAREX_REQUIRE(!bits || bits_pitch >= (N + 31) / 32, "bits_pitch < ceil(N/32)");
+  const bool aligned = (N % 4) == 0 && (pitch % 4) == 0 && (!events || (events_pitch % 4) == 0) &&
+                       (reinterpret_cast<uintptr_t>(anom) % 16) == 0 && (reinterpret_cast<uintptr_t>(thr) % 16) == 0 &&
+                       (!events || (reinterpret_cast<uintptr_t>(events) % 4) == 0);
+  if (doy_ptr && doy_rows && aligned && (N % 32 == 0 || !bits)) {
+    const int threads = 128;
+    dim3 grid((unsigned)((N / 4 + threads - 1) / threads), NDOY);
+    compare_doy_kernel<<<grid, threads, 0, (cudaStream_t)stream>>>(anom, N, pitch, doy_ptr, doy_rows, thr, events,
+                                                                   events_pitch, bits, bits_pitch, count);
+    MAREX_LAUNCH_CHECK("compare_doy_kernel");
+    return MAREX_OK;
+  }
   return launch_compare<false>(anom, T, N, pitch, doy, thr, events, events_pitch, bits, bits_pitch, count,
                                (cudaStream_t)stream);
 }

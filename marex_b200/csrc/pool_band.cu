@@ -31,7 +31,7 @@
 
 namespace marex {
 
-constexpr int BAND_LCAP = 16;  // slots of the per-thread compacted event list
+constexpr int BAND_LCAP = 18;  // slots of the per-thread compacted event list
 constexpr int BAND_CAP = 32;   // staged row indices per step and direction
 
 struct BandParams {
@@ -46,7 +46,8 @@ struct BandParams {
   float lower_bound;
   float* thr;
   float* stats;
-  int32_t* fail_list;  // [0] = count, then (y0, x0) pairs
+  int32_t* fail_list;        // [0] = count, then (y0, x0) pairs of the tiles this launch gives up on
+  const int32_t* tile_list;  // nullptr: tiles from blockIdx (x, y); else 1-D grid over the listed tiles
   int force_fail;
 };
 
@@ -82,7 +83,12 @@ __global__ void __launch_bounds__(OY * 32) hobday_band_kernel(const BandParams p
   const int nb = p.nb, half = p.w / 2;
   const int nblk = (nb + 7) >> 3;
   const int64_t nx = p.nx, ny = p.ny, N = nx * ny;
-  const int64_t y0 = (int64_t)blockIdx.y * TY, x0 = (int64_t)blockIdx.x * TX;
+  int64_t y0 = (int64_t)blockIdx.y * TY, x0 = (int64_t)blockIdx.x * TX;
+  if (p.tile_list) {  // retry launch over the tiles a narrower band gave up on
+    if ((int)blockIdx.x >= __ldg(&p.tile_list[0])) return;
+    y0 = __ldg(&p.tile_list[1 + 2 * blockIdx.x]);
+    x0 = __ldg(&p.tile_list[2 + 2 * blockIdx.x]);
+  }
 
   // ---- own gridpoint of this thread (update role) ----
   const int64_t gy = y0 - P + warp;
@@ -216,15 +222,16 @@ __global__ void __launch_bounds__(OY * 32) hobday_band_kernel(const BandParams p
     const int be0 = s_cnt[(par * 2 + 1) * 2], be1 = s_cnt[(par * 2 + 1) * 2 + 1];
     const int nl = bl1 - bl0, ne = be1 - be0;
     uint16_t* evp = ev;
-    uint16_t* const ev_full = ev + (BAND_LCAP - 13) * CS;  // a batch of 13 still fits below this fill level
+    uint16_t* const ev_full = ev + (BAND_LCAP - 15) * CS;  // a batch of 13 (+ 1 scratch slot) still fits below this
     auto flush = [&]() {
       for (uint16_t* q = ev; q < evp; q += CS) { const int e = *q; band_apply(e >> 1, 1 - 2 * (e & 1)); }
       evp = ev;
     };
     // a sample that matters (inside / above the band, or invalid) goes to the list; sign01: 0 enters, 1 leaves
-    auto scan = [&](int v, int sign01) {
+    auto scan = [&](int v, int sign01) {  // branch-free: the slot is overwritten unless the sample matters
       const int s = v - Blo;
-      if (s >= 0) { *evp = (uint16_t)(s * 2 + sign01); evp += CS; }
+      *evp = (uint16_t)(s * 2 + sign01);
+      evp += (s >= 0) ? CS : 0;
     };
     bool skip_leaving = false;
     if (dead) {  // window without a valid sample: stays so unless a valid sample enters
@@ -419,9 +426,10 @@ int launch_pool_tile_list(const uint16_t* bins, int64_t ny, int64_t nx, int64_t 
                           const float* anom_row0, float lower_bound, float* thr, float* stats,
                           const int32_t* fail_list, int max_tiles, int band_ty, int band_tx, cudaStream_t st);
 
-__global__ void init_band_kernel(float* stats, int32_t* fail_list) {
+__global__ void init_band_kernel(float* stats, int32_t* list_a, int32_t* list_b) {
   if (stats) { stats[0] = CUDART_INF_F; stats[1] = -CUDART_INF_F; }
-  fail_list[0] = 0;
+  list_a[0] = 0;
+  list_b[0] = 0;
 }
 
 }  // namespace marex
@@ -432,7 +440,7 @@ extern "C" int64_t marex_hobday_pooled_workspace_bytes(int64_t T, int64_t ny, in
   // bins (uint16 [T][ny*nx], rows padded to an even count) + fail list
   const int64_t N = ny * nx, pitch = (N + 1) & ~1LL;
   const int64_t tiles = ((ny + 0) / 1 + 1) * ((nx + 27) / 28 + 1);  // generous upper bound on band tiles
-  return T * pitch * 2 + (2 * tiles + 8) * 4 + 256;
+  return T * pitch * 2 + 2 * (2 * tiles + 8) * 4 + 512;
 }
 
 extern "C" int marex_hobday_thresholds_pooled_f32(const float* anom, int64_t T, int64_t ny, int64_t nx, int64_t pitch,
@@ -466,29 +474,32 @@ extern "C" int marex_hobday_thresholds_pooled_f32(const float* anom, int64_t T, 
         anom, T, N, pitch, edges, nb + 1, bins, bpitch, rows_per_block);
     MAREX_LAUNCH_CHECK("digitize_ffff_kernel");
   }
-  init_band_kernel<<<1, 1, 0, st>>>(stats, fail_list);
-  MAREX_LAUNCH_CHECK("init_band_kernel");
-
   const int P = ws / 2;
   const int env_k = getenv("MAREX_POOL_K") ? atoi(getenv("MAREX_POOL_K")) : 0;
   const int env_ty = getenv("MAREX_POOL_TY") ? atoi(getenv("MAREX_POOL_TY")) : 0;
+  MAREX_REQUIRE(env_k == 0 || env_k == 64 || env_k == 128, "MAREX_POOL_K must be 64 or 128");
+  const int TY = (env_ty && env_ty < 8) ? 3 : 8;  // 3: small tiles, exercised by the tests
+  const int OY = TY + 2 * P, TX = 32 - 2 * P;
+  const dim3 grid_all((unsigned)((nx + TX - 1) / TX), (unsigned)((ny + TY - 1) / TY));
+  const int max_tiles = (int)(grid_all.x * grid_all.y);
+  int32_t* list_b = fail_list + 2 * ((ny + 1) * ((nx + 27) / 28 + 1)) + 8;
+  init_band_kernel<<<1, 1, 0, st>>>(stats, fail_list, list_b);
+  MAREX_LAUNCH_CHECK("init_band_kernel");
   BandParams bp;
   bp.bins = bins; bp.ny = ny; bp.nx = nx; bp.pitch = bpitch;
   bp.doy_ptr = doy_ptr; bp.doy_rows = doy_rows; bp.centers = centers;
   bp.nb = nb; bp.w = w; bp.q = q;
-  bp.margin = getenv("MAREX_POOL_MARGIN") ? atoi(getenv("MAREX_POOL_MARGIN")) : 16;
+  bp.margin = getenv("MAREX_POOL_MARGIN") ? atoi(getenv("MAREX_POOL_MARGIN")) : 8;
   bp.anom_row0 = anom; bp.lower_bound = lower_bound; bp.thr = thr; bp.stats = stats;
-  bp.fail_list = fail_list;
   bp.force_fail = getenv("MAREX_POOL_FORCE_FAIL") ? atoi(getenv("MAREX_POOL_FORCE_FAIL")) : 0;
-  const int K = env_k ? env_k : 128;
-  MAREX_REQUIRE(K == 64 || K == 128, "MAREX_POOL_K must be 64 or 128");
-  MAREX_REQUIRE(nb <= 8 * K, "nb too large for the coarse pass of this band width");
-  const int TY = (env_ty && env_ty < 8) ? 3 : 8;  // 3: small tiles, exercised by the tests
-  const int OY = TY + 2 * P, TX = 32 - 2 * P;
-  const size_t smem = (size_t)(K + K / 8 + 2 + BAND_LCAP) * OY * 32 * 2 + 4 * BAND_CAP * 8 + (8 + 4) * sizeof(int);
-  MAREX_REQUIRE(smem <= 227 * 1024, "band tile does not fit shared memory");
-  dim3 grid((unsigned)((nx + TX - 1) / TX), (unsigned)((ny + TY - 1) / TY));
-  const int max_tiles = (int)(grid.x * grid.y);
+  // One launch of the band kernel with K band bins over all tiles (tiles == nullptr) or over a list.
+  auto launch_band = [&](int K, const int32_t* tiles, int32_t* fails) -> int {
+    if (nb > 8 * K) return fail(MAREX_ERR_UNSUPPORTED, "nb too large for the coarse pass of this band width");
+    const size_t smem = (size_t)(K + K / 8 + 2 + BAND_LCAP) * OY * 32 * 2 + 4 * BAND_CAP * 8 + (8 + 4) * sizeof(int);
+    if (smem > 227 * 1024) return fail(MAREX_ERR_UNSUPPORTED, "band tile does not fit shared memory");
+    bp.tile_list = tiles;
+    bp.fail_list = fails;
+    const dim3 grid = tiles ? dim3((unsigned)max_tiles, 1) : grid_all;
 #define MAREX_BAND(PP, KK, TT)                                                                                 \
   do {                                                                                                         \
     cudaError_t e = cudaFuncSetAttribute(hobday_band_kernel<PP, KK, TT + 2 * PP>,                              \
@@ -496,16 +507,34 @@ extern "C" int marex_hobday_thresholds_pooled_f32(const float* anom, int64_t T, 
     if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(hobday_band)");                            \
     hobday_band_kernel<PP, KK, TT + 2 * PP><<<grid, (TT + 2 * PP) * 32, smem, st>>>(bp);                       \
   } while (0)
-#define MAREX_BAND_K(PP)                                                    \
-  do {                                                                      \
+#define MAREX_BAND_K(PP)                                                                 \
+  do {                                                                                   \
     if (K == 64) { if (TY == 8) MAREX_BAND(PP, 64, 8); else MAREX_BAND(PP, 64, 3); }     \
     else { if (TY == 8) MAREX_BAND(PP, 128, 8); else MAREX_BAND(PP, 128, 3); }           \
   } while (0)
-  if (P == 1) MAREX_BAND_K(1); else if (P == 2) MAREX_BAND_K(2); else MAREX_BAND_K(3);
+    if (P == 1) MAREX_BAND_K(1); else if (P == 2) MAREX_BAND_K(2); else MAREX_BAND_K(3);
 #undef MAREX_BAND_K
 #undef MAREX_BAND
-  MAREX_LAUNCH_CHECK("hobday_band_kernel");
+    MAREX_LAUNCH_CHECK("hobday_band_kernel");
+    return MAREX_OK;
+  };
+  // 64-bin band (two tiles per SM) first; tiles whose thresholds spread wider retry with 128 bins;
+  // what is left gets full-range counters.  MAREX_POOL_K pins a single width (tuning / tests).
+  const int32_t* leftover = fail_list;
+  if (env_k) {
+    const int rc = launch_band(env_k, nullptr, fail_list);
+    if (rc) return rc;
+  } else if (nb > 8 * 64) {
+    const int rc = launch_band(128, nullptr, fail_list);
+    if (rc) return rc;
+  } else {
+    int rc = launch_band(64, nullptr, fail_list);
+    if (rc) return rc;
+    rc = launch_band(128, fail_list, list_b);
+    if (rc) return rc;
+    leftover = list_b;
+  }
   // tiles whose thresholds did not fit one band: full-range counters
   return launch_pool_tile_list(bins, ny, nx, bpitch, doy_ptr, doy_rows, centers, nb, w, ws, q, anom, lower_bound, thr,
-                               stats, fail_list, max_tiles, TY, TX, st);
+                               stats, leftover, max_tiles, TY, TX, st);
 }

@@ -768,8 +768,8 @@ def identify_extremes_arrays(
     count = torch.zeros(1, dtype=torch.int64, device=dev)
     if method_extreme == "hobday_extreme":
         _lib.call(
-            "marex_compare_hobday", _p(anom), T, N, N, h.up(doy, np.int16, dev), _p(out["thresholds_dm"]), _p(events),
-            N, _p(bits), nw, _p(count), st,
+            "marex_compare_hobday", _p(anom), T, N, N, h.up(doy, np.int16, dev), _p(ptr_d), _p(rows_d),
+            _p(out["thresholds_dm"]), _p(events), N, _p(bits), nw, _p(count), st,
         )  # fmt: skip
     else:
         _lib.call(
