@@ -46,16 +46,37 @@ def algorithmic_bytes_per_cell(T, T_out):
     return 4 * T + 4 * T_out + 1 * T_out + 4 * 366 + 1
 
 
-# per-kernel algorithmic bytes per gridpoint (what that launch must read + write at minimum)
+# per-stage algorithmic bytes per gridpoint: what one C-ABI call must read + write at minimum
+# (DESIGN.md section 4).  A stage may launch several kernels (the pooled-threshold call runs the
+# digitize kernel and the banded histogram kernel); scratch traffic is not algorithmic.
 def kernel_bytes_per_cell(T, T_out):
     return {
+        "marex_shift_anomaly_daily_f32": 4 * T + 4 * T_out + 1 + 4,
         "marex_shift_anomaly_f32": 4 * T + 4 * T_out + 1 + 4,
         "marex_digitize_f32": 4 * T_out + 2 * T_out,
+        "marex_hobday_thresholds_pooled_f32": 4 * T_out + 4 * 366 + 4,
         "marex_hobday_thresholds_hist": 2 * T_out + 4 * 366 + 4,
         "marex_hobday_thresholds_exact_f32": 4 * T_out + 4 * 366,
         "marex_transpose_f32": 2 * 4 * 366,
         "marex_compare_hobday": 4 * T_out + T_out + 4 * 366,
     }
+
+
+STAGE_KERNELS = {
+    "marex_shift_anomaly_daily_f32": ["shift_daily_kernel"],
+    "marex_hobday_thresholds_pooled_f32": ["digitize_ffff_kernel", "hobday_band_kernel", "hobday_pool_tile_kernel (fall-back list)"],
+    "marex_compare_hobday": ["compare_doy_kernel"],
+}
+
+
+def ncu_traffic(kernel_stage):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of the stage's kernels, from the ncu
+    --set full captures summarised in profiles/r01_ncu_traffic.json (same workload), or None."""
+    p = os.path.join(ROOT, "profiles", "r01_ncu_traffic.json")
+    if not os.path.exists(p):
+        return None
+    d = json.load(open(p))
+    return d.get(kernel_stage)
 
 
 def measured_peaks():
@@ -161,7 +182,7 @@ def run_reference(args, rank, world):
     ny, nx, start, end, kw = WORKLOADS[args.workload]
     time = np.arange(np.datetime64(start), np.datetime64(end))
     cores = os.cpu_count() or 1
-    tiles = synth_host_tiles(time, cores, tile=(6, 8))  # one 48-cell tile per core and step (~3 s each)
+    tiles = synth_host_tiles(time, 4 * cores, tile=(6, 8))  # four 48-cell tiles per core and step
     cells = sum(t.shape[1] * t.shape[2] for t in tiles)
     for _ in range(args.warmup):
         cpu_oracle_run(tiles[: max(1, cores // 4)], time, kw, cores)
@@ -312,12 +333,14 @@ def main():
     achieved = kb[dom] * n_load / (stage_ms[dom] * 1e-3) / 1e9
     roofline = {
         "kernel": dom,
+        "kernels_in_stage": STAGE_KERNELS.get(dom, [dom]),
         "bound": "hbm",
         "achieved": achieved,
         "peak": peak,
         "unit": "GB/s",
         "frac": achieved / peak,
-        "traffic": None,
+        "traffic": ncu_traffic(dom),
+        "algorithmic_bytes_per_launch": kb[dom] * n_load,
         "peak_source": peak_src,
         "ms_per_launch": stage_ms[dom],
     }
@@ -342,6 +365,8 @@ def main():
                 t0 = _time.perf_counter()
             res = marex_b200.preprocess_arrays(xh, time, output="pinned", **kw)
             d2h = sum(res[k].nbytes for k in ("dat_anomaly", "mask", "thresholds", "extreme_events"))
+            h2d = int(res.get("h2d_bytes", xh.numel() * 4))
+            n_chunks = int(res.get("chunks", 1))
             del res
         barrier()
         dt = (_time.perf_counter() - t0) / e2e_steps
@@ -352,7 +377,9 @@ def main():
         e2e = {
             "value": n_own * world * T / dt,
             "unit": "gridpoint-days/s",
-            "h2d_bytes_per_step": int(xh.numel() * 4),
+            "h2d_bytes_per_step": h2d,
+            "chunks": n_chunks,
+            "path": "marex_b200.preprocess_arrays(host pinned array) -> host arrays; latitude-band chunks streamed on 3 CUDA streams",
             "d2h_bytes_per_step": int(d2h),
             "steps": e2e_steps,
             "warmup": 1,
@@ -370,9 +397,10 @@ def main():
         th, tw = 6, 8
         tiles = []
         r0 = (x_sample_src.shape[1] // 2) // th * th
-        for i in range(cores):
+        for i in range(cores * 8):  # ~15-30 s of CPU work on the box's cores
             c0 = (i * 5 * tw) % (nx - tw)
-            tiles.append(np.ascontiguousarray(x_sample_src[:, r0 : r0 + th, c0 : c0 + tw].cpu().numpy()))
+            rr = (r0 + (i // 32) * 3 * th) % (x_sample_src.shape[1] - th)
+            tiles.append(np.ascontiguousarray(x_sample_src[:, rr : rr + th, c0 : c0 + tw].cpu().numpy()))
         dtc = cpu_oracle_run(tiles, time, kw, cores)
         cells = len(tiles) * th * tw
         cpu = {

@@ -174,10 +174,11 @@ int marex_global_threshold_exact_f64(const float* anom, int64_t T, int64_t N, in
  * bits[t * bits_pitch ...], bit (c & 31) of word (c >> 5).  `count` (optional, device
  * uint64, accumulated into) receives the number of extreme gridpoint-days.  When the optional CSR
  * (doy_ptr, doy_rows) of the rows of each day of year is given and N % 4 == 0, the hobday compare
- * runs day-of-year major (each threshold row is read once, 16-byte loads). */
+ * runs day-of-year major (each threshold row is read once, 16-byte loads).  thr_pitch (elements,
+ * >= N) is the row stride of thr, so a sub-range of gridpoints of a larger field can be compared. */
 int marex_compare_hobday(const float* anom, int64_t T, int64_t N, int64_t pitch,
                          const int16_t* doy, const int32_t* doy_ptr, const int32_t* doy_rows,
-                         const float* thr,
+                         const float* thr, int64_t thr_pitch,
                          uint8_t* events, int64_t events_pitch,
                          uint32_t* bits, int64_t bits_pitch,
                          unsigned long long* count, void* stream);
@@ -188,6 +189,11 @@ int marex_compare_global(const float* anom, int64_t T, int64_t N, int64_t pitch,
                          unsigned long long* count, void* stream);
 
 /* ---- utilities --------------------------------------------------------------------------
+ * Strided host<->device copy (cudaMemcpy2DAsync) of `height` rows of `width_bytes`: the streamed
+ * host path moves one latitude band of a (time, lat, lon) host array per call. */
+int marex_memcpy2d_async(void* dst, int64_t dpitch_bytes, const void* src, int64_t spitch_bytes,
+                         int64_t width_bytes, int64_t height, int32_t to_device, void* stream);
+/*
  * out[c, r] = in[r, c] : doy-major thr[366, N] -> the reference's (..space, dayofyear) layout. */
 int marex_transpose_f32(const float* in, int64_t rows, int64_t cols, float* out, void* stream);
 

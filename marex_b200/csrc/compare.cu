@@ -14,10 +14,10 @@ std::atomic<long long> g_launches{0};
 template <bool THR_GLOBAL>
 __global__ void __launch_bounds__(256) compare_kernel(const float* __restrict__ anom, int64_t T, int64_t N,
                                                       int64_t pitch, const int16_t* __restrict__ doy,
-                                                      const void* __restrict__ thr_v, uint8_t* __restrict__ events,
-                                                      int64_t events_pitch, uint32_t* __restrict__ bits,
-                                                      int64_t bits_pitch, unsigned long long* __restrict__ count,
-                                                      int rows_per_block) {
+                                                      const void* __restrict__ thr_v, int64_t thr_pitch,
+                                                      uint8_t* __restrict__ events, int64_t events_pitch,
+                                                      uint32_t* __restrict__ bits, int64_t bits_pitch,
+                                                      unsigned long long* __restrict__ count, int rows_per_block) {
   const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;  // blockDim.x multiple of 32
   const bool live = c < N;
   const int64_t cc = live ? c : N - 1;
@@ -31,7 +31,7 @@ __global__ void __launch_bounds__(256) compare_kernel(const float* __restrict__ 
     const float a = ld_stream(&anom[t * pitch + cc]);
     bool e;
     if (THR_GLOBAL) e = (double)a >= thr_g;
-    else e = a >= __ldg(&thr_f[(int64_t)(__ldg(&doy[t]) - 1) * N + cc]);
+    else e = a >= __ldg(&thr_f[(int64_t)(__ldg(&doy[t]) - 1) * thr_pitch + cc]);
     e = e && live;
     if (events && live) events[t * events_pitch + c] = e ? 1 : 0;
     const unsigned int word = __ballot_sync(0xffffffffu, e);
@@ -50,15 +50,16 @@ __global__ void __launch_bounds__(256) compare_kernel(const float* __restrict__ 
 __global__ void __launch_bounds__(128) compare_doy_kernel(const float* __restrict__ anom, int64_t N, int64_t pitch,
                                                           const int32_t* __restrict__ doy_ptr,
                                                           const int32_t* __restrict__ doy_rows,
-                                                          const float* __restrict__ thr, uint8_t* __restrict__ events,
-                                                          int64_t events_pitch, uint32_t* __restrict__ bits,
-                                                          int64_t bits_pitch, unsigned long long* __restrict__ count) {
+                                                          const float* __restrict__ thr, int64_t thr_pitch,
+                                                          uint8_t* __restrict__ events, int64_t events_pitch,
+                                                          uint32_t* __restrict__ bits, int64_t bits_pitch,
+                                                          unsigned long long* __restrict__ count) {
   const int d = blockIdx.y;
   const int64_t c = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * 4;  // N % 4 == 0: all four live or none
   const bool live = c < N;
   const int64_t cc = live ? c : 0;
   const int b0 = __ldg(&doy_ptr[d]), b1 = __ldg(&doy_ptr[d + 1]);
-  const float4 th = __ldg(reinterpret_cast<const float4*>(thr + (int64_t)d * N + cc));
+  const float4 th = __ldg(reinterpret_cast<const float4*>(thr + (int64_t)d * thr_pitch + cc));
   const int lane = threadIdx.x & 31;
   unsigned int local = 0;
   for (int j0 = b0; j0 < b1; j0 += 5) {
@@ -157,7 +158,7 @@ extern "C" long long marex_launch_count(void) { return g_launches.load(); }
 
 template <bool G>
 static int launch_compare(const float* anom, int64_t T, int64_t N, int64_t pitch, const int16_t* doy, const void* thr,
-                          uint8_t* events, int64_t events_pitch, uint32_t* bits, int64_t bits_pitch,
+                          int64_t thr_pitch, uint8_t* events, int64_t events_pitch, uint32_t* bits, int64_t bits_pitch,
                           unsigned long long* count, cudaStream_t st) {
   const int threads = 128;
   const int64_t bx = (N + threads - 1) / threads;
@@ -166,7 +167,7 @@ static int launch_compare(const float* anom, int64_t T, int64_t N, int64_t pitch
   if (by > 65535) by = 65535;
   const int rows_per_block = (int)((T + by - 1) / by);
   by = (T + rows_per_block - 1) / rows_per_block;
-  compare_kernel<G><<<dim3((unsigned)bx, (unsigned)by), threads, 0, st>>>(anom, T, N, pitch, doy, thr, events,
+  compare_kernel<G><<<dim3((unsigned)bx, (unsigned)by), threads, 0, st>>>(anom, T, N, pitch, doy, thr, thr_pitch, events,
                                                                           events_pitch, bits, bits_pitch, count,
                                                                           rows_per_block);
   MAREX_LAUNCH_CHECK("compare_kernel");
@@ -175,24 +176,24 @@ static int launch_compare(const float* anom, int64_t T, int64_t N, int64_t pitch
 
 extern "C" int marex_compare_hobday(const float* anom, int64_t T, int64_t N, int64_t pitch, const int16_t* doy,
                                     const int32_t* doy_ptr, const int32_t* doy_rows, const float* thr,
-                                    uint8_t* events, int64_t events_pitch, uint32_t* bits, int64_t bits_pitch,
-                                    unsigned long long* count, void* stream) {
+                                    int64_t thr_pitch, uint8_t* events, int64_t events_pitch, uint32_t* bits,
+                                    int64_t bits_pitch, unsigned long long* count, void* stream) {
   MAREX_REQUIRE(anom && doy && thr && (events || bits || count), "null pointer");
-  MAREX_REQUIRE(T > 0 && N > 0 && pitch >= N, "bad shape");
+  MAREX_REQUIRE(T > 0 && N > 0 && pitch >= N && thr_pitch >= N, "bad shape");
   MAREX_REQUIRE(!events || events_pitch >= N, "events_pitch < N");
   MAREX_REQUIRE(!bits || bits_pitch >= (N + 31) / 32, "bits_pitch < ceil(N/32)");
-  const bool aligned = (N % 4) == 0 && (pitch % 4) == 0 && (!events || (events_pitch % 4) == 0) &&
+  const bool aligned = (N % 4) == 0 && (pitch % 4) == 0 && (thr_pitch % 4) == 0 && (!events || (events_pitch % 4) == 0) &&
                        (reinterpret_cast<uintptr_t>(anom) % 16) == 0 && (reinterpret_cast<uintptr_t>(thr) % 16) == 0 &&
                        (!events || (reinterpret_cast<uintptr_t>(events) % 4) == 0);
   if (doy_ptr && doy_rows && aligned && (N % 32 == 0 || !bits)) {
     const int threads = 128;
     dim3 grid((unsigned)((N / 4 + threads - 1) / threads), NDOY);
-    compare_doy_kernel<<<grid, threads, 0, (cudaStream_t)stream>>>(anom, N, pitch, doy_ptr, doy_rows, thr, events,
-                                                                   events_pitch, bits, bits_pitch, count);
+    compare_doy_kernel<<<grid, threads, 0, (cudaStream_t)stream>>>(anom, N, pitch, doy_ptr, doy_rows, thr, thr_pitch,
+                                                                   events, events_pitch, bits, bits_pitch, count);
     MAREX_LAUNCH_CHECK("compare_doy_kernel");
     return MAREX_OK;
   }
-  return launch_compare<false>(anom, T, N, pitch, doy, thr, events, events_pitch, bits, bits_pitch, count,
+  return launch_compare<false>(anom, T, N, pitch, doy, thr, thr_pitch, events, events_pitch, bits, bits_pitch, count,
                                (cudaStream_t)stream);
 }
 
@@ -203,8 +204,17 @@ extern "C" int marex_compare_global(const float* anom, int64_t T, int64_t N, int
   MAREX_REQUIRE(T > 0 && N > 0 && pitch >= N, "bad shape");
   MAREX_REQUIRE(!events || events_pitch >= N, "events_pitch < N");
   MAREX_REQUIRE(!bits || bits_pitch >= (N + 31) / 32, "bits_pitch < ceil(N/32)");
-  return launch_compare<true>(anom, T, N, pitch, nullptr, thr, events, events_pitch, bits, bits_pitch, count,
+  return launch_compare<true>(anom, T, N, pitch, nullptr, thr, 0, events, events_pitch, bits, bits_pitch, count,
                               (cudaStream_t)stream);
+}
+
+extern "C" int marex_memcpy2d_async(void* dst, int64_t dpitch_bytes, const void* src, int64_t spitch_bytes,
+                                    int64_t width_bytes, int64_t height, int32_t to_device, void* stream) {
+  MAREX_REQUIRE(dst && src && width_bytes > 0 && height > 0 && dpitch_bytes >= width_bytes && spitch_bytes >= width_bytes,
+                "bad argument");
+  MAREX_CUDA(cudaMemcpy2DAsync(dst, (size_t)dpitch_bytes, src, (size_t)spitch_bytes, (size_t)width_bytes, (size_t)height,
+                               to_device ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+  return MAREX_OK;
 }
 
 extern "C" int marex_transpose_f32(const float* in, int64_t rows, int64_t cols, float* out, void* stream) {

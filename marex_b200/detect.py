@@ -563,7 +563,7 @@ def compute_normalised_anomaly_arrays(
         _shift_anomaly_call(h, x_dev, cal, W, S, out_row, 0, anom, mask0, nonfinite)
         if validate:
             check_data_values(mask0, nonfinite, T, T * N)
-        return {"dat_anomaly": anom, "mask": mask0.bool(), "keep": keep, "mask_raw": mask0.bool()}
+        return {"dat_anomaly": anom, "mask": mask0.bool(), "keep": keep, "mask_raw": mask0.bool(), "nonfinite": nonfinite}
 
     keep = np.ones(T, dtype=bool)
     rows = None
@@ -583,7 +583,7 @@ def compute_normalised_anomaly_arrays(
         )  # fmt: skip
         if validate:
             check_data_values(mask0, nonfinite, T, T * N)
-        return {"dat_anomaly": anom, "mask": mask0.bool(), "keep": keep, "mask_raw": mask0.bool(), "climatology": clim}
+        return {"dat_anomaly": anom, "mask": mask0.bool(), "keep": keep, "mask_raw": mask0.bool(), "climatology": clim, "nonfinite": nonfinite}
 
     # detrend_fixed_baseline (detect.py:2400-2462)
     validate_detrend_orders(detrend_orders)
@@ -610,7 +610,7 @@ def compute_normalised_anomaly_arrays(
     _lib.call(
         "marex_sub_doy_climatology_f32", _p(xd), T, N, N, _p(doy_d), _p(mean), _p(clim), _p(xd), N, _p(mask1), None, st
     )
-    return {"dat_anomaly": xd, "mask": mask1.bool(), "keep": keep, "mask_raw": mask_raw, "climatology": clim}
+    return {"dat_anomaly": xd, "mask": mask1.bool(), "keep": keep, "mask_raw": mask_raw, "climatology": clim, "nonfinite": nonfinite}
 
 
 # --------------------------------------------------------------------------------------
@@ -668,11 +668,17 @@ def identify_extremes_arrays(
     want_events: bool = True,
     want_bits: bool = False,
     n_years: Optional[int] = None,
+    cells: Optional[Tuple[int, int]] = None,
+    warn: bool = True,
 ) -> Dict[str, Any]:
     """Array-level ``identify_extremes`` (detect.py:1119-1503).  ``anom`` float32 CUDA (T, N);
     ``grid=(ny, nx)`` for gridded data (enables the default 5x5 pooling), ``None`` for
     unstructured.  Returns the doy-major thresholds (``thresholds_dm``), the thresholds in the
-    reference's layout (``thresholds``), ``extreme_events`` (bool) and/or ``bits``."""
+    reference's layout (``thresholds``), ``extreme_events`` (bool) and/or ``bits``.
+    ``cells=(lo, hi)`` restricts the compare and every returned array to that range of flattened
+    gridpoints (the streamed host path computes thresholds on a band with halo rows and keeps the
+    rows it owns); ``warn=False`` returns the pre-clamp threshold range in ``stats`` instead of
+    raising the reference's UserWarnings."""
     gridded = grid is not None
     ws = resolve_extreme_config(
         method_extreme, threshold_percentile, window_days_hobday, window_spatial_hobday, method_percentile, precision,
@@ -738,8 +744,10 @@ def identify_extremes_arrays(
                     float(edges[3]), _p(thr), _p(stats), st,
                 )  # fmt: skip
                 del bins
-            vmin, vmax = (float(v) for v in stats.cpu())
-            _warn_threshold_range(vmin, vmax, float(edges[-2]), float(edges[3]), max_anomaly)
+            out["stats"], out["stats_bounds"] = stats, (float(edges[-2]), float(edges[3]))
+            if warn:
+                vmin, vmax = (float(v) for v in stats.cpu())
+                _warn_threshold_range(vmin, vmax, float(edges[-2]), float(edges[3]), max_anomaly)
             thr_cm = torch.empty((N, NDOY), dtype=torch.float32, device=dev)
             _lib.call("marex_transpose_f32", _p(thr), NDOY, N, _p(thr_cm), st)
             out["thresholds"] = thr_cm if not gridded else thr_cm.reshape(tuple(grid) + (NDOY,))
@@ -756,30 +764,273 @@ def identify_extremes_arrays(
                 "marex_global_threshold_hist_f64", _p(anom), T, N, N, h.up(edges, np.float64, dev),
                 h.up(centers, np.float64, dev), len(centers), float(q), float(edges[3]), _p(thr), _p(stats), st,
             )  # fmt: skip
-            vmin, vmax = (float(v) for v in stats.cpu())
-            _warn_threshold_range(vmin, vmax, float(edges[-2]), float(edges[3]), max_anomaly)
+            out["stats"], out["stats_bounds"] = stats, (float(edges[-2]), float(edges[3]))
+            if warn:
+                vmin, vmax = (float(v) for v in stats.cpu())
+                _warn_threshold_range(vmin, vmax, float(edges[-2]), float(edges[3]), max_anomaly)
         out["thresholds"] = thr if not gridded else thr.reshape(tuple(grid))
         out["thresholds_layout"] = "space"
         out["thresholds_dm"] = thr
 
-    events = torch.empty((T, N), dtype=torch.uint8, device=dev) if want_events else None
-    nw = (N + 31) // 32
+    c_lo, c_hi = cells if cells is not None else (0, N)
+    n_c = c_hi - c_lo
+    events = torch.empty((T, n_c), dtype=torch.uint8, device=dev) if want_events else None
+    nw = (n_c + 31) // 32
     bits = torch.empty((T, nw), dtype=torch.int32, device=dev) if want_bits else None
     count = torch.zeros(1, dtype=torch.int64, device=dev)
+    a_ptr = ctypes.c_void_p(anom.data_ptr() + 4 * c_lo)
+    thr_dm = out["thresholds_dm"]
     if method_extreme == "hobday_extreme":
         _lib.call(
-            "marex_compare_hobday", _p(anom), T, N, N, h.up(doy, np.int16, dev), _p(ptr_d), _p(rows_d),
-            _p(out["thresholds_dm"]), _p(events), N, _p(bits), nw, _p(count), st,
+            "marex_compare_hobday", a_ptr, T, n_c, N, h.up(doy, np.int16, dev), _p(ptr_d), _p(rows_d),
+            ctypes.c_void_p(thr_dm.data_ptr() + 4 * c_lo), N, _p(events), n_c, _p(bits), nw, _p(count), st,
         )  # fmt: skip
     else:
         _lib.call(
-            "marex_compare_global", _p(anom), T, N, N, _p(out["thresholds_dm"]), _p(events), N, _p(bits), nw, _p(count), st
-        )
+            "marex_compare_global", a_ptr, T, n_c, N, ctypes.c_void_p(thr_dm.data_ptr() + 8 * c_lo), _p(events), n_c,
+            _p(bits), nw, _p(count), st,
+        )  # fmt: skip
+    if cells is not None:  # returned arrays cover the requested gridpoints only
+        lay = out["thresholds_layout"]
+        flat = out["thresholds"].reshape(N, NDOY) if lay == "doy_last" else (
+            out["thresholds"].reshape(NDOY, N) if lay == "doy_first" else out["thresholds"].reshape(N))
+        out["thresholds"] = flat[c_lo:c_hi] if lay != "doy_first" else flat[:, c_lo:c_hi]
     if events is not None:
         out["extreme_events"] = events.view(torch.bool)
     if bits is not None:
         out["bits"] = bits
     out["count"] = count
+    return out
+
+
+def _dataset_attrs(method_anomaly, method_extreme, threshold_percentile, std_normalise, detrend_orders,
+                   window_year_baseline, smooth_days_baseline, window_days_hobday, window_spatial_hobday,
+                   reference_period, force_zero_mean, method_percentile, precision, max_anomaly) -> Dict[str, Any]:
+    """The Dataset attrs of detect.py:731-783."""
+    attrs: Dict[str, Any] = {
+        "method_anomaly": method_anomaly,
+        "method_extreme": method_extreme,
+        "threshold_percentile": threshold_percentile,
+        "preprocessing_steps": get_preprocessing_steps(
+            method_anomaly, method_extreme, std_normalise, list(detrend_orders), window_year_baseline,
+            smooth_days_baseline, window_days_hobday, window_spatial_hobday, reference_period,
+        ),
+    }  # fmt: skip
+    if method_anomaly == "shifting_baseline":
+        attrs.update({"window_year_baseline": window_year_baseline, "smooth_days_baseline": smooth_days_baseline})
+    elif method_anomaly == "fixed_baseline":
+        if reference_period is not None:
+            attrs["reference_period"] = list(reference_period)
+    elif method_anomaly == "detrend_fixed_baseline":
+        attrs.update({"detrend_orders": list(detrend_orders), "force_zero_mean": force_zero_mean})
+        if reference_period is not None:
+            attrs["reference_period"] = list(reference_period)
+    if method_extreme == "hobday_extreme":
+        attrs["window_days_hobday"] = window_days_hobday
+    attrs.update({"method_percentile": method_percentile, "precision": precision, "max_anomaly": max_anomaly})
+    return attrs
+
+
+def _host_buffer(key: str, shape, dtype, pinned: bool) -> torch.Tensor:
+    """Host tensor for a streamed output; page-locked buffers are cached per (key, shape, dtype)."""
+    if not pinned:
+        return torch.empty(shape, dtype=dtype)
+    k = (key, tuple(shape), dtype)
+    buf = _PINNED.get(k)
+    if buf is None:
+        buf = torch.empty(shape, dtype=dtype, pin_memory=True)
+        _PINNED[k] = buf
+    return buf
+
+
+def _copy2d(dst_ptr: int, dpitch: int, src_ptr: int, spitch: int, width: int, height: int, to_device: bool, stream) -> None:
+    _lib.call(
+        "marex_memcpy2d_async", ctypes.c_void_p(dst_ptr), dpitch, ctypes.c_void_p(src_ptr), spitch, width, height,
+        1 if to_device else 0, ctypes.c_void_p(stream.cuda_stream),
+    )  # fmt: skip
+
+
+def _chunk_bounds(n_units: int, n_chunks: int, align: int) -> List[Tuple[int, int]]:
+    """Split [0, n_units) into at most n_chunks contiguous ranges whose interior boundaries are multiples of `align`."""
+    n_chunks = max(1, min(n_chunks, n_units // max(align, 1) or 1))
+    edges = sorted({min(n_units, int(round(i * n_units / n_chunks / align)) * align) for i in range(1, n_chunks)} | {0, n_units})
+    return [(a, b) for a, b in zip(edges[:-1], edges[1:]) if b > a]
+
+
+def _preprocess_host_streamed(xh: torch.Tensor, cal: Calendar, gridded: bool, dev: torch.device, n_chunks: int,
+                              output: str, want_events: bool, kw: Dict[str, Any]) -> Dict[str, Any]:
+    """The whole pipeline on a HOST field, streamed through the GPU in spatial chunks: latitude
+    bands (with the ws//2-row pooling halo re-loaded, SURVEY.md 8e) or cell ranges.  Three streams
+    overlap the strided host->device copy of chunk k+1, the kernels of chunk k and the
+    device->host copy of chunk k-1, so a call costs about max(PCIe in, PCIe out, compute) instead
+    of their sum, and the field may be larger than HBM.  Validation (detect.py:205-279) and the
+    threshold-range warnings are evaluated once, over all chunks, as the reference does."""
+    from .sharding import effective_halo
+
+    T = int(xh.shape[0])
+    space = tuple(int(v) for v in xh.shape[1:])
+    method_anomaly, method_extreme = kw["method_anomaly"], kw["method_extreme"]
+    if gridded:
+        ny, nx = space
+        unit, n_units = nx, ny
+        halo = effective_halo(method_extreme, kw["method_percentile"], kw["window_spatial_hobday"], True)
+        align = 1
+    else:
+        unit, n_units, halo, align = 1, space[0], 0, 32
+    n_total = n_units * unit
+    if method_anomaly == "shifting_baseline":
+        check_sufficient_years(cal, int(kw["window_year_baseline"]))
+        _, keep = shifting_out_rows(cal, int(kw["window_year_baseline"]))
+    else:
+        keep = np.ones(T, dtype=bool)
+    T_out = int(keep.sum())
+    if T_out == 0:
+        raise IndexError("shifting_baseline: no time steps remain after removing the first window_year_baseline years")
+    doy_out = cal.doy[keep]
+    n_years_out = int(np.unique(cal.year[keep]).size)
+    pinned = output == "pinned"
+    hobday = method_extreme == "hobday_extreme"
+    exact = kw["method_percentile"] == "exact"
+    if hobday and not exact:
+        thr_shape, thr_dtype, layout = (n_total, NDOY), torch.float32, "doy_last"
+    elif hobday:
+        thr_shape, thr_dtype, layout = (NDOY, n_total), torch.float32, "doy_first"
+    else:
+        thr_shape, thr_dtype, layout = (n_total,), torch.float64, "space"
+    anom_h = _host_buffer("dat_anomaly", (T_out, n_total), torch.float32, pinned)
+    ev_h = _host_buffer("extreme_events", (T_out, n_total), torch.uint8, pinned) if want_events else None
+    thr_h = _host_buffer("thresholds", thr_shape, thr_dtype, pinned)
+    mask_h = _host_buffer("mask", (n_total,), torch.uint8, pinned)
+
+    bounds = _chunk_bounds(n_units, n_chunks, align)
+    loads = [(max(0, lo - halo), min(n_units, hi + halo)) for lo, hi in bounds]
+    max_load = max(b - a for a, b in loads) * unit
+    slots = [torch.empty(T * max_load, dtype=torch.float32, device=dev) for _ in range(min(2, len(bounds)))]
+    s_comp = torch.cuda.current_stream(dev)
+    s_in, s_out = torch.cuda.Stream(dev), torch.cuda.Stream(dev)
+    ev_in = [torch.cuda.Event() for _ in bounds]
+    ev_comp = [torch.cuda.Event() for _ in bounds]
+    ev_out = [torch.cuda.Event() for _ in bounds]
+    alive: Dict[int, Any] = {}
+    # validation / warning statistics, accumulated on the device (no host sync inside the loop)
+    z = lambda dt: torch.zeros((), dtype=dt, device=dev)  # noqa: E731
+    n_ocean, n_affected, n_invalid, max_invalid, n_events = z(torch.int64), z(torch.int64), z(torch.int64), z(torch.int64), z(torch.int64)
+    st_dtype = torch.float64 if not hobday else torch.float32
+    smin = torch.full((), float("inf"), dtype=st_dtype, device=dev)
+    smax = torch.full((), float("-inf"), dtype=st_dtype, device=dev)
+    stats_bounds = None
+    src_base, esz = xh.data_ptr(), 4
+
+    def h2d(k: int) -> None:
+        a, b = loads[k]
+        if k >= 2:  # the slot is free once chunk k-2 has been computed and copied out
+            s_in.wait_event(ev_comp[k - 2])
+            s_in.wait_event(ev_out[k - 2])
+        _copy2d(slots[k % 2].data_ptr(), (b - a) * unit * esz, src_base + a * unit * esz, n_total * esz,
+                (b - a) * unit * esz, T, True, s_in)  # fmt: skip
+        ev_in[k].record(s_in)
+
+    def compute(k: int) -> None:
+        nonlocal n_ocean, n_affected, n_invalid, max_invalid, n_events, smin, smax, stats_bounds
+        (lo, hi), (a, b) = bounds[k], loads[k]
+        n_load = (b - a) * unit
+        c_lo, c_hi = (lo - a) * unit, (hi - a) * unit
+        s_comp.wait_event(ev_in[k])
+        xd = slots[k % 2][: T * n_load].view(T, n_load)
+        res = compute_normalised_anomaly_arrays(
+            xd, cal, method_anomaly, kw["window_year_baseline"], kw["smooth_days_baseline"], kw["detrend_orders"],
+            kw["force_zero_mean"], kw["reference_period"], validate=False, in_place=method_anomaly != "shifting_baseline",
+        )  # fmt: skip
+        anom = res["dat_anomaly"]
+        ext = identify_extremes_arrays(
+            anom, doy_out, (b - a, nx) if gridded else None, method_extreme, kw["threshold_percentile"],
+            kw["window_days_hobday"], kw["window_spatial_hobday"], kw["method_percentile"], kw["precision"],
+            kw["max_anomaly"], want_events=want_events, want_bits=False, n_years=n_years_out if k == 0 else None,
+            cells=(c_lo, c_hi), warn=False,
+        )  # fmt: skip
+        m = res["mask_raw"][c_lo:c_hi]
+        inv = torch.where(m, res["nonfinite"][c_lo:c_hi], torch.zeros_like(res["nonfinite"][c_lo:c_hi])).to(torch.int64)
+        n_ocean = n_ocean + m.sum()
+        n_affected = n_affected + (inv > 0).sum()
+        n_invalid = n_invalid + inv.sum()
+        max_invalid = torch.maximum(max_invalid, inv.max())
+        n_events = n_events + ext["count"][0]
+        if "stats" in ext:
+            smin, smax = torch.minimum(smin, ext["stats"][0]), torch.maximum(smax, ext["stats"][1])
+            stats_bounds = ext["stats_bounds"]
+        mask_u8 = res["mask"][c_lo:c_hi].to(torch.uint8)
+        thr = ext["thresholds"]
+        if layout == "doy_last":
+            thr = thr.contiguous()
+        ev_comp[k].record(s_comp)
+        # ---- device -> host on its own stream ----
+        s_out.wait_event(ev_comp[k])
+        n_own, g0 = (hi - lo) * unit, lo * unit
+        _copy2d(anom_h.data_ptr() + g0 * 4, n_total * 4, anom.data_ptr() + c_lo * 4, n_load * 4, n_own * 4, T_out, False, s_out)
+        if want_events:
+            e = ext["extreme_events"]
+            _copy2d(ev_h.data_ptr() + g0, n_total, e.data_ptr(), n_own, n_own, T_out, False, s_out)
+        if layout == "doy_last":
+            _copy2d(thr_h.data_ptr() + g0 * NDOY * 4, n_own * NDOY * 4, thr.data_ptr(), n_own * NDOY * 4, n_own * NDOY * 4, 1, False, s_out)
+        elif layout == "doy_first":
+            _copy2d(thr_h.data_ptr() + g0 * 4, n_total * 4, thr.data_ptr(), n_load * 4, n_own * 4, NDOY, False, s_out)
+        else:
+            _copy2d(thr_h.data_ptr() + g0 * 8, n_own * 8, thr.data_ptr(), n_own * 8, n_own * 8, 1, False, s_out)
+        _copy2d(mask_h.data_ptr() + g0, n_own, mask_u8.data_ptr(), n_own, n_own, 1, False, s_out)
+        ev_out[k].record(s_out)
+        alive[k] = (res, ext, mask_u8, thr, anom)  # keep the device buffers until the copies have run
+
+    n = len(bounds)
+    h2d(0)
+    for k in range(n):
+        if k + 1 < n:
+            h2d(k + 1)  # queued before the kernels of chunk k: the copy engine runs ahead
+        compute(k)
+        if k >= 1:
+            ev_out[k - 1].synchronize()
+            alive.pop(k - 1, None)
+    ev_out[n - 1].synchronize()
+    alive.clear()
+
+    # ---- _validate_data_values over the whole field (detect.py:205-279) ----
+    vals = torch.stack([n_ocean, n_affected, n_invalid, max_invalid, n_events]).cpu().tolist()
+    ocean, affected, total_invalid, worst, count = (int(v) for v in vals)
+    if ocean == 0:
+        check_data_values(torch.zeros(1, dtype=torch.uint8), torch.zeros(1, dtype=torch.int32), T, T * n_total)
+    if worst > 0:
+        raise create_data_validation_error(
+            f"Dataset contains {total_invalid} invalid values in {affected} ocean locations",
+            details=f"Found invalid data across time series. Worst location has {worst} invalid time steps out of {T}.",
+            suggestions=[
+                "Remove or interpolate NaN/infinite values before preprocessing",
+                "Check data quality and loading procedures",
+                "Consider using data.fillna() or data.interpolate_na() methods",
+                "Verify coordinate/dimension alignment in your dataset",
+                "For ocean data, ensure land mask is properly applied before preprocessing",
+            ],
+            data_info={
+                "total_invalid_values_in_ocean": total_invalid,
+                "locations_affected": affected,
+                "total_ocean_locations": ocean,
+                "max_invalid_at_one_location": worst,
+                "total_time_steps": int(T),
+                "percentage_affected": f"{100.0 * affected / ocean:.2f}%",
+            },
+        )
+    if stats_bounds is not None:
+        _warn_threshold_range(float(smin), float(smax), stats_bounds[0], stats_bounds[1], kw["max_anomaly"])
+    out: Dict[str, Any] = {
+        "dat_anomaly": anom_h.view((T_out,) + space).numpy(),
+        "mask": mask_h.view(space).numpy().view(np.bool_),
+        "thresholds": (thr_h.view(space + (NDOY,)) if layout == "doy_last" else thr_h.view((NDOY,) + space) if layout == "doy_first" else thr_h.view(space)).numpy(),
+        "thresholds_layout": layout,
+        "time": cal.time[keep],
+        "extreme_count": count,
+        "chunks": len(bounds),
+        "h2d_bytes": int(sum((b - a) for a, b in loads) * unit * esz * T),
+    }
+    if want_events:
+        out["extreme_events"] = ev_h.view((T_out,) + space).numpy().view(np.bool_)
     return out
 
 
@@ -808,6 +1059,7 @@ def preprocess_arrays(
     want_events: bool = True,
     want_bits: bool = False,
     gridded: Optional[bool] = None,
+    chunks: Optional[int] = None,
 ) -> Dict[str, Any]:
     """``preprocess_data`` (detect.py:287-841) on arrays: ``x`` is ``(time, lat, lon)`` (gridded)
     or ``(time, ncells)`` (unstructured), numpy or torch, host or device; ``time`` a datetime64
@@ -815,7 +1067,9 @@ def preprocess_arrays(
     ``thresholds`` in the reference's layout and dtype, ``extreme_events`` (T_out, ..space) bool,
     ``time`` (trimmed), ``attrs`` (the Dataset attrs, detect.py:731-783) -- numpy arrays
     (``output="numpy"``), numpy views of cached page-locked buffers that the next call overwrites
-    (``output="pinned"``) or CUDA tensors (``output="torch"``)."""
+    (``output="pinned"``) or CUDA tensors (``output="torch"``).  A HOST field larger than 1 GiB (or
+    any host field when ``chunks`` > 1) is streamed through the GPU in ``chunks`` spatial pieces with
+    copies and kernels overlapped (``_preprocess_host_streamed``); ``chunks=1`` forces one piece."""
     if detrend_orders is None:
         detrend_orders = [1]
     if std_normalise:
@@ -824,6 +1078,36 @@ def preprocess_arrays(
     validate_reference_period_method(reference_period, method_anomaly)
     validate_anomaly_method(method_anomaly)
     cal = build_calendar(time)
+    on_host = not (isinstance(x, torch.Tensor) and x.is_cuda)
+    if on_host and output in ("numpy", "pinned") and not want_bits:
+        xh = x if isinstance(x, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(x))
+        nbytes = xh.numel() * 4
+        n_chunks = chunks if chunks is not None else (1 if nbytes < (1 << 30) else int(min(16, max(2, round(nbytes / 6e9)))))
+        if n_chunks > 1:
+            if xh.dtype != torch.float32 or not xh.is_contiguous():
+                xh = xh.to(torch.float32).contiguous()  # da.astype(np.float32), detect.py:600
+            if xh.shape[0] != cal.T:
+                raise ValueError("time axis length does not match the data")
+            g = (xh.dim() == 3) if gridded is None else gridded
+            resolve_extreme_config(
+                method_extreme, threshold_percentile, window_days_hobday, window_spatial_hobday, method_percentile,
+                precision, max_anomaly, g,
+            )  # fmt: skip
+            kw = dict(
+                method_anomaly=method_anomaly, method_extreme=method_extreme, threshold_percentile=threshold_percentile,
+                window_year_baseline=window_year_baseline, smooth_days_baseline=smooth_days_baseline,
+                window_days_hobday=window_days_hobday, window_spatial_hobday=window_spatial_hobday,
+                detrend_orders=detrend_orders, force_zero_mean=force_zero_mean, reference_period=reference_period,
+                method_percentile=method_percentile, precision=precision, max_anomaly=max_anomaly,
+            )  # fmt: skip
+            out = _preprocess_host_streamed(xh, cal, g, dev, n_chunks, output, want_events, kw)
+            out["attrs"] = _dataset_attrs(
+                method_anomaly, method_extreme, threshold_percentile, std_normalise, detrend_orders, window_year_baseline,
+                smooth_days_baseline, window_days_hobday, window_spatial_hobday, reference_period, force_zero_mean,
+                method_percentile, precision, max_anomaly,
+            )  # fmt: skip
+            logger.info("Preprocessing completed successfully - %d extreme events identified", out["extreme_count"])
+            return out
     owns_input = not (isinstance(x, torch.Tensor) and x.is_cuda and x.dtype == torch.float32)
     x_dev, space = _to_device_field(x, dev)
     if gridded is None:
@@ -846,27 +1130,11 @@ def preprocess_arrays(
         n_years=int(np.unique(cal.year[keep]).size),
     )  # fmt: skip
 
-    attrs: Dict[str, Any] = {
-        "method_anomaly": method_anomaly,
-        "method_extreme": method_extreme,
-        "threshold_percentile": threshold_percentile,
-        "preprocessing_steps": get_preprocessing_steps(
-            method_anomaly, method_extreme, std_normalise, list(detrend_orders), window_year_baseline,
-            smooth_days_baseline, window_days_hobday, window_spatial_hobday, reference_period,
-        ),
-    }  # fmt: skip
-    if method_anomaly == "shifting_baseline":
-        attrs.update({"window_year_baseline": window_year_baseline, "smooth_days_baseline": smooth_days_baseline})
-    elif method_anomaly == "fixed_baseline":
-        if reference_period is not None:
-            attrs["reference_period"] = list(reference_period)
-    elif method_anomaly == "detrend_fixed_baseline":
-        attrs.update({"detrend_orders": list(detrend_orders), "force_zero_mean": force_zero_mean})
-        if reference_period is not None:
-            attrs["reference_period"] = list(reference_period)
-    if method_extreme == "hobday_extreme":
-        attrs["window_days_hobday"] = window_days_hobday
-    attrs.update({"method_percentile": method_percentile, "precision": precision, "max_anomaly": max_anomaly})
+    attrs = _dataset_attrs(
+        method_anomaly, method_extreme, threshold_percentile, std_normalise, detrend_orders, window_year_baseline,
+        smooth_days_baseline, window_days_hobday, window_spatial_hobday, reference_period, force_zero_mean,
+        method_percentile, precision, max_anomaly,
+    )  # fmt: skip
 
     T_out = anom.shape[0]
     out: Dict[str, Any] = {

@@ -480,3 +480,49 @@ def test_digitize_ffff_matches_numpy_digitize():
     ref = mo.hobday_thresholds_approx(a.reshape(len(time), -1), doy, 0.9, 5, 3, (6, 33))
     res = mb.identify_extremes_arrays(torch.from_numpy(a.reshape(len(time), -1)).cuda(), doy, (6, 33), "hobday_extreme", 90, 5, 3)
     _ulp_equal(res["thresholds"].cpu().numpy().reshape(-1, 366), ref)
+
+
+# ---------------------------------------------------------------- streamed host path == one-piece path
+@pytest.mark.parametrize(
+    "kw,unstructured",
+    [
+        (dict(window_year_baseline=4, smooth_days_baseline=9, window_days_hobday=5), False),
+        (dict(method_anomaly="detrend_fixed_baseline", method_extreme="global_extreme", detrend_orders=[1, 2]), False),
+        (dict(method_anomaly="fixed_baseline", method_percentile="exact", window_days_hobday=7), True),
+        (dict(window_year_baseline=3, smooth_days_baseline=5, method_extreme="global_extreme", method_percentile="exact"), True),
+    ],
+)
+def test_streamed_host_path_matches_one_piece(kw, unstructured):
+    """Chunked, copy/compute-overlapped processing of a host array (latitude bands with the pooling
+    halo re-loaded, or cell ranges) must reproduce the one-piece result bit for bit."""
+    mb = _cuda()
+    x, time = _field(T1="2000-01-01", ny=23, nx=36, seed=4)
+    if unstructured:
+        x = x.reshape(len(time), -1)[:, : 23 * 36 // 32 * 32 + 5]
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        one = mb.preprocess_arrays(x, time, chunks=1, **kw)
+        many = mb.preprocess_arrays(x, time, chunks=4, output="pinned", **kw)
+    assert many["chunks"] >= 2 and "chunks" not in one
+    for k in ("dat_anomaly", "thresholds"):
+        _ulp_equal(np.asarray(many[k]), np.asarray(one[k]))
+    np.testing.assert_array_equal(many["mask"], one["mask"])
+    np.testing.assert_array_equal(many["extreme_events"], one["extreme_events"])
+    assert many["extreme_count"] == one["extreme_count"] == int(one["extreme_events"].sum())
+    assert many["thresholds_layout"] == one["thresholds_layout"] and many["attrs"] == one["attrs"]
+    np.testing.assert_array_equal(many["time"], one["time"])
+
+
+def test_streamed_host_path_validation_is_global():
+    """A band that is all land must not raise; invalid values in an ocean cell of any band must."""
+    mb = _cuda()
+    x, time = _field(T1="1998-01-01", ny=12, nx=36, seed=6)
+    x[:, :4, :] = np.nan  # the first chunk is entirely land
+    kw = dict(window_year_baseline=3, smooth_days_baseline=5, window_days_hobday=5)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        out = mb.preprocess_arrays(x, time, chunks=3, **kw)
+    assert not out["mask"][:4].any() and out["mask"][4:].any()
+    x[700, 9, 5] = np.nan
+    with pytest.raises(mb.DataValidationError, match="invalid values in 1 ocean locations"):
+        mb.preprocess_arrays(x, time, chunks=3, **kw)
