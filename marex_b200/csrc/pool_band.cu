@@ -221,17 +221,19 @@ __global__ void __launch_bounds__(OY * 32) hobday_band_kernel(const BandParams p
     const int bl0 = s_cnt[(par * 2 + 0) * 2], bl1 = s_cnt[(par * 2 + 0) * 2 + 1];
     const int be0 = s_cnt[(par * 2 + 1) * 2], be1 = s_cnt[(par * 2 + 1) * 2 + 1];
     const int nl = bl1 - bl0, ne = be1 - be0;
-    uint16_t* evp = ev;
-    uint16_t* const ev_full = ev + (BAND_LCAP - 15) * CS;  // a batch of 13 (+ 1 scratch slot) still fits below this
-    auto flush = [&]() {
-      for (uint16_t* q = ev; q < evp; q += CS) { const int e = *q; band_apply(e >> 1, 1 - 2 * (e & 1)); }
-      evp = ev;
+    // Event list: ev[n_ev] with n_ev a multiple of CS (32-bit index arithmetic, one slot per sample that
+    // matters).  Entering and leaving samples are flushed separately, so a list carries one sign.
+    int n_ev = 0;
+    constexpr int EV_FULL = (BAND_LCAP - 15) * CS;  // a batch of 13 (+ 1 scratch slot) still fits below this
+    auto flush = [&](int sign) {
+      for (int j = 0; j < n_ev; j += CS) band_apply((int)ev[j], sign);
+      n_ev = 0;
     };
-    // a sample that matters (inside / above the band, or invalid) goes to the list; sign01: 0 enters, 1 leaves
-    auto scan = [&](int v, int sign01) {  // branch-free: the slot is overwritten unless the sample matters
+    // branch-free scan: the slot is overwritten unless the sample matters (inside / above the band, or invalid)
+    auto scan = [&](int v) {
       const int s = v - Blo;
-      *evp = (uint16_t)(s * 2 + sign01);
-      evp += (s >= 0) ? CS : 0;
+      ev[n_ev] = (uint16_t)s;
+      n_ev += (s >= 0) ? CS : 0;
     };
     bool skip_leaving = false;
     if (dead) {  // window without a valid sample: stays so unless a valid sample enters
@@ -246,10 +248,11 @@ __global__ void __launch_bounds__(OY * 32) hobday_band_kernel(const BandParams p
     // entering samples (prefetched)
 #pragma unroll
     for (int u = 0; u < BAND_PRE; ++u) {
-      if (u == 13 && evp > ev_full) flush();
-      if (pre[u] >= 0) scan(pre[u], 0);
+      if (u == 13 && n_ev > EV_FULL) flush(+1);
+      if (u < ne) scan(pre[u]);  // warp-uniform guard
     }
-    for (int b = be0 + BAND_PRE; b < be1; ++b) { if (evp > ev_full) flush(); scan(load_row(b), 0); }
+    for (int b = be0 + BAND_PRE; b < be1; ++b) { if (n_ev > EV_FULL) flush(+1); scan(load_row(b)); }
+    flush(+1);
     NT += ne;
     if (!skip_leaving) {
       NT -= nl;
@@ -258,14 +261,14 @@ __global__ void __launch_bounds__(OY * 32) hobday_band_kernel(const BandParams p
       for (int u0 = 0; u0 < nlc; u0 += BATCH) {
         int vl[BATCH];
 #pragma unroll
-        for (int u = 0; u < BATCH; ++u) vl[u] = (u0 + u < nlc) ? load_at(ol[u0 + u]) : -1;
-        if (evp > ev_full) flush();
+        for (int u = 0; u < BATCH; ++u) vl[u] = (u0 + u < nlc) ? load_at(ol[u0 + u]) : 0;
+        if (n_ev > EV_FULL) flush(-1);
 #pragma unroll
-        for (int u = 0; u < BATCH; ++u) if (vl[u] >= 0) scan(vl[u], 1);
+        for (int u = 0; u < BATCH; ++u) if (u0 + u < nlc) scan(vl[u]);
       }
-      for (int a = bl0 + BAND_CAP; a < bl1; ++a) { if (evp > ev_full) flush(); scan(load_row(a), 1); }
+      for (int a = bl0 + BAND_CAP; a < bl1; ++a) { if (n_ev > EV_FULL) flush(-1); scan(load_row(a)); }
+      flush(-1);
     }
-    flush();
     NTr[tid] = (uint16_t)NT;
     TBr[tid] = (uint16_t)TB;
   };
@@ -393,9 +396,9 @@ __global__ void __launch_bounds__(256) digitize_ffff_kernel(const float* __restr
   __syncthreads();
   const float e1 = s_edges[1];
   const float inv_step = (n_edges > 2) ? 1.f / (s_edges[2] - s_edges[1]) : 1.f;
-  const int64_t c = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * 2;  // two gridpoints per thread
+  const int64_t c = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * 4;  // four gridpoints per thread
   if (c >= N) return;
-  const bool pair = c + 1 < N && ((pitch | bins_pitch) & 1) == 0;
+  const bool quad = c + 3 < N && (pitch & 3) == 0 && (bins_pitch & 3) == 0;
   const int64_t t0 = (int64_t)blockIdx.y * rows_per_block, t1 = min(T, t0 + rows_per_block);
   auto dig = [&](float v) -> uint32_t {
     if (v != v) return (uint32_t)BAND_INV;
@@ -406,17 +409,30 @@ __global__ void __launch_bounds__(256) digitize_ffff_kernel(const float* __restr
     while (i < n_edges - 1 && v >= s_edges[i + 1]) ++i;
     return i >= n_edges - 1 ? (uint32_t)BAND_INV : (uint32_t)i;
   };
-  if (pair) {
-#pragma unroll 4
-    for (int64_t t = t0; t < t1; ++t) {
-      const float2 v = __ldcs(reinterpret_cast<const float2*>(a + t * pitch + c));
-      *reinterpret_cast<uint32_t*>(bins + t * bins_pitch + c) = dig(v.x) | (dig(v.y) << 16);
+  if (quad) {
+    int64_t t = t0;
+    for (; t + 4 <= t1; t += 4) {  // four independent 16-byte loads in flight per thread
+      float4 v[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) v[u] = __ldcs(reinterpret_cast<const float4*>(a + (t + u) * pitch + c));
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        uint2 o;
+        o.x = dig(v[u].x) | (dig(v[u].y) << 16);
+        o.y = dig(v[u].z) | (dig(v[u].w) << 16);
+        *reinterpret_cast<uint2*>(bins + (t + u) * bins_pitch + c) = o;
+      }
+    }
+    for (; t < t1; ++t) {
+      const float4 v = __ldcs(reinterpret_cast<const float4*>(a + t * pitch + c));
+      uint2 o;
+      o.x = dig(v.x) | (dig(v.y) << 16);
+      o.y = dig(v.z) | (dig(v.w) << 16);
+      *reinterpret_cast<uint2*>(bins + t * bins_pitch + c) = o;
     }
   } else {
-    for (int64_t t = t0; t < t1; ++t) {
-      bins[t * bins_pitch + c] = (uint16_t)dig(a[t * pitch + c]);
-      if (c + 1 < N) bins[t * bins_pitch + c + 1] = (uint16_t)dig(a[t * pitch + c + 1]);
-    }
+    for (int64_t t = t0; t < t1; ++t)
+      for (int k = 0; k < 4 && c + k < N; ++k) bins[t * bins_pitch + c + k] = (uint16_t)dig(a[t * pitch + c + k]);
   }
 }
 
@@ -438,7 +454,7 @@ using namespace marex;
 
 extern "C" int64_t marex_hobday_pooled_workspace_bytes(int64_t T, int64_t ny, int64_t nx) {
   // bins (uint16 [T][ny*nx], rows padded to an even count) + fail list
-  const int64_t N = ny * nx, pitch = (N + 1) & ~1LL;
+  const int64_t N = ny * nx, pitch = (N + 3) & ~3LL;
   const int64_t tiles = ((ny + 0) / 1 + 1) * ((nx + 27) / 28 + 1);  // generous upper bound on band tiles
   return T * pitch * 2 + 2 * (2 * tiles + 8) * 4 + 512;
 }
@@ -458,14 +474,14 @@ extern "C" int marex_hobday_thresholds_pooled_f32(const float* anom, int64_t T, 
   MAREX_REQUIRE(nx >= 32 && ny <= 65535 * 4, "grid too small or too tall for the band tiles");
   MAREX_REQUIRE(workspace_bytes >= marex_hobday_pooled_workspace_bytes(T, ny, nx), "workspace too small");
   cudaStream_t st = (cudaStream_t)stream;
-  const int64_t N = ny * nx, bpitch = (N + 1) & ~1LL;
+  const int64_t N = ny * nx, bpitch = (N + 3) & ~3LL;
   uint16_t* bins = reinterpret_cast<uint16_t*>(workspace);
   int32_t* fail_list = reinterpret_cast<int32_t*>(reinterpret_cast<unsigned char*>(workspace) +
                                                   (((size_t)T * bpitch * 2 + 255) & ~(size_t)255));
   {  // digitize (detect.py:2622-2631)
     const int threads = 256;
-    const int64_t bx = ((N + 1) / 2 + threads - 1) / threads;
-    int64_t by = (8LL * sm_count() + bx - 1) / bx;
+    const int64_t bx = ((N + 3) / 4 + threads - 1) / threads;
+    int64_t by = (16LL * sm_count() + bx - 1) / bx;
     by = by < 1 ? 1 : (by > T ? T : by);
     if (by > 65535) by = 65535;
     const int rows_per_block = (int)((T + by - 1) / by);
