@@ -36,14 +36,20 @@ WORKLOADS = {
     "0.25deg_40yr_shifting_hobday_approx": (720, 1440, "1982-01-01", "2022-01-01", dict()),
     "0.25deg_40yr_shifting_hobday_exact": (720, 1440, "1982-01-01", "2022-01-01", dict(method_percentile="exact")),
     "1deg_40yr_shifting_hobday_approx": (180, 360, "1982-01-01", "2022-01-01", dict()),
+    "1deg_40yr_shifting_hobday_exact": (180, 360, "1982-01-01", "2022-01-01", dict(method_percentile="exact")),
     "smoke_0.5deg_20yr": (90, 180, "2000-01-01", "2020-01-01", dict(window_year_baseline=5)),
+    # BASELINE.json configs[3] per GPU: 8 Mi-cell unstructured mesh / 8 GPUs, 30 yr, detrend_fixed + global p95
+    "icon_1Mi_cells_30yr_detrend_global": (1, 1 << 20, "1991-01-01", "2021-01-01",
+                                           dict(method_anomaly="detrend_fixed_baseline", method_extreme="global_extreme")),
+    # BASELINE.json configs[4] per GPU: 0.1 deg (3600 x 1800) / 8 GPUs = 225 rows, 30 yr
+    "0.1deg_30yr_shifting_hobday_approx_per_gpu": (225, 3600, "1991-01-01", "2021-01-01", dict()),
 }
 PUBLISHED_PER_CORE = 3.1e4  # gridpoint-days/s/core, docs/modules/detect.rst:729-732
 
 
-def algorithmic_bytes_per_cell(T, T_out):
+def algorithmic_bytes_per_cell(T, T_out, hobday=True):
     """read x once, write dat_anomaly f32 + extreme_events bool + thresholds + mask."""
-    return 4 * T + 4 * T_out + 1 * T_out + 4 * 366 + 1
+    return 4 * T + 4 * T_out + 1 * T_out + (4 * 366 if hobday else 8) + 1
 
 
 # per-stage algorithmic bytes per gridpoint: what one C-ABI call must read + write at minimum
@@ -59,6 +65,14 @@ def kernel_bytes_per_cell(T, T_out):
         "marex_hobday_thresholds_exact_f32": 4 * T_out + 4 * 366,
         "marex_transpose_f32": 2 * 4 * 366,
         "marex_compare_hobday": 4 * T_out + T_out + 4 * 366,
+        "marex_detrend_coef_f64": 4 * T + 16,
+        "marex_detrend_apply_f32": 8 * T + 16,
+        "marex_doy_climatology_f32": 4 * T + 4 * 366,
+        "marex_sub_doy_climatology_f32": 8 * T + 4 * 366,
+        "marex_global_threshold_hist_f64": 4 * T + 8,
+        "marex_global_threshold_hist_fast_f64": 4 * T + 8,
+        "marex_global_threshold_exact_f64": 4 * T + 8,
+        "marex_compare_global": 5 * T + 8,
     }
 
 
@@ -258,13 +272,22 @@ def main():
     T = len(time)
     W = kw.get("window_year_baseline", 15)
     cal = marex_b200.detect.build_calendar(time)
-    T_out = int((cal.year >= cal.year_val[0] + W).sum())
+    shifting = kw.get("method_anomaly", "shifting_baseline") == "shifting_baseline"
+    hobday = kw.get("method_extreme", "hobday_extreme") == "hobday_extreme"
+    T_out = int((cal.year >= cal.year_val[0] + W).sum()) if shifting else T
+    unstructured = ny == 1
 
     # this rank's latitude band of the global (ny * world) x nx grid, with its pooling halo
-    halo = sharding.effective_halo("hobday_extreme", kw.get("method_percentile", "approximate"), None, True)
+    # (unstructured: a contiguous range of cells, no halo)
+    halo = 0 if unstructured else sharding.effective_halo(
+        kw.get("method_extreme", "hobday_extreme"), kw.get("method_percentile", "approximate"), None, True)
     ny_g = ny * world
-    own_lo, own_hi, lo, hi = sharding.lat_band(ny_g, world, rank, halo)
-    x = synthetic.synth_sst(time, (ny_g, nx), rows=(lo, hi), seed=2, device=dev)
+    if unstructured:
+        own_lo, own_hi, lo, hi = 0, 1, 0, 1
+        x = synthetic.synth_sst(time, (world, nx), rows=(rank, rank + 1), seed=2, land_fraction=0.0, device=dev).reshape(T, nx)
+    else:
+        own_lo, own_hi, lo, hi = sharding.lat_band(ny_g, world, rank, halo)
+        x = synthetic.synth_sst(time, (ny_g, nx), rows=(lo, hi), seed=2, device=dev)
     torch.cuda.synchronize()
     n_own = (own_hi - own_lo) * nx
 
@@ -273,10 +296,10 @@ def main():
 
     def step():
         res = marex_b200.preprocess_arrays(x, time, output="torch", **kw)
-        out = sharding.crop_owned(res, (own_lo, own_hi), (lo, hi))
+        out = res if unstructured else sharding.crop_owned(res, (own_lo, own_hi), (lo, hi))
         if world > 1:
             lay = out["thresholds_layout"]
-            out["thresholds_global"] = sharding.dist_gather(out["thresholds"], 1 if lay == "doy_first" else 0)
+            out["thresholds_global"] = sharding.dist_gather(out["thresholds"], 1 if lay == "doy_first" else 0)  # NCCL
             out["mask_global"] = sharding.dist_gather(out["mask"], 0)
             dist.all_reduce(out["extreme_count"])
         return out
@@ -344,7 +367,7 @@ def main():
         "peak_source": peak_src,
         "ms_per_launch": stage_ms[dom],
     }
-    B = algorithmic_bytes_per_cell(T, T_out)
+    B = algorithmic_bytes_per_cell(T, T_out, hobday)
     pipe_gbs = B * n_own / (ms * 1e-3) / 1e9
     stages = {k: {"ms": v, "GBps": (kb[k] * n_load / (v * 1e-3) / 1e9) if k in kb and v > 0 else None} for k, v in stage_ms.items()}
 
@@ -396,11 +419,14 @@ def main():
         cores = os.cpu_count() or 1
         th, tw = 6, 8
         tiles = []
-        r0 = (x_sample_src.shape[1] // 2) // th * th
+        r0 = 0 if unstructured else (x_sample_src.shape[1] // 2) // th * th
         for i in range(cores * 8):  # ~15-30 s of CPU work on the box's cores
             c0 = (i * 5 * tw) % (nx - tw)
             rr = (r0 + (i // 32) * 3 * th) % (x_sample_src.shape[1] - th)
-            tiles.append(np.ascontiguousarray(x_sample_src[:, rr : rr + th, c0 : c0 + tw].cpu().numpy()))
+            if unstructured:
+                tiles.append(np.ascontiguousarray(x_sample_src[:, (i * 48) % (nx - 48) : (i * 48) % (nx - 48) + 48].cpu().numpy()))
+            else:
+                tiles.append(np.ascontiguousarray(x_sample_src[:, rr : rr + th, c0 : c0 + tw].cpu().numpy()))
         dtc = cpu_oracle_run(tiles, time, kw, cores)
         cells = len(tiles) * th * tw
         cpu = {

@@ -161,6 +161,16 @@ int marex_global_threshold_hist_f64(const float* anom, int64_t T, int64_t N, int
                                     const double* edges, const double* centers, int32_t nb,
                                     double q, double lower_bound, double* thr, double* stats,
                                     void* stream);
+/* Same result, fast path for T <= 65535: thread = gridpoint, two passes (8-bin blocks, then the bins
+ * of the block that holds the rank); gridpoints whose quantile bin is not decided by integer
+ * counts alone (see thresholds.cu) are recomputed in the reference's float64 order.
+ * edges_up[nb + 1] float32: the smallest float32 >= each float64 edge (edges_up[0] = -inf);
+ * e_last_dn: the largest float32 <= edges[nb].  work: device scratch of N + 1 int32. */
+int marex_global_threshold_hist_fast_f64(const float* anom, int64_t T, int64_t N, int64_t pitch,
+                                         const double* edges, const float* edges_up, float e_last_dn,
+                                         const double* centers, int32_t nb, double q,
+                                         double lower_bound, double* thr, double* stats,
+                                         int32_t* work, void* stream);
 /* Global thresholds, exact: np.nanquantile(a, q) with a float64 q ('linear'), float64 result
  * (xarray .quantile, detect.py:2899). */
 int marex_global_threshold_exact_f64(const float* anom, int64_t T, int64_t N, int64_t pitch,

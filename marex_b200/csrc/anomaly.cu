@@ -191,6 +191,52 @@ __global__ void __launch_bounds__(256) sub_doy_climatology_kernel(
   if (nonfinite && bad) atomicAdd(&nonfinite[c], bad);
 }
 
+// Same, four adjacent gridpoints per thread (16-byte loads and stores, four rows in flight).
+__global__ void __launch_bounds__(128) sub_doy_climatology4_kernel(
+    const float* x, int64_t T, int64_t N, int64_t pitch, const int16_t* __restrict__ doy,
+    const float* __restrict__ shift, const float* __restrict__ clim, float* anom, int64_t anom_pitch,
+    uint8_t* __restrict__ mask0, int32_t* __restrict__ nonfinite, int rows_per_block) {
+  const int64_t c = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * 4;
+  if (c >= N) return;
+  float4 sh = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (shift) sh = *reinterpret_cast<const float4*>(shift + c);
+  const int64_t t0 = (int64_t)blockIdx.y * rows_per_block;
+  const int64_t t1 = min(T, t0 + rows_per_block);
+  int bad[4] = {0, 0, 0, 0};
+  for (int64_t tb = t0; tb < t1; tb += 4) {
+    float4 v[4], cl[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      if (tb + u < t1) {
+        v[u] = __ldcs(reinterpret_cast<const float4*>(x + (tb + u) * pitch + c));
+        cl[u] = __ldg(reinterpret_cast<const float4*>(clim + (int64_t)(__ldg(&doy[tb + u]) - 1) * N + c));
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      if (tb + u >= t1) continue;
+      float f[4] = {v[u].x, v[u].y, v[u].z, v[u].w};
+      const float s4[4] = {sh.x, sh.y, sh.z, sh.w};
+      const float c4[4] = {cl[u].x, cl[u].y, cl[u].z, cl[u].w};
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        if (!is_finite_f(f[j])) ++bad[j];
+        if (shift) f[j] = f[j] - s4[j];
+      }
+      if (tb + u == 0 && mask0) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) mask0[c + j] = is_finite_f(f[j]) ? 1 : 0;
+      }
+      __stcs(reinterpret_cast<float4*>(anom + (tb + u) * anom_pitch + c),
+             make_float4(f[0] - c4[0], f[1] - c4[1], f[2] - c4[2], f[3] - c4[3]));
+    }
+  }
+  if (nonfinite) {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) if (bad[j]) atomicAdd(&nonfinite[c + j], bad[j]);
+  }
+}
+
 // =======================================================================================
 // (a'') polynomial detrend -- reference: detect.py:2061-2296 (remove_harmonics=False)
 // =======================================================================================
@@ -218,6 +264,51 @@ __global__ void __launch_bounds__(256) detrend_coef_kernel(
 #pragma unroll
   for (int k = 0; k < K; ++k) coef[(int64_t)k * N + c] = acc[k];
   if (nonfinite) nonfinite[c] = bad;
+}
+
+// Same, four adjacent gridpoints per thread (16-byte loads, four rows in flight); N % 4 == 0.
+template <int K>
+__global__ void __launch_bounds__(128) detrend_coef4_kernel(
+    const float* __restrict__ x, int64_t T, int64_t N, int64_t pitch, const double* __restrict__ P,
+    double* __restrict__ coef, uint8_t* __restrict__ mask0, int32_t* __restrict__ nonfinite) {
+  const int64_t c = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * 4;
+  if (c >= N) return;
+  double acc[K][4];
+#pragma unroll
+  for (int k = 0; k < K; ++k)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[k][j] = 0.0;
+  int bad[4] = {0, 0, 0, 0};
+  for (int64_t t0 = 0; t0 < T; t0 += 4) {
+    float4 v[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u)
+      if (t0 + u < T) v[u] = __ldcs(reinterpret_cast<const float4*>(x + (t0 + u) * pitch + c));
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      if (t0 + u >= T) continue;
+      const float f[4] = {v[u].x, v[u].y, v[u].z, v[u].w};
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        if (!is_finite_f(f[j])) ++bad[j];
+        const double dv = (double)f[j];
+#pragma unroll
+        for (int k = 0; k < K; ++k) acc[k][j] = fma(__ldg(&P[(t0 + u) * K + k]), dv, acc[k][j]);
+      }
+      if (t0 + u == 0 && mask0) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) mask0[c + j] = is_finite_f(f[j]) ? 1 : 0;
+      }
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < K; ++k)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) coef[(int64_t)k * N + c + j] = acc[k][j];
+  if (nonfinite) {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) nonfinite[c + j] = bad[j];
+  }
 }
 
 // xd[t, c] = x[t, c] - f32(sum_k M[k, t] * coef[k, c]);  mean[c] = f32(nanmean_t xd).
@@ -252,6 +343,57 @@ __global__ void __launch_bounds__(256) detrend_apply_kernel(
     else if (nf) m = nonfinite_result(nf);
     else m = (float)(sum / (double)cnt);
     mean[c] = m;
+  }
+}
+
+// Same, four adjacent gridpoints per thread; N % 4 == 0.
+template <int K>
+__global__ void __launch_bounds__(128) detrend_apply4_kernel(
+    const float* x, int64_t T, int64_t N, int64_t pitch, const double* __restrict__ M,
+    const double* __restrict__ coef, float* xd, int64_t xd_pitch, float* __restrict__ mean) {
+  const int64_t c = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * 4;
+  if (c >= N) return;
+  double cf[K][4];
+#pragma unroll
+  for (int k = 0; k < K; ++k)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) cf[k][j] = coef[(int64_t)k * N + c + j];
+  double sum[4] = {0.0, 0.0, 0.0, 0.0};
+  int cnt[4] = {0, 0, 0, 0};
+  uint32_t nf[4] = {0u, 0u, 0u, 0u};
+  for (int64_t t0 = 0; t0 < T; t0 += 4) {
+    float4 v[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u)
+      if (t0 + u < T) v[u] = __ldcs(reinterpret_cast<const float4*>(x + (t0 + u) * pitch + c));
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      if (t0 + u >= T) continue;
+      const float f[4] = {v[u].x, v[u].y, v[u].z, v[u].w};
+      float r[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        double fit = 0.0;
+#pragma unroll
+        for (int k = 0; k < K; ++k) fit = fma(__ldg(&M[(int64_t)k * T + t0 + u]), cf[k][j], fit);
+        r[j] = f[j] - (float)fit;
+        if (r[j] == r[j]) {
+          ++cnt[j];
+          if (is_finite_f(r[j])) sum[j] += (double)r[j]; else nf[j] |= nonfinite_code(r[j]);
+        }
+      }
+      __stcs(reinterpret_cast<float4*>(xd + (t0 + u) * xd_pitch + c), make_float4(r[0], r[1], r[2], r[3]));
+    }
+  }
+  if (mean) {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      float m;
+      if (cnt[j] == 0) m = CUDART_NAN_F;
+      else if (nf[j]) m = nonfinite_result(nf[j]);
+      else m = (float)(sum[j] / (double)cnt[j]);
+      mean[c + j] = m;
+    }
   }
 }
 
@@ -328,6 +470,21 @@ extern "C" int marex_sub_doy_climatology_f32(const float* x, int64_t T, int64_t 
   cudaStream_t st = (cudaStream_t)stream;
   if (nonfinite) MAREX_CUDA(cudaMemsetAsync(nonfinite, 0, sizeof(int32_t) * N, st));
   const int threads = 128;
+  if ((N % 4) == 0 && (pitch % 4) == 0 && (anom_pitch % 4) == 0 && (reinterpret_cast<uintptr_t>(x) % 16) == 0 &&
+      (reinterpret_cast<uintptr_t>(anom) % 16) == 0 && (reinterpret_cast<uintptr_t>(clim) % 16) == 0 &&
+      (!shift || (reinterpret_cast<uintptr_t>(shift) % 16) == 0)) {
+    const int64_t bx4 = (N / 4 + threads - 1) / threads;
+    int64_t by4 = (16LL * sm_count() + bx4 - 1) / bx4;
+    by4 = by4 < 1 ? 1 : (by4 > T ? T : by4);
+    if (by4 > 65535) by4 = 65535;
+    int rpb = (int)((T + by4 - 1) / by4);
+    rpb = (rpb + 3) & ~3;
+    by4 = (T + rpb - 1) / rpb;
+    sub_doy_climatology4_kernel<<<dim3((unsigned)bx4, (unsigned)by4), threads, 0, st>>>(
+        x, T, N, pitch, doy, shift, clim, anom, anom_pitch, mask0, nonfinite, rpb);
+    MAREX_LAUNCH_CHECK("sub_doy_climatology4_kernel");
+    return MAREX_OK;
+  }
   const int64_t bx = (N + threads - 1) / threads;
   int64_t by = (8LL * sm_count() + bx - 1) / bx;
   if (by < 1) by = 1;
@@ -345,6 +502,12 @@ template <int K>
 static int launch_detrend_coef(const float* x, int64_t T, int64_t N, int64_t pitch, const double* P, double* coef,
                                uint8_t* mask0, int32_t* nonfinite, cudaStream_t st) {
   const int threads = 128;
+  if (K <= 4 && (N % 4) == 0 && (pitch % 4) == 0 && (reinterpret_cast<uintptr_t>(x) % 16) == 0) {
+    detrend_coef4_kernel<K><<<(unsigned)((N / 4 + threads - 1) / threads), threads, 0, st>>>(x, T, N, pitch, P, coef,
+                                                                                            mask0, nonfinite);
+    MAREX_LAUNCH_CHECK("detrend_coef4_kernel");
+    return MAREX_OK;
+  }
   detrend_coef_kernel<K><<<(unsigned)((N + threads - 1) / threads), threads, 0, st>>>(x, T, N, pitch, P, coef, mask0,
                                                                                       nonfinite);
   MAREX_LAUNCH_CHECK("detrend_coef_kernel");
@@ -354,6 +517,13 @@ template <int K>
 static int launch_detrend_apply(const float* x, int64_t T, int64_t N, int64_t pitch, const double* M,
                                 const double* coef, float* xd, int64_t xd_pitch, float* mean, cudaStream_t st) {
   const int threads = 128;
+  if (K <= 4 && (N % 4) == 0 && (pitch % 4) == 0 && (xd_pitch % 4) == 0 && (reinterpret_cast<uintptr_t>(x) % 16) == 0 &&
+      (reinterpret_cast<uintptr_t>(xd) % 16) == 0) {
+    detrend_apply4_kernel<K><<<(unsigned)((N / 4 + threads - 1) / threads), threads, 0, st>>>(x, T, N, pitch, M, coef,
+                                                                                             xd, xd_pitch, mean);
+    MAREX_LAUNCH_CHECK("detrend_apply4_kernel");
+    return MAREX_OK;
+  }
   detrend_apply_kernel<K><<<(unsigned)((N + threads - 1) / threads), threads, 0, st>>>(x, T, N, pitch, M, coef, xd,
                                                                                        xd_pitch, mean);
   MAREX_LAUNCH_CHECK("detrend_apply_kernel");

@@ -94,6 +94,57 @@ __global__ void __launch_bounds__(128) compare_doy_kernel(const float* __restric
   }
 }
 
+// Global compare, four gridpoints per thread.  a >= thr with a float32 and thr float64 is decided
+// exactly by a >= (smallest float32 >= thr), so the row loop stays in float32 (detect.py:2915).
+__global__ void __launch_bounds__(128) compare_global4_kernel(const float* __restrict__ anom, int64_t T, int64_t N,
+                                                              int64_t pitch, const double* __restrict__ thr,
+                                                              uint8_t* __restrict__ events, int64_t events_pitch,
+                                                              uint32_t* __restrict__ bits, int64_t bits_pitch,
+                                                              unsigned long long* __restrict__ count,
+                                                              int rows_per_block) {
+  const int64_t c = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * 4;
+  const bool live = c < N;
+  const int64_t cc = live ? c : 0;
+  const int lane = threadIdx.x & 31;
+  float th[4];
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const double t64 = thr[cc + k];
+    float f = (float)t64;  // round to nearest; NaN stays NaN (compares false)
+    if ((double)f < t64) f = nextafterf(f, CUDART_INF_F);
+    th[k] = f;
+  }
+  const int64_t t0 = (int64_t)blockIdx.y * rows_per_block, t1 = min(T, t0 + rows_per_block);
+  unsigned int local = 0;
+  for (int64_t tb = t0; tb < t1; tb += 4) {
+    float4 a[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u)
+      if (tb + u < t1) a[u] = __ldcs(reinterpret_cast<const float4*>(anom + (tb + u) * pitch + cc));
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      if (tb + u >= t1) continue;
+      const unsigned e0 = (a[u].x >= th[0]) && live, e1 = (a[u].y >= th[1]) && live, e2 = (a[u].z >= th[2]) && live,
+                     e3 = (a[u].w >= th[3]) && live;
+      const unsigned nib = e0 | (e1 << 1) | (e2 << 2) | (e3 << 3);
+      local += __popc(nib);
+      if (events && live)
+        __stcs(reinterpret_cast<unsigned int*>(events + (tb + u) * events_pitch + c), e0 | (e1 << 8) | (e2 << 16) | (e3 << 24));
+      if (bits) {
+        unsigned w = nib << ((lane & 7) * 4);
+        w |= __shfl_xor_sync(0xffffffffu, w, 1);
+        w |= __shfl_xor_sync(0xffffffffu, w, 2);
+        w |= __shfl_xor_sync(0xffffffffu, w, 4);
+        if ((lane & 7) == 0 && live) bits[(tb + u) * bits_pitch + (c >> 5)] = w;
+      }
+    }
+  }
+  if (count) {
+    for (int o = 16; o; o >>= 1) local += __shfl_xor_sync(0xffffffffu, local, o);
+    if (lane == 0 && local) atomicAdd(count, (unsigned long long)local);
+  }
+}
+
 __global__ void transpose_kernel(const float* __restrict__ in, int64_t rows, int64_t cols, float* __restrict__ out) {
   __shared__ float tile[32][33];
   const int64_t c0 = (int64_t)blockIdx.x * 32, r0 = (int64_t)blockIdx.y * 32;
@@ -204,6 +255,23 @@ extern "C" int marex_compare_global(const float* anom, int64_t T, int64_t N, int
   MAREX_REQUIRE(T > 0 && N > 0 && pitch >= N, "bad shape");
   MAREX_REQUIRE(!events || events_pitch >= N, "events_pitch < N");
   MAREX_REQUIRE(!bits || bits_pitch >= (N + 31) / 32, "bits_pitch < ceil(N/32)");
+  const bool aligned = (N % 4) == 0 && (pitch % 4) == 0 && (!events || (events_pitch % 4) == 0) &&
+                       (reinterpret_cast<uintptr_t>(anom) % 16) == 0 &&
+                       (!events || (reinterpret_cast<uintptr_t>(events) % 4) == 0) && (N % 32 == 0 || !bits);
+  if (aligned) {
+    const int threads = 128;
+    const int64_t bx = (N / 4 + threads - 1) / threads;
+    int64_t by = (16LL * sm_count() + bx - 1) / bx;
+    by = by < 1 ? 1 : (by > T ? T : by);
+    if (by > 65535) by = 65535;
+    int rows_per_block = (int)((T + by - 1) / by);
+    rows_per_block = (rows_per_block + 3) & ~3;
+    by = (T + rows_per_block - 1) / rows_per_block;
+    compare_global4_kernel<<<dim3((unsigned)bx, (unsigned)by), threads, 0, (cudaStream_t)stream>>>(
+        anom, T, N, pitch, thr, events, events_pitch, bits, bits_pitch, count, rows_per_block);
+    MAREX_LAUNCH_CHECK("compare_global4_kernel");
+    return MAREX_OK;
+  }
   return launch_compare<true>(anom, T, N, pitch, nullptr, thr, 0, events, events_pitch, bits, bits_pitch, count,
                               (cudaStream_t)stream);
 }

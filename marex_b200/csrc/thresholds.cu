@@ -611,16 +611,21 @@ __global__ void __launch_bounds__(32) global_hist_kernel(const float* __restrict
                                                          int64_t pitch, const double* __restrict__ edges,
                                                          const double* __restrict__ centers, int nb, double q,
                                                          double lower_bound, double* __restrict__ thr,
-                                                         double* __restrict__ stats) {
+                                                         double* __restrict__ stats,
+                                                         const int32_t* __restrict__ cell_list) {
   extern __shared__ unsigned char smem_raw[];
   CT* hist = reinterpret_cast<CT*>(smem_raw);                         // [nb][32]
   double* s_edges = reinterpret_cast<double*>(smem_raw + (((size_t)nb * 32 * sizeof(CT) + 15) & ~(size_t)15));  // [nb+1]
   const int lane = threadIdx.x;
-  const int64_t c = (int64_t)blockIdx.x * 32 + lane;
-  const bool live = c < N;
-  const int64_t cc = live ? c : N - 1;
-  for (int b = 0; b < nb; ++b) hist[b * 32 + lane] = 0;
+  // all gridpoints, or (list mode) the gridpoints cell_list[1 .. 1 + cell_list[0]) the fast kernel deferred
+  const int64_t n_cells = cell_list ? (int64_t)__ldg(&cell_list[0]) : N;
   for (int i = lane; i <= nb; i += 32) s_edges[i] = edges[i];
+  for (int64_t g = blockIdx.x; g * 32 < n_cells; g += gridDim.x) {
+  const int64_t idx = g * 32 + lane;
+  const bool live = idx < n_cells;
+  const int64_t c = cell_list ? (int64_t)__ldg(&cell_list[1 + (live ? idx : n_cells - 1)]) : (live ? idx : N - 1);
+  const int64_t cc = c;
+  for (int b = 0; b < nb; ++b) hist[b * 32 + lane] = 0;
   __syncwarp();
   const double e1 = s_edges[1];
   const double inv_step = (nb > 1) ? 1.0 / (s_edges[2] - s_edges[1]) : 1.0;
@@ -696,6 +701,99 @@ __global__ void __launch_bounds__(32) global_hist_kernel(const float* __restrict
   if (lane == 0 && stats) {
     if (vmin != CUDART_INF) atomic_min_d(&stats[0], vmin);
     if (vmax != -CUDART_INF) atomic_max_d(&stats[1], vmax);
+  }
+  __syncwarp();
+  }
+}
+
+// ---------------------------------------------------------------------------------------
+// Global approximate threshold, fast path.  For a quantile bin iu in [1, nb - 2] the reference's
+// rule collapses to thr = centers[iu] (SURVEY.md 3.5 b-global), and iu is decided by
+// cdf[b] >= q - 1e-10 with cdf[b] = K_b / (S + 1e-10) up to < 1e-13 of float64 rounding, i.e. by
+// the integer test K_b >= R, R = (q - 1e-10) (S + 1e-10), whenever R is not within 1e-3 of an
+// integer.  So: thread = gridpoint, pass 1 counts 8-bin blocks (uint16 column in shared memory)
+// and finds the block of rank ceil(R), pass 2 counts the 8 bins of that block.  Gridpoints with a
+// near-integer R, iu outside [1, nb - 2] or no in-range sample are appended to `slow_list` and
+// recomputed by global_hist_kernel in the reference's float64 order.  Binning compares float32
+// samples with edges_up[i] = the smallest float32 >= the float64 edge, which is exact.
+// ---------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) global_hist_fast_kernel(const float* __restrict__ anom, int64_t T, int64_t N,
+                                                               int64_t pitch, const float* __restrict__ edges_up,
+                                                               float e_last_dn, const double* __restrict__ centers,
+                                                               int nb, double q, double lower_bound,
+                                                               double* __restrict__ thr, double* __restrict__ stats,
+                                                               int32_t* __restrict__ slow_list) {
+  extern __shared__ unsigned char smem_raw[];
+  const int nblk = (nb + 7) >> 3;
+  uint16_t* cnt = reinterpret_cast<uint16_t*>(smem_raw);  // [nblk][256]
+  float* s_edges = reinterpret_cast<float*>(smem_raw + (size_t)nblk * 256 * 2);  // [nb + 1]
+  for (int i = threadIdx.x; i <= nb; i += 256) s_edges[i] = edges_up[i];
+  uint16_t* my = cnt + threadIdx.x;
+  for (int j = 0; j < nblk; ++j) my[j * 256] = 0;
+  __syncthreads();
+  const float e1 = s_edges[1];
+  const float inv_step = (nb > 1) ? 1.f / (s_edges[2] - s_edges[1]) : 1.f;
+  const int64_t c = (int64_t)blockIdx.x * 256 + threadIdx.x;
+  const bool live = c < N;
+  const float* col = anom + (live ? c : N - 1);
+  auto bin_of = [&](float v) -> int {  // largest i in [0, nb - 1] with edge[i] <= v, given v <= last edge
+    const int i = digitize_f32(v, s_edges, nb + 1, e1, inv_step);
+    return i > nb - 1 ? nb - 1 : i;
+  };
+  bool has_nan = false;
+  int total = 0;
+  for (int64_t t0 = 0; t0 < T; t0 += 8) {
+    float v[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) v[u] = (t0 + u < T) ? ld_stream(col + (t0 + u) * pitch) : CUDART_INF_F;
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      if (v[u] != v[u]) { has_nan = true; continue; }
+      if (v[u] <= e_last_dn) { const int j = bin_of(v[u]) >> 3; my[j * 256] = (uint16_t)(my[j * 256] + 1); ++total; }
+    }
+  }
+  const double R = __dmul_rn(q - 1e-10, (double)total + 1e-10);
+  const double Rc = ceil(R);
+  bool slow = total <= 0 || fabs(R - rint(R)) < 1e-3;
+  const int kneed = (int)Rc;
+  int run = 0, jb = -1;
+  for (int j = 0; j < nblk && jb < 0; ++j) {
+    const int h = my[j * 256];
+    if (run + h >= kneed) jb = j; else run += h;
+  }
+  if (jb < 0) slow = true;
+  double res = CUDART_NAN;
+  if (!slow) {
+    for (int b = 0; b < 8; ++b) my[b * 256] = 0;  // the column is free again: bins of block jb
+    for (int64_t t0 = 0; t0 < T; t0 += 8) {
+      float v[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) v[u] = (t0 + u < T) ? __ldg(col + (t0 + u) * pitch) : CUDART_INF_F;
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        if (v[u] <= e_last_dn) {  // false for NaN
+          const int i = bin_of(v[u]);
+          if ((i >> 3) == jb) my[(i & 7) * 256] = (uint16_t)(my[(i & 7) * 256] + 1);
+        }
+      }
+    }
+    int iu = -1;
+    for (int b = 0; b < 8 && iu < 0; ++b) {
+      const int h = my[b * 256];
+      if (run + h >= kneed) iu = 8 * jb + b; else run += h;
+    }
+    if (iu < 1 || iu > nb - 2) slow = true;
+    else res = centers[iu];
+  }
+  if (slow && !has_nan) {
+    if (live) slow_list[1 + atomicAdd(&slow_list[0], 1)] = (int32_t)c;
+    return;  // the exact kernel writes thr and stats of this gridpoint
+  }
+  if (has_nan) res = CUDART_NAN;  // detect.py:2835-2836
+  if (live) {
+    if (res == res && stats) { atomic_min_d(&stats[0], res); atomic_max_d(&stats[1], res); }
+    if (res < lower_bound) res = lower_bound;
+    thr[c] = res;
   }
 }
 
@@ -904,13 +1002,43 @@ extern "C" int marex_global_threshold_hist_f64(const float* anom, int64_t T, int
     int rc = set_smem(global_hist_kernel<uint32_t>, smem);
     if (rc) return rc;
     global_hist_kernel<uint32_t><<<grid, 32, smem, st>>>(anom, T, N, pitch, edges, centers, nb, q, lower_bound, thr,
-                                                         stats);
+                                                         stats, nullptr);
   } else {
     int rc = set_smem(global_hist_kernel<uint16_t>, smem);
     if (rc) return rc;
     global_hist_kernel<uint16_t><<<grid, 32, smem, st>>>(anom, T, N, pitch, edges, centers, nb, q, lower_bound, thr,
-                                                         stats);
+                                                         stats, nullptr);
   }
+  MAREX_LAUNCH_CHECK("global_hist_kernel");
+  return MAREX_OK;
+}
+
+extern "C" int marex_global_threshold_hist_fast_f64(const float* anom, int64_t T, int64_t N, int64_t pitch,
+                                                    const double* edges, const float* edges_up, float e_last_dn,
+                                                    const double* centers, int32_t nb, double q, double lower_bound,
+                                                    double* thr, double* stats, int32_t* work, void* stream) {
+  MAREX_REQUIRE(anom && edges && edges_up && centers && thr && work, "null pointer");
+  MAREX_REQUIRE(T > 0 && T <= 65535 && N > 0 && pitch >= N, "bad shape (the fast path counts in 16 bits: T <= 65535)");
+  MAREX_REQUIRE(nb >= 16 && nb <= 1600, "nb must be in 16..1600");
+  cudaStream_t st = (cudaStream_t)stream;
+  if (stats) {
+    init_stats_kernel<double><<<1, 1, 0, st>>>(stats);
+    MAREX_LAUNCH_CHECK("init_stats_kernel");
+  }
+  MAREX_CUDA(cudaMemsetAsync(work, 0, sizeof(int32_t), st));
+  const int nblk = (nb + 7) >> 3;
+  const size_t smem_f = (size_t)nblk * 256 * 2 + (size_t)(nb + 1) * sizeof(float);
+  int rc = set_smem(global_hist_fast_kernel, smem_f);
+  if (rc) return rc;
+  global_hist_fast_kernel<<<(unsigned)((N + 255) / 256), 256, smem_f, st>>>(anom, T, N, pitch, edges_up, e_last_dn,
+                                                                            centers, nb, q, lower_bound, thr, stats, work);
+  MAREX_LAUNCH_CHECK("global_hist_fast_kernel");
+  // deferred gridpoints, in the reference's float64 order
+  const size_t smem = (((size_t)nb * 32 * 2 + 15) & ~(size_t)15) + (size_t)(nb + 1) * sizeof(double);
+  rc = set_smem(global_hist_kernel<uint16_t>, smem);
+  if (rc) return rc;
+  global_hist_kernel<uint16_t><<<2 * sm_count(), 32, smem, st>>>(anom, T, N, pitch, edges, centers, nb, q, lower_bound,
+                                                                  thr, stats, work);
   MAREX_LAUNCH_CHECK("global_hist_kernel");
   return MAREX_OK;
 }

@@ -760,10 +760,25 @@ def identify_extremes_arrays(
         else:
             edges, centers = global_bins(precision, max_anomaly)
             stats = torch.empty(2, dtype=torch.float64, device=dev)
-            _lib.call(
-                "marex_global_threshold_hist_f64", _p(anom), T, N, N, h.up(edges, np.float64, dev),
-                h.up(centers, np.float64, dev), len(centers), float(q), float(edges[3]), _p(thr), _p(stats), st,
-            )  # fmt: skip
+            if T <= 65535 and len(centers) >= 16:
+                eup = edges.astype(np.float32)  # smallest float32 >= each float64 edge: exact float32 binning
+                low = eup.astype(np.float64) < edges
+                eup[low] = np.nextafter(eup[low], np.float32(np.inf))
+                e_dn = np.float32(edges[-1])
+                if np.float64(e_dn) > edges[-1]:
+                    e_dn = np.nextafter(e_dn, np.float32(-np.inf))
+                work = torch.empty(N + 1, dtype=torch.int32, device=dev)
+                h.append(work)
+                _lib.call(
+                    "marex_global_threshold_hist_fast_f64", _p(anom), T, N, N, h.up(edges, np.float64, dev),
+                    h.up(eup, np.float32, dev), float(e_dn), h.up(centers, np.float64, dev), len(centers), float(q),
+                    float(edges[3]), _p(thr), _p(stats), _p(work), st,
+                )  # fmt: skip
+            else:
+                _lib.call(
+                    "marex_global_threshold_hist_f64", _p(anom), T, N, N, h.up(edges, np.float64, dev),
+                    h.up(centers, np.float64, dev), len(centers), float(q), float(edges[3]), _p(thr), _p(stats), st,
+                )  # fmt: skip
             out["stats"], out["stats_bounds"] = stats, (float(edges[-2]), float(edges[3]))
             if warn:
                 vmin, vmax = (float(v) for v in stats.cpu())

@@ -526,3 +526,28 @@ def test_streamed_host_path_validation_is_global():
     x[700, 9, 5] = np.nan
     with pytest.raises(mb.DataValidationError, match="invalid values in 1 ocean locations"):
         mb.preprocess_arrays(x, time, chunks=3, **kw)
+
+
+@pytest.mark.parametrize("p,T1,nx", [(95, "1995-06-24", 36), (80, "1992-09-27", 40), (97.5, "2001-01-01", 64), (99.9, "1994-02-08", 33)])
+def test_global_approx_fast_path_ties_and_edges(p, T1, nx):
+    """Fast global-histogram path: series lengths for which q*S is an integer (decided by the 1e-10
+    slack, deferred to the float64-order kernel), quantile in the first / last bins, dropped and NaN
+    samples, aligned (float4 compare) and unaligned widths."""
+    mb = _cuda()
+    a, time = _anoms(T1=T1, ny=3, nx=nx, seed=8)
+    f = a.reshape(len(time), -1)
+    f[:, 11] = 4.995  # quantile in the last bins
+    f[:, 12] = np.linspace(-3, 4.99, len(time), dtype=np.float32)
+    f[:, 13] = 5.0  # exactly the last edge: right-closed last bin
+    f[::2, 14] = 6.0  # half of the samples out of range
+    _, doy = mo.calendar_tables(time)
+    ref = mo.global_threshold_approx(f, p / 100.0)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        res = mb.identify_extremes_arrays(torch.from_numpy(f).cuda(), doy, a.shape[1:], "global_extreme", p, want_bits=(nx % 32 == 0))
+    _ulp_equal(res["thresholds"].cpu().numpy().reshape(-1), ref)
+    ev = mo.compare_global(f, ref)
+    np.testing.assert_array_equal(res["extreme_events"].cpu().numpy(), ev)
+    assert int(res["count"]) == int(ev.sum())
+    if nx % 32 == 0:
+        np.testing.assert_array_equal(res["bits"].cpu().numpy().view(np.uint32), mo.pack_bits_time_major(ev))
