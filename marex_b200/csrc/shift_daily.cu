@@ -6,7 +6,9 @@
 // (cp.async.bulk.tensor.2d, D + S - 1 rows x 32 cells) stages the strip's rows plus the
 // smoothing halo in shared memory, NST years ahead of the arithmetic, so HBM latency is hidden
 // by the copy engine and not by resident warps.  Thread = (gridpoint, R consecutive days):
-//   * the S-day centred window sum slides along the R days in float64 (exact for float32 data),
+//   * the S-day centred window sum is assembled from float64 sums of R-row blocks (each staged row
+//     is converted once per block) and then slides along the R days; float64 sums of float32 data
+//     are exact, so the grouping does not change the result,
 //   * a ring in shared memory keeps the smoothed value of the last W years for every
 //     (day, gridpoint) of the strip; the float64 running sum of the ring and its valid count sit
 //     in registers, so clim[year, doy] = sum / count costs one multiply,
@@ -48,6 +50,8 @@ __global__ void __launch_bounds__(R >= 12 ? 256 : 512) shift_daily_kernel(const 
   float* xs = reinterpret_cast<float*>(smem_raw + 128 + inv_bytes);              // [NST][rows_box][32]
   const int stage_elems = p.rows_box * 32;
   float* ring = xs + (size_t)NST * stage_elems;                                  // [W][D][32]
+  double* bs = reinterpret_cast<double*>(ring + (size_t)W * D * 32);            // [n_blk][32] sums of R box rows
+  const int n_blk = (p.rows_box + R - 1) / R;
 
   // strips of one 32-gridpoint group are adjacent CTAs: they run at the same time and at the
   // same pace, so the S - 1 halo rows a strip shares with its neighbour are L2 hits
@@ -126,24 +130,46 @@ __global__ void __launch_bounds__(R >= 12 ? 256 : 512) shift_daily_kernel(const 
       if (live) st_stream(outp, MODE ? clim : xv - clim);
     };
 
+    // Block sums: the float64 sum of every group of R consecutive box rows, each row converted once.
+    // A window of S rows is then S / R block sums + S % R single rows instead of S conversions
+    // (the sums are exact for float32 data, so the grouping does not change the result).
+    double own[R];
+    {
+      double b = 0.0;
+#pragma unroll
+      for (int r = 0; r < R; ++r) { own[r] = (double)X[r * 32]; b += own[r]; }
+      bs[warp * 32 + lane] = b;
+      const int nw = blockDim.x >> 5;
+      for (int blk = nw + warp; blk < n_blk; blk += nw) {  // the halo rows behind the last sub-strip
+        const float* Xb = xs + st * stage_elems + blk * R * 32 + lane;
+        double e = 0.0;
+#pragma unroll
+        for (int r = 0; r < R; ++r) if (blk * R + r < p.rows_box) e += (double)Xb[r * 32];
+        bs[blk * 32 + lane] = e;
+      }
+    }
+    __syncthreads();
+
     if (rbase + R <= nd && t0 - off >= 0 && t0 + (R - 1) - off + S <= p.T) {
       // ---- whole sub-strip inside the year and the series: no per-day checks ----
       if (t0 == 0 && live) p.mask0[c] = is_finite_f(X[off * 32]) ? 1 : 0;  // only reachable when S == 1
       const float* Xhi = X + (S - 1) * 32;
       const float* Xc = X + off * 32;
-      double wa = 0.0, wb = 0.0, wc = 0.0;  // three chains: the sum is exact, so its order is free
-      int k = 0;
-      for (; k + 3 <= S; k += 3) {
-        wa += (double)X[k * 32];
-        wb += (double)X[(k + 1) * 32];
-        wc += (double)X[(k + 2) * 32];
+      const int nfull = S / R;
+      double ws = own[0];
+#pragma unroll
+      for (int r = 1; r < R; ++r) ws += own[r];
+      if (nfull == 0) {  // S < R: the window is a prefix of the own block
+        ws = 0.0;
+        for (int k = 0; k < S; ++k) ws += (double)X[k * 32];
+      } else {
+        for (int b = 1; b < nfull; ++b) ws += bs[(warp + b) * 32 + lane];
+        for (int k = nfull * R; k < S; ++k) ws += (double)X[k * 32];
       }
-      for (; k < S; ++k) wa += (double)X[k * 32];
-      double ws = (wa + wb) + wc;
       if (target) {
 #pragma unroll
         for (int r = 0; r < R; ++r) {
-          if (r > 0) ws += (double)Xhi[r * 32] - (double)X[(r - 1) * 32];
+          if (r > 0) ws += (double)Xhi[r * 32] - own[r - 1];
           const float xv = Xc[r * 32];
           bad += is_finite_f(xv) ? 0 : 1;
           emit(r, xv);
@@ -153,7 +179,7 @@ __global__ void __launch_bounds__(R >= 12 ? 256 : 512) shift_daily_kernel(const 
       } else {
 #pragma unroll
         for (int r = 0; r < R; ++r) {
-          if (r > 0) ws += (double)Xhi[r * 32] - (double)X[(r - 1) * 32];
+          if (r > 0) ws += (double)Xhi[r * 32] - own[r - 1];
           bad += is_finite_f(Xc[r * 32]) ? 0 : 1;
           turnover(r, (float)(ws * invS));
         }
@@ -250,8 +276,10 @@ extern "C" int marex_shift_anomaly_daily_f32(const float* x, int64_t T, int64_t 
   const int env_nst = getenv("MAREX_SHIFT_NST") ? atoi(getenv("MAREX_SHIFT_NST")) : 0;
   const int env_cps = getenv("MAREX_SHIFT_CPS") ? atoi(getenv("MAREX_SHIFT_CPS")) : 0;
   const size_t fixed = 128 + (((size_t)(W + 1) * 8 + 127) / 128) * 128;
-  auto smem_of = [&](int D, int nst) { return fixed + (size_t)nst * (D + S - 1) * 128 + (size_t)W * D * 128; };
   auto launch = [&](auto kern, int R, int nst, int cps) -> int {
+    auto smem_of = [&](int D, int ns) {
+      return fixed + (size_t)ns * (D + S - 1) * 128 + (size_t)W * D * 128 + (size_t)((D + S - 1 + R - 1) / R) * 256;
+    };
     const size_t budget = (size_t)(227 * 1024) / cps - (cps > 1 ? 1024 : 0);
     const int nw_max = R >= 12 ? 8 : 16;
     int NW = env_nw ? env_nw : nw_max;
@@ -286,11 +314,14 @@ extern "C" int marex_shift_anomaly_daily_f32(const float* x, int64_t T, int64_t 
     if (env_r == 12) rc = nst == 3 ? MAREX_SD(12, 3, cps) : MAREX_SD(12, 2, cps);
     else if (env_r == 6) rc = nst == 3 ? MAREX_SD(6, 3, cps) : MAREX_SD(6, 2, cps);
     else if (env_r == 4) rc = MAREX_SD(4, 2, cps);
+    else if (env_r == 3) rc = MAREX_SD(3, 2, cps);
     else rc = MAREX_SD(1, 2, cps);
   } else {
-    // measured on B200 (0.25 deg, W=15, S=21): two co-resident CTAs of 8 warps x 6 days beat one CTA
-    // of 8 x 12 (57.6 vs 78.8 ms): the arithmetic is latency-bound, the staging is not
-    rc = MAREX_SD(6, 2, 2);
+    // measured on B200 (0.25 deg, W=15, S=21): two co-resident CTAs of 11 warps x 4 days: 56-57 ms; one CTA of
+    // 8 x 12: 78-89 ms.  The arithmetic is latency-bound (8-22 warps per SM: the ring limits residency), the TMA
+    // staging alone takes 21 ms and the output stores 7 ms.
+    rc = MAREX_SD(4, 2, 2);
+    if (rc == MAREX_ERR_UNSUPPORTED) rc = MAREX_SD(6, 2, 2);
     if (rc == MAREX_ERR_UNSUPPORTED) rc = MAREX_SD(12, 2, 1);
     if (rc == MAREX_ERR_UNSUPPORTED) rc = MAREX_SD(4, 2, 1);
     if (rc == MAREX_ERR_UNSUPPORTED) rc = MAREX_SD(1, 2, 1);
