@@ -93,6 +93,28 @@ def ncu_traffic(kernel_stage):
     return d.get(kernel_stage)
 
 
+def host_memory_available():
+    """Bytes of host memory this process tree may still use: the cgroup limit when there is one
+    (a container's limit is what the OOM killer enforces, not the machine's free memory)."""
+    avail = None
+    try:
+        import psutil
+
+        avail = float(psutil.virtual_memory().available)
+    except Exception:
+        pass
+    for lim_p, cur_p in (("/sys/fs/cgroup/memory.max", "/sys/fs/cgroup/memory.current"),
+                         ("/sys/fs/cgroup/memory/memory.limit_in_bytes", "/sys/fs/cgroup/memory/memory.usage_in_bytes")):
+        try:
+            lim = open(lim_p).read().strip()
+            if lim.isdigit():
+                room = float(int(lim) - int(open(cur_p).read().strip()))
+                avail = room if avail is None else min(avail, room)
+        except Exception:
+            pass
+    return avail if avail is not None else 64e9
+
+
 def measured_peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -266,6 +288,8 @@ def main():
     dev = torch.device("cuda", local)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        if os.environ.get("NCCL_DEBUG", "").upper() in ("VERSION", "INFO"):
+            os.environ["NCCL_DEBUG"] = "WARN"  # NCCL prints its banner on stdout; stdout carries one JSON line only
         dist.init_process_group("nccl", device_id=dev)
     ny, nx, start, end, kw = WORKLOADS[args.workload]
     time = np.arange(np.datetime64(start), np.datetime64(end))
@@ -379,16 +403,11 @@ def main():
         # several ranks on one box the per-rank field is cut to the latitude rows that fit (weak scaling
         # keeps the per-GPU work equal across ranks, so the e2e rate stays comparable; the cut is reported)
         e2e_rows = x.shape[1] if not unstructured else 1
-        try:
-            import psutil
-
-            local_world = int(os.environ.get("LOCAL_WORLD_SIZE", world))
-            avail = psutil.virtual_memory().available / max(1, local_world)
-            need = x.numel() * 4 * 1.85
-            if need > 0.8 * avail and not unstructured:
-                e2e_rows = max(16, int(x.shape[1] * 0.8 * avail / need))
-        except Exception:
-            pass
+        local_world = int(os.environ.get("LOCAL_WORLD_SIZE", world))
+        avail = host_memory_available() / max(1, local_world)
+        need = x.numel() * 4 * 1.85
+        if need > 0.7 * avail and not unstructured:
+            e2e_rows = max(16, int(x.shape[1] * 0.7 * avail / need))
         x_e2e = x if (unstructured or e2e_rows == x.shape[1]) else x[:, :e2e_rows].contiguous()
         e2e_cells = x_e2e[0].numel()  # the host field is processed as a stand-alone periodic domain
         xh = torch.empty(x_e2e.shape, dtype=torch.float32, pin_memory=True)

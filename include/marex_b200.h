@@ -148,11 +148,13 @@ int marex_hobday_thresholds_pooled_f32(const float* anom, int64_t T, int64_t ny,
                                        void* stream);
 
 /* Exact Hobday thresholds: np.nanpercentile (float32 'linear') over the +-w/2 doy window
- * (detect.py:1921-1956).  thr[366, N] doy-major, NaN where the window holds no valid sample. */
+ * (detect.py:1921-1956).  thr[366, N] doy-major, NaN where the window holds no valid sample.
+ * max_doy_rows = the largest number of rows of any single day of year (doy_ptr differences);
+ * when the window (w * max_doy_rows samples per gridpoint) fits shared memory it is kept there. */
 int marex_hobday_thresholds_exact_f32(const float* anom, int64_t T, int64_t N, int64_t pitch,
                                       const int32_t* doy_ptr, const int32_t* doy_rows,
-                                      int32_t max_window_rows, int32_t w, float percentile,
-                                      float* thr, void* stream);
+                                      int32_t max_window_rows, int32_t max_doy_rows, int32_t w,
+                                      float percentile, float* thr, void* stream);
 
 /* Global (constant in time) thresholds, approximate: per-cell histogram with float64 edges
  * (last bin right-closed), pdf/cdf in float64 in the reference's order

@@ -548,6 +548,100 @@ __global__ void __launch_bounds__(32) hobday_exact_kernel(const float* __restric
   }
 }
 
+// Same result with the window's samples kept in shared memory: win[slot][row][lane], one slot per day
+// of year of the window (ring over slots), so every sample is loaded from global memory once and
+// the per-step candidate scan of select_pair reads shared memory instead of re-gathering ~w * n_years
+// strided global values.  Used when the window fits (w * rowcap * 128 B + histogram <= 200 KB).
+template <typename CT>
+__global__ void __launch_bounds__(32) hobday_exact_win_kernel(const float* __restrict__ anom, int64_t T, int64_t N,
+                                                              int64_t pitch, const int32_t* __restrict__ doy_ptr,
+                                                              const int32_t* __restrict__ doy_rows, int w, int rowcap,
+                                                              float qf, float* __restrict__ thr) {
+  extern __shared__ unsigned char smem_raw[];
+  CT* hist = reinterpret_cast<CT*>(smem_raw);                                     // [NBX][32]
+  float* win = reinterpret_cast<float*>(smem_raw + (size_t)NBX * 32 * sizeof(CT)); // [w][rowcap][32]
+  int* nrow = reinterpret_cast<int*>(win + (size_t)w * rowcap * 32);              // [w] rows held by each slot
+  const int lane = threadIdx.x;
+  const int64_t c = (int64_t)blockIdx.x * 32 + lane;
+  const bool live = c < N;
+  const float* col = anom + (live ? c : N - 1);
+  for (int b = 0; b < NBX; ++b) hist[b * 32 + lane] = 0;
+  float mn = CUDART_INF_F, mx = -CUDART_INF_F;
+  for (int64_t t0 = 0; t0 < T; t0 += 8) {
+    float v[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) v[u] = (t0 + u < T) ? __ldg(col + (t0 + u) * pitch) : CUDART_NAN_F;
+#pragma unroll
+    for (int u = 0; u < 8; ++u) if (is_finite_f(v[u])) { mn = fminf(mn, v[u]); mx = fmaxf(mx, v[u]); }
+  }
+  BinMap bm;
+  bm.mn = (mn <= mx) ? mn : 0.f;
+  bm.scale = (mx > mn) ? ((float)NBX / (mx - mn)) : 0.f;
+  if (!is_finite_f(bm.scale)) bm.scale = 0.f;
+  const int half = w / 2;
+  int n = 0, ib = 0, cl = 0;
+
+  auto count = [&](float v, int sign) {
+    if (v == v) {
+      const int bi = bm(v);
+      hist[bi * 32 + lane] += (CT)sign;
+      n += sign;
+      if (bi < ib) cl += sign;
+    }
+  };
+  auto leave_slot = [&](int slot) {
+    const int m = nrow[slot];
+    const float* ws = win + (size_t)slot * rowcap * 32 + lane;
+    for (int j = 0; j < m; ++j) count(ws[j * 32], -1);
+  };
+  auto enter_slot = [&](int slot, int d) {  // rows of day-of-year index d into `slot`
+    const int b0 = __ldg(&doy_ptr[d]), b1 = min(__ldg(&doy_ptr[d + 1]), b0 + rowcap);  // (host guarantees rows <= rowcap)
+    float* ws = win + (size_t)slot * rowcap * 32 + lane;
+    for (int j0 = b0; j0 < b1; j0 += 13) {
+      float v[13];
+#pragma unroll
+      for (int u = 0; u < 13; ++u) v[u] = (j0 + u < b1) ? __ldg(col + (int64_t)__ldg(&doy_rows[j0 + u]) * pitch) : 0.f;
+#pragma unroll
+      for (int u = 0; u < 13; ++u) if (j0 + u < b1) { ws[(j0 + u - b0) * 32] = v[u]; count(v[u], +1); }
+    }
+    __syncwarp();
+    if (lane == 0) nrow[slot] = b1 - b0;
+    __syncwarp();
+  };
+  for (int k = 0; k < w; ++k) enter_slot(k, ((k - half) % NDOY + NDOY) % NDOY);
+
+  for (int d = 0; d < NDOY; ++d) {
+    if (d > 0) {
+      const int slot = (d - 1) % w;  // holds day d - 1 - half, which leaves; day d + half takes its place
+      leave_slot(slot);
+      enter_slot(slot, (d + half) % NDOY);
+    }
+    float res = CUDART_NAN_F;
+    if (n > 0) {
+      int r0, r1;
+      float g;
+      f32_rank(n, qf, r0, r1, g);
+      while (cl > r0) { --ib; cl -= (int)hist[ib * 32 + lane]; }
+      while (ib < NBX - 1 && cl + (int)hist[ib * 32 + lane] <= r0) { cl += (int)hist[ib * 32 + lane]; ++ib; }
+      const int h = (int)hist[ib * 32 + lane];
+      auto for_each = [&](auto&& fn) {
+        for (int slot = 0; slot < w; ++slot) {
+          const int m = nrow[slot];
+          const float* ws = win + (size_t)slot * rowcap * 32 + lane;
+          for (int j = 0; j < m; ++j) {
+            const float v = ws[j * 32];
+            if (v == v) fn(v);
+          }
+        }
+      };
+      float a, b;
+      select_pair(for_each, bm, ib, cl, h, r0, r1, a, b);
+      res = f32_lerp(a, b, g);
+    }
+    if (live) thr[(int64_t)d * N + c] = res;
+  }
+}
+
 // np.nanquantile(a, float64 q) 'linear' (xarray .quantile, detect.py:2899): float64 virtual
 // index and lerp, the difference (b - a) still taken in float32.
 template <typename CT>
@@ -939,8 +1033,8 @@ extern "C" int marex_hobday_thresholds_hist(const uint16_t* bins, int64_t T, int
 
 extern "C" int marex_hobday_thresholds_exact_f32(const float* anom, int64_t T, int64_t N, int64_t pitch,
                                                  const int32_t* doy_ptr, const int32_t* doy_rows,
-                                                 int32_t max_window_rows, int32_t w, float percentile, float* thr,
-                                                 void* stream) {
+                                                 int32_t max_window_rows, int32_t max_doy_rows, int32_t w,
+                                                 float percentile, float* thr, void* stream) {
   MAREX_REQUIRE(anom && doy_ptr && doy_rows && thr, "null pointer");
   MAREX_REQUIRE(T > 0 && N > 0 && pitch >= N, "bad shape");
   MAREX_REQUIRE(w >= 1 && w <= 365 && (w & 1), "window_days_hobday must be odd and in 1..365");
@@ -949,6 +1043,17 @@ extern "C" int marex_hobday_thresholds_exact_f32(const float* anom, int64_t T, i
   const size_t smem = (size_t)NBX * 32 * (wide ? 4 : 2);
   const unsigned grid = (unsigned)((N + 31) / 32);
   cudaStream_t st = (cudaStream_t)stream;
+  // window-in-shared-memory variant (max_doy_rows = most rows any single day of year has; 0 = unknown)
+  const int rowcap_day = max_doy_rows > 0 ? max_doy_rows : 1 << 20;
+  const size_t smem_win = smem + (size_t)w * (size_t)rowcap_day * 128 + (size_t)w * sizeof(int);
+  if (!wide && max_doy_rows > 0 && smem_win <= 200 * 1024 && !getenv("MAREX_EXACT_V1")) {
+    int rc = set_smem(hobday_exact_win_kernel<uint16_t>, smem_win);
+    if (rc) return rc;
+    hobday_exact_win_kernel<uint16_t><<<grid, 32, smem_win, st>>>(anom, T, N, pitch, doy_ptr, doy_rows, w, rowcap_day,
+                                                                  qf, thr);
+    MAREX_LAUNCH_CHECK("hobday_exact_win_kernel");
+    return MAREX_OK;
+  }
   if (wide) {
     int rc = set_smem(hobday_exact_kernel<uint32_t>, smem);
     if (rc) return rc;

@@ -709,8 +709,8 @@ def identify_extremes_arrays(
         thr = torch.empty((NDOY, N), dtype=torch.float32, device=dev)
         if method_percentile == "exact":
             _lib.call(
-                "marex_hobday_thresholds_exact_f32", _p(anom), T, N, N, _p(ptr_d), _p(rows_d), mwr, w,
-                float(threshold_percentile), _p(thr), st,
+                "marex_hobday_thresholds_exact_f32", _p(anom), T, N, N, _p(ptr_d), _p(rows_d), mwr,
+                int(np.diff(ptr).max()), w, float(threshold_percentile), _p(thr), st,
             )  # fmt: skip
             out["thresholds"] = thr if not gridded else thr.reshape((NDOY,) + tuple(grid))
             out["thresholds_layout"] = "doy_first"
