@@ -494,7 +494,7 @@ extern "C" int marex_hobday_thresholds_pooled_f32(const float* anom, int64_t T, 
   const int env_k = getenv("MAREX_POOL_K") ? atoi(getenv("MAREX_POOL_K")) : 0;
   const int env_ty = getenv("MAREX_POOL_TY") ? atoi(getenv("MAREX_POOL_TY")) : 0;
   MAREX_REQUIRE(env_k == 0 || env_k == 64 || env_k == 128, "MAREX_POOL_K must be 64 or 128");
-  const int TY = (env_ty && env_ty < 8) ? 3 : 8;  // 3: small tiles, exercised by the tests
+  const int TY = (env_ty && env_ty < 8) ? 3 : (env_ty >= 16 ? 16 : 8);  // 3: small tiles, exercised by the tests
   const int OY = TY + 2 * P, TX = 32 - 2 * P;
   const dim3 grid_all((unsigned)((nx + TX - 1) / TX), (unsigned)((ny + TY - 1) / TY));
   const int max_tiles = (int)(grid_all.x * grid_all.y);
@@ -525,8 +525,8 @@ extern "C" int marex_hobday_thresholds_pooled_f32(const float* anom, int64_t T, 
   } while (0)
 #define MAREX_BAND_K(PP)                                                                 \
   do {                                                                                   \
-    if (K == 64) { if (TY == 8) MAREX_BAND(PP, 64, 8); else MAREX_BAND(PP, 64, 3); }     \
-    else { if (TY == 8) MAREX_BAND(PP, 128, 8); else MAREX_BAND(PP, 128, 3); }           \
+    if (K == 64) { if (TY == 8) MAREX_BAND(PP, 64, 8); else if (TY == 16) MAREX_BAND(PP, 64, 16); else MAREX_BAND(PP, 64, 3); }     \
+    else { if (TY == 8) MAREX_BAND(PP, 128, 8); else if (TY == 16) MAREX_BAND(PP, 128, 16); else MAREX_BAND(PP, 128, 3); }           \
   } while (0)
     if (P == 1) MAREX_BAND_K(1); else if (P == 2) MAREX_BAND_K(2); else MAREX_BAND_K(3);
 #undef MAREX_BAND_K
