@@ -41,6 +41,7 @@ WORKLOADS = {
     # BASELINE.json configs[3] per GPU: 8 Mi-cell unstructured mesh / 8 GPUs, 30 yr, detrend_fixed + global p95
     "icon_1Mi_cells_30yr_detrend_global": (1, 1 << 20, "1991-01-01", "2021-01-01",
                                            dict(method_anomaly="detrend_fixed_baseline", method_extreme="global_extreme")),
+    "icon_1Mi_cells_30yr_shifting_hobday_approx": (1, 1 << 20, "1991-01-01", "2021-01-01", dict()),
     # BASELINE.json configs[4] per GPU: 0.1 deg (3600 x 1800) / 8 GPUs = 225 rows, 30 yr
     "0.1deg_30yr_shifting_hobday_approx_per_gpu": (225, 3600, "1991-01-01", "2021-01-01", dict()),
 }
