@@ -96,7 +96,8 @@ int marex_doy_climatology_f32(const float* x, int64_t T, int64_t N, int64_t pitc
                               const float* shift, float* clim, void* stream);
 /* anom[t] = f32(f32(x[t] - shift) - clim[doy[t]])  (groupby subtraction, detect.py:2377-2379);
  * mask0 = isfinite of the first shifted row (detect.py:2391).  `nonfinite` (optional) counts
- * non-finite x per cell.  x and anom may alias (in-place). */
+ * non-finite x per cell.  x and anom may alias (in-place).  clim == NULL subtracts only `shift`
+ * (the force_zero_mean step of detrend_harmonic, detect.py:2223-2224). */
 int marex_sub_doy_climatology_f32(const float* x, int64_t T, int64_t N, int64_t pitch,
                                   const int16_t* doy, const float* shift, const float* clim,
                                   float* anom, int64_t anom_pitch,

@@ -186,7 +186,7 @@ __global__ void __launch_bounds__(256) sub_doy_climatology_kernel(
     if (shift) v = v - sh;
     if (t == 0 && mask0) mask0[c] = is_finite_f(v) ? 1 : 0;
     const int d = __ldg(&doy[t]) - 1;
-    st_stream(&anom[t * anom_pitch + c], v - __ldg(&clim[(int64_t)d * N + c]));
+    st_stream(&anom[t * anom_pitch + c], clim ? v - __ldg(&clim[(int64_t)d * N + c]) : v);
   }
   if (nonfinite && bad) atomicAdd(&nonfinite[c], bad);
 }
@@ -209,7 +209,8 @@ __global__ void __launch_bounds__(128) sub_doy_climatology4_kernel(
     for (int u = 0; u < 4; ++u) {
       if (tb + u < t1) {
         v[u] = __ldcs(reinterpret_cast<const float4*>(x + (tb + u) * pitch + c));
-        cl[u] = __ldg(reinterpret_cast<const float4*>(clim + (int64_t)(__ldg(&doy[tb + u]) - 1) * N + c));
+        cl[u] = clim ? __ldg(reinterpret_cast<const float4*>(clim + (int64_t)(__ldg(&doy[tb + u]) - 1) * N + c))
+                     : make_float4(0.f, 0.f, 0.f, 0.f);
       }
     }
 #pragma unroll
@@ -228,7 +229,7 @@ __global__ void __launch_bounds__(128) sub_doy_climatology4_kernel(
         for (int j = 0; j < 4; ++j) mask0[c + j] = is_finite_f(f[j]) ? 1 : 0;
       }
       __stcs(reinterpret_cast<float4*>(anom + (tb + u) * anom_pitch + c),
-             make_float4(f[0] - c4[0], f[1] - c4[1], f[2] - c4[2], f[3] - c4[3]));
+             clim ? make_float4(f[0] - c4[0], f[1] - c4[1], f[2] - c4[2], f[3] - c4[3]) : make_float4(f[0], f[1], f[2], f[3]));
     }
   }
   if (nonfinite) {
@@ -465,13 +466,13 @@ extern "C" int marex_doy_climatology_f32(const float* x, int64_t T, int64_t N, i
 extern "C" int marex_sub_doy_climatology_f32(const float* x, int64_t T, int64_t N, int64_t pitch, const int16_t* doy,
                                              const float* shift, const float* clim, float* anom, int64_t anom_pitch,
                                              uint8_t* mask0, int32_t* nonfinite, void* stream) {
-  MAREX_REQUIRE(x && doy && clim && anom, "null pointer");
+  MAREX_REQUIRE(x && doy && anom, "null pointer");
   MAREX_REQUIRE(T > 0 && N > 0 && pitch >= N && anom_pitch >= N, "bad shape");
   cudaStream_t st = (cudaStream_t)stream;
   if (nonfinite) MAREX_CUDA(cudaMemsetAsync(nonfinite, 0, sizeof(int32_t) * N, st));
   const int threads = 128;
   if ((N % 4) == 0 && (pitch % 4) == 0 && (anom_pitch % 4) == 0 && (reinterpret_cast<uintptr_t>(x) % 16) == 0 &&
-      (reinterpret_cast<uintptr_t>(anom) % 16) == 0 && (reinterpret_cast<uintptr_t>(clim) % 16) == 0 &&
+      (reinterpret_cast<uintptr_t>(anom) % 16) == 0 && (!clim || (reinterpret_cast<uintptr_t>(clim) % 16) == 0) &&
       (!shift || (reinterpret_cast<uintptr_t>(shift) % 16) == 0)) {
     const int64_t bx4 = (N / 4 + threads - 1) / threads;
     int64_t by4 = (16LL * sm_count() + bx4 - 1) / bx4;
@@ -502,7 +503,7 @@ template <int K>
 static int launch_detrend_coef(const float* x, int64_t T, int64_t N, int64_t pitch, const double* P, double* coef,
                                uint8_t* mask0, int32_t* nonfinite, cudaStream_t st) {
   const int threads = 128;
-  if (K <= 4 && (N % 4) == 0 && (pitch % 4) == 0 && (reinterpret_cast<uintptr_t>(x) % 16) == 0) {
+  if (K <= 8 && (N % 4) == 0 && (pitch % 4) == 0 && (reinterpret_cast<uintptr_t>(x) % 16) == 0) {
     detrend_coef4_kernel<K><<<(unsigned)((N / 4 + threads - 1) / threads), threads, 0, st>>>(x, T, N, pitch, P, coef,
                                                                                             mask0, nonfinite);
     MAREX_LAUNCH_CHECK("detrend_coef4_kernel");
@@ -517,7 +518,7 @@ template <int K>
 static int launch_detrend_apply(const float* x, int64_t T, int64_t N, int64_t pitch, const double* M,
                                 const double* coef, float* xd, int64_t xd_pitch, float* mean, cudaStream_t st) {
   const int threads = 128;
-  if (K <= 4 && (N % 4) == 0 && (pitch % 4) == 0 && (xd_pitch % 4) == 0 && (reinterpret_cast<uintptr_t>(x) % 16) == 0 &&
+  if (K <= 8 && (N % 4) == 0 && (pitch % 4) == 0 && (xd_pitch % 4) == 0 && (reinterpret_cast<uintptr_t>(x) % 16) == 0 &&
       (reinterpret_cast<uintptr_t>(xd) % 16) == 0) {
     detrend_apply4_kernel<K><<<(unsigned)((N / 4 + threads - 1) / threads), threads, 0, st>>>(x, T, N, pitch, M, coef,
                                                                                              xd, xd_pitch, mean);

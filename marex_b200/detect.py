@@ -31,7 +31,7 @@ from .exceptions import ConfigurationError, create_data_validation_error
 
 logger = logging.getLogger("marex_b200")
 
-VALID_ANOMALY = ("shifting_baseline", "fixed_baseline", "detrend_fixed_baseline")
+VALID_ANOMALY = ("detrend_harmonic", "shifting_baseline", "fixed_baseline", "detrend_fixed_baseline")
 VALID_EXTREME = ("global_extreme", "hobday_extreme")
 
 
@@ -115,13 +115,7 @@ def validate_reference_period_method(reference_period, method_anomaly: str) -> N
 
 
 def validate_anomaly_method(method_anomaly: str) -> None:
-    """detect.py:1100-1116.  ``detrend_harmonic`` exists upstream but is outside this
-    library's hot-path scope: it is reported as such, not silently approximated."""
-    if method_anomaly == "detrend_harmonic":
-        raise NotImplementedError(
-            "method_anomaly='detrend_harmonic' is outside the B200 hot path "
-            "(shifting_baseline, fixed_baseline, detrend_fixed_baseline)"
-        )
+    """detect.py:1100-1116."""
     if method_anomaly not in VALID_ANOMALY:
         raise ConfigurationError(
             f"Unknown anomaly method '{method_anomaly}'",
@@ -466,14 +460,17 @@ def check_sufficient_years(cal: Calendar, W: int) -> None:
 # --------------------------------------------------------------------------------------
 # (a) anomalies
 # --------------------------------------------------------------------------------------
-def detrend_model(time, detrend_orders: Sequence[int]) -> Tuple[np.ndarray, np.ndarray]:
-    """Design matrix (K, T) and its pseudo-inverse (T, K), float64 (detect.py:2139-2169),
-    polynomial terms only (``remove_harmonics=False``, detect.py:2450)."""
+def detrend_model(time, detrend_orders: Sequence[int], remove_harmonics: bool = False) -> Tuple[np.ndarray, np.ndarray]:
+    """Design matrix (K, T) and its pseudo-inverse (T, K), float64 (detect.py:2139-2169): constant,
+    centred polynomial terms and, for ``detrend_harmonic``, the annual and semi-annual sine / cosine
+    pairs (detect.py:2150-2159); ``remove_harmonics=False`` is detrend_fixed_baseline (detect.py:2450)."""
     dy = decimal_year(time)
     comps = [np.ones(len(dy))]
     centered = dy - np.mean(dy)
     for order in detrend_orders:
         comps.append(centered**order)
+    if remove_harmonics:
+        comps.extend([np.sin(2 * np.pi * dy), np.cos(2 * np.pi * dy), np.sin(4 * np.pi * dy), np.cos(4 * np.pi * dy)])
     model = np.array(comps)
     for i in range(1, model.shape[0]):
         model[i] = model[i] - np.mean(model[i]) * model[0]
@@ -585,11 +582,12 @@ def compute_normalised_anomaly_arrays(
             check_data_values(mask0, nonfinite, T, T * N)
         return {"dat_anomaly": anom, "mask": mask0.bool(), "keep": keep, "mask_raw": mask0.bool(), "climatology": clim, "nonfinite": nonfinite}
 
-    # detrend_fixed_baseline (detect.py:2400-2462)
+    # detrend_harmonic (detect.py:2061-2296, std_normalise=False) / detrend_fixed_baseline (detect.py:2400-2462)
+    harmonic = method_anomaly == "detrend_harmonic"
     validate_detrend_orders(detrend_orders)
     if 1 not in detrend_orders and len(detrend_orders) > 1:
         print("Warning: Higher-order detrending without linear term may be unstable")  # detect.py:2135-2136
-    model, pmodel = detrend_model(cal.time, list(detrend_orders))
+    model, pmodel = detrend_model(cal.time, list(detrend_orders), remove_harmonics=harmonic)
     K = model.shape[0]
     coef = torch.empty((K, N), dtype=torch.float64, device=dev)
     _lib.call(
@@ -605,6 +603,12 @@ def compute_normalised_anomaly_arrays(
         "marex_detrend_apply_f32", _p(x_dev), T, N, N, h.up(model, np.float64, dev), K, _p(coef), _p(xd), N,
         _p(mean), st,
     )  # fmt: skip
+    if harmonic:  # the detrended series is the anomaly; mask = isfinite of the raw first step (detect.py:2228)
+        if force_zero_mean:
+            _lib.call(
+                "marex_sub_doy_climatology_f32", _p(xd), T, N, N, _p(doy_d), _p(mean), None, _p(xd), N, None, None, st
+            )
+        return {"dat_anomaly": xd, "mask": mask_raw, "keep": keep, "mask_raw": mask_raw, "nonfinite": nonfinite}
     _lib.call("marex_doy_climatology_f32", _p(xd), T, N, N, _p(ptr_d), _p(rows_d), _p(mean), _p(clim), st)
     mask1 = torch.empty(N, dtype=torch.uint8, device=dev)
     _lib.call(
@@ -831,7 +835,9 @@ def _dataset_attrs(method_anomaly, method_extreme, threshold_percentile, std_nor
             smooth_days_baseline, window_days_hobday, window_spatial_hobday, reference_period,
         ),
     }  # fmt: skip
-    if method_anomaly == "shifting_baseline":
+    if method_anomaly == "detrend_harmonic":
+        attrs.update({"detrend_orders": list(detrend_orders), "force_zero_mean": force_zero_mean, "std_normalise": std_normalise})
+    elif method_anomaly == "shifting_baseline":
         attrs.update({"window_year_baseline": window_year_baseline, "smooth_days_baseline": smooth_days_baseline})
     elif method_anomaly == "fixed_baseline":
         if reference_period is not None:
@@ -1088,7 +1094,7 @@ def preprocess_arrays(
     if detrend_orders is None:
         detrend_orders = [1]
     if std_normalise:
-        raise NotImplementedError("std_normalise is only defined for detrend_harmonic, outside the B200 hot path")
+        raise NotImplementedError("std_normalise (dat_stn / STD / extreme_events_stn, detect.py:2257-2293) is not implemented yet")
     dev = _device(device)
     validate_reference_period_method(reference_period, method_anomaly)
     validate_anomaly_method(method_anomaly)

@@ -236,7 +236,7 @@ def compute_normalised_anomaly(
     dimensions, coordinates = _infer_dims_coords(da, dimensions, coordinates)
     _d.validate_reference_period_method(reference_period, method_anomaly)
     if std_normalise:
-        raise NotImplementedError("std_normalise belongs to detrend_harmonic, outside the B200 hot path")
+        raise NotImplementedError("std_normalise (dat_stn / STD, detect.py:2257-2293) is not implemented yet")
     if da.chunks is None:  # upstream: TypeError from da.chunks[0] (detect.py:2180), pinned by its tests
         raise TypeError("'NoneType' object is not subscriptable")
     tdim, sdims = dimensions["time"], _space_dims(dimensions)

@@ -548,6 +548,10 @@ def preprocess(
     elif method_anomaly == "detrend_fixed_baseline":
         anom, mask = anomaly_detrend_fixed_baseline(x, time, year, doy, detrend_orders, force_zero_mean, reference_period)
         doy_o, time_o = doy, np.asarray(time)
+    elif method_anomaly == "detrend_harmonic":  # detect.py:2061-2296 with std_normalise=False
+        anom = detrend(x, time, detrend_orders, force_zero_mean, remove_harmonics=True)
+        mask = np.isfinite(_flat(x)[0][0])  # detect.py:2228: first step of the raw field
+        doy_o, time_o = doy, np.asarray(time)
     else:
         raise ValueError(method_anomaly)
     a2 = anom.reshape(anom.shape[0], -1)

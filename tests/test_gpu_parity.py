@@ -551,3 +551,50 @@ def test_global_approx_fast_path_ties_and_edges(p, T1, nx):
     assert int(res["count"]) == int(ev.sum())
     if nx % 32 == 0:
         np.testing.assert_array_equal(res["bits"].cpu().numpy().view(np.uint32), mo.pack_bits_time_major(ev))
+
+
+# ---------------------------------------------------------------- detrend_harmonic (without std_normalise)
+@pytest.mark.parametrize("orders,fzm,nx", [([1], True, 36), ([1, 2], False, 37), ([1, 2, 3], True, 40)])
+def test_detrend_harmonic_anomaly(orders, fzm, nx):
+    """Polynomial + annual / semi-annual harmonic fit (detect.py:2143-2224): same fit kernels with 4 more
+    model columns; the detrended series is the anomaly, the mask comes from the raw first step."""
+    mb = _cuda()
+    x, time = _field(T1="1999-01-01", ny=5, nx=nx, seed=9)
+    ref = mo.detrend(x, time, orders, fzm, remove_harmonics=True)
+    cal = mb.detect.build_calendar(time)
+    xd, _ = mb.detect._to_device_field(x, "cuda")
+    res = mb.compute_normalised_anomaly_arrays(xd, cal, "detrend_harmonic", detrend_orders=orders, force_zero_mean=fzm)
+    got = res["dat_anomaly"].cpu().numpy().reshape(ref.shape)
+    np.testing.assert_array_equal(np.isnan(got), np.isnan(ref))
+    np.testing.assert_allclose(got, ref, rtol=0, atol=1e-5 * 30, equal_nan=True)
+    assert _frac_bits_differ(got, ref) < 2e-2  # float64 dot products in a different order than numpy's BLAS
+    np.testing.assert_array_equal(res["mask"].cpu().numpy().reshape(x.shape[1:]), np.isfinite(x[0]))
+
+
+@pytest.mark.parametrize("extreme,chunks", [("hobday_extreme", 1), ("global_extreme", 3)])
+def test_preprocess_detrend_harmonic(extreme, chunks):
+    mb = _cuda()
+    x, time = _field(T1="2000-01-01", ny=8, nx=36, seed=10)
+    kw = dict(method_anomaly="detrend_harmonic", method_extreme=extreme, window_days_hobday=5)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        got = mb.preprocess_arrays(x, time, chunks=chunks, **kw)
+    ref = mo.preprocess(x, time, **kw)
+    np.testing.assert_allclose(got["dat_anomaly"], ref["dat_anomaly"], rtol=0, atol=3e-4, equal_nan=True)
+    np.testing.assert_array_equal(got["mask"], ref["mask"])
+    assert got["attrs"]["method_anomaly"] == "detrend_harmonic" and got["attrs"]["std_normalise"] is False
+    assert got["attrs"]["preprocessing_steps"][0] == "Removed polynomial trend orders=[1] & seasonal cycle"
+    # thresholds / events from the SAME anomalies must agree bit for bit (stage-wise parity, SURVEY F7)
+    a2 = np.asarray(got["dat_anomaly"]).reshape(len(time), -1)
+    _, doy = mo.calendar_tables(time)
+    if extreme == "hobday_extreme":
+        thr = mo.hobday_thresholds_approx(a2, doy, 0.95, 5, 5, x.shape[1:])
+        _ulp_equal(np.asarray(got["thresholds"]).reshape(-1, 366), thr)
+        ev = mo.compare_hobday(a2, doy, np.ascontiguousarray(thr.T))
+    else:
+        thr = mo.global_threshold_approx(a2, 0.95)
+        _ulp_equal(np.asarray(got["thresholds"]).reshape(-1), thr)
+        ev = mo.compare_global(a2, thr)
+    np.testing.assert_array_equal(np.asarray(got["extreme_events"]).reshape(len(time), -1), ev)
+    with pytest.raises(NotImplementedError, match="std_normalise"):
+        mb.preprocess_arrays(x, time, std_normalise=True, **kw)

@@ -168,6 +168,22 @@ def test_configuration_errors_follow_the_reference_messages():
     np.testing.assert_array_equal(d.validate_reference_period((1992, 1993), years), [2, 3])
 
 
+def test_detrend_harmonic_model_and_attrs():
+    """detrend_harmonic: 4 harmonic columns after the polynomial ones (detect.py:2150-2159); attrs of detect.py:751-758."""
+    from marex_b200 import detect as d
+
+    time = np.arange(np.datetime64("1990-01-01"), np.datetime64("1994-01-01"))
+    M, P = d.detrend_model(time, [1], remove_harmonics=True)
+    Mo, Po = mo.detrend_model(time, [1], True)
+    assert M.shape == (6, len(time))
+    np.testing.assert_array_equal(M, Mo)
+    np.testing.assert_array_equal(P, Po)
+    d.validate_anomaly_method("detrend_harmonic")
+    a = d._dataset_attrs("detrend_harmonic", "global_extreme", 95, False, [1], 15, 21, 11, None, None, True, "approximate", 0.01, 5.0)
+    assert a["detrend_orders"] == [1] and a["force_zero_mean"] is True and a["std_normalise"] is False
+    assert a["preprocessing_steps"] == ["Removed polynomial trend orders=[1] & seasonal cycle", "Global percentile threshold applied to all days"]
+
+
 def test_preprocessing_steps_match_reference_golden(golden_dir):
     from marex_b200 import detect as d
 
