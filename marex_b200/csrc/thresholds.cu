@@ -380,7 +380,7 @@ __global__ void __launch_bounds__(768) hobday_pool_tile_kernel(
 // series localises the bin that holds the wanted rank; the few samples of that bin are then
 // gathered and ordered exactly.  `SampleIter` abstracts "all samples of the current window".
 // ---------------------------------------------------------------------------------------
-constexpr int NBX = 512;  // bins of the localising histogram
+constexpr int NBX = 256;  // bins of the localising histogram
 constexpr int CAND = 8;   // in-bin candidates handled by the fast path
 
 struct BinMap {
@@ -552,6 +552,18 @@ __global__ void __launch_bounds__(32) hobday_exact_kernel(const float* __restric
 // of year of the window (ring over slots), so every sample is loaded from global memory once and
 // the per-step candidate scan of select_pair reads shared memory instead of re-gathering ~w * n_years
 // strided global values.  Used when the window fits (w * rowcap * 128 B + histogram <= 200 KB).
+// Smallest float t with bm(t) >= target (bm is monotone non-decreasing): the analytic guess is fixed up
+// by single-ulp steps, so classifying a sample against a bin is two float compares instead of the map.
+__device__ __forceinline__ float bin_lower_bound(const BinMap& bm, int target) {
+  if (target <= 0) return -CUDART_INF_F;
+  if (bm.scale <= 0.f) return CUDART_INF_F;  // degenerate range: every finite sample maps to bin 0
+  float t = bm.mn + (float)target / bm.scale;
+  if (!(fabsf(t) < CUDART_INF_F)) t = (t > 0.f) ? 3.0e38f : -3.0e38f;
+  for (int it = 0; it < 64 && bm(t) >= target; ++it) t = nextafterf(t, -CUDART_INF_F);  // now bm(t) < target (or gave up)
+  for (int it = 0; it < 128 && bm(t) < target; ++it) t = nextafterf(t, CUDART_INF_F);   // first t with bm(t) >= target
+  return t;
+}
+
 template <typename CT>
 __global__ void __launch_bounds__(32) hobday_exact_win_kernel(const float* __restrict__ anom, int64_t T, int64_t N,
                                                               int64_t pitch, const int32_t* __restrict__ doy_ptr,
@@ -635,7 +647,45 @@ __global__ void __launch_bounds__(32) hobday_exact_win_kernel(const float* __res
         }
       };
       float a, b;
-      select_pair(for_each, bm, ib, cl, h, r0, r1, a, b);
+      // the rank is found among the bin's few samples: classify the window against the bin's value range
+      // (two compares per sample) and keep the in-bin samples sorted in registers
+      const float tlo = bin_lower_bound(bm, ib);
+      const float thi = (ib < NBX - 1) ? bin_lower_bound(bm, ib + 1) : CUDART_INF_F;
+      const bool top = ib >= NBX - 1;
+      const bool exactb = (bm(tlo) >= ib) && (ib == 0 || bm(nextafterf(tlo, -CUDART_INF_F)) < ib) &&
+                          (top || (bm(thi) > ib && bm(nextafterf(thi, -CUDART_INF_F)) <= ib));
+      const unsigned act = __activemask();  // lanes without a valid sample are not here
+      if (__all_sync(act, h <= CAND && exactb)) {
+        float cand[CAND];
+#pragma unroll
+        for (int k = 0; k < CAND; ++k) cand[k] = CUDART_INF_F;
+        float nextmin = CUDART_INF_F;  // smallest sample above the bin
+        int m_in = 0;
+        for (int slot = 0; slot < w; ++slot) {
+          const int m = nrow[slot];
+          const float* ws = win + (size_t)slot * rowcap * 32 + lane;
+          for (int j = 0; j < m; ++j) {
+            float v = ws[j * 32];
+            const bool above = !top && v >= thi;
+            if (above) nextmin = fminf(nextmin, v);
+            if (v >= tlo && !above) {  // in the bin (false for NaN): sorted insert, the larger value moves on
+              ++m_in;
+#pragma unroll
+              for (int k = 0; k < CAND; ++k) { const float lo = fminf(cand[k], v); v = fmaxf(cand[k], v); cand[k] = lo; }
+            }
+          }
+        }
+        const int j0 = r0 - cl;
+        a = cand[0];
+        float a1 = cand[1];
+#pragma unroll
+        for (int k = 1; k < CAND; ++k) {
+          if (j0 == k) { a = cand[k]; a1 = (k + 1 < CAND) ? cand[k + 1] : CUDART_INF_F; }
+        }
+        b = (r1 == r0) ? a : ((j0 + 1 < m_in) ? a1 : nextmin);
+      } else {
+        select_pair(for_each, bm, ib, cl, h, r0, r1, a, b);
+      }
       res = f32_lerp(a, b, g);
     }
     if (live) thr[(int64_t)d * N + c] = res;
