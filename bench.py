@@ -277,6 +277,11 @@ def main():
     local = int(os.environ.get("LOCAL_RANK", "0"))
     if args.impl == "reference":
         return run_reference(args, rank, world)
+    # stdout carries exactly one JSON line: whatever libraries print there while we run (NCCL's version
+    # banner, for one) is sent to stderr, and the real stdout is restored for the final line
+    sys.stdout.flush()
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
 
     import torch
     import torch.distributed as dist
@@ -515,7 +520,10 @@ def main():
             "extreme_events": n_events,
             "clocks": clk,
         }
+        sys.stdout.flush()
+        os.dup2(real_stdout, 1)
         print(json.dumps(line), flush=True)
+        os.dup2(2, 1)
     if world > 1:
         dist.destroy_process_group()
 
