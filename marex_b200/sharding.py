@@ -101,6 +101,13 @@ def dist_gather(x, axis: int):
     dist.all_gather(sizes, n)
     sizes = [int(s) for s in sizes]
     mx = max(sizes)
+    if min(sizes) == mx:  # equal shards (the usual case): one collective straight into the result, no padding / concat
+        full = torch.empty((world * mx,) + tuple(t.shape[1:]), dtype=t.dtype, device=t.device)
+        dist.all_gather_into_tensor(full, t)
+        full = full.movedim(0, axis) if axis != 0 else full
+        if was_bool:
+            full = full.to(torch.bool)
+        return full if isinstance(x, torch.Tensor) else full.numpy()
     pad = torch.zeros((mx,) + tuple(t.shape[1:]), dtype=t.dtype, device=t.device)
     pad[: t.shape[0]] = t
     parts = [torch.empty_like(pad) for _ in range(world)]

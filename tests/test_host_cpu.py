@@ -308,6 +308,10 @@ kw = dict(window_year_baseline=3, smooth_days_baseline=5, window_days_hobday=5)
 out = sharding.preprocess_sharded(lambda lo, hi: x[:, lo:hi], time, 7, rank, world, mo.preprocess,
                                   gather=sharding.dist_gather, **kw)
 cnt = torch.tensor([int(out["extreme_events"].sum())]); dist.all_reduce(cnt)
+eq = sharding.dist_gather(np.arange(6, dtype=np.float32).reshape(3, 2) + 10 * rank, 0)  # equal shards: one collective
+assert eq.shape == (3 * world, 2) and all(eq[3 * r, 0] == 10 * r for r in range(world))
+eq1 = sharding.dist_gather(np.arange(6, dtype=np.float32).reshape(2, 3) + 10 * rank, 1)
+assert eq1.shape == (2, 3 * world) and all(eq1[0, 3 * r] == 10 * r for r in range(world))
 if rank == 0:
     full = mo.preprocess(x, time, **kw)
     assert np.array_equal(out["thresholds_global"].view(np.uint32), full["thresholds"].view(np.uint32))
