@@ -412,8 +412,9 @@ def main():
         local_world = int(os.environ.get("LOCAL_WORLD_SIZE", world))
         avail = host_memory_available() / max(1, local_world)
         need = x.numel() * 4 * 1.85
-        if need > 0.7 * avail and not unstructured:
-            e2e_rows = max(16, int(x.shape[1] * 0.7 * avail / need))
+        budget = (0.7 if local_world == 1 else 0.5) * avail  # several ranks pin host memory at the same time
+        if need > budget and not unstructured:
+            e2e_rows = max(16, int(x.shape[1] * budget / need))
         x_e2e = x if (unstructured or e2e_rows == x.shape[1]) else x[:, :e2e_rows].contiguous()
         e2e_cells = x_e2e[0].numel()  # the host field is processed as a stand-alone periodic domain
         xh = torch.empty(x_e2e.shape, dtype=torch.float32, pin_memory=True)
