@@ -324,14 +324,27 @@ def main():
     marks = []
     _lib.TRACE = lambda name: marks.append((name, _ev(torch)))
 
+    pending = []  # NCCL work of the previous step (its results stay referenced until it has completed)
+
+    def drain():
+        for wk, _keep in pending:
+            wk.wait()  # the compute stream waits; the host does not
+        pending.clear()
+
     def step():
         res = marex_b200.preprocess_arrays(x, time, output="torch", **kw)
         out = res if unstructured else sharding.crop_owned(res, (own_lo, own_hi), (lo, hi))
         if world > 1:
+            # every rank owns the same number of rows (weak scaling): the gathers need no size exchange and run
+            # asynchronously on NCCL's stream, overlapping the first kernel of the next step; at most one step's
+            # collectives are in flight, and the timed region ends only after the last one has completed
+            drain()
             lay = out["thresholds_layout"]
-            out["thresholds_global"] = sharding.dist_gather(out["thresholds"], 1 if lay == "doy_first" else 0)  # NCCL
-            out["mask_global"] = sharding.dist_gather(out["mask"], 0)
-            dist.all_reduce(out["extreme_count"])
+            w1, g1 = sharding.dist_gather(out["thresholds"].contiguous(), 1 if lay == "doy_first" else 0, equal=True, async_op=True)
+            w2, g2 = sharding.dist_gather(out["mask"], 0, equal=True, async_op=True)
+            w3 = dist.all_reduce(out["extreme_count"], async_op=True)
+            out["thresholds_global"], out["mask_global"] = g1[0], g2[0]
+            pending.extend([(w1, g1), (w2, g2), (w3, out["extreme_count"])])
         return out
 
     def barrier():
@@ -342,6 +355,7 @@ def main():
     for _ in range(max(args.warmup, 3)):
         r = step()
         del r
+    drain()
     barrier()
     launches0 = _lib.launch_count()
     marks.clear()
@@ -359,12 +373,14 @@ def main():
     for _ in range(args.steps):
         marks.append(("step_begin", _ev(torch)))
         r = step()
-        n_events = int(r["extreme_count"])
+        count_t = r["extreme_count"]
         del r
         stage_marks.append(list(marks))
         marks.clear()
+    drain()
     e1.record()
     barrier()
+    n_events = int(count_t)
     clk = clocks.stop() if rank == 0 else None
     launches = _lib.launch_count() - launches0
     ms = e0.elapsed_time(e1) / args.steps

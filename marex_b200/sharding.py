@@ -84,9 +84,11 @@ def preprocess_sharded(
     return out
 
 
-def dist_gather(x, axis: int):
+def dist_gather(x, axis: int, equal: bool = False, async_op: bool = False):
     """All-gather a per-rank array with unequal extents along ``axis`` through torch.distributed
-    (NCCL for CUDA tensors over NVLink; gloo for CPU tensors in the tests)."""
+    (NCCL for CUDA tensors over NVLink; gloo for CPU tensors in the tests).  ``equal=True`` promises
+    equal extents on all ranks and skips the size exchange (a host round trip); with ``async_op``
+    it returns ``(work, result)`` so the collective overlaps whatever is launched next."""
     import torch
     import torch.distributed as dist
 
@@ -96,6 +98,15 @@ def dist_gather(x, axis: int):
         t = t.to(torch.uint8)
     t = t.movedim(axis, 0).contiguous()
     world = dist.get_world_size()
+    if equal:
+        full = torch.empty((world * t.shape[0],) + tuple(t.shape[1:]), dtype=t.dtype, device=t.device)
+        work = dist.all_gather_into_tensor(full, t, async_op=async_op)
+        res = full.movedim(0, axis) if axis != 0 else full
+        if async_op:
+            return work, (res, t)  # the caller keeps `t` alive until the work has completed
+        if was_bool:
+            res = res.to(torch.bool)
+        return res if isinstance(x, torch.Tensor) else res.numpy()
     n = torch.tensor([t.shape[0]], dtype=torch.int64, device=t.device)
     sizes = [torch.zeros_like(n) for _ in range(world)]
     dist.all_gather(sizes, n)
