@@ -1016,8 +1016,17 @@ def _preprocess_host_streamed(xh: torch.Tensor, cal: Calendar, gridded: bool, de
     # ---- _validate_data_values over the whole field (detect.py:205-279) ----
     vals = torch.stack([n_ocean, n_affected, n_invalid, max_invalid, n_events]).cpu().tolist()
     ocean, affected, total_invalid, worst, count = (int(v) for v in vals)
-    if ocean == 0:
-        check_data_values(torch.zeros(1, dtype=torch.uint8), torch.zeros(1, dtype=torch.int32), T, T * n_total)
+    if ocean == 0:  # same error as check_data_values (detect.py:226-237), with the whole field's numbers
+        raise create_data_validation_error(
+            "Dataset contains no valid (finite) data",
+            details="All values in the first time step are NaN or infinite",
+            suggestions=[
+                "Check your input data for data quality issues",
+                "Verify the data was loaded correctly",
+                "Check for issues in data preprocessing steps",
+            ],
+            data_info={"total_values": int(T * n_total), "total_spatial_locations": int(n_total)},
+        )
     if worst > 0:
         raise create_data_validation_error(
             f"Dataset contains {total_invalid} invalid values in {affected} ocean locations",
