@@ -115,6 +115,18 @@ int marex_detrend_apply_f32(const float* x, int64_t T, int64_t N, int64_t pitch,
                             const double* M, int32_t K, const double* coef,
                             float* xd, int64_t xd_pitch, float* mean, void* stream);
 
+/* ---- std_normalise of detrend_harmonic (detect.py:2257-2293) -------------------------------
+ * sd[366, N] = population standard deviation of the rows of each day of year (flox "std",
+ * :2260-2268; NaN for an empty group or a non-finite sample). */
+int marex_doy_std_f32(const float* x, int64_t T, int64_t N, int64_t pitch,
+                      const int32_t* doy_ptr, const int32_t* doy_rows, float* sd, void* stream);
+/* out[366, N] = sqrt of the centred `win`-day rolling mean of sd^2 with annual wrap (:2271-2272),
+ * values <= 1e-10 replaced by NaN (:2276).  sd and out must not alias. */
+int marex_doy_rolling_rms_f32(const float* sd, int64_t N, int32_t win, float* out, void* stream);
+/* out[t] = x[t] / sd[doy[t]]  (:2278). */
+int marex_div_doy_f32(const float* x, int64_t T, int64_t N, int64_t pitch, const int16_t* doy,
+                      const float* sd, float* out, int64_t out_pitch, void* stream);
+
 /* ---- (b) thresholds --------------------------------------------------------------------
  * np.digitize(a, edges) - 1 as uint16 (detect.py:2622-2631): NaN and a >= edges[n_edges-1]
  * give n_edges-1 (dropped).  edges[0] must be -inf. */

@@ -21,6 +21,9 @@ _SIGNATURES = {
     "marex_sub_doy_climatology_f32": ([_P, c_int64, c_int64, c_int64, _P, _P, _P, _P, c_int64, _P, _P, _P], ctypes.c_int),
     "marex_detrend_coef_f64": ([_P, c_int64, c_int64, c_int64, _P, c_int32, _P, _P, _P, _P], ctypes.c_int),
     "marex_detrend_apply_f32": ([_P, c_int64, c_int64, c_int64, _P, c_int32, _P, _P, c_int64, _P, _P], ctypes.c_int),
+    "marex_doy_std_f32": ([_P, c_int64, c_int64, c_int64, _P, _P, _P, _P], ctypes.c_int),
+    "marex_doy_rolling_rms_f32": ([_P, c_int64, c_int32, _P, _P], ctypes.c_int),
+    "marex_div_doy_f32": ([_P, c_int64, c_int64, c_int64, _P, _P, _P, c_int64, _P], ctypes.c_int),
     "marex_digitize_f32": ([_P, c_int64, c_int64, c_int64, _P, c_int32, _P, c_int64, _P], ctypes.c_int),
     "marex_hobday_thresholds_hist": ([_P, c_int64, c_int64, c_int64, c_int64, _P, _P, c_int32, _P, c_int32, c_int32, c_int32, c_double, _P, c_float, _P, _P, _P], ctypes.c_int),
     "marex_hobday_pooled_workspace_bytes": ([c_int64, c_int64, c_int64], c_int64),

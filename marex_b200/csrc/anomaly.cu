@@ -398,6 +398,66 @@ __global__ void __launch_bounds__(128) detrend_apply4_kernel(
   }
 }
 
+// =======================================================================================
+// std_normalise of detrend_harmonic -- reference: detect.py:2257-2293
+// =======================================================================================
+// std[d, c] = population standard deviation (ddof = 0) of the rows of day-of-year d (flox "std", detect.py:2260-2268):
+// float64 two-pass; a non-finite sample makes the group NaN, an empty group is NaN.
+__global__ void __launch_bounds__(128) doy_std_kernel(const float* __restrict__ x, int64_t N, int64_t pitch,
+                                                      const int32_t* __restrict__ doy_ptr,
+                                                      const int32_t* __restrict__ doy_rows, float* __restrict__ sd) {
+  const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= N) return;
+  for (int d = blockIdx.y; d < NDOY; d += gridDim.y) {
+    const int b = __ldg(&doy_ptr[d]), e = __ldg(&doy_ptr[d + 1]);
+    double sum = 0.0;
+    for (int j = b; j < e; ++j) sum += (double)__ldg(&x[(int64_t)__ldg(&doy_rows[j]) * pitch + c]);
+    const double n = (double)(e - b);
+    const double mean = sum / n;
+    double m2 = 0.0;
+    for (int j = b; j < e; ++j) {
+      const double dv = (double)__ldg(&x[(int64_t)__ldg(&doy_rows[j]) * pitch + c]) - mean;
+      m2 += dv * dv;
+    }
+    sd[(int64_t)d * N + c] = (e > b) ? (float)sqrt(m2 / n) : CUDART_NAN_F;
+  }
+}
+
+// out[d, c] = sqrt(mean over the `win` days of year [d - win/2, d - win/2 + win - 1] (wrapping at 366) of sd^2): the
+// wrap-padded centred rolling mean of detect.py:2271-2272 (xarray centres an even window on [i - win/2, i + win/2 - 1];
+// a NaN anywhere in the window gives NaN: min_periods = win); values <= 1e-10 become NaN (detect.py:2276).
+__global__ void __launch_bounds__(128) doy_rolling_rms_kernel(const float* __restrict__ sd, int64_t N, int win,
+                                                              float* __restrict__ out) {
+  const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= N) return;
+  const int half = win / 2;
+  for (int d = blockIdx.y; d < NDOY; d += gridDim.y) {
+    double acc = 0.0;
+    for (int k = 0; k < win; ++k) {
+      int dd = (d - half + k) % NDOY;
+      if (dd < 0) dd += NDOY;
+      const float v = __ldg(&sd[(int64_t)dd * N + c]);
+      acc += (double)__fmul_rn(v, v);  // (std_day_wrap**2) is a float32 array
+    }
+    const float r = sqrtf((float)(acc / (double)win));
+    out[(int64_t)d * N + c] = (r > 1e-10f) ? r : CUDART_NAN_F;
+  }
+}
+
+// out[t, c] = x[t, c] / sd[doy[t], c]  (groupby division, detect.py:2278)
+__global__ void __launch_bounds__(256) div_doy_kernel(const float* __restrict__ x, int64_t T, int64_t N, int64_t pitch,
+                                                      const int16_t* __restrict__ doy, const float* __restrict__ sd,
+                                                      float* __restrict__ out, int64_t out_pitch, int rows_per_block) {
+  const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= N) return;
+  const int64_t t0 = (int64_t)blockIdx.y * rows_per_block, t1 = min(T, t0 + rows_per_block);
+#pragma unroll 4
+  for (int64_t t = t0; t < t1; ++t) {
+    const float v = ld_stream(&x[t * pitch + c]);
+    st_stream(&out[t * out_pitch + c], __fdiv_rn(v, __ldg(&sd[(int64_t)(__ldg(&doy[t]) - 1) * N + c])));
+  }
+}
+
 }  // namespace marex
 
 using namespace marex;
@@ -560,4 +620,46 @@ extern "C" int marex_detrend_apply_f32(const float* x, int64_t T, int64_t N, int
   MAREX_REQUIRE(x && M && coef && xd, "null pointer");
   MAREX_REQUIRE(T > 0 && N > 0 && pitch >= N && xd_pitch >= N, "bad shape");
   MAREX_K_DISPATCH(launch_detrend_apply, x, T, N, pitch, M, coef, xd, xd_pitch, mean, (cudaStream_t)stream);
+}
+
+extern "C" int marex_doy_std_f32(const float* x, int64_t T, int64_t N, int64_t pitch, const int32_t* doy_ptr,
+                                 const int32_t* doy_rows, float* sd, void* stream) {
+  MAREX_REQUIRE(x && doy_ptr && doy_rows && sd, "null pointer");
+  MAREX_REQUIRE(T > 0 && N > 0 && pitch >= N, "bad shape");
+  const int threads = 128;
+  const int64_t bx = (N + threads - 1) / threads;
+  int by = (int)((16LL * sm_count() + bx - 1) / bx);
+  by = by < 1 ? 1 : (by > NDOY ? NDOY : by);
+  doy_std_kernel<<<dim3((unsigned)bx, by), threads, 0, (cudaStream_t)stream>>>(x, N, pitch, doy_ptr, doy_rows, sd);
+  MAREX_LAUNCH_CHECK("doy_std_kernel");
+  return MAREX_OK;
+}
+
+extern "C" int marex_doy_rolling_rms_f32(const float* sd, int64_t N, int32_t win, float* out, void* stream) {
+  MAREX_REQUIRE(sd && out && sd != out, "null or aliased pointer");
+  MAREX_REQUIRE(N > 0 && win >= 1 && win <= NDOY, "bad shape");
+  const int threads = 128;
+  const int64_t bx = (N + threads - 1) / threads;
+  int by = (int)((16LL * sm_count() + bx - 1) / bx);
+  by = by < 1 ? 1 : (by > NDOY ? NDOY : by);
+  doy_rolling_rms_kernel<<<dim3((unsigned)bx, by), threads, 0, (cudaStream_t)stream>>>(sd, N, win, out);
+  MAREX_LAUNCH_CHECK("doy_rolling_rms_kernel");
+  return MAREX_OK;
+}
+
+extern "C" int marex_div_doy_f32(const float* x, int64_t T, int64_t N, int64_t pitch, const int16_t* doy,
+                                 const float* sd, float* out, int64_t out_pitch, void* stream) {
+  MAREX_REQUIRE(x && doy && sd && out, "null pointer");
+  MAREX_REQUIRE(T > 0 && N > 0 && pitch >= N && out_pitch >= N, "bad shape");
+  const int threads = 256;
+  const int64_t bx = (N + threads - 1) / threads;
+  int64_t by = (8LL * sm_count() + bx - 1) / bx;
+  by = by < 1 ? 1 : (by > T ? T : by);
+  if (by > 65535) by = 65535;
+  const int rows_per_block = (int)((T + by - 1) / by);
+  by = (T + rows_per_block - 1) / rows_per_block;
+  div_doy_kernel<<<dim3((unsigned)bx, (unsigned)by), threads, 0, (cudaStream_t)stream>>>(x, T, N, pitch, doy, sd, out,
+                                                                                       out_pitch, rows_per_block);
+  MAREX_LAUNCH_CHECK("div_doy_kernel");
+  return MAREX_OK;
 }

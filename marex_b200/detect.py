@@ -531,6 +531,7 @@ def compute_normalised_anomaly_arrays(
     reference_period: Optional[Tuple[int, int]] = None,
     validate: bool = True,
     in_place: bool = False,
+    std_normalise: bool = False,
 ) -> Dict[str, Any]:
     """Array-level ``compute_normalised_anomaly`` (detect.py:891-1116) for the three hot-path
     methods.  ``x_dev`` is a float32 CUDA tensor (T, N).  Returns ``dat_anomaly`` (T_out, N)
@@ -608,7 +609,18 @@ def compute_normalised_anomaly_arrays(
             _lib.call(
                 "marex_sub_doy_climatology_f32", _p(xd), T, N, N, _p(doy_d), _p(mean), None, _p(xd), N, None, None, st
             )
-        return {"dat_anomaly": xd, "mask": mask_raw, "keep": keep, "mask_raw": mask_raw, "nonfinite": nonfinite}
+        out_h = {"dat_anomaly": xd, "mask": mask_raw, "keep": keep, "mask_raw": mask_raw, "nonfinite": nonfinite}
+        if std_normalise:  # detect.py:2257-2293
+            sd = torch.empty((NDOY, N), dtype=torch.float32, device=dev)
+            rms = torch.empty((NDOY, N), dtype=torch.float32, device=dev)
+            stn = torch.empty_like(xd)
+            _lib.call("marex_doy_std_f32", _p(xd), T, N, N, _p(ptr_d), _p(rows_d), _p(sd), st)
+            _lib.call("marex_doy_rolling_rms_f32", _p(sd), N, 30, _p(rms), st)
+            _lib.call("marex_div_doy_f32", _p(xd), T, N, N, _p(doy_d), _p(rms), _p(stn), N, st)
+            std_cm = torch.empty((N, NDOY), dtype=torch.float32, device=dev)
+            _lib.call("marex_transpose_f32", _p(rms), NDOY, N, _p(std_cm), st)
+            out_h.update({"dat_stn": stn, "STD": std_cm})
+        return out_h
     _lib.call("marex_doy_climatology_f32", _p(xd), T, N, N, _p(ptr_d), _p(rows_d), _p(mean), _p(clim), st)
     mask1 = torch.empty(N, dtype=torch.uint8, device=dev)
     _lib.call(
@@ -1102,14 +1114,13 @@ def preprocess_arrays(
     copies and kernels overlapped (``_preprocess_host_streamed``); ``chunks=1`` forces one piece."""
     if detrend_orders is None:
         detrend_orders = [1]
-    if std_normalise:
-        raise NotImplementedError("std_normalise (dat_stn / STD / extreme_events_stn, detect.py:2257-2293) is not implemented yet")
+    std_normalise = bool(std_normalise) and method_anomaly == "detrend_harmonic"  # ignored otherwise, as upstream
     dev = _device(device)
     validate_reference_period_method(reference_period, method_anomaly)
     validate_anomaly_method(method_anomaly)
     cal = build_calendar(time)
     on_host = not (isinstance(x, torch.Tensor) and x.is_cuda)
-    if on_host and output in ("numpy", "pinned") and not want_bits:
+    if on_host and output in ("numpy", "pinned") and not want_bits and not std_normalise:
         xh = x if isinstance(x, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(x))
         nbytes = xh.numel() * 4
         n_chunks = chunks if chunks is not None else (1 if nbytes < (1 << 30) else int(min(16, max(2, round(nbytes / 6e9)))))
@@ -1149,6 +1160,7 @@ def preprocess_arrays(
     res = compute_normalised_anomaly_arrays(
         x_dev, cal, method_anomaly, window_year_baseline, smooth_days_baseline, detrend_orders, force_zero_mean,
         reference_period, validate=True, in_place=owns_input and method_anomaly != "shifting_baseline",
+        std_normalise=std_normalise,
     )  # fmt: skip
     anom, keep = res["dat_anomaly"], res["keep"]
     if owns_input and method_anomaly == "shifting_baseline":
@@ -1180,9 +1192,19 @@ def preprocess_arrays(
         out["extreme_events"] = ext["extreme_events"].reshape((T_out,) + space)
     if want_bits:
         out["bits"] = ext["bits"]
+    if std_normalise:  # detect.py:686-715: the same extreme identification on the standardised anomalies
+        ext_s = identify_extremes_arrays(
+            res["dat_stn"], doy_out, grid, method_extreme, threshold_percentile, window_days_hobday, window_spatial_hobday,
+            method_percentile, precision, max_anomaly, want_events=True, want_bits=False,
+        )  # fmt: skip
+        out["dat_stn"] = res["dat_stn"].reshape((T_out,) + space)
+        out["STD"] = res["STD"].reshape(space + (NDOY,))
+        out["extreme_events_stn"] = ext_s["extreme_events"].reshape((T_out,) + space)
+        out["thresholds_stn"] = ext_s["thresholds"]
     logger.info("Preprocessing completed successfully - %d extreme events identified", int(ext["count"]))
     if output in ("numpy", "pinned"):
-        host = {k: _to_host(out[k], k, output == "pinned") for k in ("dat_anomaly", "mask", "thresholds", "extreme_events", "bits") if k in out}
+        keys = ("dat_anomaly", "mask", "thresholds", "extreme_events", "bits", "dat_stn", "STD", "extreme_events_stn", "thresholds_stn")
+        host = {k: _to_host(out[k], k, output == "pinned") for k in keys if k in out}
         out["extreme_count"] = int(out["extreme_count"])  # synchronises the stream: the copies above are complete
         for k, v in host.items():
             out[k] = v.numpy()

@@ -191,6 +191,15 @@ def preprocess_data(
         ds = ds.assign_coords(dayofyear=np.arange(1, 367))
     else:
         ds["thresholds"] = (tuple(sdims), res["thresholds"])
+    if "dat_stn" in res:  # std_normalise (detect.py:686-715, 2290-2293)
+        ds["dat_stn"] = ((tdim, *sdims), res["dat_stn"])
+        ds["STD"] = ((*sdims, "dayofyear"), res["STD"])
+        ds["extreme_events_stn"] = ((tdim, *sdims), res["extreme_events_stn"])
+        lay = res["thresholds_layout"]
+        tdims_ = (*sdims, "dayofyear") if lay == "doy_last" else (("dayofyear", *sdims) if lay == "doy_first" else tuple(sdims))
+        ds["thresholds_stn"] = (tdims_, res["thresholds_stn"])
+        if "dayofyear" not in ds.coords:
+            ds = ds.assign_coords(dayofyear=np.arange(1, 367))
     if neighbours is not None:  # detect.py:718-723
         ds["neighbours"] = neighbours.astype(np.int32)
         if "nv" in neighbours.dims:
@@ -235,8 +244,6 @@ def compute_normalised_anomaly(
 
     dimensions, coordinates = _infer_dims_coords(da, dimensions, coordinates)
     _d.validate_reference_period_method(reference_period, method_anomaly)
-    if std_normalise:
-        raise NotImplementedError("std_normalise (dat_stn / STD, detect.py:2257-2293) is not implemented yet")
     if da.chunks is None:  # upstream: TypeError from da.chunks[0] (detect.py:2180), pinned by its tests
         raise TypeError("'NoneType' object is not subscriptable")
     tdim, sdims = dimensions["time"], _space_dims(dimensions)
@@ -248,6 +255,7 @@ def compute_normalised_anomaly(
     res = _d.compute_normalised_anomaly_arrays(
         x_dev, cal, method_anomaly, window_year_baseline, smooth_days_baseline, detrend_orders, force_zero_mean,
         reference_period, validate=False, in_place=(method_anomaly != "shifting_baseline"),
+        std_normalise=bool(std_normalise) and method_anomaly == "detrend_harmonic",
     )  # fmt: skip
     anom = res["dat_anomaly"]
     if method_anomaly == "shifting_baseline":  # upstream returns the untrimmed series
@@ -258,6 +266,10 @@ def compute_normalised_anomaly(
     ds = xr.Dataset(coords={k: v for k, v in base.coords.items()})
     ds["dat_anomaly"] = ((tdim, *sdims), anom.reshape((cal.T,) + space).cpu().numpy())
     ds["mask"] = (tuple(sdims), res["mask"].reshape(space).cpu().numpy())
+    if "dat_stn" in res:  # detect.py:2290-2293
+        ds["dat_stn"] = ((tdim, *sdims), res["dat_stn"].reshape((cal.T,) + space).cpu().numpy())
+        ds["STD"] = ((*sdims, "dayofyear"), res["STD"].reshape(space + (366,)).cpu().numpy())
+        ds = ds.assign_coords(dayofyear=np.arange(1, 367))
     return ds
 
 

@@ -237,6 +237,32 @@ def detrend(x, time, detrend_orders=(1,), force_zero_mean=True, remove_harmonics
     return xd.reshape(x.shape)
 
 
+def std_normalise(xd, doy, window: int = 30):
+    """The ``std_normalise`` branch of ``_compute_anomaly_detrended`` (detect.py:2257-2293): per-day-of-year
+    population std (flox ``std``, float32 result), squared, centred ``window``-day rolling mean with annual
+    wrap (window [d-15, d+14] for 30), sqrt, values <= 1e-10 -> NaN, division by day of year.
+    Returns ``dat_stn`` like ``xd`` and ``STD`` as ``(N, 366)`` float32.  PARITY UNPINNED (flox / bottleneck
+    summation order): float64 accumulation rounded once."""
+    x2, tail = _flat(np.asarray(xd, dtype=np.float32))
+    T, N = x2.shape
+    d0 = np.asarray(doy).astype(np.int64) - 1
+    std_day = np.full((NDOY, N), np.nan, dtype=np.float32)
+    with np.errstate(invalid="ignore", over="ignore"):
+        for d in range(NDOY):
+            rows = np.nonzero(d0 == d)[0]
+            if rows.size:
+                std_day[d] = np.std(x2[rows].astype(np.float64), axis=0).astype(np.float32)
+        sq = (std_day * std_day).astype(np.float32)
+        half = window // 2
+        out = np.empty((NDOY, N), dtype=np.float32)
+        for d in range(NDOY):
+            idx = (np.arange(d - half, d - half + window)) % NDOY
+            out[d] = np.sqrt(np.mean(sq[idx].astype(np.float64), axis=0).astype(np.float32))
+        out = np.where(out > np.float32(1e-10), out, np.float32(np.nan)).astype(np.float32)
+        stn = (x2 / out[d0]).astype(np.float32)
+    return stn.reshape(np.asarray(xd).shape), np.ascontiguousarray(out.T)
+
+
 def anomaly_detrend_fixed_baseline(x, time, year, doy, detrend_orders=(1,), force_zero_mean=True, reference_period=None):
     """``_compute_anomaly_detrend_fixed_baseline`` (detect.py:2400-2462)."""
     xd = detrend(x, time, detrend_orders, force_zero_mean, remove_harmonics=False)
@@ -530,6 +556,7 @@ def preprocess(
     method_percentile: str = "approximate",
     precision: float = 0.01,
     max_anomaly: float = 5.0,
+    std_normalise_flag: bool = False,
 ) -> Dict[str, np.ndarray]:
     """Array-level ``preprocess_data`` (detect.py:287-841).  ``x[T, ny, nx]`` (gridded)
     or ``x[T, ncells]`` (unstructured).  Thresholds are returned in the reference's
@@ -579,10 +606,43 @@ def preprocess(
         events = compare_global(a2, thr)
     else:
         raise ValueError(method_extreme)
-    return {
+    out = {
         "dat_anomaly": anom,
         "mask": mask.reshape(space),
         "thresholds": thr_out,
         "extreme_events": events.reshape(anom.shape),
         "time": time_o,
     }
+    if std_normalise_flag and method_anomaly == "detrend_harmonic":  # detect.py:686-715
+        stn, std = std_normalise(anom, doy_o)
+        sub = preprocess_from_anomaly(stn, doy_o, method_extreme, threshold_percentile, window_days_hobday,
+                                      window_spatial_hobday, method_percentile, precision, max_anomaly)
+        out.update({"dat_stn": stn, "STD": std.reshape(space + (NDOY,)), "extreme_events_stn": sub[0], "thresholds_stn": sub[1]})
+    return out
+
+
+def preprocess_from_anomaly(anom, doy_o, method_extreme, threshold_percentile, window_days_hobday, window_spatial_hobday,
+                            method_percentile, precision, max_anomaly):
+    """``identify_extremes`` (detect.py:1119-1503) on an anomaly field: (events, thresholds in the reference's layout)."""
+    anom = np.asarray(anom, dtype=np.float32)
+    space = anom.shape[1:]
+    gridded = len(space) == 2
+    a2 = anom.reshape(anom.shape[0], -1)
+    q = threshold_percentile / 100.0
+    if method_extreme == "hobday_extreme":
+        if method_percentile == "exact":
+            thr_dm = hobday_thresholds_exact(a2, doy_o, threshold_percentile, window_days_hobday)
+            thr_out = thr_dm.reshape((NDOY,) + space)
+        else:
+            ws = window_spatial_hobday
+            if ws is None and gridded:
+                ws = 5
+            thr_cm = hobday_thresholds_approx(a2, doy_o, q, window_days_hobday, ws, space if gridded else None, precision, max_anomaly)
+            thr_dm = np.ascontiguousarray(thr_cm.T)
+            thr_out = thr_cm.reshape(space + (NDOY,))
+        events = compare_hobday(a2, doy_o, thr_dm)
+    else:
+        thr = global_threshold_exact(a2, threshold_percentile) if method_percentile == "exact" else global_threshold_approx(a2, q, precision, max_anomaly)
+        thr_out = thr.reshape(space)
+        events = compare_global(a2, thr)
+    return events.reshape(anom.shape), thr_out

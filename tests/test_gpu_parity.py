@@ -596,5 +596,34 @@ def test_preprocess_detrend_harmonic(extreme, chunks):
         _ulp_equal(np.asarray(got["thresholds"]).reshape(-1), thr)
         ev = mo.compare_global(a2, thr)
     np.testing.assert_array_equal(np.asarray(got["extreme_events"]).reshape(len(time), -1), ev)
-    with pytest.raises(NotImplementedError, match="std_normalise"):
-        mb.preprocess_arrays(x, time, std_normalise=True, **kw)
+
+
+# ---------------------------------------------------------------- std_normalise (detect.py:2257-2293, 686-715)
+@pytest.mark.parametrize("extreme", ["global_extreme", "hobday_extreme"])
+def test_std_normalise(extreme):
+    mb = _cuda()
+    x, time = _field(T1="2001-01-01", ny=6, nx=36, seed=12)
+    kw = dict(method_anomaly="detrend_harmonic", method_extreme=extreme, window_days_hobday=5)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        got = mb.preprocess_arrays(x, time, std_normalise=True, **kw)
+        ref = mo.preprocess(x, time, std_normalise_flag=True, **kw)
+    for k in ("dat_stn", "STD", "extreme_events_stn", "thresholds_stn"):
+        assert k in got, k
+    assert got["attrs"]["std_normalise"] is True
+    assert got["attrs"]["preprocessing_steps"][1] == "Normalised by 30-day rolling STD"
+    # stage-wise: from the GPU's own detrended anomalies, STD and dat_stn within float32 rounding of the oracle
+    _, doy = mo.calendar_tables(time)
+    stn_ref, std_ref = mo.std_normalise(np.asarray(got["dat_anomaly"]), doy)
+    np.testing.assert_array_equal(np.isnan(got["STD"].reshape(-1, 366)), np.isnan(std_ref))
+    np.testing.assert_allclose(got["STD"].reshape(-1, 366), std_ref, rtol=2e-6, atol=0, equal_nan=True)
+    np.testing.assert_allclose(got["dat_stn"], stn_ref, rtol=4e-6, atol=0, equal_nan=True)
+    # thresholds / events of the standardised field: bit-exact from identical dat_stn
+    ev_ref, thr_ref = mo.preprocess_from_anomaly(np.asarray(got["dat_stn"]), doy, extreme, 95, 5, None, "approximate", 0.01, 5.0)
+    _ulp_equal(np.asarray(got["thresholds_stn"]), thr_ref)
+    np.testing.assert_array_equal(np.asarray(got["extreme_events_stn"]), ev_ref)
+    # and the end-to-end oracle agrees to tolerance
+    np.testing.assert_allclose(got["dat_stn"], ref["dat_stn"], rtol=0, atol=2e-3, equal_nan=True)
+    # std_normalise is ignored for the other baselines, as upstream
+    other = mb.preprocess_arrays(x, time, std_normalise=True, method_anomaly="fixed_baseline", method_extreme="global_extreme")
+    assert "dat_stn" not in other
