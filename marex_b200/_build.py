@@ -28,22 +28,34 @@ def needs_build() -> bool:
 
 
 def build(force: bool = False, verbose: bool = False) -> str:
+    """Compile every .cu to an object file in parallel, then link the shared library."""
     if not force and not needs_build():
         return LIB
-    cmd = [
-        _nvcc(),
-        "-gencode", "arch=compute_100a,code=sm_100a",
-        "-O3", "-lineinfo", "-std=c++17",
-        "--shared", "-Xcompiler", "-fPIC",
-        "-Xptxas", "-v" if verbose else "-O3",
-        "-o", LIB,
-    ] + [os.path.join(CSRC, s) for s in SOURCES]
-    res = subprocess.run(cmd, capture_output=True, text=True)
-    if res.returncode != 0:
-        sys.stderr.write(res.stdout + res.stderr)
-        raise RuntimeError("nvcc failed building libmarex_b200.so")
-    if verbose:
-        sys.stderr.write(res.stdout + res.stderr)
+    from concurrent.futures import ThreadPoolExecutor
+
+    nvcc = _nvcc()
+    objdir = os.path.join(HERE, "build")
+    os.makedirs(objdir, exist_ok=True)
+    flags = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17", "-Xcompiler", "-fPIC",
+             "-Xptxas", "-v" if verbose else "-O3"]  # fmt: skip
+
+    def compile_one(src):
+        obj = os.path.join(objdir, src.replace(".cu", ".o"))
+        res = subprocess.run([nvcc] + flags + ["-c", os.path.join(CSRC, src), "-o", obj], capture_output=True, text=True)
+        return src, obj, res
+
+    with ThreadPoolExecutor(max_workers=min(len(SOURCES), os.cpu_count() or 1)) as pool:
+        results = list(pool.map(compile_one, SOURCES))
+    for src, _obj, res in results:
+        if res.returncode != 0:
+            sys.stderr.write(res.stdout + res.stderr)
+            raise RuntimeError(f"nvcc failed compiling {src}")
+        if verbose:
+            sys.stderr.write(res.stdout + res.stderr)
+    link = subprocess.run([nvcc, "--shared", "-o", LIB] + [o for _s, o, _r in results], capture_output=True, text=True)
+    if link.returncode != 0:
+        sys.stderr.write(link.stdout + link.stderr)
+        raise RuntimeError("nvcc failed linking libmarex_b200.so")
     return LIB
 
 

@@ -500,8 +500,9 @@ extern "C" int marex_hobday_thresholds_pooled_f32(const float* anom, int64_t T, 
   const int env_ty = getenv("MAREX_POOL_TY") ? atoi(getenv("MAREX_POOL_TY")) : 0;
   MAREX_REQUIRE(env_k == 0 || env_k == 64 || env_k == 128, "MAREX_POOL_K must be 64 or 128");
   // 12 target rows (16 x 32 own gridpoints, two tiles per SM at 64 registers) measured best on B200:
-  // 71.2 ms vs 74.6 (8 rows) and 74.1 (16 rows) for the threshold + compare stages at 0.25 deg; 3: small tiles (tests)
-  const int TY = (env_ty && env_ty < 8) ? 3 : (env_ty >= 16 ? 16 : (env_ty == 8 ? 8 : 12));
+  // 71.2 ms vs 74.6 (8 rows) and 74.1 (16 rows) for the threshold + compare stages at 0.25 deg.
+  // MAREX_POOL_TY < 8 selects 3-row tiles (exercised by the tests).
+  const int TY = (env_ty && env_ty < 8) ? 3 : 12;
   const int OY = TY + 2 * P, TX = 32 - 2 * P;
   const dim3 grid_all((unsigned)((nx + TX - 1) / TX), (unsigned)((ny + TY - 1) / TY));
   const int max_tiles = (int)(grid_all.x * grid_all.y);
@@ -532,8 +533,8 @@ extern "C" int marex_hobday_thresholds_pooled_f32(const float* anom, int64_t T, 
   } while (0)
 #define MAREX_BAND_K(PP)                                                                 \
   do {                                                                                   \
-    if (K == 64) { if (TY == 8) MAREX_BAND(PP, 64, 8); else if (TY == 16) MAREX_BAND(PP, 64, 16); else if (TY == 12) MAREX_BAND(PP, 64, 12); else MAREX_BAND(PP, 64, 3); }     \
-    else { if (TY == 8) MAREX_BAND(PP, 128, 8); else if (TY == 16) MAREX_BAND(PP, 128, 16); else if (TY == 12) MAREX_BAND(PP, 128, 12); else MAREX_BAND(PP, 128, 3); }           \
+    if (K == 64) { if (TY == 12) MAREX_BAND(PP, 64, 12); else MAREX_BAND(PP, 64, 3); }   \
+    else { if (TY == 12) MAREX_BAND(PP, 128, 12); else MAREX_BAND(PP, 128, 3); }         \
   } while (0)
     if (P == 1) MAREX_BAND_K(1); else if (P == 2) MAREX_BAND_K(2); else MAREX_BAND_K(3);
 #undef MAREX_BAND_K
