@@ -116,6 +116,21 @@ def host_memory_available():
     return avail if avail is not None else 64e9
 
 
+def gpu_cpu_affinity(index):
+    """CPUs NVML reports as local to GPU `index` (its NUMA node), or None."""
+    try:
+        import pynvml
+
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(index)
+        n = os.cpu_count() or 64
+        words = pynvml.nvmlDeviceGetCpuAffinity(h, (n + 63) // 64)
+        cpus = {64 * i + b for i, w in enumerate(words) for b in range(64) if (int(w) >> b) & 1}
+        return cpus or None
+    except Exception:
+        return None
+
+
 def measured_peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -291,6 +306,14 @@ def main():
 
     assert torch.cuda.is_available(), "bench.py needs a CUDA device"
     torch.cuda.set_device(local)
+    # NUMA: run (and first-touch the pinned host buffers of the e2e leg) on the CPUs next to this GPU's PCIe root
+    all_cpus = os.sched_getaffinity(0)
+    near_cpus = gpu_cpu_affinity(local)
+    if near_cpus:
+        try:
+            os.sched_setaffinity(0, near_cpus & all_cpus or all_cpus)
+        except Exception:
+            near_cpus = None
     dev = torch.device("cuda", local)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
@@ -467,6 +490,7 @@ def main():
             "warmup": 1,
             "ms_per_step": dt * 1e3,
             "timer": "host perf_counter around the public call (copies + kernels + sync), max over ranks",
+            "cpu_affinity": "GPU-local NUMA node" if near_cpus else "unchanged",
         }
         x_sample_src = xh
     else:
@@ -475,7 +499,11 @@ def main():
     # ---- CPU baseline on rank 0, N = 1 only: oracle on a bounded sample of this very field ----
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
-        cores = os.cpu_count() or 1
+        try:
+            os.sched_setaffinity(0, all_cpus)  # the CPU baseline uses every core of the box
+        except Exception:
+            pass
+        cores = len(all_cpus) or os.cpu_count() or 1
         th, tw = 6, 8
         tiles = []
         r0 = 0 if unstructured else (x_sample_src.shape[1] // 2) // th * th

@@ -292,6 +292,18 @@ def test_lat_band_and_cell_range_partition():
     assert sharding.effective_halo("hobday_extreme", "approximate", None, False) == 0
 
 
+def test_streamed_chunk_bounds_cover_the_field_once():
+    """Chunks of the streamed host path: contiguous, disjoint, complete, interior boundaries aligned."""
+    from marex_b200 import detect as d
+
+    for n_units, n_chunks, align in [(720, 10, 1), (7, 16, 1), (1 << 20, 8, 32), (1000, 3, 32), (33, 4, 32), (5, 1, 1)]:
+        b = d._chunk_bounds(n_units, n_chunks, align)
+        assert b[0][0] == 0 and b[-1][1] == n_units and len(b) <= max(1, n_chunks)
+        for (a0, a1), (b0, b1) in zip(b[:-1], b[1:]):
+            assert a1 == b0 and a0 < a1 and b0 % align == 0
+        assert all(hi > lo for lo, hi in b)
+
+
 # ------------------------------------------------------------------ world_size-2 gloo run of the N > 1 path
 _WORKER = r"""
 import os, sys, numpy as np, torch, torch.distributed as dist
