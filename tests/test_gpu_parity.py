@@ -627,3 +627,28 @@ def test_std_normalise(extreme):
     # std_normalise is ignored for the other baselines, as upstream
     other = mb.preprocess_arrays(x, time, std_normalise=True, method_anomaly="fixed_baseline", method_extreme="global_extreme")
     assert "dat_stn" not in other
+
+
+def test_banded_kernel_long_series_many_rows_per_day():
+    """More rows per day of year than the kernel stages / prefetches in one go (34 years: 34 rows > the 26
+    prefetched and the 32 staged), through the un-trimmed fixed baseline."""
+    mb = _cuda()
+    rng = np.random.default_rng(21)
+    time = np.arange(np.datetime64("1980-01-01"), np.datetime64("2014-01-01"))
+    a = (rng.standard_normal((len(time), 5, 34)) * rng.uniform(0.3, 1.5, (5, 34))).astype(np.float32)
+    a[:, 2, 5] = np.nan
+    _, doy = mo.calendar_tables(time)
+    a2 = a.reshape(len(time), -1)
+    for ws, w in ((5, 11), (3, 5)):
+        ref = mo.hobday_thresholds_approx(a2, doy, 0.95, w, ws, a.shape[1:])
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            res = mb.identify_extremes_arrays(torch.from_numpy(a2).cuda(), doy, a.shape[1:], "hobday_extreme", 95, w, ws)
+        _ulp_equal(res["thresholds"].cpu().numpy().reshape(-1, 366), ref)
+        np.testing.assert_array_equal(
+            res["extreme_events"].cpu().numpy(), mo.compare_hobday(a2, doy, np.ascontiguousarray(ref.T))
+        )
+    # exact path with the same row counts (window kept in shared memory: 11 x 34 rows)
+    ref_e = mo.hobday_thresholds_exact(a2, doy, 95.0, 11)
+    res_e = mb.identify_extremes_arrays(torch.from_numpy(a2).cuda(), doy, a.shape[1:], "hobday_extreme", 95, 11, None, "exact")
+    _ulp_equal(res_e["thresholds"].cpu().numpy().reshape(366, -1), ref_e)
