@@ -652,3 +652,31 @@ def test_banded_kernel_long_series_many_rows_per_day():
     ref_e = mo.hobday_thresholds_exact(a2, doy, 95.0, 11)
     res_e = mb.identify_extremes_arrays(torch.from_numpy(a2).cuda(), doy, a.shape[1:], "hobday_extreme", 95, 11, None, "exact")
     _ulp_equal(res_e["thresholds"].cpu().numpy().reshape(366, -1), ref_e)
+
+
+def test_preprocess_zarr_roundtrip(tmp_path):
+    """zarr v2 store -> pinned host field -> pipeline -> zarr v2 group: same result as the array API."""
+    mb = _cuda()
+    from marex_b200 import io_zarr as zio
+
+    x, time = _field(T1="1998-01-01", ny=6, nx=36, seed=13)
+    src, dst = str(tmp_path / "in.zarr"), str(tmp_path / "out.zarr")
+    zio.write_array(src, "sst", x.astype(np.float64), (40, 6, 36), ["time", "lat", "lon"])  # float64 store, cast on read
+    days = (time - np.datetime64("1981-01-01")).astype(np.int64)
+    zio.write_array(src, "time", (days * 86400).astype(np.int64), (100,), ["time"],
+                    {"units": "seconds since 1981-01-01", "calendar": "proleptic_gregorian"})  # fmt: skip
+    kw = dict(window_year_baseline=3, smooth_days_baseline=5, window_days_hobday=5)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        got = zio.preprocess_zarr(src, "sst", out_store=dst, **kw)
+        ref = mb.preprocess_arrays(x, time, **kw)
+    for k in ("dat_anomaly", "thresholds"):
+        _ulp_equal(np.asarray(got[k]), np.asarray(ref[k]))
+    np.testing.assert_array_equal(got["extreme_events"], ref["extreme_events"])
+    back = zio.read_array(dst, "extreme_events")
+    assert back.dtype == np.bool_
+    np.testing.assert_array_equal(back, ref["extreme_events"])
+    _ulp_equal(zio.read_array(dst, "thresholds"), np.asarray(ref["thresholds"]))
+    _, t_back, dims = zio.read_field(dst, "dat_anomaly", pinned=False)
+    assert dims == ["time", "lat", "lon"]
+    np.testing.assert_array_equal(t_back.astype("datetime64[D]"), ref["time"])
