@@ -8,9 +8,60 @@ import numpy as np
 NDOY = 366
 
 
+_MONTH_DAYS = np.array([31, 28, 31, 30, 31, 30, 31, 31, 30, 31, 30, 31])
+MODEL_CALENDARS = {"noleap": 365, "365_day": 365, "all_leap": 366, "366_day": 366, "360_day": 360}
+
+
+@dataclass
+class ModelTime:
+    """A time axis on a fixed-length model calendar (CF ``noleap`` / ``365_day``, ``all_leap`` / ``366_day``,
+    ``360_day``) -- SURVEY.md 8f row 4.  numpy has no datetime type for these, so the axis is carried as
+    ``year`` / ``doy`` (what the reference reads through ``.dt.year`` / ``.dt.dayofyear``, detect.py:1605-1606,
+    on a cftime index) plus the length of the calendar year."""
+
+    year: np.ndarray  # int32 (T,)
+    doy: np.ndarray  # int16 (T,) 1..days_in_year
+    days_in_year: int
+    label: np.ndarray  # (T,) the caller's own time values (returned, trimmed, as ``time``)
+
+    def __len__(self) -> int:
+        return int(self.year.shape[0])
+
+    @property
+    def decimal_year(self) -> np.ndarray:
+        return self.year.astype(np.float64) + (self.doy.astype(np.float64) - 1.0) / float(self.days_in_year)
+
+
+def _model_doy0(month: int, day: int, calendar: str) -> int:
+    """0-based day of year of (month, day) on a model calendar."""
+    if MODEL_CALENDARS[calendar] == 360:
+        return (month - 1) * 30 + (day - 1)
+    md = _MONTH_DAYS.copy()
+    if MODEL_CALENDARS[calendar] == 366:
+        md[1] = 29
+    return int(md[: month - 1].sum()) + (day - 1)
+
+
+def model_time_from_cf(values, units: str, calendar: str) -> ModelTime:
+    """CF ``"<unit> since YYYY-MM-DD[ hh:mm:ss]"`` numbers on a model calendar -> ``ModelTime`` (whole days;
+    sub-daily samples of one day map to the same day and are rejected by ``build_calendar``)."""
+    if calendar not in MODEL_CALENDARS:
+        raise NotImplementedError(f"calendar '{calendar}' is not a supported model calendar {sorted(MODEL_CALENDARS)}")
+    unit, _, epoch = units.partition(" since ")
+    per_day = {"days": 1.0, "day": 1.0, "hours": 24.0, "hour": 24.0, "minutes": 1440.0, "seconds": 86400.0, "second": 86400.0}
+    if unit.strip() not in per_day or not epoch:
+        raise ValueError(f"cannot parse time units '{units}'")
+    date = epoch.strip().replace("T", " ").split(" ")[0]
+    ey, em, ed = (int(v) for v in date.split("-"))
+    L = MODEL_CALENDARS[calendar]
+    v = np.asarray(values, dtype=np.float64) / per_day[unit.strip()]
+    ordinal = np.floor(v + 1e-9).astype(np.int64) + ey * L + _model_doy0(em, ed, calendar)
+    return ModelTime((ordinal // L).astype(np.int32), (ordinal % L + 1).astype(np.int16), L, np.asarray(values))
+
+
 @dataclass
 class Calendar:
-    time: np.ndarray  # datetime64[D] (T,)
+    time: np.ndarray  # datetime64[D] (T,)  (ModelTime: the caller's labels)
     year: np.ndarray  # int32 (T,)
     doy: np.ndarray  # int16 (T,) 1..366
     year_val: np.ndarray  # int32 (n_years,) ascending distinct years
@@ -24,11 +75,21 @@ class Calendar:
     def n_years(self) -> int:
         return int(self.year_val.shape[0])
 
+    model_dy: Optional[np.ndarray] = None  # decimal year of a ModelTime axis (None: Gregorian datetime64 axis)
+
     @property
     def is_daily(self) -> bool:
-        """Gap-free daily axis: every row is the day after the previous one (what the TMA-staged
-        shifting-baseline kernel assumes; anything else takes the generic table-driven kernel)."""
+        """Gap-free daily proleptic-Gregorian axis: every row is the day after the previous one (what the
+        TMA-staged shifting-baseline kernel assumes; model calendars, gaps and sub-sampled axes take the generic
+        table-driven kernel)."""
+        if self.model_dy is not None:
+            return False
         return bool(np.all(np.diff(self.time.astype("datetime64[D]").astype(np.int64)) == 1))
+
+    @property
+    def decimal_year(self) -> np.ndarray:
+        """detect.py:2031-2058 (Gregorian), year + (doy - 1) / days_in_year on a model calendar."""
+        return self.model_dy if self.model_dy is not None else decimal_year(self.time)
 
 
 def year_doy(time) -> Tuple[np.ndarray, np.ndarray]:
@@ -49,10 +110,18 @@ def decimal_year(time) -> np.ndarray:
 
 
 def build_calendar(time) -> Calendar:
-    t = np.asarray(time).astype("datetime64[D]")
-    if t.ndim != 1 or t.size == 0:
-        raise ValueError("time must be a non-empty 1-D datetime64 array")
-    year, doy = year_doy(t)
+    model_dy = None
+    if isinstance(time, ModelTime):
+        t, year, doy, model_dy = np.asarray(time.label), time.year.astype(np.int32), time.doy.astype(np.int16), time.decimal_year
+        if year.ndim != 1 or year.size == 0 or doy.shape != year.shape or t.shape != year.shape:
+            raise ValueError("ModelTime needs matching non-empty 1-D year / doy / label arrays")
+        if doy.min() < 1 or doy.max() > NDOY:
+            raise ValueError("day of year out of range 1..366")
+    else:
+        t = np.asarray(time).astype("datetime64[D]")
+        if t.ndim != 1 or t.size == 0:
+            raise ValueError("time must be a non-empty 1-D datetime64 array")
+        year, doy = year_doy(t)
     year_val, yi = np.unique(year, return_inverse=True)
     key = yi.astype(np.int64) * NDOY + (doy.astype(np.int64) - 1)
     if np.unique(key).size != key.size:
@@ -62,7 +131,7 @@ def build_calendar(time) -> Calendar:
         )
     tidx = np.full(year_val.size * NDOY, -1, dtype=np.int32)
     tidx[key] = np.arange(t.size, dtype=np.int32)
-    return Calendar(t, year, doy, year_val.astype(np.int32), tidx)
+    return Calendar(t, year, doy, year_val.astype(np.int32), tidx, model_dy)
 
 
 def doy_csr(doy: np.ndarray, rows: Optional[np.ndarray] = None) -> Tuple[np.ndarray, np.ndarray]:

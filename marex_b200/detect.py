@@ -464,7 +464,7 @@ def detrend_model(time, detrend_orders: Sequence[int], remove_harmonics: bool = 
     """Design matrix (K, T) and its pseudo-inverse (T, K), float64 (detect.py:2139-2169): constant,
     centred polynomial terms and, for ``detrend_harmonic``, the annual and semi-annual sine / cosine
     pairs (detect.py:2150-2159); ``remove_harmonics=False`` is detrend_fixed_baseline (detect.py:2450)."""
-    dy = decimal_year(time)
+    dy = time.decimal_year if isinstance(time, Calendar) else decimal_year(time)
     comps = [np.ones(len(dy))]
     centered = dy - np.mean(dy)
     for order in detrend_orders:
@@ -588,7 +588,7 @@ def compute_normalised_anomaly_arrays(
     validate_detrend_orders(detrend_orders)
     if 1 not in detrend_orders and len(detrend_orders) > 1:
         print("Warning: Higher-order detrending without linear term may be unstable")  # detect.py:2135-2136
-    model, pmodel = detrend_model(cal.time, list(detrend_orders), remove_harmonics=harmonic)
+    model, pmodel = detrend_model(cal, list(detrend_orders), remove_harmonics=harmonic)
     K = model.shape[0]
     coef = torch.empty((K, N), dtype=torch.float64, device=dev)
     _lib.call(

@@ -208,8 +208,8 @@ def anomaly_fixed_baseline(x, year, doy, reference_period=None):
 
 def detrend_model(time, detrend_orders: Sequence[int], remove_harmonics: bool = False):
     """Design matrix ``model`` (K, T) float64 and its pseudo-inverse ``pmodel`` (T, K)
-    (detect.py:2139-2169)."""
-    dy = decimal_year(time)
+    (detect.py:2139-2169).  ``time``: datetime64 axis, or a float64 decimal-year array (model calendars)."""
+    dy = np.asarray(time) if np.asarray(time).dtype.kind == "f" else decimal_year(time)
     comps = [np.ones(len(dy))]
     centered = dy - np.mean(dy)
     for order in detrend_orders:
@@ -557,6 +557,7 @@ def preprocess(
     precision: float = 0.01,
     max_anomaly: float = 5.0,
     std_normalise_flag: bool = False,
+    year_doy=None,
 ) -> Dict[str, np.ndarray]:
     """Array-level ``preprocess_data`` (detect.py:287-841).  ``x[T, ny, nx]`` (gridded)
     or ``x[T, ncells]`` (unstructured).  Thresholds are returned in the reference's
@@ -565,7 +566,12 @@ def preprocess(
     x = np.asarray(x, dtype=np.float32)
     space = x.shape[1:]
     gridded = len(space) == 2
-    year, doy = calendar_tables(time)
+    if year_doy is not None:  # model calendar (noleap / 360_day ...): (year, doy, decimal_year) given, `time` = labels
+        year, doy, dy_model = (np.asarray(v) for v in year_doy)
+        time_fit = dy_model.astype(np.float64)
+    else:
+        year, doy = calendar_tables(time)
+        time_fit = time
     if method_anomaly == "shifting_baseline":
         anom, mask, keep = anomaly_shifting_baseline(x, year, doy, window_year_baseline, smooth_days_baseline)
         doy_o, time_o = doy[keep], np.asarray(time)[keep]
@@ -573,10 +579,10 @@ def preprocess(
         anom, mask = anomaly_fixed_baseline(x, year, doy, reference_period)
         doy_o, time_o = doy, np.asarray(time)
     elif method_anomaly == "detrend_fixed_baseline":
-        anom, mask = anomaly_detrend_fixed_baseline(x, time, year, doy, detrend_orders, force_zero_mean, reference_period)
+        anom, mask = anomaly_detrend_fixed_baseline(x, time_fit, year, doy, detrend_orders, force_zero_mean, reference_period)
         doy_o, time_o = doy, np.asarray(time)
     elif method_anomaly == "detrend_harmonic":  # detect.py:2061-2296 with std_normalise=False
-        anom = detrend(x, time, detrend_orders, force_zero_mean, remove_harmonics=True)
+        anom = detrend(x, time_fit, detrend_orders, force_zero_mean, remove_harmonics=True)
         mask = np.isfinite(_flat(x)[0][0])  # detect.py:2228: first step of the raw field
         doy_o, time_o = doy, np.asarray(time)
     else:

@@ -680,3 +680,33 @@ def test_preprocess_zarr_roundtrip(tmp_path):
     _, t_back, dims = zio.read_field(dst, "dat_anomaly", pinned=False)
     assert dims == ["time", "lat", "lon"]
     np.testing.assert_array_equal(t_back.astype("datetime64[D]"), ref["time"])
+
+
+@pytest.mark.parametrize("kw", [dict(window_year_baseline=3, smooth_days_baseline=5, window_days_hobday=5),
+                                dict(method_anomaly="detrend_fixed_baseline", method_extreme="global_extreme")])
+def test_model_calendar_noleap(kw):
+    """A CF `noleap` axis: generic table-driven kernels, same arithmetic as the oracle on the
+    (year, day-of-year, decimal-year) tables."""
+    mb = _cuda()
+    from marex_b200 import calendar as cal
+
+    rng = np.random.default_rng(31)
+    T = 9 * 365
+    mt = cal.model_time_from_cf(np.arange(T), "days since 1990-01-01", "noleap")
+    frac = (mt.doy - 1) / 365.0
+    x = (12 + 3 * np.cos(2 * np.pi * frac)[:, None, None] + rng.standard_normal((T, 5, 36))).astype(np.float32)
+    x[:, 1, 1] = np.nan
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        got = mb.preprocess_arrays(x, mt, **kw)
+        ref = mo.preprocess(x, np.arange(T), year_doy=(mt.year, mt.doy, mt.decimal_year), **kw)
+    np.testing.assert_array_equal(np.isnan(got["dat_anomaly"]), np.isnan(ref["dat_anomaly"]))
+    np.testing.assert_allclose(got["dat_anomaly"], ref["dat_anomaly"], rtol=0, atol=3e-4, equal_nan=True)
+    np.testing.assert_array_equal(got["mask"], ref["mask"])
+    np.testing.assert_array_equal(got["time"], ref["time"])
+    # stage-wise: thresholds and events from the GPU's own anomalies, bit for bit
+    keep_doy = mt.doy[np.isin(np.arange(T), got["time"])]
+    ev, thr = mo.preprocess_from_anomaly(np.asarray(got["dat_anomaly"]), keep_doy, kw.get("method_extreme", "hobday_extreme"),
+                                         95, kw.get("window_days_hobday", 11), None, "approximate", 0.01, 5.0)  # fmt: skip
+    _ulp_equal(np.asarray(got["thresholds"]), thr)
+    np.testing.assert_array_equal(np.asarray(got["extreme_events"]), ev)

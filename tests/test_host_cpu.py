@@ -103,6 +103,30 @@ def test_calendar_tables_and_csr():
         cal.build_calendar(np.array(["2000-01-01T00", "2000-01-01T12"], dtype="datetime64[h]"))
 
 
+def test_model_calendars_noleap_360_all_leap():
+    """year / day-of-year tables for CF model calendars (what `.dt.year/.dt.dayofyear` give on a
+    cftime index), decimal year, and the kernels' tables built from them."""
+    from marex_b200 import calendar as cal
+
+    mt = cal.model_time_from_cf(np.arange(0, 800), "days since 2000-01-01", "noleap")
+    assert mt.days_in_year == 365 and mt.year[0] == 2000 and mt.doy[0] == 1
+    assert (mt.year[364], mt.doy[364], mt.year[365], mt.doy[365]) == (2000, 365, 2001, 1)
+    assert mt.doy.max() == 365 and mt.year[-1] == 2002 and mt.doy[-1] == 800 - 2 * 365
+    m360 = cal.model_time_from_cf(np.array([0.0, 29.5, 30.0, 359.0, 360.0]) * 24, "hours since 1850-02-01 00:00:00", "360_day")
+    assert list(m360.doy) == [31, 60, 61, 30, 31] and list(m360.year) == [1850, 1850, 1850, 1851, 1851]
+    mal = cal.model_time_from_cf(np.array([59, 60, 365, 366]), "days since 1999-01-01", "all_leap")
+    assert list(mal.doy) == [60, 61, 366, 1] and list(mal.year) == [1999, 1999, 1999, 2000]
+    np.testing.assert_allclose(mt.decimal_year[[0, 365]], [2000.0, 2001.0])
+    c = cal.build_calendar(mt)
+    assert not c.is_daily and c.n_years == 3 and c.T == 800 and c.model_dy is not None
+    assert c.tidx[0] == 0 and c.tidx[366 + 0] == 365 and c.tidx[365] == -1  # doy 366 never occurs on noleap
+    np.testing.assert_array_equal(c.decimal_year, mt.decimal_year)
+    with pytest.raises(NotImplementedError):
+        cal.model_time_from_cf([0], "days since 2000-01-01", "julian")
+    with pytest.raises(NotImplementedError):  # two samples on one model day
+        cal.build_calendar(cal.model_time_from_cf([0, 12], "hours since 2000-01-01", "noleap"))
+
+
 def test_bin_tables_match_oracle_and_reference_expression():
     from marex_b200 import detect as d
 
