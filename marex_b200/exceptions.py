@@ -1,71 +1,68 @@
-"""Exception types of the detection path, mirroring marEx/exceptions.py:11-120, 180-215, 338-361:
-same class names, constructor arguments and message layout (the reference's tests match on the
-message text)."""
-from typing import Any, Dict, List, Optional
+"""Exception types of the detection path.  Interface contract of marEx/exceptions.py:11-120, 180-215,
+338-361: the class names, the constructor keywords (``details``, ``suggestions``, ``error_code``,
+``context``) and the rendered message layout, which the reference's tests match with regular
+expressions.  The rendering itself is a table of sections, written for this package."""
+from typing import Any, Callable, Dict, Iterable, List, Optional, Tuple
+
+# (attribute, renderer) in the order the sections appear in the message text
+_SECTIONS: Tuple[Tuple[str, Callable[[Any], str]], ...] = (
+    ("details", lambda v: "Details: " + str(v)),
+    ("context", lambda v: "Context: " + ", ".join(f"{key}={val}" for key, val in v.items())),
+    ("suggestions", lambda v: "Suggestions:\n" + "\n".join("  - " + str(item) for item in v)),
+    ("error_code", lambda v: "Error Code: " + str(v)),
+)
+
+
+def _render(head: str, fields: Dict[str, Any]) -> str:
+    lines: List[str] = [head]
+    lines.extend(draw(fields[name]) for name, draw in _SECTIONS if fields.get(name))
+    return "\n".join(lines)
 
 
 class MarExError(Exception):
-    """Base class (marEx/exceptions.py:11-82)."""
+    """Root of the hierarchy: a headline plus optional details, context, suggestions and a code."""
 
-    def __init__(
-        self,
-        message: str,
-        details: Optional[str] = None,
-        suggestions: Optional[List[str]] = None,
-        error_code: Optional[str] = None,
-        context: Optional[Dict[str, Any]] = None,
-    ):
+    default_code: Optional[str] = None
+
+    def __init__(self, message: str, details: Optional[str] = None, suggestions: Optional[Iterable[str]] = None,
+                 error_code: Optional[str] = None, context: Optional[Dict[str, Any]] = None):  # fmt: skip
         self.message = message
         self.details = details
-        self.suggestions = suggestions or []
-        self.error_code = error_code
-        self.context = context or {}
+        self.suggestions: List[str] = list(suggestions) if suggestions else []
+        self.error_code = error_code if error_code is not None else self.default_code
+        self.context: Dict[str, Any] = dict(context) if context else {}
         super().__init__(self._format_error_message())
 
     def _format_error_message(self) -> str:
-        parts = [self.message]
-        if self.details:
-            parts.append(f"Details: {self.details}")
-        if self.context:
-            parts.append("Context: " + ", ".join(f"{k}={v}" for k, v in self.context.items()))
-        if self.suggestions:
-            parts.append("Suggestions:\n" + "\n".join(f"  - {s}" for s in self.suggestions))
-        if self.error_code:
-            parts.append(f"Error Code: {self.error_code}")
-        return "\n".join(parts)
+        return _render(self.message, vars(self))
 
     def add_suggestion(self, suggestion: str) -> None:
-        self.suggestions.append(suggestion)
+        self.suggestions += [suggestion]
 
     def add_context(self, key: str, value: Any) -> None:
         self.context[key] = value
 
 
 class DataValidationError(MarExError):
-    """Input data problems (marEx/exceptions.py:84-120)."""
+    """The input data cannot be processed (missing dims / coords, no finite data, too few years ...)."""
 
-    def __init__(self, message, details=None, suggestions=None, error_code="DATA_VALIDATION", context=None):
-        super().__init__(message, details, suggestions, error_code, context)
+    default_code = "DATA_VALIDATION"
 
 
 class ConfigurationError(MarExError):
-    """Invalid parameter combinations (marEx/exceptions.py:180-215)."""
+    """A parameter, or a combination of parameters, is not valid."""
 
-    def __init__(self, message, details=None, suggestions=None, error_code="CONFIGURATION", context=None):
-        super().__init__(message, details, suggestions, error_code, context)
+    default_code = "CONFIGURATION_ERROR"
 
 
 class ProcessingError(MarExError):
-    """Failures inside the CUDA library (negative MAREX_ERR_* return codes)."""
+    """libmarex_b200 reported a failure (a negative MAREX_ERR_* return code) or is not built."""
 
-    def __init__(self, message, details=None, suggestions=None, error_code="PROCESSING", context=None):
-        super().__init__(message, details, suggestions, error_code, context)
+    default_code = "PROCESSING_ERROR"
 
 
 def create_data_validation_error(message: str, data_info: Optional[Dict[str, Any]] = None, **kwargs) -> DataValidationError:
-    """marEx/exceptions.py:338-361."""
-    context = kwargs.get("context", {})
-    if data_info:
-        context.update(data_info)
-    kwargs["context"] = context
-    return DataValidationError(message, **kwargs)
+    """Factory used by the validators: ``data_info`` is merged into the error's context."""
+    merged = dict(kwargs.pop("context", None) or {})
+    merged.update(data_info or {})
+    return DataValidationError(message, context=merged, **kwargs)

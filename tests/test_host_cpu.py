@@ -370,3 +370,18 @@ def test_sharded_world2_gloo(tmp_path):
     res = subprocess.run(cmd, capture_output=True, text=True, env=env, timeout=300)
     assert res.returncode == 0, res.stdout[-2000:] + res.stderr[-2000:]
     assert "GLOO_OK" in res.stdout
+
+
+def test_exception_rendering_matches_reference_layout():
+    """Message layout and default codes of marEx/exceptions.py (the reference's tests regex-match the text)."""
+    from marex_b200 import ConfigurationError, DataValidationError, ProcessingError, create_data_validation_error
+
+    e = ConfigurationError("Unknown x", details="d", suggestions=["a", "b"], context={"k": 1})
+    assert str(e) == "Unknown x\nDetails: d\nContext: k=1\nSuggestions:\n  - a\n  - b\nError Code: CONFIGURATION_ERROR"
+    assert str(DataValidationError("m")) == "m\nError Code: DATA_VALIDATION"
+    assert ProcessingError("m").error_code == "PROCESSING_ERROR"
+    v = create_data_validation_error("bad", data_info={"n": 3}, details="dd")
+    assert isinstance(v, DataValidationError) and v.context == {"n": 3} and "Context: n=3" in str(v)
+    v.add_suggestion("s")
+    v.add_context("z", 1)
+    assert v.suggestions == ["s"] and v.context["z"] == 1
