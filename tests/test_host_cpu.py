@@ -55,6 +55,13 @@ def test_library_is_sm100a_with_tma():
     if out.returncode != 0:
         pytest.skip("cuobjdump not available")
     assert "sm_100a" in out.stdout
+    # SASS evidence of the TMA path of the shifting-baseline kernel: UTMALDG (cp.async.bulk.tensor) and the
+    # mbarrier transaction-count arrive (B200_PROFILING.md "What proves a Blackwell-native kernel")
+    obj = os.path.join(os.path.dirname(path), "build", "shift_daily.o")
+    if not os.path.exists(obj):
+        _build.build(force=True)
+    sass = subprocess.run(["cuobjdump", "-sass", obj], capture_output=True, text=True).stdout
+    assert "UTMALDG.2D" in sass and "SYNCS.ARRIVE.TRANS64" in sass
 
 
 def test_no_product_import_of_the_oracle():
