@@ -9,6 +9,7 @@ from .detect import (
     compute_normalised_anomaly_arrays,
     identify_extremes_arrays,
     preprocess_arrays,
+    release_host_buffers,
     rolling_climatology_arrays,
 )
 from .exceptions import ConfigurationError, DataValidationError, MarExError, ProcessingError, create_data_validation_error
@@ -31,6 +32,7 @@ __all__ = [
     "compute_normalised_anomaly_arrays",
     "identify_extremes_arrays",
     "rolling_climatology_arrays",
+    "release_host_buffers",
     "MarExError",
     "ConfigurationError",
     "DataValidationError",

@@ -75,6 +75,13 @@ def _to_host(t: torch.Tensor, key: str, pinned: bool):
     return buf
 
 
+def release_host_buffers() -> None:
+    """Drop the cached page-locked output buffers (``output="pinned"`` reuses one buffer per output name,
+    shape and dtype so that repeated calls pay the PCIe transfer, not ``cudaHostAlloc``; arrays returned by
+    earlier ``output="pinned"`` calls become invalid)."""
+    _PINNED.clear()
+
+
 class _Hold(list):
     """Keeps uploaded table tensors alive until the call that uses them has been enqueued: a
     temporary freed right after ``data_ptr()`` could be handed out again by the caching
