@@ -213,6 +213,64 @@ int marex_compare_global(const float* anom, int64_t T, int64_t N, int64_t pitch,
                          uint32_t* bits, int64_t bits_pitch,
                          unsigned long long* count, void* stream);
 
+/* ---- tracker stage 1 on bit-packed masks -------------------------------
+ * fill_holes (marEx/track.py:1520-1669) and fill_time_gaps (track.py:1671-1726), the first consumers
+ * of `extreme_events`.  Gridded fields are processed as row-aligned padded BIT SLABS: a padded time step
+ * is Hp = ny + 2*pad rows of Wpw = ceil((nx + 2*pad) / 32) words, bit i of word w = padded column 32*w + i
+ * (marex_morph_slab_words() words per time step).  A "source" is either bool bytes (src_bytes) or bits
+ * (src_bits): cell (y, x) of time step t is element / bit  src_origin + y * src_row_stride + x  of the time
+ * step starting at t * src_t_pitch (bytes, or uint32 words).  So [T, N] bool bytes are (events, NULL, pitch,
+ * nx, 0), the flattened bits of marex_compare_* are (NULL, bits, bits_pitch, nx, 0), and the interior of a
+ * slab is (NULL, slab, Hp*Wpw, Wpw*32, pad*Wpw*32 + pad).  `mask` (optional, [ny*nx] bytes) zeroes cells
+ * outside the ocean mask at read time (`data_bin.where(self.mask, other=False)`, track.py:1667).
+ *
+ *  marex_morph_pad_bits  np.pad of every time step by `pad` cells, mode "wrap" (wrap = 1, track.py:1617)
+ *                        or "edge" (wrap = 0, regional_mode), into a slab (track.py:1625).
+ *  marex_morph_disk      one binary dilation (erode = 0) or erosion (erode = 1) of every padded time step
+ *                        by the disk x^2 + y^2 < R^2 + 1 (track.py:1613-1616) with border_value 0, as
+ *                        dask_image.ndmorph / scipy.ndimage do inside binary_closing / binary_opening
+ *                        (track.py:1630-1634).  Hp, Wp are the PADDED sizes in cells.  0 <= R <= 32.
+ *  marex_morph_time      out[t] = OR / AND over k = 0..K-1 of in[t + off + k], whole slabs of `words` words,
+ *                        time steps outside [0, T_in) False: the temporal closing of track.py:1695-1719 is
+ *                        a dilation (T_out = T + 2*half, off = -2*half) then an erosion (T_out = T, off = 0)
+ *                        with K = T_fill + 1 = 2*half + 1.
+ *  marex_morph_extract   source cells -> bool bytes [T, N] and / or flattened bits (+ count of True cells,
+ *                        accumulated into a device uint64), the trim of track.py:1638-1643 + the mask.
+ *
+ * Unstructured meshes (track.py:1543-1607) use CELL-MAJOR, TIME-PACKED words: cell c owns
+ * marex_morph_tpack_words(T) = ceil(T/32) + 2 words, word k holds time steps 32*(k-1) .. 32*(k-1)+31 (word 0 and
+ * the last word are margins for the temporal closing), so one neighbour gather serves 32 days.
+ *  marex_morph_tpack     [T, N] bool bytes or flattened bits -> time-packed.
+ *  marex_morph_nbr       one application of the sparse dilation matrix "neighbours + identity"
+ *                        (track.py:1093-1115; sparse_bool_power track.py:5423-5470 applies it R_fill times):
+ *                        nbr is int32 [nv, N], 0-based, negative = no neighbour.  erode = 1 computes
+ *                        ~dilate(~x); set_land = 1 first sets cells outside `mask` to True (track.py:1566, 1574).
+ *  marex_morph_tshift    dilation / erosion by +-half time steps along the packed time axis; clip = 1 reads only
+ *                        real time steps [0, T) (the constant False padding of track.py:1706).
+ *  marex_morph_tunpack   time-packed -> bool bytes [T, N] and / or flattened bits (+ optional mask, count). */
+int64_t marex_morph_slab_words(int64_t ny, int64_t nx, int32_t pad);
+int marex_morph_pad_bits(const uint8_t* src_bytes, const uint32_t* src_bits, int64_t src_t_pitch,
+                         int64_t src_row_stride, int64_t src_origin, const uint8_t* mask, int64_t T,
+                         int64_t ny, int64_t nx, int32_t pad, int32_t wrap, uint32_t* slab, void* stream);
+int marex_morph_disk(const uint32_t* in, uint32_t* out, int64_t T, int64_t Hp, int64_t Wp, int32_t R,
+                     int32_t erode, void* stream);
+int marex_morph_time(const uint32_t* in, int64_t T_in, int64_t words, uint32_t* out, int64_t T_out,
+                     int32_t off, int32_t K, int32_t erode, void* stream);
+int marex_morph_extract(const uint8_t* src_bytes, const uint32_t* src_bits, int64_t src_t_pitch,
+                        int64_t src_row_stride, int64_t src_origin, const uint8_t* mask, int64_t T,
+                        int64_t ny, int64_t nx, uint8_t* events, int64_t events_pitch, uint32_t* bits,
+                        int64_t bits_pitch, unsigned long long* count, void* stream);
+int64_t marex_morph_tpack_words(int64_t T);
+int marex_morph_tpack(const uint8_t* src_bytes, const uint32_t* src_bits, int64_t src_t_pitch, int64_t T,
+                      int64_t N, uint32_t* packed, void* stream);
+int marex_morph_nbr(const uint32_t* in, uint32_t* out, int64_t T, int64_t N, const int32_t* nbr, int32_t nv,
+                    const uint8_t* mask, int32_t erode, int32_t set_land, void* stream);
+int marex_morph_tshift(const uint32_t* in, uint32_t* out, int64_t T, int64_t N, int32_t half, int32_t erode,
+                       int32_t clip, void* stream);
+int marex_morph_tunpack(const uint32_t* packed, int64_t T, int64_t N, const uint8_t* mask, uint8_t* events,
+                        int64_t events_pitch, uint32_t* bits, int64_t bits_pitch, unsigned long long* count,
+                        void* stream);
+
 /* ---- utilities --------------------------------------------------------------------------
  * Strided host<->device copy (cudaMemcpy2DAsync) of `height` rows of `width_bytes`: the streamed
  * host path moves one latitude band of a (time, lat, lon) host array per call. */

@@ -35,6 +35,16 @@ _SIGNATURES = {
     "marex_compare_hobday": ([_P, c_int64, c_int64, c_int64, _P, _P, _P, _P, c_int64, _P, c_int64, _P, c_int64, _P, _P], ctypes.c_int),
     "marex_memcpy2d_async": ([_P, c_int64, _P, c_int64, c_int64, c_int64, c_int32, _P], ctypes.c_int),
     "marex_compare_global": ([_P, c_int64, c_int64, c_int64, _P, _P, c_int64, _P, c_int64, _P, _P], ctypes.c_int),
+    "marex_morph_slab_words": ([c_int64, c_int64, c_int32], c_int64),
+    "marex_morph_pad_bits": ([_P, _P, c_int64, c_int64, c_int64, _P, c_int64, c_int64, c_int64, c_int32, c_int32, _P, _P], ctypes.c_int),
+    "marex_morph_disk": ([_P, _P, c_int64, c_int64, c_int64, c_int32, c_int32, _P], ctypes.c_int),
+    "marex_morph_time": ([_P, c_int64, c_int64, _P, c_int64, c_int32, c_int32, c_int32, _P], ctypes.c_int),
+    "marex_morph_extract": ([_P, _P, c_int64, c_int64, c_int64, _P, c_int64, c_int64, c_int64, _P, c_int64, _P, c_int64, _P, _P], ctypes.c_int),
+    "marex_morph_tpack_words": ([c_int64], c_int64),
+    "marex_morph_tpack": ([_P, _P, c_int64, c_int64, c_int64, _P, _P], ctypes.c_int),
+    "marex_morph_nbr": ([_P, _P, c_int64, c_int64, _P, c_int32, _P, c_int32, c_int32, _P], ctypes.c_int),
+    "marex_morph_tshift": ([_P, _P, c_int64, c_int64, c_int32, c_int32, c_int32, _P], ctypes.c_int),
+    "marex_morph_tunpack": ([_P, c_int64, c_int64, _P, _P, c_int64, _P, c_int64, _P, _P], ctypes.c_int),
     "marex_transpose_f32": ([_P, c_int64, c_int64, _P, _P], ctypes.c_int),
     "marex_synth_sst_f32": ([_P, c_int64, c_int64, c_int64, c_int64, c_int64, c_int64, _P, c_uint64, c_float, _P], ctypes.c_int),
 }

@@ -1,0 +1,231 @@
+"""CPU tests of tracker stage 1 (marEx/track.py:1520-1726).
+
+1. The oracle (oracle/track_oracle.py) against scipy.ndimage's own binary_closing / binary_opening, i.e. against the
+   reference's non-dask branch (track.py:1646-1660), and against the committed golden vectors.
+2. The per-word code of marex_b200/csrc/morph_core.cuh -- the functions the CUDA kernels call -- compiled for the HOST
+   (tests/morph_host.cu) and driven by the product's own host logic (marex_b200/track.py with its C-ABI calls
+   redirected to the harness), bit for bit against the oracle.  The GPU tests (tests/test_track_gpu.py) then run the
+   same cases through the real kernels.
+"""
+import ctypes
+import os
+import shutil
+import subprocess
+
+import numpy as np
+import pytest
+from scipy import ndimage
+
+from oracle import track_oracle as to
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+
+
+def events_field(T=9, ny=20, nx=45, seed=0, density=0.35, noise=0.03):
+    """Blobby random events + ocean mask with a land block and a land column."""
+    rng = np.random.default_rng(seed)
+    raw = rng.random((T, ny, nx))
+    sm = ndimage.uniform_filter(raw, size=(3, 3, 3), mode="wrap")
+    ev = sm > np.quantile(sm, 1 - density)
+    ev ^= rng.random((T, ny, nx)) < noise  # salt and pepper: small holes and specks
+    mask = np.ones((ny, nx), dtype=bool)
+    mask[ny // 3 : ny // 3 + 4, nx // 4 : nx // 4 + 6] = False
+    mask[:, nx - 3] = False
+    mask[0, :5] = False
+    return ev & mask, mask
+
+
+def mesh(n_side=12, seed=0):
+    """A triangulated periodic-free patch: cell ids of a (n_side x 2 n_side) strip of triangles, 3 neighbours each,
+    -1 at the boundary (the reference drops negative neighbours, track.py:1099-1101)."""
+    ncol = 2 * n_side
+    N = n_side * ncol
+    nb = -np.ones((3, N), dtype=np.int32)
+    for r in range(n_side):
+        for c in range(ncol):
+            i = r * ncol + c
+            if c > 0:
+                nb[0, i] = i - 1
+            if c < ncol - 1:
+                nb[1, i] = i + 1
+            up = c % 2 == 0  # upward triangles touch the row below, downward ones the row above
+            rr = r + 1 if up else r - 1
+            cc = c + 1 if up else c - 1
+            if 0 <= rr < n_side and 0 <= cc < ncol:
+                nb[2, i] = rr * ncol + cc
+    rng = np.random.default_rng(seed)
+    perm = rng.permutation(N).astype(np.int32)  # unstructured meshes are not stored in raster order
+    inv = np.empty_like(perm)
+    inv[perm] = np.arange(N, dtype=np.int32)
+    nb2 = np.where(nb >= 0, inv[np.clip(nb, 0, None)], -1).astype(np.int32)
+    out = np.empty_like(nb2)
+    out[:, inv] = nb2
+    return np.ascontiguousarray(out)
+
+
+# ------------------------------------------------------------------------------------------------ oracle pins
+@pytest.mark.parametrize("R", [1, 2, 3, 5])
+@pytest.mark.parametrize("regional", [False, True])
+def test_oracle_equals_reference_scipy_branch(R, regional):
+    """track.py:1646-1660: np.pad(diameter) -> scipy binary_closing -> binary_opening -> unpad, per time step."""
+    ev, mask = events_field(seed=R)
+    got = to.fill_holes(ev, mask, R, regional)
+    se = to.disk(R)
+    d = 2 * R
+    for t in range(ev.shape[0]):
+        padded = np.pad(ev[t], ((d, d), (d, d)), mode="edge" if regional else "wrap")
+        s2 = ndimage.binary_opening(ndimage.binary_closing(padded, se, iterations=1), se, iterations=1)
+        np.testing.assert_array_equal(got[t], s2[d:-d, d:-d] & mask)
+
+
+def test_oracle_time_closing_is_scipy_binary_closing():
+    ev, mask = events_field(T=15, seed=3)
+    k = 3
+    padded = np.pad(ev, ((k, k), (0, 0), (0, 0)))
+    ref = ndimage.binary_closing(padded, np.ones((k, 1, 1), bool))[k:-k]
+    np.testing.assert_array_equal(to.fill_time_gaps(ev, mask, 0, 2), ref & mask)
+    # a one- or two-step gap is closed, a three-step gap is not (T_fill = 2)
+    col = np.zeros((12, 1, 1), bool)
+    col[[1, 3, 6, 10], 0, 0] = True
+    out = to.fill_time_gaps(col, np.ones((1, 1), bool), 0, 2)[:, 0, 0]
+    np.testing.assert_array_equal(out, [0, 1, 1, 1, 1, 1, 1, 0, 0, 0, 1, 0])
+
+
+def test_oracle_golden(golden_dir):
+    g = np.load(os.path.join(golden_dir, "track_stage1.npz"))
+    ev, mask = g["events"], g["mask"]
+    np.testing.assert_array_equal(to.fill_holes(ev, mask, 3), g["fill_holes_R3"])
+    np.testing.assert_array_equal(to.stage1(ev, mask, 4, 2), g["stage1_R4_T2"])
+    np.testing.assert_array_equal(to.stage1(ev, mask, 3, 4, True), g["stage1_R3_T4_regional"])
+    np.testing.assert_array_equal(to.stage1_unstructured(g["events_u"], g["mask_u"], g["neighbours"], 2, 2), g["stage1_u_R2_T2"])
+
+
+# ------------------------------------------------------------------------------------------------ host harness
+@pytest.fixture(scope="session")
+def harness(tmp_path_factory):
+    nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
+    if not os.path.exists(nvcc):
+        pytest.skip("nvcc not available")
+    out = str(tmp_path_factory.mktemp("morph") / "libmorph_host.so")
+    subprocess.run([nvcc, "-O2", "-std=c++17", "--shared", "-Xcompiler", "-fPIC", "-o", out, os.path.join(HERE, "morph_host.cu")],
+                   check=True, capture_output=True)  # fmt: skip
+    lib = ctypes.CDLL(out)
+    from marex_b200 import _lib
+
+    for name, (argtypes, restype) in _lib._SIGNATURES.items():
+        if name.startswith("marex_morph_"):
+            fn = getattr(lib, name)
+            fn.argtypes, fn.restype = argtypes, restype
+    return lib
+
+
+@pytest.fixture()
+def host_track(harness, monkeypatch):
+    """marex_b200.track with its device set to the CPU and every C-ABI call redirected to the host harness."""
+    import torch
+
+    from marex_b200 import track
+
+    def call(name, *args):
+        assert name.startswith("marex_morph_"), name
+        rc = getattr(harness, name)(*args)
+        assert rc == 0, (name, rc)
+
+    monkeypatch.setattr(track, "_device", lambda device=None: torch.device("cpu"))
+    monkeypatch.setattr(track, "_call", call)
+    return track
+
+
+def test_h1_window_is_exact_for_32_steps(harness):
+    rng = np.random.default_rng(0)
+    for steps in (1, 7, 31, 32):
+        bits = rng.random(96) < 0.05  # words w-1, w, w+1; whatever lies beyond them cannot reach word w in <= 32 steps
+        ref = ndimage.binary_dilation(bits, np.ones(2 * steps + 1, bool))[32:64]
+        words = np.packbits(bits, bitorder="little").view(np.uint32).copy()
+        harness.host_h1_steps(words.ctypes.data_as(ctypes.c_void_p), steps)
+        got = np.unpackbits(words.view(np.uint8), bitorder="little")[32:64].astype(bool)
+        np.testing.assert_array_equal(got, ref)
+
+
+GRID_CASES = [
+    # (T, ny, nx, R, T_fill, regional, density, noise): densities chosen so that the filled field is neither empty nor full
+    (5, 20, 45, 1, 2, False, 0.35, 0.03),
+    (5, 20, 45, 3, 2, False, 0.12, 0.03),
+    (4, 24, 70, 5, 4, False, 0.03, 0.004),  # two words per row + tail, R//2 = 2
+    (4, 24, 64, 4, 2, True, 0.12, 0.03),  # word-aligned rows, edge padding
+    (3, 48, 97, 8, 2, False, 0.02, 0.001),  # the usual 0.25-degree radius
+    (6, 12, 100, 2, 0, False, 0.35, 0.03),  # T_fill = 0: fill_time_gaps is the identity
+    (6, 12, 31, 0, 2, False, 0.35, 0.03),  # R_fill = 0: only the mask and the temporal closing
+]
+
+
+@pytest.mark.parametrize("T,ny,nx,R,T_fill,regional,density,noise", GRID_CASES)
+def test_host_word_code_gridded(host_track, T, ny, nx, R, T_fill, regional, density, noise):
+    ev, mask = events_field(T, ny, nx, seed=R + nx, density=density, noise=noise)
+    f = host_track.MaskFiller(mask, R, T_fill, regional)
+    ref_h = to.fill_holes(ev, mask, R, regional)
+    got_h = f.fill_holes(ev)
+    np.testing.assert_array_equal(got_h, ref_h)
+    assert f.last_count == int(ref_h.sum())
+    assert 0.02 < ref_h.mean() < 0.9 * mask.mean()  # a saturated field would test nothing
+    ref_t = to.fill_time_gaps(ref_h, mask, R, T_fill, regional)
+    np.testing.assert_array_equal(f.fill_time_gaps(ref_h), ref_t)
+    np.testing.assert_array_equal(f.run(ev), ref_t)
+    assert f.last_count == int(ref_t.sum())
+    # packed in / packed out (the layout of marex_compare_*)
+    import torch
+
+    flat = ev.reshape(T, -1)
+    nw = (flat.shape[1] + 31) // 32
+    padded = np.zeros((T, nw * 32), bool)
+    padded[:, : flat.shape[1]] = flat
+    bits = np.packbits(padded, axis=1, bitorder="little").view(np.uint32).view(np.int32)
+    out_bits = f.run(from_bits=(torch.from_numpy(bits.copy()), T), packed=True).numpy()
+    ref_bits = np.zeros((T, nw * 32), bool)
+    ref_bits[:, : flat.shape[1]] = ref_t.reshape(T, -1)
+    np.testing.assert_array_equal(out_bits.view(np.uint32), np.packbits(ref_bits, axis=1, bitorder="little").view(np.uint32))
+
+
+@pytest.mark.parametrize("T,R,T_fill", [(7, 1, 2), (40, 2, 2), (70, 3, 4), (33, 0, 2), (9, 2, 0)])
+def test_host_word_code_unstructured(host_track, T, R, T_fill):
+    nb = mesh(10, seed=T)
+    N = nb.shape[1]
+    rng = np.random.default_rng(T)
+    mask = rng.random(N) > 0.15
+    ev = (rng.random((T, N)) < 0.3) & mask
+    ev[:, :5] |= rng.random((T, 5)) < 0.5
+    f = host_track.MaskFiller(mask, R, T_fill, neighbours=nb)
+    ref_h = to.fill_holes_unstructured(ev, mask, nb, R)
+    np.testing.assert_array_equal(f.fill_holes(ev), ref_h)
+    ref_t = to.fill_time_gaps_unstructured(ref_h, mask, nb, R, T_fill)
+    np.testing.assert_array_equal(f.fill_time_gaps(ref_h), ref_t)
+    np.testing.assert_array_equal(f.run(ev), ref_t)
+    assert f.last_count == int(ref_t.sum())
+
+
+def test_validation_messages(host_track):
+    from marex_b200.exceptions import ConfigurationError, DataValidationError
+
+    mask = np.ones((8, 8), bool)
+    with pytest.raises(ConfigurationError, match="T_fill must be even for temporal symmetry"):
+        host_track.MaskFiller(mask, 2, 3)
+    with pytest.raises(ConfigurationError, match="outside the range"):
+        host_track.MaskFiller(mask, 40, 2)
+    with pytest.raises(DataValidationError, match="does not match the mask"):
+        host_track.MaskFiller(mask, 1, 2).fill_holes(np.zeros((3, 8, 9), bool))
+    with pytest.raises(DataValidationError, match="smaller than the padding"):
+        host_track.MaskFiller(mask, 5, 2).fill_holes(np.zeros((3, 8, 8), bool))
+    with pytest.raises(NotImplementedError):
+        host_track.MaskFiller(np.ones(4, bool), 1, 2, regional_mode=True, neighbours=-np.ones((3, 4), np.int32))
+
+
+def test_product_track_fails_loudly_without_cuda():
+    import torch
+
+    if torch.cuda.is_available():
+        pytest.skip("CUDA present")
+    from marex_b200 import track
+
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        track.MaskFiller(np.ones((8, 8), bool), 2, 2)
