@@ -221,8 +221,10 @@ int marex_compare_global(const float* anom, int64_t T, int64_t N, int64_t pitch,
  * (src_bits): cell (y, x) of time step t is element / bit  src_origin + y * src_row_stride + x  of the time
  * step starting at t * src_t_pitch (bytes, or uint32 words).  So [T, N] bool bytes are (events, NULL, pitch,
  * nx, 0), the flattened bits of marex_compare_* are (NULL, bits, bits_pitch, nx, 0), and the interior of a
- * slab is (NULL, slab, Hp*Wpw, Wpw*32, pad*Wpw*32 + pad).  `mask` (optional, [ny*nx] bytes) zeroes cells
- * outside the ocean mask at read time (`data_bin.where(self.mask, other=False)`, track.py:1667).
+ * slab is (NULL, slab, Hp*Wpw, Wpw*32, pad*Wpw*32 + pad).  `mask_bits` (optional: the ocean mask as flattened
+ * bits, ceil(ny*nx / 32) words, bit c & 31 of word c >> 5) zeroes cells outside the mask at read time
+ * (`data_bin.where(self.mask, other=False)`, track.py:1667).  Bits sources are moved a word at a time (two
+ * loads + a funnel shift per run of cells); bool bytes go through a lane-per-cell __ballot_sync path.
  *
  *  marex_morph_pad_bits  np.pad of every time step by `pad` cells, mode "wrap" (wrap = 1, track.py:1617)
  *                        or "edge" (wrap = 0, regional_mode), into a slab (track.py:1625).
@@ -230,6 +232,11 @@ int marex_compare_global(const float* anom, int64_t T, int64_t N, int64_t pitch,
  *                        by the disk x^2 + y^2 < R^2 + 1 (track.py:1613-1616) with border_value 0, as
  *                        dask_image.ndmorph / scipy.ndimage do inside binary_closing / binary_opening
  *                        (track.py:1630-1634).  Hp, Wp are the PADDED sizes in cells.  0 <= R <= 32.
+ *  marex_morph_disk_sep  the same pass in separable form: pass H widens every input row once, step by step, and stores
+ *                        it at the disk's marex_morph_disk_levels(R) distinct non-zero half-widths; pass V ORs
+ *                        2R+1 single words per output word.  `scratch` (caller-owned, scratch_words uint32, at
+ *                        least levels * Hp * ceil(Wp/32)) holds the level buffers of a CHUNK of time steps; size
+ *                        it to stay in L2 (tens of MB) and the H -> V traffic never reaches HBM.  1 <= R <= 32.
  *  marex_morph_time      out[t] = OR / AND over k = 0..K-1 of in[t + off + k], whole slabs of `words` words,
  *                        time steps outside [0, T_in) False: the temporal closing of track.py:1695-1719 is
  *                        a dilation (T_out = T + 2*half, off = -2*half) then an erosion (T_out = T, off = 0)
@@ -244,20 +251,24 @@ int marex_compare_global(const float* anom, int64_t T, int64_t N, int64_t pitch,
  *  marex_morph_nbr       one application of the sparse dilation matrix "neighbours + identity"
  *                        (track.py:1093-1115; sparse_bool_power track.py:5423-5470 applies it R_fill times):
  *                        nbr is int32 [nv, N], 0-based, negative = no neighbour.  erode = 1 computes
- *                        ~dilate(~x); set_land = 1 first sets cells outside `mask` to True (track.py:1566, 1574).
+ *                        ~dilate(~x); set_land = 1 first sets cells outside `mask` ([N] bool BYTES here: one byte per
+ *                        cell is what a per-cell gather wants) to True (track.py:1566, 1574).
  *  marex_morph_tshift    dilation / erosion by +-half time steps along the packed time axis; clip = 1 reads only
  *                        real time steps [0, T) (the constant False padding of track.py:1706).
  *  marex_morph_tunpack   time-packed -> bool bytes [T, N] and / or flattened bits (+ optional mask, count). */
 int64_t marex_morph_slab_words(int64_t ny, int64_t nx, int32_t pad);
 int marex_morph_pad_bits(const uint8_t* src_bytes, const uint32_t* src_bits, int64_t src_t_pitch,
-                         int64_t src_row_stride, int64_t src_origin, const uint8_t* mask, int64_t T,
+                         int64_t src_row_stride, int64_t src_origin, const uint32_t* mask_bits, int64_t T,
                          int64_t ny, int64_t nx, int32_t pad, int32_t wrap, uint32_t* slab, void* stream);
 int marex_morph_disk(const uint32_t* in, uint32_t* out, int64_t T, int64_t Hp, int64_t Wp, int32_t R,
                      int32_t erode, void* stream);
+int32_t marex_morph_disk_levels(int32_t R);
+int marex_morph_disk_sep(const uint32_t* in, uint32_t* out, int64_t T, int64_t Hp, int64_t Wp, int32_t R,
+                         int32_t erode, uint32_t* scratch, int64_t scratch_words, void* stream);
 int marex_morph_time(const uint32_t* in, int64_t T_in, int64_t words, uint32_t* out, int64_t T_out,
                      int32_t off, int32_t K, int32_t erode, void* stream);
 int marex_morph_extract(const uint8_t* src_bytes, const uint32_t* src_bits, int64_t src_t_pitch,
-                        int64_t src_row_stride, int64_t src_origin, const uint8_t* mask, int64_t T,
+                        int64_t src_row_stride, int64_t src_origin, const uint32_t* mask_bits, int64_t T,
                         int64_t ny, int64_t nx, uint8_t* events, int64_t events_pitch, uint32_t* bits,
                         int64_t bits_pitch, unsigned long long* count, void* stream);
 int64_t marex_morph_tpack_words(int64_t T);

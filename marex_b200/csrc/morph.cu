@@ -40,18 +40,55 @@ __global__ void __launch_bounds__(256) morph_pad_kernel(MorphSrc src, int64_t T,
   }
 }
 
+// The same for a BITS source (flattened bits or the interior of another slab): thread = output word, runs of source
+// cells are fetched 32 bits at a time with two loads and a funnel shift (morph_pad_word), no per-bit work.
+__global__ void __launch_bounds__(256) morph_pad_words_kernel(MorphSrc src, int64_t T, int ny, int nx, int pad, int wrap,
+                                                              uint32_t* __restrict__ dst) {
+  const int Hp = ny + 2 * pad, Wp = nx + 2 * pad, Wpw = (Wp + 31) >> 5;
+  const int64_t per_t = (int64_t)Hp * Wpw, total = T * per_t;
+  for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t t = idx / per_t;
+    const int r = (int)(idx - t * per_t);
+    const int yp = r / Wpw, wp = r - yp * Wpw;
+    dst[idx] = morph_pad_word(src, T, t, morph_pad_index(yp, pad, ny, wrap), wp, Wp, pad, ny, nx, wrap);
+  }
+}
+
 // One morphological pass over all padded time steps; thread = output word, w fastest (coalesced; the 3 x (2R+1)
 // input words of neighbouring threads overlap and are served by L1).
 __global__ void __launch_bounds__(256) morph_disk_kernel(const uint32_t* __restrict__ in, uint32_t* __restrict__ out,
-                                                         int64_t T, int Hp, int Wpw, uint32_t tailmask, MorphDisk disk,
-                                                         int erode) {
-  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  const int64_t per_t = (int64_t)Hp * Wpw;
-  if (idx >= T * per_t) return;
-  const int64_t t = idx / per_t;
-  const int r = (int)(idx - t * per_t);
+                                                         int Hp, int Wpw, uint32_t tailmask, const __grid_constant__ MorphDisk disk, int erode) {
+  const int per_t = Hp * Wpw;  // < 2^31 (checked by the caller); blockIdx.y = time step: no 64-bit division
+  const int r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= per_t) return;
+  const int64_t base = (int64_t)blockIdx.y * per_t;
   const int y = r / Wpw, w = r - y * Wpw;
-  out[idx] = morph_disk_word(in + t * per_t, Hp, Wpw, tailmask, y, w, disk, erode);
+  out[base + r] = morph_disk_word(in + base, Hp, Wpw, tailmask, y, w, disk, erode);
+}
+
+// Separable form (morph_core.cuh): pass H widens every input word once and stores it at the disk's distinct half-widths,
+// pass V ORs 2R+1 single words.  blockIdx.y = time step inside the chunk whose level buffers fit the scratch (and L2).
+__global__ void __launch_bounds__(256) morph_disk_h_kernel(const uint32_t* __restrict__ in, uint32_t* __restrict__ hbuf,
+                                                           int64_t lvl_stride, int Hp, int Wpw,
+                                                           const __grid_constant__ MorphPlan plan, int erode) {
+  const int per_t = Hp * Wpw;
+  const int r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= per_t) return;
+  const int64_t base = (int64_t)blockIdx.y * per_t;
+  const int y = r / Wpw, w = r - y * Wpw;
+  morph_disk_h_word(in + base, Wpw, y, w, plan, hbuf + base + r, lvl_stride, erode);
+}
+
+__global__ void __launch_bounds__(256) morph_disk_v_kernel(const uint32_t* __restrict__ in, const uint32_t* __restrict__ hbuf,
+                                                           int64_t lvl_stride, uint32_t* __restrict__ out, int Hp, int Wpw,
+                                                           uint32_t tailmask, const __grid_constant__ MorphPlan plan,
+                                                           int erode) {
+  const int per_t = Hp * Wpw;
+  const int r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= per_t) return;
+  const int64_t base = (int64_t)blockIdx.y * per_t;
+  const int y = r / Wpw, w = r - y * Wpw;
+  out[base + r] = morph_disk_v_word(in + base, hbuf + base, lvl_stride, Hp, Wpw, tailmask, y, w, plan, erode);
 }
 
 // Temporal dilation / erosion of whole slabs, bit-parallel over the 32 cells of a word.
@@ -92,6 +129,44 @@ __global__ void __launch_bounds__(256) morph_extract_kernel(MorphSrc src, int64_
     }
   }
   if (count && lane == 0 && local) atomicAdd(count, (unsigned long long)local);
+}
+
+// The same for a BITS source: thread = output word (morph_extract_word), bool bytes written as two 16-byte stores,
+// True cells counted per thread and reduced once per block.
+__global__ void __launch_bounds__(256) morph_extract_words_kernel(MorphSrc src, int64_t T, int ny, int nx,
+                                                                  uint8_t* __restrict__ events, int64_t events_pitch,
+                                                                  uint32_t* __restrict__ bits, int64_t bits_pitch,
+                                                                  unsigned long long* __restrict__ count) {
+  const int64_t N = (int64_t)ny * nx, nwords = (N + 31) >> 5, total = T * nwords;
+  unsigned int local = 0;
+  for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t t = idx / nwords, w = idx - t * nwords;
+    const uint32_t word = morph_extract_word(src, T, t, w, nx, N);
+    local += __popc(word);
+    if (bits) bits[t * bits_pitch + w] = word;
+    if (events) {
+      uint8_t* dst = events + t * events_pitch + w * 32;
+      const int64_t ncell = min((int64_t)32, N - w * 32);
+      if (ncell == 32 && (reinterpret_cast<uintptr_t>(dst) & 15) == 0) {
+        uint4 a, b;
+        a.x = morph_expand4(word), a.y = morph_expand4(word >> 4), a.z = morph_expand4(word >> 8), a.w = morph_expand4(word >> 12);
+        b.x = morph_expand4(word >> 16), b.y = morph_expand4(word >> 20), b.z = morph_expand4(word >> 24), b.w = morph_expand4(word >> 28);
+        reinterpret_cast<uint4*>(dst)[0] = a;
+        reinterpret_cast<uint4*>(dst)[1] = b;
+      } else {
+        for (int j = 0; j < (int)ncell; ++j) dst[j] = (uint8_t)((word >> j) & 1u);
+      }
+    }
+  }
+  if (count) {
+    __shared__ unsigned int block_sum;
+    if (threadIdx.x == 0) block_sum = 0;
+    __syncthreads();
+    for (int o = 16; o; o >>= 1) local += __shfl_xor_sync(0xffffffffu, local, o);
+    if ((threadIdx.x & 31) == 0 && local) atomicAdd(&block_sum, local);
+    __syncthreads();
+    if (threadIdx.x == 0 && block_sum) atomicAdd(count, (unsigned long long)block_sum);
+  }
 }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -169,14 +244,14 @@ static int grid_for(int64_t n_threads, int block, int64_t* out_blocks) {
 }
 
 static MorphSrc make_src(const uint8_t* bytes, const uint32_t* bits, int64_t t_pitch, int64_t row_stride, int64_t origin,
-                         const uint8_t* mask) {
+                         const uint32_t* mask_bits) {
   MorphSrc s;
   s.bytes = bytes;
   s.bits = bits;
   s.t_pitch = t_pitch;
   s.row_stride = row_stride;
   s.origin = origin;
-  s.mask = mask;
+  s.mask_bits = mask_bits;
   return s;
 }
 
@@ -190,16 +265,22 @@ extern "C" int64_t marex_morph_slab_words(int64_t ny, int64_t nx, int32_t pad) {
 }
 
 extern "C" int marex_morph_pad_bits(const uint8_t* src_bytes, const uint32_t* src_bits, int64_t src_t_pitch,
-                                    int64_t src_row_stride, int64_t src_origin, const uint8_t* mask, int64_t T,
+                                    int64_t src_row_stride, int64_t src_origin, const uint32_t* mask_bits, int64_t T,
                                     int64_t ny, int64_t nx, int32_t pad, int32_t wrap, uint32_t* slab, void* stream) {
   MAREX_REQUIRE((src_bytes != nullptr) != (src_bits != nullptr), "exactly one of src_bytes / src_bits");
   MAREX_REQUIRE(slab && T > 0 && ny > 0 && nx > 0 && pad >= 0, "bad shape");
   MAREX_REQUIRE(ny + 2 * (int64_t)pad < (1 << 30) && nx + 2 * (int64_t)pad < (1 << 30), "grid too large");
   const int Hp = (int)ny + 2 * pad, Wpw = ((int)nx + 2 * pad + 31) >> 5, groups = (Wpw + 31) >> 5;
+  const MorphSrc src = make_src(src_bytes, src_bits, src_t_pitch, src_row_stride, src_origin, mask_bits);
+  if (src_bits) {
+    const int64_t blocks = std::min<int64_t>((T * Hp * Wpw + 255) / 256, (int64_t)sm_count() * 64);
+    morph_pad_words_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(src, T, (int)ny, (int)nx, pad, wrap, slab);
+    MAREX_LAUNCH_CHECK("morph_pad_words_kernel");
+    return MAREX_OK;
+  }
   const int64_t items = T * Hp * groups;
   const int64_t blocks = std::min<int64_t>((items + 7) / 8, (int64_t)sm_count() * 64);
-  morph_pad_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(
-      make_src(src_bytes, src_bits, src_t_pitch, src_row_stride, src_origin, mask), T, (int)ny, (int)nx, pad, wrap, slab);
+  morph_pad_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(src, T, (int)ny, (int)nx, pad, wrap, slab);
   MAREX_LAUNCH_CHECK("morph_pad_kernel");
   return MAREX_OK;
 }
@@ -208,21 +289,48 @@ extern "C" int marex_morph_disk(const uint32_t* in, uint32_t* out, int64_t T, in
                                 int32_t erode, void* stream) {
   MAREX_REQUIRE(in && out && in != out && T > 0 && Hp > 0 && Wp > 0, "bad arguments");
   if (R < 0 || R > MORPH_MAX_R) return fail(MAREX_ERR_UNSUPPORTED, "R_fill must be in 0..32");
-  MorphDisk d;
-  d.R = R;
-  for (int a = 0; a <= MORPH_MAX_R; ++a) d.hw[a] = 0;
-  for (int a = 0; a <= R; ++a) {
-    int h = 0;
-    while ((h + 1) * (h + 1) + a * a < R * R + 1) ++h;  // x^2 + y^2 < R^2 + 1 (track.py:1614-1616)
-    d.hw[a] = (int8_t)h;
-  }
+  const MorphDisk d = morph_make_disk(R);
   const int Wpw = (int)((Wp + 31) >> 5);
-  int64_t blocks;
-  if (grid_for(T * Hp * Wpw, 256, &blocks)) return fail(MAREX_ERR_INVALID_ARG, "mask too large for one launch");
-  morph_disk_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(in, out, T, (int)Hp, Wpw, morph_tailmask((int)Wp), d,
-                                                                          erode ? 1 : 0);
-  MAREX_LAUNCH_CHECK("morph_disk_kernel");
+  MAREX_REQUIRE(Hp * (int64_t)Wpw < (1LL << 31), "padded time step too large");
+  const int64_t per_t = Hp * (int64_t)Wpw;
+  for (int64_t t0 = 0; t0 < T; t0 += 65535) {  // gridDim.y <= 65535
+    const dim3 grid((unsigned)((per_t + 255) / 256), (unsigned)std::min<int64_t>(65535, T - t0));
+    morph_disk_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(in + t0 * per_t, out + t0 * per_t, (int)Hp, Wpw,
+                                                              morph_tailmask((int)Wp), d, erode ? 1 : 0);
+    MAREX_LAUNCH_CHECK("morph_disk_kernel");
+  }
   return MAREX_OK;
+}
+
+extern "C" int32_t marex_morph_disk_levels(int32_t R) { return (R < 1 || R > MORPH_MAX_R) ? 0 : morph_make_plan(R).nlev; }
+
+extern "C" int marex_morph_disk_sep(const uint32_t* in, uint32_t* out, int64_t T, int64_t Hp, int64_t Wp, int32_t R,
+                                    int32_t erode, uint32_t* scratch, int64_t scratch_words, void* stream) {
+  MAREX_REQUIRE(in && out && scratch && in != out && T > 0 && Hp > 0 && Wp > 0, "bad arguments");
+  if (R < 1 || R > MORPH_MAX_R) return fail(MAREX_ERR_UNSUPPORTED, "R_fill must be in 1..32");
+  const MorphPlan pl = morph_make_plan(R);
+  const int Wpw = (int)((Wp + 31) >> 5);
+  MAREX_REQUIRE(Hp * (int64_t)Wpw < (1LL << 31), "padded time step too large");
+  const int64_t per_t = Hp * (int64_t)Wpw;
+  const unsigned gx = (unsigned)((per_t + 255) / 256);
+  cudaStream_t st = (cudaStream_t)stream;
+  const int e = erode ? 1 : 0;
+  const uint32_t tail = morph_tailmask((int)Wp);
+  const int rc = morph_disk_separable_chunks(
+      T, per_t, pl.nlev, scratch_words,
+      [&](int64_t t0, int64_t n, int64_t lvl_stride) -> int {
+        morph_disk_h_kernel<<<dim3(gx, (unsigned)n), 256, 0, st>>>(in + t0 * per_t, scratch, lvl_stride, (int)Hp, Wpw, pl, e);
+        MAREX_LAUNCH_CHECK("morph_disk_h_kernel");
+        return MAREX_OK;
+      },
+      [&](int64_t t0, int64_t n, int64_t lvl_stride) -> int {
+        morph_disk_v_kernel<<<dim3(gx, (unsigned)n), 256, 0, st>>>(in + t0 * per_t, scratch, lvl_stride, out + t0 * per_t,
+                                                                    (int)Hp, Wpw, tail, pl, e);
+        MAREX_LAUNCH_CHECK("morph_disk_v_kernel");
+        return MAREX_OK;
+      });
+  if (rc == -1) return fail(MAREX_ERR_INVALID_ARG, "scratch smaller than marex_morph_disk_levels(R) padded time steps");
+  return rc;
 }
 
 extern "C" int marex_morph_time(const uint32_t* in, int64_t T_in, int64_t words, uint32_t* out, int64_t T_out, int32_t off,
@@ -236,19 +344,26 @@ extern "C" int marex_morph_time(const uint32_t* in, int64_t T_in, int64_t words,
 }
 
 extern "C" int marex_morph_extract(const uint8_t* src_bytes, const uint32_t* src_bits, int64_t src_t_pitch,
-                                   int64_t src_row_stride, int64_t src_origin, const uint8_t* mask, int64_t T, int64_t ny,
-                                   int64_t nx, uint8_t* events, int64_t events_pitch, uint32_t* bits, int64_t bits_pitch,
-                                   unsigned long long* count, void* stream) {
+                                   int64_t src_row_stride, int64_t src_origin, const uint32_t* mask_bits, int64_t T,
+                                   int64_t ny, int64_t nx, uint8_t* events, int64_t events_pitch, uint32_t* bits,
+                                   int64_t bits_pitch, unsigned long long* count, void* stream) {
   MAREX_REQUIRE((src_bytes != nullptr) != (src_bits != nullptr), "exactly one of src_bytes / src_bits");
   MAREX_REQUIRE(T > 0 && ny > 0 && nx > 0 && (events || bits || count), "bad arguments");
   const int64_t N = ny * nx;
   MAREX_REQUIRE(!events || events_pitch >= N, "events_pitch < N");
   MAREX_REQUIRE(!bits || bits_pitch >= (N + 31) / 32, "bits_pitch < ceil(N / 32)");
+  const MorphSrc src = make_src(src_bytes, src_bits, src_t_pitch, src_row_stride, src_origin, mask_bits);
   const int64_t items = T * ((N + 31) / 32);
+  if (src_bits) {
+    const int64_t blocks = std::min<int64_t>((items + 255) / 256, (int64_t)sm_count() * 32);
+    morph_extract_words_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(src, T, (int)ny, (int)nx, events,
+                                                                                     events_pitch, bits, bits_pitch, count);
+    MAREX_LAUNCH_CHECK("morph_extract_words_kernel");
+    return MAREX_OK;
+  }
   const int64_t blocks = std::min<int64_t>((items + 7) / 8, (int64_t)sm_count() * 64);
-  morph_extract_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(
-      make_src(src_bytes, src_bits, src_t_pitch, src_row_stride, src_origin, mask), T, (int)ny, (int)nx, events,
-      events_pitch, bits, bits_pitch, count);
+  morph_extract_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(src, T, (int)ny, (int)nx, events, events_pitch,
+                                                                             bits, bits_pitch, count);
   MAREX_LAUNCH_CHECK("morph_extract_kernel");
   return MAREX_OK;
 }

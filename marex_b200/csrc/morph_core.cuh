@@ -21,19 +21,23 @@ constexpr int MORPH_MAX_R = 32;  // the 96-bit (previous, current, next word) wi
 
 // Where the cells of one time step come from: bool bytes or bits; `origin` + y * row_stride + x is the
 // element (byte) or bit offset of cell (y, x) inside a time step, t_pitch the stride between time steps
-// in bytes (bytes source) or uint32 words (bits source).  `mask` (optional, [ny * nx] bytes) zeroes
-// cells outside the ocean mask at read time (`data_bin.where(self.mask, other=False)`, track.py:1667).
+// in bytes (bytes source) or uint32 words (bits source).  `mask_bits` (optional, the ocean mask as flattened bits,
+// bit c & 31 of word c >> 5, c = y * nx + x) zeroes cells outside the mask at read time
+// (`data_bin.where(self.mask, other=False)`, track.py:1667).
 struct MorphSrc {
   const uint8_t* bytes;
   const uint32_t* bits;
   int64_t t_pitch;
   int64_t row_stride;
   int64_t origin;
-  const uint8_t* mask;
+  const uint32_t* mask_bits;
 };
 
 MAREX_HD uint32_t morph_src_bit(const MorphSrc& s, int64_t t, int y, int x, int nx) {
-  if (s.mask && !s.mask[(int64_t)y * nx + x]) return 0u;
+  if (s.mask_bits) {
+    const int64_t c = (int64_t)y * nx + x;
+    if (!((s.mask_bits[c >> 5] >> (c & 31)) & 1u)) return 0u;
+  }
   const int64_t o = s.origin + (int64_t)y * s.row_stride + x;
   if (s.bytes) return s.bytes[t * s.t_pitch + o] != 0 ? 1u : 0u;
   return (s.bits[t * s.t_pitch + (o >> 5)] >> (o & 31)) & 1u;
@@ -76,9 +80,10 @@ MAREX_HD void morph_h1(uint32_t& p, uint32_t& c, uint32_t& n) {
 //   rows are OR-ed in from the centre outwards and the accumulated window is widened by the DIFFERENCE of
 //   consecutive half-widths, R single-bit steps in total (H_a o H_b = H_{a+b}, H distributes over OR).
 //   erosion by a symmetric element = complement of the dilation of the complement (outside -> True).
-MAREX_HD uint32_t morph_disk_word(const uint32_t* in, int Hp, int Wpw, uint32_t tailmask, int y, int w,
-                                  const MorphDisk& d, int erode) {
-  const uint32_t flip = erode ? 0xffffffffu : 0u;
+template <bool ERODE>
+MAREX_HD uint32_t morph_disk_word_t(const uint32_t* in, int Hp, int Wpw, uint32_t tailmask, int y, int w,
+                                    const MorphDisk& d) {
+  constexpr uint32_t flip = ERODE ? 0xffffffffu : 0u;
   const bool wl = w - 1 >= 0, wr = w + 1 < Wpw;
   uint32_t p, c, n;
   {
@@ -113,6 +118,118 @@ MAREX_HD uint32_t morph_disk_word(const uint32_t* in, int Hp, int Wpw, uint32_t 
   return res;
 }
 
+// `erode` is uniform over a launch, so the dispatch does not diverge.  (Measured on B200: a second dispatch on
+// "all inputs inside the slab" made the kernel SLOWER -- rows are 46 words at 0.25 degree, so almost every warp
+// straddles a row end and ran both variants.)
+MAREX_HD uint32_t morph_disk_word(const uint32_t* in, int Hp, int Wpw, uint32_t tailmask, int y, int w,
+                                  const MorphDisk& d, int erode) {
+  return erode ? morph_disk_word_t<true>(in, Hp, Wpw, tailmask, y, w, d)
+               : morph_disk_word_t<false>(in, Hp, Wpw, tailmask, y, w, d);
+}
+
+inline MorphDisk morph_make_disk(int R) {
+  MorphDisk d;
+  d.R = R;
+  for (int a = 0; a <= MORPH_MAX_R; ++a) d.hw[a] = 0;
+  for (int a = 0; a <= R; ++a) {
+    int h = 0;
+    while ((h + 1) * (h + 1) + a * a < R * R + 1) ++h;  // x^2 + y^2 < R^2 + 1 (track.py:1614-1616)
+    d.hw[a] = (int8_t)h;
+  }
+  return d;
+}
+
+// ---- separable form of the same pass ---------------------------------------------------------------------------
+// The disk is a stack of horizontal runs, so  dilate(x)[y] = OR_dy  H_{hw[|dy|]}(x[y + dy])  with H_h the 1-D dilation
+// of a row by +-h.  Pass H widens every input row ONCE step by step and stores it at the distinct half-widths the
+// disk uses ("levels", 5 for R = 8); pass V then ORs 2R+1 single words per output word.  The level buffers live in a
+// caller-provided scratch that is sized for a chunk of time steps small enough to stay in L2 between the two passes.
+struct MorphPlan {
+  int32_t R, hmax, nlev;
+  int8_t row_lvl[MORPH_MAX_R + 1];   // level buffer read for rows at distance a, -1 = the input itself (half-width 0)
+  int8_t store_at[MORPH_MAX_R + 1];  // level buffer written after s widening steps, -1 = none
+};
+
+inline MorphPlan morph_make_plan(int R) {
+  const MorphDisk d = morph_make_disk(R);
+  MorphPlan pl;
+  pl.R = R;
+  pl.hmax = d.hw[0];
+  pl.nlev = 0;
+  for (int i = 0; i <= MORPH_MAX_R; ++i) pl.row_lvl[i] = pl.store_at[i] = -1;
+  for (int a = 0; a <= R; ++a) {
+    const int h = d.hw[a];
+    if (h > 0 && pl.store_at[h] < 0) pl.store_at[h] = (int8_t)pl.nlev++;
+    pl.row_lvl[a] = h > 0 ? pl.store_at[h] : (int8_t)-1;
+  }
+  return pl;
+}
+
+// Pass H for input word (y, w) of one time step: `hb` points at this word in level buffer 0, level j is lvl_stride
+// words further.  Bits beyond the row end may be set in the stored words; pass V clears them.
+template <bool ERODE>
+MAREX_HD void morph_disk_h_word_t(const uint32_t* in, int Wpw, int y, int w, const MorphPlan& pl, uint32_t* hb,
+                                  int64_t lvl_stride) {
+  constexpr uint32_t flip = ERODE ? 0xffffffffu : 0u;
+  const uint32_t* row = in + (int64_t)y * Wpw;
+  uint32_t p = (w - 1 >= 0 ? row[w - 1] : 0u) ^ flip;
+  uint32_t c = row[w] ^ flip;
+  uint32_t n = (w + 1 < Wpw ? row[w + 1] : 0u) ^ flip;
+  for (int s = 1; s <= pl.hmax; ++s) {
+    morph_h1(p, c, n);
+    const int j = pl.store_at[s];
+    if (j >= 0) hb[j * lvl_stride] = c;
+  }
+}
+MAREX_HD void morph_disk_h_word(const uint32_t* in, int Wpw, int y, int w, const MorphPlan& pl, uint32_t* hb,
+                                int64_t lvl_stride, int erode) {
+  if (erode) morph_disk_h_word_t<true>(in, Wpw, y, w, pl, hb, lvl_stride);
+  else morph_disk_h_word_t<false>(in, Wpw, y, w, pl, hb, lvl_stride);
+}
+
+// Pass V for output word (y, w): `in` and `hb0` are the time step's input and its level-0 buffer.
+template <bool ERODE>
+MAREX_HD uint32_t morph_disk_v_word_t(const uint32_t* in, const uint32_t* hb0, int64_t lvl_stride, int Hp, int Wpw,
+                                      uint32_t tailmask, int y, int w, const MorphPlan& pl) {
+  constexpr uint32_t flip = ERODE ? 0xffffffffu : 0u;
+  uint32_t acc = 0;
+  for (int a = 0; a <= pl.R; ++a) {
+    const int j = pl.row_lvl[a];
+    const uint32_t* src = j < 0 ? in : hb0 + j * lvl_stride;
+    const uint32_t f = j < 0 ? flip : 0u;  // the level buffers already hold the complemented field
+    for (int sgn = (a == 0 ? 1 : -1); sgn <= 1; sgn += 2) {
+      const int yy = y + sgn * a;
+      acc |= (yy >= 0 && yy < Hp) ? (src[(int64_t)yy * Wpw + w] ^ f) : flip;
+    }
+  }
+  uint32_t res = acc ^ flip;
+  if (w == Wpw - 1) res &= tailmask;
+  return res;
+}
+MAREX_HD uint32_t morph_disk_v_word(const uint32_t* in, const uint32_t* hb0, int64_t lvl_stride, int Hp, int Wpw,
+                                    uint32_t tailmask, int y, int w, const MorphPlan& pl, int erode) {
+  return erode ? morph_disk_v_word_t<true>(in, hb0, lvl_stride, Hp, Wpw, tailmask, y, w, pl)
+               : morph_disk_v_word_t<false>(in, hb0, lvl_stride, Hp, Wpw, tailmask, y, w, pl);
+}
+
+// Chunk loop shared by the library (kernel launches) and the host test harness (plain loops): pass_h(t0, n, lvl_stride)
+// then pass_v(t0, n, lvl_stride) for consecutive chunks of n <= chunk time steps.
+template <class FH, class FV>
+inline int morph_disk_separable_chunks(int64_t T, int64_t per_t, int nlev, int64_t scratch_words, FH&& pass_h, FV&& pass_v) {
+  int64_t chunk = scratch_words / ((int64_t)nlev * per_t);
+  if (chunk < 1) return -1;
+  if (chunk > 65535) chunk = 65535;  // gridDim.y
+  if (chunk > T) chunk = T;
+  for (int64_t t0 = 0; t0 < T; t0 += chunk) {
+    const int64_t n = chunk < T - t0 ? chunk : T - t0;
+    int rc = pass_h(t0, n, chunk * per_t);
+    if (rc) return rc;
+    rc = pass_v(t0, n, chunk * per_t);
+    if (rc) return rc;
+  }
+  return 0;
+}
+
 // Temporal operator on whole slabs (per word, bit-parallel over 32 cells): out[t] = OP_{k=0..K-1} in[t + off + k],
 // time steps outside [0, T_in) read as False (scipy border_value = 0 / the constant False padding of track.py:1706).
 MAREX_HD uint32_t morph_time_word(const uint32_t* in, int64_t T_in, int64_t words, int64_t t, int64_t i, int off,
@@ -125,6 +242,80 @@ MAREX_HD uint32_t morph_time_word(const uint32_t* in, int64_t T_in, int64_t word
   }
   return acc;
 }
+
+// ---- whole-word gathers for BITS sources (no per-bit work) ---------------------------------------------------------
+
+MAREX_HD uint32_t morph_lowmask(int n) { return n >= 32 ? 0xffffffffu : ((1u << n) - 1u); }
+
+// 32 consecutive bits of a bit array starting at bit offset o >= 0; words at index >= nwords read as 0.
+MAREX_HD uint32_t morph_get32(const uint32_t* base, int64_t nwords, int64_t o) {
+  const int64_t i = o >> 5;
+  const int sh = (int)(o & 31);
+  const uint32_t lo = i < nwords ? base[i] : 0u;
+  if (sh == 0) return lo;
+  const uint32_t hi = (i + 1 < nwords) ? base[i + 1] : 0u;
+  return (lo >> sh) | (hi << (32 - sh));
+}
+
+// Word wp of padded row (source row ys) of time step t: runs of consecutive source cells are fetched 32 bits at a time.
+// wrap: a run ends where the source row ends (then continues at x = 0); edge: the pad columns replicate one cell.
+MAREX_HD uint32_t morph_pad_word(const MorphSrc& s, int64_t T, int64_t t, int ys, int wp, int Wp, int pad, int ny, int nx,
+                                 int wrap) {
+  const uint32_t* base = s.bits + t * s.t_pitch;
+  const int64_t left = (T - t) * s.t_pitch, mwords = ((int64_t)ny * nx + 31) >> 5;
+  uint32_t out = 0;
+  int filled = 0, xp = wp * 32;
+  while (filled < 32 && xp < Wp) {
+    const int want = (32 - filled) < (Wp - xp) ? (32 - filled) : (Wp - xp);
+    int xs, n;
+    bool rep = false;
+    if (wrap) {
+      xs = morph_pad_index(xp, pad, nx, 1);
+      n = want < nx - xs ? want : nx - xs;
+    } else if (xp < pad) {
+      xs = 0;
+      n = want < pad - xp ? want : pad - xp;
+      rep = true;
+    } else if (xp >= pad + nx) {
+      xs = nx - 1;
+      n = want;
+      rep = true;
+    } else {
+      xs = xp - pad;
+      n = want < nx - xs ? want : nx - xs;
+    }
+    uint32_t v = morph_get32(base, left, s.origin + (int64_t)ys * s.row_stride + xs);
+    if (s.mask_bits) v &= morph_get32(s.mask_bits, mwords, (int64_t)ys * nx + xs);
+    if (rep) v = (v & 1u) ? 0xffffffffu : 0u;
+    out |= (v & morph_lowmask(n)) << filled;
+    filled += n;
+    xp += n;
+  }
+  return out;
+}
+
+// Word w of the flattened bit mask of time step t (cells 32*w .. 32*w+31, row-major over (y, x)).
+MAREX_HD uint32_t morph_extract_word(const MorphSrc& s, int64_t T, int64_t t, int64_t w, int nx, int64_t N) {
+  const uint32_t* base = s.bits + t * s.t_pitch;
+  const int64_t left = (T - t) * s.t_pitch;
+  const int64_t c = w * 32;
+  int y = (int)(c / nx), x = (int)(c - (int64_t)y * nx);
+  uint32_t out = 0;
+  int filled = 0;
+  while (filled < 32 && c + filled < N) {
+    const int n = (32 - filled) < (nx - x) ? (32 - filled) : (nx - x);
+    const uint32_t v = morph_get32(base, left, s.origin + (int64_t)y * s.row_stride + x);
+    out |= (v & morph_lowmask(n)) << filled;
+    filled += n;
+    x = 0;
+    ++y;
+  }
+  if (s.mask_bits) out &= s.mask_bits[w];
+  return out;
+}
+
+// 4 bits -> 4 bool bytes (bit k -> byte k): the products b_j * 2^(7i) land on distinct bit positions, no carries.
+MAREX_HD uint32_t morph_expand4(uint32_t b) { return ((b & 0xfu) * 0x00204081u) & 0x01010101u; }
 
 // ---- unstructured: cell-major, time-packed words (word k of a cell = time steps 32*(k-1) .. 32*(k-1)+31) ----------
 

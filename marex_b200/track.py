@@ -13,6 +13,7 @@ neighbour gather of the sparse "neighbours + identity" dilation serves 32 days.
 There is no CPU fallback: every step is a call into libmarex_b200.so on CUDA buffers.
 """
 import ctypes
+import os
 from typing import Optional, Tuple
 
 import numpy as np
@@ -23,6 +24,7 @@ from .exceptions import ConfigurationError, DataValidationError
 
 MAX_R_FILL = 32  # the word-level disk kernel looks one word to either side
 MAX_T_FILL = 32
+SEPARABLE_SCRATCH_BYTES = 48 << 20  # level buffers of one chunk of time steps: well inside the 126 MB L2
 
 
 def _device(device=None) -> torch.device:
@@ -51,9 +53,9 @@ class _Source:
     def __init__(self, tensor: torch.Tensor, is_bits: bool, t_pitch: int, row_stride: int, origin: int):
         self.tensor, self.is_bits, self.t_pitch, self.row_stride, self.origin = tensor, is_bits, t_pitch, row_stride, origin
 
-    def args(self, mask: Optional[torch.Tensor]):
+    def args(self, mask_bits: Optional[torch.Tensor]):
         return (None if self.is_bits else _p(self.tensor), _p(self.tensor) if self.is_bits else None, self.t_pitch,
-                self.row_stride, self.origin, _p(mask))  # fmt: skip
+                self.row_stride, self.origin, _p(mask_bits))  # fmt: skip
 
 
 class MaskFiller:
@@ -64,6 +66,8 @@ class MaskFiller:
     T_fill         largest temporal gap that is closed; must be even (track.py:704-709)
     regional_mode  pad with the edge value instead of wrapping periodically (track.py:1617)
     neighbours     unstructured only: (nv, ncells) int32, 0-based, negative = no neighbour (track.py:1095-1101)
+    separable      gridded only: run the disk passes in separable form (same bits, fewer instructions); default from
+                   the environment variable MAREX_MORPH_SEPARABLE
 
     ``fill_holes`` / ``fill_time_gaps`` take and return (time, ...space) bool arrays: a numpy array in gives a numpy
     array out, a torch tensor (any device) gives a CUDA bool tensor.  ``packed=True`` returns the flattened bit mask
@@ -71,7 +75,9 @@ class MaskFiller:
     as the input (what ``marex_compare_*`` writes).  ``last_count`` holds the number of True cells of the last result.
     """
 
-    def __init__(self, mask, R_fill, T_fill: int = 2, regional_mode: bool = False, neighbours=None, device=None):
+    def __init__(self, mask, R_fill, T_fill: int = 2, regional_mode: bool = False, neighbours=None, device=None,
+                 separable: Optional[bool] = None):
+        self.separable = (os.environ.get("MAREX_MORPH_SEPARABLE", "0") == "1") if separable is None else bool(separable)
         self.R_fill = int(R_fill)
         self.T_fill = T_fill
         self.regional_mode = bool(regional_mode)
@@ -109,6 +115,10 @@ class MaskFiller:
             self.space = (int(mask.shape[0]), int(mask.shape[1]))
         self.N = int(np.prod(self.space))
         self.mask = torch.from_numpy(np.ascontiguousarray(mask.reshape(-1)).view(np.uint8)).to(self.device)
+        flat = np.zeros(((self.N + 31) // 32) * 32, dtype=bool)
+        flat[: self.N] = mask.reshape(-1)
+        # the ocean mask as flattened bits (bit c & 31 of word c >> 5): what the gridded kernels apply a word at a time
+        self.mask_bits = torch.from_numpy(np.packbits(flat, bitorder="little").view(np.int32).copy()).to(self.device)
         self.last_count: Optional[int] = None
 
     # ------------------------------------------------------------------ input / output plumbing
@@ -162,12 +172,22 @@ class MaskFiller:
         return _Source(slab, True, Hp * Wpw, Wpw * 32, pad * Wpw * 32 + pad)
 
     def _close_open(self, slab: torch.Tensor, pad: int, R: int) -> torch.Tensor:
-        """binary_closing then binary_opening with the disk of radius R (track.py:1630-1634): dilate, erode, erode, dilate."""
-        T, Hp, _ = (int(s) for s in slab.shape)
+        """binary_closing then binary_opening with the disk of radius R (track.py:1630-1634): dilate, erode, erode, dilate.
+        ``separable`` runs each pass as marex_morph_disk_sep (rows widened once, then 2R+1 single-word ORs) with level
+        buffers for a chunk of time steps that stays in L2; otherwise as the direct marex_morph_disk."""
+        T, Hp, Wpw = (int(s) for s in slab.shape)
         Wp = self.space[1] + 2 * pad
         other = torch.empty_like(slab)
+        scratch = None
+        if self.separable:
+            nlev = int(_lib.load().marex_morph_disk_levels(R))
+            chunk = max(1, min(T, SEPARABLE_SCRATCH_BYTES // (4 * nlev * Hp * Wpw)))
+            scratch = self._words(nlev * chunk * Hp * Wpw)
         for erode in (0, 1, 1, 0):
-            _call("marex_morph_disk", _p(slab), _p(other), T, Hp, Wp, R, erode, _stream(self.device))
+            if scratch is not None:
+                _call("marex_morph_disk_sep", _p(slab), _p(other), T, Hp, Wp, R, erode, _p(scratch), scratch.numel(), _stream(self.device))
+            else:
+                _call("marex_morph_disk", _p(slab), _p(other), T, Hp, Wp, R, erode, _stream(self.device))
             slab, other = other, slab
         return slab
 
@@ -186,7 +206,7 @@ class MaskFiller:
     def _extract(self, src: _Source, T: int, packed: bool, as_numpy: bool):
         ny, nx = self.space
         events, bits, count = self._output(T, packed)
-        _call("marex_morph_extract", *src.args(self.mask), T, ny, nx, _p(events), self.N, _p(bits),
+        _call("marex_morph_extract", *src.args(self.mask_bits), T, ny, nx, _p(events), self.N, _p(bits),
               (self.N + 31) // 32, _p(count), _stream(self.device))  # fmt: skip
         return self._finish(events, bits, count, T, as_numpy)
 
@@ -265,10 +285,10 @@ class MaskFiller:
                 x = self._fill_holes_unstructured(self._time_close_unstructured(x, T), T, R // 2)
             return self._tunpack(x, T, packed, as_numpy)
         if R == 0:
-            return self._time_gaps_gridded(src, self.mask, T, packed, as_numpy)
+            return self._time_gaps_gridded(src, self.mask_bits, T, packed, as_numpy)
         self._check_pad(2 * R)
         slab = self._close_open(self._pad(src, None, T, 2 * R), 2 * R, R)
-        return self._time_gaps_gridded(self._interior(slab, 2 * R), self.mask, T, packed, as_numpy)
+        return self._time_gaps_gridded(self._interior(slab, 2 * R), self.mask_bits, T, packed, as_numpy)
 
     # ------------------------------------------------------------------
     def _time_gaps_gridded(self, src: _Source, src_mask, T: int, packed: bool, as_numpy: bool):

@@ -10,18 +10,6 @@
 
 using namespace marex;
 
-static MorphDisk make_disk(int R) {
-  MorphDisk d;
-  d.R = R;
-  for (int a = 0; a <= MORPH_MAX_R; ++a) d.hw[a] = 0;
-  for (int a = 0; a <= R; ++a) {
-    int h = 0;
-    while ((h + 1) * (h + 1) + a * a < R * R + 1) ++h;
-    d.hw[a] = (int8_t)h;
-  }
-  return d;
-}
-
 static int popc(uint32_t v) { return __builtin_popcount(v); }
 
 extern "C" {
@@ -30,19 +18,22 @@ int64_t marex_morph_slab_words(int64_t ny, int64_t nx, int32_t pad) { return (ny
 int64_t marex_morph_tpack_words(int64_t T) { return (T + 31) / 32 + 2; }
 
 int marex_morph_pad_bits(const uint8_t* bytes, const uint32_t* bits, int64_t t_pitch, int64_t row_stride, int64_t origin,
-                         const uint8_t* mask, int64_t T, int64_t ny, int64_t nx, int32_t pad, int32_t wrap, uint32_t* dst,
+                         const uint32_t* mask_bits, int64_t T, int64_t ny, int64_t nx, int32_t pad, int32_t wrap, uint32_t* dst,
                          void*) {
-  MorphSrc s{bytes, bits, t_pitch, row_stride, origin, mask};
+  MorphSrc s{bytes, bits, t_pitch, row_stride, origin, mask_bits};
   const int Hp = (int)ny + 2 * pad, Wp = (int)nx + 2 * pad, Wpw = (Wp + 31) >> 5;
   for (int64_t t = 0; t < T; ++t)
     for (int yp = 0; yp < Hp; ++yp)
       for (int w = 0; w < Wpw; ++w) {
+        const int ys = morph_pad_index(yp, pad, (int)ny, wrap);
         uint32_t word = 0;
-        for (int lane = 0; lane < 32; ++lane) {
-          const int xp = w * 32 + lane;
-          if (xp < Wp)
-            word |= morph_src_bit(s, t, morph_pad_index(yp, pad, (int)ny, wrap), morph_pad_index(xp, pad, (int)nx, wrap), (int)nx)
-                    << lane;
+        if (bits) {  // the word-gather path of morph_pad_words_kernel
+          word = morph_pad_word(s, T, t, ys, w, Wp, pad, (int)ny, (int)nx, wrap);
+        } else {  // the lane-per-cell path of morph_pad_kernel
+          for (int lane = 0; lane < 32; ++lane) {
+            const int xp = w * 32 + lane;
+            if (xp < Wp) word |= morph_src_bit(s, t, ys, morph_pad_index(xp, pad, (int)nx, wrap), (int)nx) << lane;
+          }
         }
         dst[(t * Hp + yp) * Wpw + w] = word;
       }
@@ -51,7 +42,7 @@ int marex_morph_pad_bits(const uint8_t* bytes, const uint32_t* bits, int64_t t_p
 
 int marex_morph_disk(const uint32_t* in, uint32_t* out, int64_t T, int64_t Hp, int64_t Wp, int32_t R, int32_t erode, void*) {
   if (R < 0 || R > MORPH_MAX_R) return -3;
-  const MorphDisk d = make_disk(R);
+  const MorphDisk d = morph_make_disk(R);
   const int Wpw = (int)((Wp + 31) >> 5);
   const int64_t per_t = Hp * Wpw;
   for (int64_t t = 0; t < T; ++t)
@@ -62,6 +53,32 @@ int marex_morph_disk(const uint32_t* in, uint32_t* out, int64_t T, int64_t Hp, i
   return 0;
 }
 
+int32_t marex_morph_disk_levels(int32_t R) { return (R < 1 || R > MORPH_MAX_R) ? 0 : morph_make_plan(R).nlev; }
+
+int marex_morph_disk_sep(const uint32_t* in, uint32_t* out, int64_t T, int64_t Hp, int64_t Wp, int32_t R, int32_t erode,
+                         uint32_t* scratch, int64_t scratch_words, void*) {
+  if (R < 1 || R > MORPH_MAX_R) return -3;
+  const MorphPlan pl = morph_make_plan(R);
+  const int Wpw = (int)((Wp + 31) >> 5);
+  const int64_t per_t = Hp * Wpw;
+  const int e = erode ? 1 : 0;
+  return morph_disk_separable_chunks(
+      T, per_t, pl.nlev, scratch_words,
+      [&](int64_t t0, int64_t n, int64_t lvl_stride) -> int {
+        for (int64_t tc = 0; tc < n; ++tc)  // blockIdx.y
+          for (int r = 0; r < per_t; ++r)
+            morph_disk_h_word(in + (t0 + tc) * per_t, Wpw, r / Wpw, r % Wpw, pl, scratch + tc * per_t + r, lvl_stride, e);
+        return 0;
+      },
+      [&](int64_t t0, int64_t n, int64_t lvl_stride) -> int {
+        for (int64_t tc = 0; tc < n; ++tc)
+          for (int r = 0; r < per_t; ++r)
+            out[(t0 + tc) * per_t + r] = morph_disk_v_word(in + (t0 + tc) * per_t, scratch + tc * per_t, lvl_stride, (int)Hp, Wpw,
+                                                           morph_tailmask((int)Wp), r / Wpw, r % Wpw, pl, e);
+        return 0;
+      });
+}
+
 int marex_morph_time(const uint32_t* in, int64_t T_in, int64_t words, uint32_t* out, int64_t T_out, int32_t off, int32_t K,
                      int32_t erode, void*) {
   for (int64_t t = 0; t < T_out; ++t)
@@ -70,19 +87,35 @@ int marex_morph_time(const uint32_t* in, int64_t T_in, int64_t words, uint32_t* 
 }
 
 int marex_morph_extract(const uint8_t* bytes, const uint32_t* bits_in, int64_t t_pitch, int64_t row_stride, int64_t origin,
-                        const uint8_t* mask, int64_t T, int64_t ny, int64_t nx, uint8_t* events, int64_t events_pitch,
+                        const uint32_t* mask_bits, int64_t T, int64_t ny, int64_t nx, uint8_t* events, int64_t events_pitch,
                         uint32_t* bits, int64_t bits_pitch, unsigned long long* count, void*) {
-  MorphSrc s{bytes, bits_in, t_pitch, row_stride, origin, mask};
+  MorphSrc s{bytes, bits_in, t_pitch, row_stride, origin, mask_bits};
   const int64_t N = ny * nx, nwords = (N + 31) / 32;
   for (int64_t t = 0; t < T; ++t)
     for (int64_t w = 0; w < nwords; ++w) {
       uint32_t word = 0;
-      for (int lane = 0; lane < 32; ++lane) {
-        const int64_t c = w * 32 + lane;
-        if (c >= N) break;
-        const uint32_t b = morph_src_bit(s, t, (int)(c / nx), (int)(c % nx), (int)nx);
-        if (events) events[t * events_pitch + c] = (uint8_t)b;
-        word |= b << lane;
+      if (bits_in) {  // morph_extract_words_kernel
+        word = morph_extract_word(s, T, t, w, (int)nx, N);
+        if (events) {
+          uint8_t* dst = events + t * events_pitch + w * 32;
+          const int64_t ncell = N - w * 32 < 32 ? N - w * 32 : 32;
+          if (ncell == 32) {
+            for (int q = 0; q < 8; ++q) {
+              const uint32_t four = morph_expand4(word >> (4 * q));
+              for (int j = 0; j < 4; ++j) dst[4 * q + j] = (uint8_t)(four >> (8 * j));
+            }
+          } else {
+            for (int j = 0; j < (int)ncell; ++j) dst[j] = (uint8_t)((word >> j) & 1u);
+          }
+        }
+      } else {  // morph_extract_kernel
+        for (int lane = 0; lane < 32; ++lane) {
+          const int64_t c = w * 32 + lane;
+          if (c >= N) break;
+          const uint32_t b = morph_src_bit(s, t, (int)(c / nx), (int)(c % nx), (int)nx);
+          if (events) events[t * events_pitch + c] = (uint8_t)b;
+          word |= b << lane;
+        }
       }
       if (bits) bits[t * bits_pitch + w] = word;
       if (count) *count += popc(word);

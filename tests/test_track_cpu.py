@@ -157,13 +157,21 @@ GRID_CASES = [
     (3, 48, 97, 8, 2, False, 0.02, 0.001),  # the usual 0.25-degree radius
     (6, 12, 100, 2, 0, False, 0.35, 0.03),  # T_fill = 0: fill_time_gaps is the identity
     (6, 12, 31, 0, 2, False, 0.35, 0.03),  # R_fill = 0: only the mask and the temporal closing
+    (3, 9, 10, 1, 2, False, 0.4, 0.03),  # rows shorter than a word: one flattened word spans several rows
+    (3, 10, 9, 1, 2, True, 0.25, 0.02),
+    (2, 70, 80, 17, 2, True, 0.004, 0.0),  # pad = 34 > 32: whole words of replicated edge cells
+    (2, 70, 80, 17, 2, False, 0.004, 0.0),  # ... and of wrapped cells
 ]
 
 
+@pytest.mark.parametrize("separable", [False, True])
 @pytest.mark.parametrize("T,ny,nx,R,T_fill,regional,density,noise", GRID_CASES)
-def test_host_word_code_gridded(host_track, T, ny, nx, R, T_fill, regional, density, noise):
+def test_host_word_code_gridded(host_track, monkeypatch, T, ny, nx, R, T_fill, regional, density, noise, separable):
     ev, mask = events_field(T, ny, nx, seed=R + nx, density=density, noise=noise)
-    f = host_track.MaskFiller(mask, R, T_fill, regional)
+    if separable:  # a scratch of two time steps' level buffers: the chunk loop runs several times, with a ragged tail
+        nlev = max(1, host_track._lib.load().marex_morph_disk_levels(R))
+        monkeypatch.setattr(host_track, "SEPARABLE_SCRATCH_BYTES", 2 * 4 * nlev * (ny + 4 * R) * ((nx + 4 * R + 31) // 32))
+    f = host_track.MaskFiller(mask, R, T_fill, regional, separable=separable)
     ref_h = to.fill_holes(ev, mask, R, regional)
     got_h = f.fill_holes(ev)
     np.testing.assert_array_equal(got_h, ref_h)

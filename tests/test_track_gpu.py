@@ -29,11 +29,15 @@ def _pack(flat):
     return np.packbits(padded, axis=1, bitorder="little").view(np.uint32)
 
 
+@pytest.mark.parametrize("separable", [False, True])
 @pytest.mark.parametrize("T,ny,nx,R,T_fill,regional,density,noise", GRID_CASES)
-def test_gridded_fill(T, ny, nx, R, T_fill, regional, density, noise):
+def test_gridded_fill(monkeypatch, T, ny, nx, R, T_fill, regional, density, noise, separable):
     track = _track()
     ev, mask = events_field(T, ny, nx, seed=R + nx, density=density, noise=noise)
-    f = track.MaskFiller(mask, R, T_fill, regional)
+    if separable:  # scratch for two time steps: several chunks with a ragged tail
+        nlev = max(1, track._lib.load().marex_morph_disk_levels(R))
+        monkeypatch.setattr(track, "SEPARABLE_SCRATCH_BYTES", 2 * 4 * nlev * (ny + 4 * R) * ((nx + 4 * R + 31) // 32))
+    f = track.MaskFiller(mask, R, T_fill, regional, separable=separable)
     ref_h = to.fill_holes(ev, mask, R, regional)
     np.testing.assert_array_equal(f.fill_holes(ev), ref_h)
     assert f.last_count == int(ref_h.sum())
@@ -85,10 +89,10 @@ def test_quarter_degree_slices():
     track = _track()
     T, ny, nx = 4, 720, 1440
     ev, mask = events_field(T, ny, nx, seed=5, density=0.02, noise=0.0005)
-    f = track.MaskFiller(mask, 8, 2)
     ref = to.stage1(ev, mask, 8, 2)
     assert 0.02 < ref.mean() < 0.9
-    np.testing.assert_array_equal(f.run(ev), ref)
+    np.testing.assert_array_equal(track.MaskFiller(mask, 8, 2, separable=False).run(ev), ref)
+    np.testing.assert_array_equal(track.MaskFiller(mask, 8, 2, separable=True).run(ev), ref)
 
 
 def test_stage1_consumes_the_packed_mask_of_preprocess():

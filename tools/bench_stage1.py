@@ -59,7 +59,6 @@ def main():
     mask[: ny // 12] = False  # a polar cap of land
     mask[ny // 3 : ny // 2, nx // 5 : nx // 3] = False
     bits = synthetic_bits(T, ny, nx, a.density, dev)
-    f = track.MaskFiller(mask, R, a.T_fill, device=dev)
 
     # algorithmic bytes per call (read once + write once), from the arguments of the call itself
     def call_bytes(name, args):
@@ -68,7 +67,7 @@ def main():
             T_, ny_, nx_, pad = v[6], v[7], v[8], v[9]
             out = T_ * (ny_ + 2 * pad) * ((nx_ + 2 * pad + 31) // 32) * 4
             return T_ * ny_ * nx_ / 8 + out
-        if name == "marex_morph_disk":
+        if name in ("marex_morph_disk", "marex_morph_disk_sep"):
             return 2 * v[2] * v[3] * ((v[4] + 31) // 32) * 4
         if name == "marex_morph_time":
             return (v[1] + v[4]) * v[2] * 4
@@ -86,10 +85,12 @@ def main():
         e0.record()
         real_call(name, *args)
         e1.record()
-        records.append((name, args[-2] if name == "marex_morph_disk" else None, call_bytes(name, args), e0, e1))
+        records.append((name, args[6] if name.startswith("marex_morph_disk") else None, call_bytes(name, args), e0, e1))
 
     out = {}
-    for packed in (True, False):
+    for label, packed, separable in (("direct_packed_out", True, False), ("separable_packed_out", True, True),
+                                     ("separable_bool_out", False, True)):
+        f = track.MaskFiller(mask, R, a.T_fill, device=dev, separable=separable)
         f.run(from_bits=(bits, T), packed=packed)  # warm-up (allocator, first launches)
         torch.cuda.synchronize()
         track._call = timed_call
@@ -108,7 +109,7 @@ def main():
                 per_kernel.setdefault(key, {"ms": [], "bytes": nbytes})["ms"].append(e0.elapsed_time(e1))
         track._call = real_call
         ms = float(np.median(whole))
-        out["packed_out" if packed else "bool_out"] = {
+        out[label] = {
             "ms": ms,
             "gridpoint_days_per_s": N * T / (ms * 1e-3),
             "true_cells": f.last_count,
