@@ -203,11 +203,14 @@ class MaskFiller:
         _call("marex_morph_time", _p(dil), T + 2 * half, words, _p(out), T, 0, K, 1, _stream(self.device))
         return out
 
-    def _extract(self, src: _Source, T: int, packed: bool, as_numpy: bool):
+    _OCEAN = object()  # default of _extract: apply the ocean mask
+
+    def _extract(self, src: _Source, T: int, packed: bool, as_numpy: bool, mask_bits=_OCEAN):
+        """Trim + ``where(mask)`` (track.py:1638-1643, 1667); ``mask_bits=None`` extracts without masking."""
         ny, nx = self.space
         events, bits, count = self._output(T, packed)
-        _call("marex_morph_extract", *src.args(self.mask_bits), T, ny, nx, _p(events), self.N, _p(bits),
-              (self.N + 31) // 32, _p(count), _stream(self.device))  # fmt: skip
+        _call("marex_morph_extract", *src.args(self.mask_bits if mask_bits is MaskFiller._OCEAN else mask_bits), T, ny, nx,
+              _p(events), self.N, _p(bits), (self.N + 31) // 32, _p(count), _stream(self.device))  # fmt: skip
         return self._finish(events, bits, count, T, as_numpy)
 
     # ------------------------------------------------------------------ unstructured primitives
@@ -301,20 +304,13 @@ class MaskFiller:
                 self.last_count = int(events.count_nonzero().item())
                 out = events.view(torch.bool).reshape((T,) + self.space)
                 return out.cpu().numpy() if as_numpy else out
-            return self._extract_with(src, src_mask, T, packed, as_numpy)
+            return self._extract(src, T, packed, as_numpy, mask_bits=src_mask)
         R2 = self.R_fill // 2
         self._check_pad(2 * R2)
         slab = self._time_close(self._pad(src, src_mask, T, 2 * R2))
         if R2 > 0:
             slab = self._close_open(slab, 2 * R2, R2)
         return self._extract(self._interior(slab, 2 * R2), T, packed, as_numpy)
-
-    def _extract_with(self, src: _Source, mask, T: int, packed: bool, as_numpy: bool):
-        ny, nx = self.space
-        events, bits, count = self._output(T, packed)
-        _call("marex_morph_extract", *src.args(mask), T, ny, nx, _p(events), self.N, _p(bits), (self.N + 31) // 32,
-              _p(count), _stream(self.device))  # fmt: skip
-        return self._finish(events, bits, count, T, as_numpy)
 
     def _check_pad(self, pad: int) -> None:
         ny, nx = self.space
