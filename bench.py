@@ -547,6 +547,7 @@ def main():
                 "days_out": T_out,
                 "halo_rows": halo,
                 "l2": "inputs (60 GB per GPU at 0.25 deg) are far larger than L2; no flush needed",
+                **({"shift_acc": os.environ["MAREX_SHIFT_ACC"]} if os.environ.get("MAREX_SHIFT_ACC") else {}),
                 **kw,
             },
             "roofline": roofline,

@@ -37,7 +37,33 @@ struct DailyParams {
 
 __host__ __device__ __forceinline__ bool is_leap(int y) { return (y % 4 == 0 && y % 100 != 0) || (y % 400 == 0); }
 
-template <int R, int NST, int MODE>
+// Running sum of the ring of one (day, gridpoint).  double: float64 sums of float32 data are exact, the result is rounded
+// once (what the oracle does).  float (MAREX_SHIFT_ACC=f32, a round-2 experiment, see tools/study_f32_accumulation.py):
+// Kahan-compensated float32; measured against the oracle on the CPU: max error 2e-7 of the field scale over 41 years,
+// 50 times below the 1e-5 bar, and no F2F / DADD on the XU and FP64 pipes.
+template <typename Acc>
+struct RingSum;
+template <>
+struct RingSum<double> {
+  double s = 0.0;
+  __device__ __forceinline__ void add(float v) { s += (double)v; }
+  __device__ __forceinline__ void sub(float v) { s -= (double)v; }
+  __device__ __forceinline__ double value() const { return s; }
+};
+template <>
+struct RingSum<float> {
+  float s = 0.f, c = 0.f;
+  __device__ __forceinline__ void add(float v) {
+    const float y = v - c;
+    const float t = s + y;
+    c = (t - s) - y;
+    s = t;
+  }
+  __device__ __forceinline__ void sub(float v) { add(-v); }
+  __device__ __forceinline__ float value() const { return s; }
+};
+
+template <int R, int NST, int MODE, typename Acc = double>
 __global__ void __launch_bounds__(R >= 12 ? 256 : 512) shift_daily_kernel(const __grid_constant__ CUtensorMap tmap,
                                                                          const DailyParams p) {
   extern __shared__ __align__(1024) unsigned char smem_raw[];
@@ -45,12 +71,12 @@ __global__ void __launch_bounds__(R >= 12 ? 256 : 512) shift_daily_kernel(const 
   const int D = p.D, W = p.W, S = p.S, off = p.S / 2;
   // shared memory carve-up (all offsets multiples of 128 bytes)
   uint64_t* bar = reinterpret_cast<uint64_t*>(smem_raw);                         // [NST]
-  double* invtab = reinterpret_cast<double*>(smem_raw + 128);                    // [W + 1], invtab[0] = NaN
+  Acc* invtab = reinterpret_cast<Acc*>(smem_raw + 128);                          // [W + 1], invtab[0] = NaN
   const size_t inv_bytes = (((size_t)(W + 1) * 8 + 127) / 128) * 128;
   float* xs = reinterpret_cast<float*>(smem_raw + 128 + inv_bytes);              // [NST][rows_box][32]
   const int stage_elems = p.rows_box * 32;
   float* ring = xs + (size_t)NST * stage_elems;                                  // [W][D][32]
-  double* bs = reinterpret_cast<double*>(ring + (size_t)W * D * 32);            // [n_blk][32] sums of R box rows
+  Acc* bs = reinterpret_cast<Acc*>(ring + (size_t)W * D * 32);                  // [n_blk][32] sums of R box rows
   const int n_blk = (p.rows_box + R - 1) / R;
 
   // strips of one 32-gridpoint group are adjacent CTAs: they run at the same time and at the
@@ -67,7 +93,7 @@ __global__ void __launch_bounds__(R >= 12 ? 256 : 512) shift_daily_kernel(const 
     for (int s = 0; s < NST; ++s) mbar_init(&bar[s], 1);
     mbar_fence_init();
   }
-  for (int i = threadIdx.x; i <= W; i += blockDim.x) invtab[i] = i ? 1.0 / (double)i : (double)CUDART_NAN;
+  for (int i = threadIdx.x; i <= W; i += blockDim.x) invtab[i] = i ? (Acc)(1.0 / (double)i) : (Acc)CUDART_NAN;
   for (int i = threadIdx.x; i < W * D * 32; i += blockDim.x) ring[i] = CUDART_NAN_F;
   __syncthreads();
 
@@ -89,12 +115,12 @@ __global__ void __launch_bounds__(R >= 12 ? 256 : 512) shift_daily_kernel(const 
     for (int k = 0; k < NST && k < p.n_years; ++k) issue();
   }
 
-  double sum[R];
+  RingSum<Acc> sum[R];
   int cnt[R];
 #pragma unroll
-  for (int r = 0; r < R; ++r) { sum[r] = 0.0; cnt[r] = 0; }
+  for (int r = 0; r < R; ++r) cnt[r] = 0;
   int bad = 0;
-  const double invS = 1.0 / (double)S;
+  const Acc invS = (Acc)(1.0 / (double)S);
   int64_t base = -(int64_t)p.doy0;
   uint32_t phase = 0;  // bit st = parity of the next completion of stage st
   int st = 0, slot = 0;
@@ -121,30 +147,30 @@ __global__ void __launch_bounds__(R >= 12 ? 256 : 512) shift_daily_kernel(const 
     // ring turnover of one (day, gridpoint): year i - W leaves, year i enters
     auto turnover = [&](int r, float s) {
       const float old = ringslot[r * 32];
-      if (old == old) { sum[r] -= (double)old; --cnt[r]; }
+      if (old == old) { sum[r].sub(old); --cnt[r]; }
       ringslot[r * 32] = s;
-      if (s == s) { sum[r] += (double)s; ++cnt[r]; }
+      if (s == s) { sum[r].add(s); ++cnt[r]; }
     };
     auto emit = [&](int r, float xv) {  // anomaly (or climatology) of a target-year day
-      const float clim = (float)(sum[r] * invtab[cnt[r]]);
+      const float clim = (float)(sum[r].value() * invtab[cnt[r]]);
       if (live) st_stream(outp, MODE ? clim : xv - clim);
     };
 
     // Block sums: the float64 sum of every group of R consecutive box rows, each row converted once.
     // A window of S rows is then S / R block sums + S % R single rows instead of S conversions
     // (the sums are exact for float32 data, so the grouping does not change the result).
-    double own[R];
+    Acc own[R];
     {
-      double b = 0.0;
+      Acc b = 0;
 #pragma unroll
-      for (int r = 0; r < R; ++r) { own[r] = (double)X[r * 32]; b += own[r]; }
+      for (int r = 0; r < R; ++r) { own[r] = (Acc)X[r * 32]; b += own[r]; }
       bs[warp * 32 + lane] = b;
       const int nw = blockDim.x >> 5;
       for (int blk = nw + warp; blk < n_blk; blk += nw) {  // the halo rows behind the last sub-strip
         const float* Xb = xs + st * stage_elems + blk * R * 32 + lane;
-        double e = 0.0;
+        Acc e = 0;
 #pragma unroll
-        for (int r = 0; r < R; ++r) if (blk * R + r < p.rows_box) e += (double)Xb[r * 32];
+        for (int r = 0; r < R; ++r) if (blk * R + r < p.rows_box) e += (Acc)Xb[r * 32];
         bs[blk * 32 + lane] = e;
       }
     }
@@ -156,20 +182,20 @@ __global__ void __launch_bounds__(R >= 12 ? 256 : 512) shift_daily_kernel(const 
       const float* Xhi = X + (S - 1) * 32;
       const float* Xc = X + off * 32;
       const int nfull = S / R;
-      double ws = own[0];
+      Acc ws = own[0];
 #pragma unroll
       for (int r = 1; r < R; ++r) ws += own[r];
       if (nfull == 0) {  // S < R: the window is a prefix of the own block
-        ws = 0.0;
-        for (int k = 0; k < S; ++k) ws += (double)X[k * 32];
+        ws = 0;
+        for (int k = 0; k < S; ++k) ws += (Acc)X[k * 32];
       } else {
         for (int b = 1; b < nfull; ++b) ws += bs[(warp + b) * 32 + lane];
-        for (int k = nfull * R; k < S; ++k) ws += (double)X[k * 32];
+        for (int k = nfull * R; k < S; ++k) ws += (Acc)X[k * 32];
       }
       if (target) {
 #pragma unroll
         for (int r = 0; r < R; ++r) {
-          if (r > 0) ws += (double)Xhi[r * 32] - own[r - 1];
+          if (r > 0) ws += (Acc)Xhi[r * 32] - own[r - 1];
           const float xv = Xc[r * 32];
           bad += is_finite_f(xv) ? 0 : 1;
           emit(r, xv);
@@ -179,14 +205,14 @@ __global__ void __launch_bounds__(R >= 12 ? 256 : 512) shift_daily_kernel(const 
       } else {
 #pragma unroll
         for (int r = 0; r < R; ++r) {
-          if (r > 0) ws += (double)Xhi[r * 32] - own[r - 1];
+          if (r > 0) ws += (Acc)Xhi[r * 32] - own[r - 1];
           bad += is_finite_f(Xc[r * 32]) ? 0 : 1;
           turnover(r, (float)(ws * invS));
         }
       }
     } else {
       // ---- series edges / last days of the year: checked path ----
-      double ws = 0.0;
+      Acc ws = 0;
       bool have = false;
 #pragma unroll
       for (int r = 0; r < R; ++r) {
@@ -197,10 +223,10 @@ __global__ void __launch_bounds__(R >= 12 ? 256 : 512) shift_daily_kernel(const 
           float s = CUDART_NAN_F;
           if (t - off >= 0 && t - off + S <= p.T) {  // full window inside the series (min_periods = S)
             if (have) {
-              ws += (double)X[(r + S - 1) * 32] - (double)X[(r - 1) * 32];
+              ws += (Acc)X[(r + S - 1) * 32] - (Acc)X[(r - 1) * 32];
             } else {
-              ws = 0.0;
-              for (int k = 0; k < S; ++k) ws += (double)X[(r + k) * 32];
+              ws = 0;
+              for (int k = 0; k < S; ++k) ws += (Acc)X[(r + k) * 32];
               have = true;
             }
             s = (float)(ws * invS);
@@ -213,7 +239,7 @@ __global__ void __launch_bounds__(R >= 12 ? 256 : 512) shift_daily_kernel(const 
         } else {
           have = false;  // (year, day) without a sample: year i - W still has to leave the ring
           const float old = ringslot[r * 32];
-          if (old == old) { sum[r] -= (double)old; --cnt[r]; ringslot[r * 32] = CUDART_NAN_F; }
+          if (old == old) { sum[r].sub(old); --cnt[r]; ringslot[r * 32] = CUDART_NAN_F; }
         }
         outp += p.out_pitch;
       }
@@ -275,6 +301,8 @@ extern "C" int marex_shift_anomaly_daily_f32(const float* x, int64_t T, int64_t 
   const int env_nw = getenv("MAREX_SHIFT_NW") ? atoi(getenv("MAREX_SHIFT_NW")) : 0;
   const int env_nst = getenv("MAREX_SHIFT_NST") ? atoi(getenv("MAREX_SHIFT_NST")) : 0;
   const int env_cps = getenv("MAREX_SHIFT_CPS") ? atoi(getenv("MAREX_SHIFT_CPS")) : 0;
+  const char* env_acc = getenv("MAREX_SHIFT_ACC");
+  const bool acc_f32 = env_acc && std::string(env_acc) == "f32";  // experiment: float32 sums (Kahan ring), within 1e-5
   const size_t fixed = 128 + (((size_t)(W + 1) * 8 + 127) / 128) * 128;
   auto launch = [&](auto kern, int R, int nst, int cps) -> int {
     auto smem_of = [&](int D, int ns) {
@@ -306,8 +334,11 @@ extern "C" int marex_shift_anomaly_daily_f32(const float* x, int64_t T, int64_t 
     MAREX_LAUNCH_CHECK("shift_daily_kernel");
     return MAREX_OK;
   };
-#define MAREX_SD(R_, NST_, CPS_)                                                          \
-  (mode ? launch(shift_daily_kernel<R_, NST_, 1>, R_, NST_, CPS_) : launch(shift_daily_kernel<R_, NST_, 0>, R_, NST_, CPS_))
+#define MAREX_SD(R_, NST_, CPS_)                                                                                  \
+  (acc_f32 ? (mode ? launch(shift_daily_kernel<R_, NST_, 1, float>, R_, NST_, CPS_)                              \
+                   : launch(shift_daily_kernel<R_, NST_, 0, float>, R_, NST_, CPS_))                             \
+           : (mode ? launch(shift_daily_kernel<R_, NST_, 1, double>, R_, NST_, CPS_)                             \
+                   : launch(shift_daily_kernel<R_, NST_, 0, double>, R_, NST_, CPS_)))
   int rc = MAREX_ERR_UNSUPPORTED;
   if (env_r) {  // tuning knobs (MAREX_SHIFT_R / _NW / _NST / _CPS), not part of the API
     const int nst = env_nst ? env_nst : 2, cps = env_cps ? env_cps : 1;

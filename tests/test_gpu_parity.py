@@ -84,6 +84,26 @@ def test_shifting_baseline_anomaly(W, S):
     assert _frac_bits_differ(got, ref) < 1e-3
 
 
+@pytest.mark.skipif(os.environ.get("MAREX_TEST_EXPERIMENTAL") != "1", reason="round-2 experiment: set MAREX_TEST_EXPERIMENTAL=1")
+@pytest.mark.parametrize("W,S,kelvin", [(5, 11, False), (15, 21, True)])
+def test_shifting_baseline_anomaly_float32_sums(monkeypatch, W, S, kelvin):
+    """MAREX_SHIFT_ACC=f32: float32 window sums + Kahan ring sum in the TMA kernel.  Not bit-identical to the oracle's
+    float64 sums, but far inside the north-star tolerance (tools/study_f32_accumulation.py: 2e-7 of the field scale)."""
+    mb = _cuda()
+    monkeypatch.setenv("MAREX_SHIFT_ACC", "f32")
+    x, time = _field(T1="2031-03-05" if W == 15 else "2001-07-01", kelvin=kelvin)
+    year, doy = mo.calendar_tables(time)
+    ref, mask, keep = mo.anomaly_shifting_baseline(x, year, doy, W, S)
+    cal = mb.detect.build_calendar(time)
+    xd, _space = mb.detect._to_device_field(x, "cuda")
+    res = mb.compute_normalised_anomaly_arrays(xd, cal, "shifting_baseline", W, S)
+    got = res["dat_anomaly"].cpu().numpy().reshape(ref.shape)
+    np.testing.assert_array_equal(res["keep"], keep)
+    np.testing.assert_array_equal(np.isnan(got), np.isnan(ref))
+    scale = float(np.nanmax(np.abs(x)))
+    np.testing.assert_allclose(got, ref, rtol=0, atol=1e-6 * scale, equal_nan=True)  # ten times inside the 1e-5 bar
+
+
 def test_shifting_baseline_nonfinite_and_gaps():
     """NaN / inf bookkeeping in the running sums, missing days and a missing year."""
     mb = _cuda()

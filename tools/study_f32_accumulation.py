@@ -1,0 +1,117 @@
+"""Numerics study for the round-2 float32 variant of the shifting-baseline kernel: how far are
+anomalies from the oracle (float64 sums rounded once) if the kernel accumulates in float32?
+
+  window sum   re-assembled every year from float32 sums of R-row blocks plus at most R - 1 slides
+  ring sum     Kahan-compensated float32 running sum over the W ring values (add the entering year, subtract the leaving)
+
+Pure numpy emulation on the CPU (float32 arithmetic op by op); prints the error relative to the field scale and the share
+of bit-identical anomalies.  Run:  python tools/study_f32_accumulation.py
+"""
+import os
+import sys
+
+import numpy as np
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from oracle import marex_oracle as mo  # noqa: E402  (a study tool, not product code)
+
+f32 = np.float32
+
+
+def field(T0, T1, n, seed, kelvin):
+    rng = np.random.default_rng(seed)
+    time = np.arange(np.datetime64(T0), np.datetime64(T1))
+    T = len(time)
+    frac = (time - time.astype("datetime64[Y]")).astype(float) / 365.25
+    amp, ph = rng.uniform(0.5, 6, n), rng.uniform(0, 1, n)
+    x = 15 + amp * np.cos(2 * np.pi * (frac[:, None] - ph)) + 0.02 * np.arange(T)[:, None] / 365.25
+    ar = np.zeros(n)
+    for t in range(T):
+        ar = 0.9 * ar + 0.26 * rng.standard_normal(n)
+        x[t] += ar
+    return (x + (273.15 if kelvin else 0)).astype(f32), time
+
+
+def smooth_f32_blocks(x, S, R):
+    """Window sums in float32: blocks of R rows summed sequentially, a window = S // R block sums + S % R single rows,
+    then R - 1 slides (+ entering - leaving) before the next re-assembly."""
+    T, n = x.shape
+    off = S // 2
+    out = np.full((T, n), np.nan, f32)
+    t = off
+    while t + (S - off) <= T:
+        lo = t - off
+        ws = np.zeros(n, f32)
+        nfull = S // R
+        for b in range(nfull):
+            blk = np.zeros(n, f32)
+            for r in range(R):
+                blk = (blk + x[lo + b * R + r]).astype(f32)
+            ws = (ws + blk).astype(f32)
+        for k in range(nfull * R, S):
+            ws = (ws + x[lo + k]).astype(f32)
+        out[t] = (ws * f32(1.0 / S)).astype(f32)
+        for r in range(1, R):
+            tt = t + r
+            if tt + (S - off) > T:
+                break
+            ws = (ws + (x[tt - off + S - 1] - x[tt - off - 1]).astype(f32)).astype(f32)
+            out[tt] = (ws * f32(1.0 / S)).astype(f32)
+        t += R
+    return out
+
+
+def clim_kahan(s, year, doy, W):
+    """Per (target year, doy): mean of s over the previous W years, by a Kahan-compensated float32 running sum."""
+    T, n = s.shape
+    years = np.unique(year)
+    clim = np.full((T, n), np.nan, f32)
+    for d in np.unique(doy):
+        rows = {int(year[t]): t for t in np.nonzero(doy == d)[0]}
+        total, comp, cnt = np.zeros(n, f32), np.zeros(n, f32), 0
+
+        def kadd(v, total, comp):
+            y = (v - comp).astype(f32)
+            tnew = (total + y).astype(f32)
+            comp = ((tnew - total).astype(f32) - y).astype(f32)
+            return tnew, comp
+
+        ring = []
+        for y in years:
+            if int(y) in rows and len(ring) == W and cnt:
+                clim[rows[int(y)]] = (total * f32(1.0 / cnt)).astype(f32)
+            elif int(y) in rows and y - years[0] >= W and cnt:
+                clim[rows[int(y)]] = (total * f32(1.0 / cnt)).astype(f32)
+            if len(ring) == W:
+                old = ring.pop(0)
+                if old is not None:
+                    total, comp = kadd(-old, total, comp)
+                    cnt -= 1
+            if int(y) in rows and not np.isnan(s[rows[int(y)]]).any():
+                v = s[rows[int(y)]]
+                total, comp = kadd(v, total, comp)
+                cnt += 1
+                ring.append(v)
+            else:
+                ring.append(None)
+    return clim
+
+
+def main():
+    for name, kelvin, T1, W, S in (("celsius 16 yr W=5 S=11", False, "2006-01-01", 5, 11), ("kelvin 41 yr W=15 S=21", True, "2031-01-01", 15, 21)):
+        x, time = field("1990-01-01", T1, 24, 1, kelvin)
+        year, doy = mo.calendar_tables(time)
+        ref, _mask, keep = mo.anomaly_shifting_baseline(x, year, doy, W, S)
+        s = smooth_f32_blocks(x, S, 4)
+        clim = clim_kahan(s, year, doy, W)
+        got = (x - clim).astype(f32)[keep]
+        ok = ~np.isnan(ref) & ~np.isnan(got)
+        assert (np.isnan(ref) == np.isnan(got)).all()
+        err = np.abs(got[ok].astype(np.float64) - ref[ok])
+        scale = np.abs(x).max()
+        print(f"{name}: max |err| / field = {err.max() / scale:.2e}, mean = {err.mean() / scale:.2e}, "
+              f"bit-identical {100 * (got[ok] == ref[ok]).mean():.1f} %  (tolerance 1e-5)")
+
+
+if __name__ == "__main__":
+    main()
