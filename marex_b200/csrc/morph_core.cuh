@@ -65,10 +65,13 @@ struct MorphDisk {
 // One step of 1-D dilation (radius 1) of the 96-bit window (p, c, n) = words w-1, w, w+1.  Nothing is known
 // left of p or right of n, so p's low bits / n's high bits go stale by one bit per step; after <= 32 steps the
 // stale bits have not reached c.
+// Written through 64-bit shifts of (hi:lo) pairs so that each neighbour term is ONE funnel shift (SHF) on the device.
+MAREX_HD uint32_t morph_shl1(uint32_t lo, uint32_t hi) { return (uint32_t)((((uint64_t)hi << 32) | lo) << 1 >> 32); }  // hi<<1 | lo>>31
+MAREX_HD uint32_t morph_shr1(uint32_t lo, uint32_t hi) { return (uint32_t)((((uint64_t)hi << 32) | lo) >> 1); }        // lo>>1 | hi<<31
 MAREX_HD void morph_h1(uint32_t& p, uint32_t& c, uint32_t& n) {
-  const uint32_t np = p | (p << 1) | (p >> 1) | (c << 31);
-  const uint32_t nc = c | (c << 1) | (c >> 1) | (p >> 31) | (n << 31);
-  const uint32_t nn = n | (n << 1) | (n >> 1) | (c >> 31);
+  const uint32_t np = p | (p << 1) | morph_shr1(p, c);
+  const uint32_t nc = c | morph_shl1(p, c) | morph_shr1(c, n);
+  const uint32_t nn = n | morph_shl1(c, n) | (n >> 1);
   p = np;
   c = nc;
   n = nn;
@@ -84,33 +87,27 @@ template <bool ERODE>
 MAREX_HD uint32_t morph_disk_word_t(const uint32_t* in, int Hp, int Wpw, uint32_t tailmask, int y, int w,
                                     const MorphDisk& d) {
   constexpr uint32_t flip = ERODE ? 0xffffffffu : 0u;
-  const bool wl = w - 1 >= 0, wr = w + 1 < Wpw;
-  uint32_t p, c, n;
-  {
-    const uint32_t* row = in + (int64_t)y * Wpw;
-    p = (wl ? row[w - 1] : 0u) ^ flip;
-    c = row[w] ^ flip;
-    n = (wr ? row[w + 1] : 0u) ^ flip;
-  }
+  // Branch-free borders: rows are CLAMPED into the slab (every load is in bounds) and a row outside is masked to 0 before
+  // the complement, so `acc |= (v & m) ^ flip` is one LOP3 per loaded word; one pointer per row, the neighbour columns
+  // at immediate offsets -1 / +1.  (The first version branched on every row and did 64-bit address arithmetic per
+  // load: ~100 of its ~120 instructions per row pair were checks and addressing.)
+  const bool wl = w > 0, wr = w + 1 < Wpw;  // per thread constants: the column loads are predicated, not branched
+  const uint32_t* ctr = in + (y * Wpw + w);  // 32-bit word offsets inside the time step (Hp * Wpw < 2^31)
+  uint32_t p = (wl ? ctr[-1] : 0u) ^ flip;
+  uint32_t c = ctr[0] ^ flip;
+  uint32_t n = (wr ? ctr[1] : 0u) ^ flip;
   int hcur = d.hw[0];
   for (int a = 1; a <= d.R; ++a) {
     const int h = d.hw[a];
     for (int k = hcur - h; k > 0; --k) morph_h1(p, c, n);
     hcur = h;
-#pragma unroll
-    for (int sgn = -1; sgn <= 1; sgn += 2) {
-      const int yy = y + sgn * a;
-      if (yy >= 0 && yy < Hp) {
-        const uint32_t* row = in + (int64_t)yy * Wpw;
-        p |= (wl ? row[w - 1] : 0u) ^ flip;
-        c |= row[w] ^ flip;
-        n |= (wr ? row[w + 1] : 0u) ^ flip;
-      } else {
-        p |= flip;
-        c |= flip;
-        n |= flip;
-      }
-    }
+    const int yu = y - a, yd = y + a;
+    const uint32_t mu = yu >= 0 ? 0xffffffffu : 0u, md = yd < Hp ? 0xffffffffu : 0u;
+    const uint32_t* pu = in + ((yu >= 0 ? yu : 0) * Wpw + w);
+    const uint32_t* pd = in + ((yd < Hp ? yd : Hp - 1) * Wpw + w);
+    p |= (((wl ? pu[-1] : 0u) & mu) ^ flip) | (((wl ? pd[-1] : 0u) & md) ^ flip);
+    c |= ((pu[0] & mu) ^ flip) | ((pd[0] & md) ^ flip);
+    n |= (((wr ? pu[1] : 0u) & mu) ^ flip) | (((wr ? pd[1] : 0u) & md) ^ flip);
   }
   for (int k = hcur; k > 0; --k) morph_h1(p, c, n);
   uint32_t res = c ^ flip;
