@@ -83,6 +83,7 @@ def test_full_size_properties(ny, nx):
     time = synthetic.daily_time_axis("1982-01-01", "2022-01-01")
     x = synthetic.synth_sst(time, (ny, nx), seed=2)
     res = marex_b200.preprocess_arrays(x, time, output="torch", want_bits=True)
+    assert res["thresholds_layout"] == "doy_last"  # (lat, lon, dayofyear), the reference's layout of the approximate path
     T_out = res["dat_anomaly"].shape[0]
     N = ny * nx
     events = res["extreme_events"].reshape(T_out, N)
