@@ -38,7 +38,7 @@ struct DailyParams {
 __host__ __device__ __forceinline__ bool is_leap(int y) { return (y % 4 == 0 && y % 100 != 0) || (y % 400 == 0); }
 
 // Running sum of the ring of one (day, gridpoint).  double: float64 sums of float32 data are exact, the result is rounded
-// once (what the oracle does).  float (MAREX_SHIFT_ACC=f32, a round-2 experiment, see tools/study_f32_accumulation.py):
+// once (what the oracle does).  float (MAREX_SHIFT_ACC=f32, a round-2 experiment, see tests/test_f32_accumulation_study.py):
 // Kahan-compensated float32; measured against the oracle on the CPU: max error 2e-7 of the field scale over 41 years,
 // 50 times below the 1e-5 bar, and no F2F / DADD on the XU and FP64 pipes.
 template <typename Acc>

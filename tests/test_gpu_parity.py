@@ -88,7 +88,7 @@ def test_shifting_baseline_anomaly(W, S):
 @pytest.mark.parametrize("W,S,kelvin", [(5, 11, False), (15, 21, True)])
 def test_shifting_baseline_anomaly_float32_sums(monkeypatch, W, S, kelvin):
     """MAREX_SHIFT_ACC=f32: float32 window sums + Kahan ring sum in the TMA kernel.  Not bit-identical to the oracle's
-    float64 sums, but far inside the north-star tolerance (tools/study_f32_accumulation.py: 2e-7 of the field scale)."""
+    float64 sums, but far inside the north-star tolerance (tests/test_f32_accumulation_study.py: 2e-7 of the field scale)."""
     mb = _cuda()
     monkeypatch.setenv("MAREX_SHIFT_ACC", "f32")
     x, time = _field(T1="2031-03-05" if W == 15 else "2001-07-01", kelvin=kelvin)
