@@ -237,3 +237,31 @@ def test_product_track_fails_loudly_without_cuda():
 
     with pytest.raises(RuntimeError, match="no CPU fallback"):
         track.MaskFiller(np.ones((8, 8), bool), 2, 2)
+
+
+def test_api_forms_and_input_kinds(host_track):
+    """R_fill override, functional forms, torch / integer inputs, packed output shape, from_bits validation."""
+    import torch
+
+    from marex_b200.exceptions import ConfigurationError, DataValidationError
+
+    ev, mask = events_field(5, 20, 45, seed=9, density=0.12)
+    f = host_track.MaskFiller(mask, 3, 2)
+    np.testing.assert_array_equal(f.fill_holes(ev, R_fill=1), to.fill_holes(ev, mask, 1))  # fill_time_gaps calls it with R_fill // 2
+    np.testing.assert_array_equal(host_track.fill_holes(ev, mask, 3), to.fill_holes(ev, mask, 3))
+    np.testing.assert_array_equal(host_track.fill_time_gaps(ev, mask, 3, 2), to.fill_time_gaps(ev, mask, 3, 2))
+    got = f.run(torch.from_numpy(ev.astype(np.int32) * 7))  # any integer dtype counts as "!= 0"; a tensor in gives a tensor out
+    assert isinstance(got, torch.Tensor) and got.dtype == torch.bool and tuple(got.shape) == ev.shape
+    np.testing.assert_array_equal(got.numpy(), to.stage1(ev, mask, 3, 2))
+    packed = f.run(ev, packed=True)
+    assert packed.dtype == np.int32 and packed.shape == (5, (20 * 45 + 31) // 32)
+    with pytest.raises(ConfigurationError, match="outside the range"):
+        f.fill_holes(ev, R_fill=33)
+    with pytest.raises(DataValidationError, match="from_bits expects"):
+        f.run(from_bits=(torch.zeros((5, 3), dtype=torch.int32), 5))  # too few words for 900 cells
+    with pytest.raises(DataValidationError, match="from_bits expects"):
+        f.run(from_bits=(torch.zeros((5, 29), dtype=torch.float32), 5))
+    # T_fill = 0: fill_time_gaps hands the data back untouched, even outside the mask (track.py:1692-1693)
+    f0 = host_track.MaskFiller(mask, 3, 0)
+    raw = np.ones_like(ev)
+    np.testing.assert_array_equal(f0.fill_time_gaps(raw), raw)
