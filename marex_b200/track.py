@@ -330,3 +330,80 @@ def fill_holes(data_bin, mask, R_fill, regional_mode: bool = False, neighbours=N
 def fill_time_gaps(data_bin, mask, R_fill, T_fill: int = 2, regional_mode: bool = False, neighbours=None, device=None, **kw):
     """Functional form of ``tracker.fill_time_gaps`` (track.py:1671-1726)."""
     return MaskFiller(mask, R_fill, T_fill, regional_mode, neighbours, device).fill_time_gaps(data_bin, **kw)
+
+
+# --------------------------------------------------------------------------------------------------------------
+# multi-GPU: space-sharded mask -> time-sharded stage 1
+# --------------------------------------------------------------------------------------------------------------
+def time_blocks(T: int, world: int, halo: int):
+    """Even split of the T time steps over the ranks: [(own_lo, own_hi, load_lo, load_hi)] per rank; the loaded range
+    carries ``halo`` extra steps on interior edges (truncated at the series' ends, where the reference pads with False)."""
+    out = []
+    base, rem = divmod(T, world)
+    lo = 0
+    for r in range(world):
+        hi = lo + base + (1 if r < rem else 0)
+        out.append((lo, hi, max(0, lo - halo), min(T, hi + halo)))
+        lo = hi
+    return out
+
+
+def stage1_time_sharded(bits_band: torch.Tensor, T: int, rows: int, mask, R_fill, T_fill: int = 2, regional_mode: bool = False,
+                        group=None, packed: bool = True, device=None):
+    """Stage 1 after a SPACE-sharded ``preprocess_data`` (marex_b200/sharding.py: every rank owns a latitude band).
+
+    ``fill_holes`` couples every cell with cells up to 6 * R_fill rows away (four disk passes with R_fill, four with
+    R_fill // 2), which is most of a band, while ``fill_time_gaps`` only couples a cell with itself +- T_fill steps.  So
+    the packed mask is RE-SHARDED BY TIME -- the one real exchange of this stage: every rank sends each peer the peer's
+    block of days (plus a T_fill halo) of its own band, packed bits only (1.2 GB in total for 0.25 deg x 25 yr), with
+    point-to-point sends over NCCL (NVLink) or gloo -- and each rank then runs the unchanged single-GPU stage on whole
+    (lat, lon) fields of its block of days.  Exact: steps beyond the halo cannot reach the owned steps, and at the ends of
+    the series the missing halo is the reference's own False padding (track.py:1706).
+
+    bits_band  int32 [T, rows * nx / 32]: this rank's band of the flattened bit mask (``rows * nx`` must be a multiple
+               of 32 so that bands concatenate on word boundaries); bands are ordered by rank
+    mask       the FULL (ny, nx) ocean mask
+    Returns ``(result, (t_lo, t_hi))``: the filled mask of this rank's block of days, packed int32 [t_hi - t_lo, N / 32]
+    or bool [t_hi - t_lo, ny, nx].
+    """
+    import torch.distributed as dist
+
+    mask = np.asarray(mask.cpu() if isinstance(mask, torch.Tensor) else mask).astype(bool)
+    ny, nx = mask.shape
+    world = dist.get_world_size(group) if dist.is_initialized() else 1
+    rank = dist.get_rank(group) if dist.is_initialized() else 0
+    if (rows * nx) % 32 != 0 or bits_band.dim() != 2 or bits_band.shape[0] != T or bits_band.shape[1] != rows * nx // 32:
+        raise DataValidationError(
+            "bits_band must be int32 [T, rows * nx / 32] with rows * nx a multiple of 32",
+            details=f"got {tuple(bits_band.shape)} for T={T}, rows={rows}, nx={nx}",
+        )
+    filler = MaskFiller(mask, R_fill, T_fill, regional_mode, device=device)
+    if world == 1:
+        if rows != ny:
+            raise DataValidationError("a single rank must own the whole grid", details=f"rows={rows}, ny={ny}")
+        return filler.run(from_bits=(bits_band.contiguous(), T), packed=packed), (0, T)
+    dev = bits_band.device  # NCCL moves CUDA tensors, gloo CPU tensors: keep the bookkeeping where the data is
+    all_rows = [torch.zeros(1, dtype=torch.int64, device=dev) for _ in range(world)]
+    dist.all_gather(all_rows, torch.tensor([rows], dtype=torch.int64, device=dev), group=group)
+    all_rows = [int(r.item()) for r in all_rows]
+    if sum(all_rows) != ny or any((r * nx) % 32 for r in all_rows):
+        raise DataValidationError("the bands of all ranks must tile the grid on word boundaries", details=f"rows per rank {all_rows}, ny={ny}")
+    blocks = time_blocks(T, world, int(T_fill))
+    own_lo, own_hi, load_lo, load_hi = blocks[rank]
+    n_load = load_hi - load_lo
+    bits_band = bits_band.contiguous()
+    recv = [torch.empty((n_load, all_rows[p] * nx // 32), dtype=torch.int32, device=bits_band.device) for p in range(world)]
+    ops, keep = [], []
+    for q in range(world):
+        if q == rank:
+            recv[rank].copy_(bits_band[load_lo:load_hi])
+            continue
+        piece = bits_band[blocks[q][2] : blocks[q][3]].contiguous()
+        keep.append(piece)
+        ops.append(dist.P2POp(dist.isend, piece, q if group is None else dist.get_global_rank(group, q), group))
+        ops.append(dist.P2POp(dist.irecv, recv[q], q if group is None else dist.get_global_rank(group, q), group))
+    for req in dist.batch_isend_irecv(ops):
+        req.wait()
+    field = torch.cat(recv, dim=1)  # bands are whole words: the flattened bit mask of the full grid, n_load time steps
+    out = filler.run(from_bits=(field, n_load), packed=packed)
+    return out[own_lo - load_lo : own_hi - load_lo], (own_lo, own_hi)

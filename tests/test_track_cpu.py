@@ -265,3 +265,68 @@ def test_api_forms_and_input_kinds(host_track):
     f0 = host_track.MaskFiller(mask, 3, 0)
     raw = np.ones_like(ev)
     np.testing.assert_array_equal(f0.fill_time_gaps(raw), raw)
+
+
+# ------------------------------------------------------------------ world_size-2 gloo run of the time-sharded stage 1
+_SHARD_WORKER = r"""
+import ctypes, os, sys, numpy as np, torch, torch.distributed as dist
+sys.path.insert(0, os.environ["MAREX_ROOT"]); sys.path.insert(0, os.path.join(os.environ["MAREX_ROOT"], "tests"))
+from marex_b200 import _lib, track
+from oracle import track_oracle as to
+from test_track_cpu import events_field
+lib = ctypes.CDLL(os.environ["MORPH_HOST_LIB"])
+for name, (argtypes, restype) in _lib._SIGNATURES.items():
+    if name.startswith("marex_morph_"):
+        fn = getattr(lib, name); fn.argtypes, fn.restype = argtypes, restype
+def call(name, *args):
+    assert getattr(lib, name)(*args) == 0, name
+track._device = lambda device=None: torch.device("cpu")   # the kernels' per-word code on the host (tests/morph_host.cu)
+track._call = call
+dist.init_process_group("gloo")
+rank, world = dist.get_rank(), dist.get_world_size()
+T, ny, nx, R, T_fill = 11, 16, 64, 2, 4
+ev, mask = events_field(T, ny, nx, seed=4, density=0.2)
+rows = ny // world
+band = ev[:, rank * rows:(rank + 1) * rows].reshape(T, -1)
+bits = torch.from_numpy(np.packbits(band, axis=1, bitorder="little").view(np.uint32).view(np.int32).copy())
+ref = to.stage1(ev, mask, R, T_fill)
+out, (lo, hi) = track.stage1_time_sharded(bits, T, rows, mask, R, T_fill, packed=False)
+assert np.array_equal(out.numpy(), ref[lo:hi]), (rank, lo, hi)
+outp, _ = track.stage1_time_sharded(bits, T, rows, mask, R, T_fill, packed=True)
+flat = np.unpackbits(outp.numpy().view(np.uint8), axis=1, bitorder="little")[:, : ny * nx].astype(bool)
+assert np.array_equal(flat.reshape(hi - lo, ny, nx), ref[lo:hi])
+n = torch.tensor([hi - lo]); dist.all_reduce(n)
+if rank == 0:
+    assert int(n) == T
+    print("STAGE1_GLOO_OK", lo, hi)
+dist.destroy_process_group()
+"""
+
+
+def test_time_blocks_cover_the_series():
+    from marex_b200.track import time_blocks
+
+    for T, world, halo in [(11, 2, 4), (9131, 8, 2), (5, 8, 2), (100, 3, 0)]:
+        b = time_blocks(T, world, halo)
+        assert b[0][0] == 0 and b[-1][1] == T and len(b) == world
+        for (lo, hi, llo, lhi), nxt in zip(b, b[1:] + [None]):
+            assert llo == max(0, lo - halo) and lhi == min(T, hi + halo) and lo <= hi
+            if nxt is not None:
+                assert hi == nxt[0]
+
+
+def test_stage1_time_sharded_world2_gloo(harness, tmp_path):
+    import socket
+    import sys
+
+    script = tmp_path / "worker.py"
+    script.write_text(_SHARD_WORKER)
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    env = dict(os.environ, MAREX_ROOT=ROOT, MORPH_HOST_LIB=harness._name, OMP_NUM_THREADS="1")
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
+           "--master-port", str(port), str(script)]  # fmt: skip
+    res = subprocess.run(cmd, capture_output=True, text=True, env=env, timeout=300)
+    assert res.returncode == 0, res.stdout[-2000:] + res.stderr[-2000:]
+    assert "STAGE1_GLOO_OK" in res.stdout
