@@ -19,6 +19,8 @@ MAREX_SHIFT_ACC=f32 run bench_shift_f32 300 python bench.py --steps 10 --warmup 
 # 3. tracker stage 1 with the third version of the disk kernel
 run bench_stage1 120 python tools/bench_stage1.py --days 2048 --out "$out/bench_stage1.json"
 
+# (with `gpurun --gpus 2`: python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 tools/stage1_sharded_check.py)
+
 # 4. launch lists (share of the step per kernel)
 run ncu_bench 400 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file "$out/launches_bench.csv" python bench.py --steps 2 --warmup 3 --no-e2e --no-cpu
 run ncu_stage1 200 ncu --metrics gpu__time_duration.sum --clock-control none -c 200 --csv --log-file "$out/launches_stage1.csv" python tools/bench_stage1.py --days 256 --reps 1
