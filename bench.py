@@ -548,6 +548,7 @@ def main():
                 "halo_rows": halo,
                 "l2": "inputs (60 GB per GPU at 0.25 deg) are far larger than L2; no flush needed",
                 **({"shift_acc": os.environ["MAREX_SHIFT_ACC"]} if os.environ.get("MAREX_SHIFT_ACC") else {}),
+                **({"shift_lean": os.environ["MAREX_SHIFT_LEAN"]} if os.environ.get("MAREX_SHIFT_LEAN") else {}),
                 **kw,
             },
             "roofline": roofline,

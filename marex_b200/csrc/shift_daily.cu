@@ -21,6 +21,7 @@
 // same numbers _validate_data_values needs, detect.py:205-279); marex_shift_anomaly_fixup_f32
 // then recomputes the few gridpoints with 0 < count < T with the generic kernel (anomaly.cu).
 #include <cstdlib>
+#include <type_traits>
 
 #include "tma.cuh"
 
@@ -33,6 +34,7 @@ struct DailyParams {
   float* out;
   uint8_t* mask0;
   int32_t* nonfinite;
+  uint32_t leap_bits[8];  // bit i: year index i is a leap year (first 256 years; only the LEAN instantiations read it)
 };
 
 __host__ __device__ __forceinline__ bool is_leap(int y) { return (y % 4 == 0 && y % 100 != 0) || (y % 400 == 0); }
@@ -63,10 +65,21 @@ struct RingSum<float> {
   __device__ __forceinline__ float value() const { return s; }
 };
 
-template <int R, int NST, int MODE, typename Acc = double>
+// LEAN (MAREX_SHIFT_LEAN=1, a round-2 experiment): the two items of the source-level profile that are pure overhead --
+// `is_leap` by integer modulo per thread and year (6.4 % of the instructions) becomes a bit test on a host-built mask in
+// the parameters, and the row arithmetic is 32-bit (T < 2^31 is required by the TMA coordinates anyway).
+template <bool LEAN>
+__device__ __forceinline__ bool year_is_leap(const DailyParams& p, int i) {
+  if (LEAN && i < 256) return (p.leap_bits[i >> 5] >> (i & 31)) & 1u;
+  return is_leap(p.year0 + i);
+}
+
+template <int R, int NST, int MODE, typename Acc = double, bool LEAN = false>
 __global__ void __launch_bounds__(R >= 12 ? 256 : 512) shift_daily_kernel(const __grid_constant__ CUtensorMap tmap,
                                                                          const DailyParams p) {
   extern __shared__ __align__(1024) unsigned char smem_raw[];
+  using Row = typename std::conditional<LEAN, int, int64_t>::type;  // input row indices
+  const Row Tn = (Row)p.T;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int D = p.D, W = p.W, S = p.S, off = p.S / 2;
   // shared memory carve-up (all offsets multiples of 128 bytes)
@@ -99,14 +112,14 @@ __global__ void __launch_bounds__(R >= 12 ? 256 : 512) shift_daily_kernel(const 
 
   // producer state (thread 0): first row of the box of the next year to issue
   int issue_year = 0, issue_st = 0;
-  int64_t issue_base = -(int64_t)p.doy0;  // row index of day-of-year 0 of year `issue_year`
+  Row issue_base = -(Row)p.doy0;  // row index of day-of-year 0 of year `issue_year`
   auto issue = [&]() {  // a box that lies entirely outside the series is neither loaded nor waited for
-    const int64_t tb = issue_base + d0 - off;
-    if (tb < p.T && tb + p.rows_box > 0) {
+    const Row tb = issue_base + d0 - off;
+    if (tb < Tn && tb + p.rows_box > 0) {
       mbar_expect_tx(&bar[issue_st], box_bytes);
       tma_load_2d(xs + (size_t)issue_st * stage_elems, &tmap, (int)c0, (int)tb, &bar[issue_st]);
     }
-    issue_base += is_leap(p.year0 + issue_year) ? 366 : 365;
+    issue_base += year_is_leap<LEAN>(p, issue_year) ? 366 : 365;
     ++issue_year;
     if (++issue_st == NST) issue_st = 0;
   };
@@ -121,7 +134,7 @@ __global__ void __launch_bounds__(R >= 12 ? 256 : 512) shift_daily_kernel(const 
   for (int r = 0; r < R; ++r) cnt[r] = 0;
   int bad = 0;
   const Acc invS = (Acc)(1.0 / (double)S);
-  int64_t base = -(int64_t)p.doy0;
+  Row base = -(Row)p.doy0;
   uint32_t phase = 0;  // bit st = parity of the next completion of stage st
   int st = 0, slot = 0;
   const float* Xst = xs + rbase * 32 + lane;          // this thread's first window row in stage 0
@@ -129,20 +142,20 @@ __global__ void __launch_bounds__(R >= 12 ? 256 : 512) shift_daily_kernel(const 
   float* const outc = p.out + c;                      // column of this gridpoint (dead lanes never store)
 
   for (int i = 0; i < p.n_years; ++i) {
-    const int ylen = is_leap(p.year0 + i) ? 366 : 365;
+    const int ylen = year_is_leap<LEAN>(p, i) ? 366 : 365;
     const float* X = Xst + st * stage_elems;          // X[j * 32]: row rbase + j of the box
     float* ringslot = ringp + slot * (D * 32);
     const int nd = min(D, ylen - d0);                 // days of this strip that exist in year i
-    const int64_t t0 = base + d0 + rbase;             // input row of this thread's first day
+    const Row t0 = base + d0 + rbase;                 // input row of this thread's first day
     const bool target = i >= W;
     {
-      const int64_t tb = base + d0 - off;
-      if (tb < p.T && tb + p.rows_box > 0) {
+      const Row tb = base + d0 - off;
+      if (tb < Tn && tb + p.rows_box > 0) {
         mbar_wait(&bar[st], (phase >> st) & 1u);
         phase ^= 1u << st;
       }
     }
-    float* outp = outc + (t0 - p.out_off) * p.out_pitch;  // only dereferenced for target years
+    float* outp = outc + (int64_t)(t0 - (Row)p.out_off) * p.out_pitch;  // only dereferenced for target years
 
     // ring turnover of one (day, gridpoint): year i - W leaves, year i enters
     auto turnover = [&](int r, float s) {
@@ -176,7 +189,7 @@ __global__ void __launch_bounds__(R >= 12 ? 256 : 512) shift_daily_kernel(const 
     }
     __syncthreads();
 
-    if (rbase + R <= nd && t0 - off >= 0 && t0 + (R - 1) - off + S <= p.T) {
+    if (rbase + R <= nd && t0 - off >= 0 && t0 + (R - 1) - off + S <= Tn) {
       // ---- whole sub-strip inside the year and the series: no per-day checks ----
       if (t0 == 0 && live) p.mask0[c] = is_finite_f(X[off * 32]) ? 1 : 0;  // only reachable when S == 1
       const float* Xhi = X + (S - 1) * 32;
@@ -216,12 +229,12 @@ __global__ void __launch_bounds__(R >= 12 ? 256 : 512) shift_daily_kernel(const 
       bool have = false;
 #pragma unroll
       for (int r = 0; r < R; ++r) {
-        const int64_t t = t0 + r;
-        if (rbase + r < nd && t >= 0 && t < p.T) {
+        const Row t = t0 + r;
+        if (rbase + r < nd && t >= 0 && t < Tn) {
           const float xv = X[(r + off) * 32];
           if (t == 0 && live) p.mask0[c] = is_finite_f(xv) ? 1 : 0;
           float s = CUDART_NAN_F;
-          if (t - off >= 0 && t - off + S <= p.T) {  // full window inside the series (min_periods = S)
+          if (t - off >= 0 && t - off + S <= Tn) {  // full window inside the series (min_periods = S)
             if (have) {
               ws += (Acc)X[(r + S - 1) * 32] - (Acc)X[(r - 1) * 32];
             } else {
@@ -286,9 +299,12 @@ extern "C" int marex_shift_anomaly_daily_f32(const float* x, int64_t T, int64_t 
   // years covered by T daily rows starting at (year0, doy0); row of Jan 1 of year index W
   int64_t base = -(int64_t)(doy0 - 1), base_w = -1;
   int n_years = 0;
+  for (int k = 0; k < 8; ++k) p.leap_bits[k] = 0;
   while (base < T) {
     if (n_years == W) base_w = base;
-    base += is_leap(year0 + n_years) ? 366 : 365;
+    const bool leap = is_leap(year0 + n_years);
+    if (leap && n_years < 256) p.leap_bits[n_years >> 5] |= 1u << (n_years & 31);
+    base += leap ? 366 : 365;
     ++n_years;
   }
   p.n_years = n_years;
@@ -303,6 +319,7 @@ extern "C" int marex_shift_anomaly_daily_f32(const float* x, int64_t T, int64_t 
   const int env_cps = getenv("MAREX_SHIFT_CPS") ? atoi(getenv("MAREX_SHIFT_CPS")) : 0;
   const char* env_acc = getenv("MAREX_SHIFT_ACC");
   const bool acc_f32 = env_acc && std::string(env_acc) == "f32";  // experiment: float32 sums (Kahan ring), within 1e-5
+  const bool lean = getenv("MAREX_SHIFT_LEAN") && atoi(getenv("MAREX_SHIFT_LEAN")) == 1;  // experiment, default shape only
   const size_t fixed = 128 + (((size_t)(W + 1) * 8 + 127) / 128) * 128;
   auto launch = [&](auto kern, int R, int nst, int cps) -> int {
     auto smem_of = [&](int D, int ns) {
@@ -351,7 +368,12 @@ extern "C" int marex_shift_anomaly_daily_f32(const float* x, int64_t T, int64_t 
     // measured on B200 (0.25 deg, W=15, S=21): two co-resident CTAs of 11 warps x 4 days: 56-57 ms; one CTA of
     // 8 x 12: 78-89 ms.  The arithmetic is latency-bound (8-22 warps per SM: the ring limits residency), the TMA
     // staging alone takes 21 ms and the output stores 7 ms.
-    rc = MAREX_SD(4, 2, 2);
+    if (lean) {
+      rc = acc_f32 ? (mode ? launch(shift_daily_kernel<4, 2, 1, float, true>, 4, 2, 2) : launch(shift_daily_kernel<4, 2, 0, float, true>, 4, 2, 2))
+                   : (mode ? launch(shift_daily_kernel<4, 2, 1, double, true>, 4, 2, 2) : launch(shift_daily_kernel<4, 2, 0, double, true>, 4, 2, 2));
+    } else {
+      rc = MAREX_SD(4, 2, 2);
+    }
     if (rc == MAREX_ERR_UNSUPPORTED) rc = MAREX_SD(6, 2, 2);
     if (rc == MAREX_ERR_UNSUPPORTED) rc = MAREX_SD(12, 2, 1);
     if (rc == MAREX_ERR_UNSUPPORTED) rc = MAREX_SD(4, 2, 1);

@@ -104,6 +104,27 @@ def test_shifting_baseline_anomaly_float32_sums(monkeypatch, W, S, kelvin):
     np.testing.assert_allclose(got, ref, rtol=0, atol=1e-6 * scale, equal_nan=True)  # ten times inside the 1e-5 bar
 
 
+@pytest.mark.skipif(os.environ.get("MAREX_TEST_EXPERIMENTAL") != "1", reason="round-2 experiment: set MAREX_TEST_EXPERIMENTAL=1")
+@pytest.mark.parametrize("W,S", [(5, 11), (15, 21)])
+def test_shifting_baseline_anomaly_lean_variant(monkeypatch, W, S):
+    """MAREX_SHIFT_LEAN=1 (leap-year bit mask, 32-bit row arithmetic) changes no arithmetic: same bars as the default kernel,
+    and bit-identical to it."""
+    mb = _cuda()
+    x, time = _field(T1="2010-03-05" if W == 15 else "2001-07-01")
+    if W == 15:
+        time = np.arange(np.datetime64("1982-01-01"), np.datetime64("1982-01-01") + len(time))
+    year, doy = mo.calendar_tables(time)
+    ref, _mask, _keep = mo.anomaly_shifting_baseline(x, year, doy, W, S)
+    cal = mb.detect.build_calendar(time)
+    xd, _space = mb.detect._to_device_field(x, "cuda")
+    base = mb.compute_normalised_anomaly_arrays(xd, cal, "shifting_baseline", W, S)["dat_anomaly"].cpu().numpy()
+    monkeypatch.setenv("MAREX_SHIFT_LEAN", "1")
+    res = mb.compute_normalised_anomaly_arrays(xd, cal, "shifting_baseline", W, S)
+    got = res["dat_anomaly"].cpu().numpy()
+    np.testing.assert_array_equal(_canon(got), _canon(base))
+    assert _frac_bits_differ(got.reshape(ref.shape), ref) < 1e-3
+
+
 def test_shifting_baseline_nonfinite_and_gaps():
     """NaN / inf bookkeeping in the running sums, missing days and a missing year."""
     mb = _cuda()

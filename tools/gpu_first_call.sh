@@ -10,11 +10,13 @@ run() { name=$1; shift; echo "== $name" | tee -a "$out/steps.log"; ( time timeou
 
 # 1. parity: the whole GPU suite, then the experiments (float32 sums in the shifting-baseline kernel)
 run pytest_gpu 400 python -m pytest tests -m gpu -x -q
-MAREX_TEST_EXPERIMENTAL=1 run pytest_experimental 200 python -m pytest tests/test_gpu_parity.py -m gpu -q -k float32_sums
+MAREX_TEST_EXPERIMENTAL=1 run pytest_experimental 200 python -m pytest tests/test_gpu_parity.py -m gpu -q -k "float32_sums or lean_variant"
 
 # 2. config 2, device-resident: default (float64 sums) against MAREX_SHIFT_ACC=f32
 run bench_default 300 python bench.py --steps 10 --warmup 3 --no-e2e --no-cpu
 MAREX_SHIFT_ACC=f32 run bench_shift_f32 300 python bench.py --steps 10 --warmup 3 --no-e2e --no-cpu
+MAREX_SHIFT_LEAN=1 run bench_shift_lean 300 python bench.py --steps 10 --warmup 3 --no-e2e --no-cpu
+MAREX_SHIFT_LEAN=1 MAREX_SHIFT_ACC=f32 run bench_shift_lean_f32 300 python bench.py --steps 10 --warmup 3 --no-e2e --no-cpu
 
 # 3. tracker stage 1 with the third version of the disk kernel
 run bench_stage1 120 python tools/bench_stage1.py --days 2048 --out "$out/bench_stage1.json"
@@ -25,5 +27,5 @@ run bench_stage1 120 python tools/bench_stage1.py --days 2048 --out "$out/bench_
 run ncu_bench 400 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file "$out/launches_bench.csv" python bench.py --steps 2 --warmup 3 --no-e2e --no-cpu
 run ncu_stage1 200 ncu --metrics gpu__time_duration.sum --clock-control none -c 200 --csv --log-file "$out/launches_stage1.csv" python tools/bench_stage1.py --days 256 --reps 1
 
-grep -h '"metric"' "$out"/bench_default.log "$out"/bench_shift_f32.log | cut -c1-400
+grep -h '"metric"' "$out"/bench_default.log "$out"/bench_shift_f32.log "$out"/bench_shift_lean.log "$out"/bench_shift_lean_f32.log | cut -c1-400
 tail -3 "$out/pytest_gpu.log" "$out/pytest_experimental.log"
