@@ -127,8 +127,9 @@ class MaskFiller:
         if from_bits is not None:
             bits, T = from_bits
             bits = bits.to(self.device)
-            if bits.dtype not in (torch.int32, torch.uint32) or bits.dim() != 2 or bits.shape[1] * 32 < self.N or not bits.is_contiguous():
-                raise DataValidationError("from_bits expects a contiguous int32 [T, >= ceil(N / 32)] tensor", details=f"got {tuple(bits.shape)} {bits.dtype}")
+            if (bits.dtype not in (torch.int32, torch.uint32) or bits.dim() != 2 or bits.shape[1] * 32 < self.N
+                    or not bits.is_contiguous() or not 0 < int(T) <= bits.shape[0]):  # fmt: skip
+                raise DataValidationError("from_bits expects a contiguous int32 [T, >= ceil(N / 32)] tensor", details=f"got {tuple(bits.shape)} {bits.dtype} for T={T}")
             return _Source(bits, True, int(bits.shape[1]), row_stride, 0), int(T), False
         as_numpy = not isinstance(data_bin, torch.Tensor)
         t = torch.from_numpy(np.ascontiguousarray(data_bin)) if as_numpy else data_bin

@@ -261,6 +261,8 @@ def test_api_forms_and_input_kinds(host_track):
         f.run(from_bits=(torch.zeros((5, 3), dtype=torch.int32), 5))  # too few words for 900 cells
     with pytest.raises(DataValidationError, match="from_bits expects"):
         f.run(from_bits=(torch.zeros((5, 29), dtype=torch.float32), 5))
+    with pytest.raises(DataValidationError, match="from_bits expects"):
+        f.run(from_bits=(torch.zeros((5, 29), dtype=torch.int32), 6))  # more time steps than rows
     # T_fill = 0: fill_time_gaps hands the data back untouched, even outside the mask (track.py:1692-1693)
     f0 = host_track.MaskFiller(mask, 3, 0)
     raw = np.ones_like(ev)
