@@ -3,6 +3,8 @@
 // fields (row-aligned padded bit slabs, 32 cells per word) and unstructured meshes (cell-major words holding
 // 32 TIME steps, so that one neighbour gather serves 32 days).  Integer / bit work, HBM- and L1-bound: no tensor cores.
 // The per-word arithmetic lives in morph_core.cuh (shared with the host test harness).
+#include <cstdlib>
+
 #include "common.cuh"
 #include "morph_core.cuh"
 
@@ -57,13 +59,14 @@ __global__ void __launch_bounds__(256) morph_pad_words_kernel(MorphSrc src, int6
 // One morphological pass over all padded time steps; thread = output word, w fastest (coalesced; the 3 x (2R+1)
 // input words of neighbouring threads overlap and are served by L1).
 __global__ void __launch_bounds__(256) morph_disk_kernel(const uint32_t* __restrict__ in, uint32_t* __restrict__ out,
-                                                         int Hp, int Wpw, uint32_t tailmask, const __grid_constant__ MorphDisk disk, int erode) {
+                                                         int Hp, int Wpw, uint32_t tailmask, const __grid_constant__ MorphDisk disk, int erode,
+                                                         int variant) {
   const int per_t = Hp * Wpw;  // < 2^31 (checked by the caller); blockIdx.y = time step: no 64-bit division
   const int r = blockIdx.x * blockDim.x + threadIdx.x;
   if (r >= per_t) return;
   const int64_t base = (int64_t)blockIdx.y * per_t;
   const int y = r / Wpw, w = r - y * Wpw;
-  out[base + r] = morph_disk_word(in + base, Hp, Wpw, tailmask, y, w, disk, erode);
+  out[base + r] = morph_disk_word(in + base, Hp, Wpw, tailmask, y, w, disk, erode, variant);
 }
 
 // Separable form (morph_core.cuh): pass H widens every input word once and stores it at the disk's distinct half-widths,
@@ -290,13 +293,14 @@ extern "C" int marex_morph_disk(const uint32_t* in, uint32_t* out, int64_t T, in
   MAREX_REQUIRE(in && out && in != out && T > 0 && Hp > 0 && Wp > 0, "bad arguments");
   if (R < 0 || R > MORPH_MAX_R) return fail(MAREX_ERR_UNSUPPORTED, "R_fill must be in 0..32");
   const MorphDisk d = morph_make_disk(R);
+  const int variant = (getenv("MAREX_MORPH_DISK") && atoi(getenv("MAREX_MORPH_DISK")) == 3) ? 3 : 2;  // tuning knob
   const int Wpw = (int)((Wp + 31) >> 5);
   MAREX_REQUIRE(Hp * (int64_t)Wpw < (1LL << 31), "padded time step too large");
   const int64_t per_t = Hp * (int64_t)Wpw;
   for (int64_t t0 = 0; t0 < T; t0 += 65535) {  // gridDim.y <= 65535
     const dim3 grid((unsigned)((per_t + 255) / 256), (unsigned)std::min<int64_t>(65535, T - t0));
     morph_disk_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(in + t0 * per_t, out + t0 * per_t, (int)Hp, Wpw,
-                                                              morph_tailmask((int)Wp), d, erode ? 1 : 0);
+                                                              morph_tailmask((int)Wp), d, erode ? 1 : 0, variant);
     MAREX_LAUNCH_CHECK("morph_disk_kernel");
   }
   return MAREX_OK;

@@ -65,10 +65,20 @@ struct MorphDisk {
 // One step of 1-D dilation (radius 1) of the 96-bit window (p, c, n) = words w-1, w, w+1.  Nothing is known
 // left of p or right of n, so p's low bits / n's high bits go stale by one bit per step; after <= 32 steps the
 // stale bits have not reached c.
-// Written through 64-bit shifts of (hi:lo) pairs so that each neighbour term is ONE funnel shift (SHF) on the device.
+MAREX_HD void morph_h1(uint32_t& p, uint32_t& c, uint32_t& n) {
+  const uint32_t np = p | (p << 1) | (p >> 1) | (c << 31);
+  const uint32_t nc = c | (c << 1) | (c >> 1) | (p >> 31) | (n << 31);
+  const uint32_t nn = n | (n << 1) | (n >> 1) | (c >> 31);
+  p = np;
+  c = nc;
+  n = nn;
+}
+
+// The same step written through 64-bit shifts of (hi:lo) pairs, which compile to one funnel shift (SHF) per neighbour
+// term: 13 instead of 16 instructions.  Used by the third disk variant only (not yet measured on a GPU).
 MAREX_HD uint32_t morph_shl1(uint32_t lo, uint32_t hi) { return (uint32_t)((((uint64_t)hi << 32) | lo) << 1 >> 32); }  // hi<<1 | lo>>31
 MAREX_HD uint32_t morph_shr1(uint32_t lo, uint32_t hi) { return (uint32_t)((((uint64_t)hi << 32) | lo) >> 1); }        // lo>>1 | hi<<31
-MAREX_HD void morph_h1(uint32_t& p, uint32_t& c, uint32_t& n) {
+MAREX_HD void morph_h1f(uint32_t& p, uint32_t& c, uint32_t& n) {
   const uint32_t np = p | (p << 1) | morph_shr1(p, c);
   const uint32_t nc = c | morph_shl1(p, c) | morph_shr1(c, n);
   const uint32_t nn = n | morph_shl1(c, n) | (n >> 1);
@@ -87,6 +97,46 @@ template <bool ERODE>
 MAREX_HD uint32_t morph_disk_word_t(const uint32_t* in, int Hp, int Wpw, uint32_t tailmask, int y, int w,
                                     const MorphDisk& d) {
   constexpr uint32_t flip = ERODE ? 0xffffffffu : 0u;
+  const bool wl = w - 1 >= 0, wr = w + 1 < Wpw;
+  uint32_t p, c, n;
+  {
+    const uint32_t* row = in + (int64_t)y * Wpw;
+    p = (wl ? row[w - 1] : 0u) ^ flip;
+    c = row[w] ^ flip;
+    n = (wr ? row[w + 1] : 0u) ^ flip;
+  }
+  int hcur = d.hw[0];
+  for (int a = 1; a <= d.R; ++a) {
+    const int h = d.hw[a];
+    for (int k = hcur - h; k > 0; --k) morph_h1(p, c, n);
+    hcur = h;
+#pragma unroll
+    for (int sgn = -1; sgn <= 1; sgn += 2) {
+      const int yy = y + sgn * a;
+      if (yy >= 0 && yy < Hp) {
+        const uint32_t* row = in + (int64_t)yy * Wpw;
+        p |= (wl ? row[w - 1] : 0u) ^ flip;
+        c |= row[w] ^ flip;
+        n |= (wr ? row[w + 1] : 0u) ^ flip;
+      } else {
+        p |= flip;
+        c |= flip;
+        n |= flip;
+      }
+    }
+  }
+  for (int k = hcur; k > 0; --k) morph_h1(p, c, n);
+  uint32_t res = c ^ flip;
+  if (w == Wpw - 1) res &= tailmask;
+  return res;
+}
+
+// Third variant (variant = 3, MAREX_MORPH_DISK=3; its bits are checked on the host, its speed is NOT yet measured on a GPU):
+// the SASS of the version above spends ~100 of ~120 instructions per row pair on bounds branches and 64-bit addressing.
+template <bool ERODE>
+MAREX_HD uint32_t morph_disk_word3_t(const uint32_t* in, int Hp, int Wpw, uint32_t tailmask, int y, int w,
+                                    const MorphDisk& d) {
+  constexpr uint32_t flip = ERODE ? 0xffffffffu : 0u;
   // Branch-free borders: rows are CLAMPED into the slab (every load is in bounds) and a row outside is masked to 0 before
   // the complement, so `acc |= (v & m) ^ flip` is one LOP3 per loaded word; one pointer per row, the neighbour columns
   // at immediate offsets -1 / +1.  (The first version branched on every row and did 64-bit address arithmetic per
@@ -99,7 +149,7 @@ MAREX_HD uint32_t morph_disk_word_t(const uint32_t* in, int Hp, int Wpw, uint32_
   int hcur = d.hw[0];
   for (int a = 1; a <= d.R; ++a) {
     const int h = d.hw[a];
-    for (int k = hcur - h; k > 0; --k) morph_h1(p, c, n);
+    for (int k = hcur - h; k > 0; --k) morph_h1f(p, c, n);
     hcur = h;
     const int yu = y - a, yd = y + a;
     const uint32_t mu = yu >= 0 ? 0xffffffffu : 0u, md = yd < Hp ? 0xffffffffu : 0u;
@@ -109,17 +159,20 @@ MAREX_HD uint32_t morph_disk_word_t(const uint32_t* in, int Hp, int Wpw, uint32_
     c |= ((pu[0] & mu) ^ flip) | ((pd[0] & md) ^ flip);
     n |= (((wr ? pu[1] : 0u) & mu) ^ flip) | (((wr ? pd[1] : 0u) & md) ^ flip);
   }
-  for (int k = hcur; k > 0; --k) morph_h1(p, c, n);
+  for (int k = hcur; k > 0; --k) morph_h1f(p, c, n);
   uint32_t res = c ^ flip;
   if (w == Wpw - 1) res &= tailmask;
   return res;
 }
 
-// `erode` is uniform over a launch, so the dispatch does not diverge.  (Measured on B200: a second dispatch on
+// `erode` and `variant` are uniform over a launch, so the dispatch does not diverge.  (Measured on B200: a dispatch on
 // "all inputs inside the slab" made the kernel SLOWER -- rows are 46 words at 0.25 degree, so almost every warp
 // straddles a row end and ran both variants.)
 MAREX_HD uint32_t morph_disk_word(const uint32_t* in, int Hp, int Wpw, uint32_t tailmask, int y, int w,
-                                  const MorphDisk& d, int erode) {
+                                  const MorphDisk& d, int erode, int variant = 2) {
+  if (variant == 3)
+    return erode ? morph_disk_word3_t<true>(in, Hp, Wpw, tailmask, y, w, d)
+                 : morph_disk_word3_t<false>(in, Hp, Wpw, tailmask, y, w, d);
   return erode ? morph_disk_word_t<true>(in, Hp, Wpw, tailmask, y, w, d)
                : morph_disk_word_t<false>(in, Hp, Wpw, tailmask, y, w, d);
 }

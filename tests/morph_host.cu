@@ -5,6 +5,7 @@
 // tests then only have to establish that the kernels index and launch correctly.  Built by tests/test_track_cpu.py
 // with `nvcc -shared` (host code only, no CUDA runtime call).  Pointers are HOST pointers here.
 #include <stdint.h>
+#include <stdlib.h>
 
 #include "../marex_b200/csrc/morph_core.cuh"
 
@@ -43,13 +44,14 @@ int marex_morph_pad_bits(const uint8_t* bytes, const uint32_t* bits, int64_t t_p
 int marex_morph_disk(const uint32_t* in, uint32_t* out, int64_t T, int64_t Hp, int64_t Wp, int32_t R, int32_t erode, void*) {
   if (R < 0 || R > MORPH_MAX_R) return -3;
   const MorphDisk d = morph_make_disk(R);
+  const int variant = (getenv("MAREX_MORPH_DISK") && atoi(getenv("MAREX_MORPH_DISK")) == 3) ? 3 : 2;  // as morph.cu
   const int Wpw = (int)((Wp + 31) >> 5);
   const int64_t per_t = Hp * Wpw;
   for (int64_t t = 0; t < T; ++t)
     for (int y = 0; y < Hp; ++y)
       for (int w = 0; w < Wpw; ++w)
         out[t * per_t + (int64_t)y * Wpw + w] =
-            morph_disk_word(in + t * per_t, (int)Hp, Wpw, morph_tailmask((int)Wp), y, w, d, erode ? 1 : 0);
+            morph_disk_word(in + t * per_t, (int)Hp, Wpw, morph_tailmask((int)Wp), y, w, d, erode ? 1 : 0, variant);
   return 0;
 }
 

@@ -164,10 +164,13 @@ GRID_CASES = [
 ]
 
 
-@pytest.mark.parametrize("separable", [False, True])
+@pytest.mark.parametrize("separable", [False, True, "disk3"])
 @pytest.mark.parametrize("T,ny,nx,R,T_fill,regional,density,noise", GRID_CASES)
 def test_host_word_code_gridded(host_track, monkeypatch, T, ny, nx, R, T_fill, regional, density, noise, separable):
     ev, mask = events_field(T, ny, nx, seed=R + nx, density=density, noise=noise)
+    if separable == "disk3":  # the third variant of the direct disk pass (MAREX_MORPH_DISK=3)
+        monkeypatch.setenv("MAREX_MORPH_DISK", "3")
+        separable = False
     if separable:  # a scratch of two time steps' level buffers: the chunk loop runs several times, with a ragged tail
         nlev = max(1, host_track._lib.load().marex_morph_disk_levels(R))
         monkeypatch.setattr(host_track, "SEPARABLE_SCRATCH_BYTES", 2 * 4 * nlev * (ny + 4 * R) * ((nx + 4 * R + 31) // 32))

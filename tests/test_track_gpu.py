@@ -115,3 +115,14 @@ def test_stage1_consumes_the_packed_mask_of_preprocess():
     got = f.run(from_bits=(res["bits"], ev.shape[0]))  # the bit-packed mask straight from marex_compare_hobday
     np.testing.assert_array_equal(got.cpu().numpy(), ref)
     np.testing.assert_array_equal(f.run(res["extreme_events"]).cpu().numpy(), ref)
+
+
+@pytest.mark.skipif(os.environ.get("MAREX_TEST_EXPERIMENTAL") != "1", reason="round-2 experiment: set MAREX_TEST_EXPERIMENTAL=1")
+@pytest.mark.parametrize("T,ny,nx,R,T_fill,regional,density,noise", GRID_CASES)
+def test_gridded_fill_disk_variant_3(monkeypatch, T, ny, nx, R, T_fill, regional, density, noise):
+    """MAREX_MORPH_DISK=3: branch-free borders + funnel-shift widening (same bits, fewer instructions; checked on the host,
+    not yet run on a GPU)."""
+    track = _track()
+    monkeypatch.setenv("MAREX_MORPH_DISK", "3")
+    ev, mask = events_field(T, ny, nx, seed=R + nx, density=density, noise=noise)
+    np.testing.assert_array_equal(track.MaskFiller(mask, R, T_fill, regional).run(ev), to.stage1(ev, mask, R, T_fill, regional))
