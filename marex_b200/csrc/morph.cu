@@ -94,6 +94,31 @@ __global__ void __launch_bounds__(256) morph_disk_v_kernel(const uint32_t* __res
   out[base + r] = morph_disk_v_word(in + base, hbuf + base, lvl_stride, Hp, Wpw, tailmask, y, w, plan, erode);
 }
 
+// Variant 4: the separable pass inside one shared-memory tile (morph_core.cuh).  grid = (tiles of TH rows, time steps).
+__global__ void __launch_bounds__(256) morph_disk_tile_kernel(const uint32_t* __restrict__ in, uint32_t* __restrict__ out, int Hp,
+                                                              int Wpw, uint32_t tailmask, const __grid_constant__ MorphPlan plan,
+                                                              int erode, int TH) {
+  extern __shared__ uint32_t tile_smem[];
+  const int R = plan.R, rows = TH + 2 * R, n_stage = rows * Wpw;
+  uint32_t* in_s = tile_smem;
+  uint32_t* lvl_s = tile_smem + n_stage;
+  const uint32_t flip = erode ? 0xffffffffu : 0u;
+  const int64_t base = (int64_t)blockIdx.y * Hp * Wpw;
+  const int y0 = blockIdx.x * TH;
+  for (int item = threadIdx.x; item < n_stage; item += blockDim.x)
+    in_s[item] = morph_tile_load_item(in + base, Hp, Wpw, y0, R, item, flip);
+  __syncthreads();
+  for (int item = threadIdx.x; item < n_stage; item += blockDim.x) morph_tile_h_item(in_s, lvl_s, n_stage, Wpw, plan, item, flip);
+  __syncthreads();
+  const int n_out = min(TH, Hp - y0) * Wpw;
+  for (int item = threadIdx.x; item < n_out; item += blockDim.x) {
+    const int orow = item / Wpw, w = item - orow * Wpw;
+    uint32_t res = morph_tile_v_item(in_s, lvl_s, n_stage, Wpw, plan, orow, w, flip);
+    if (w == Wpw - 1) res &= tailmask;
+    out[base + (int64_t)(y0 + orow) * Wpw + w] = res;
+  }
+}
+
 // Temporal dilation / erosion of whole slabs, bit-parallel over the 32 cells of a word.
 __global__ void __launch_bounds__(256) morph_time_kernel(const uint32_t* __restrict__ in, int64_t T_in, int64_t words,
                                                          uint32_t* __restrict__ out, int64_t T_out, int off, int K,
@@ -293,10 +318,27 @@ extern "C" int marex_morph_disk(const uint32_t* in, uint32_t* out, int64_t T, in
   MAREX_REQUIRE(in && out && in != out && T > 0 && Hp > 0 && Wp > 0, "bad arguments");
   if (R < 0 || R > MORPH_MAX_R) return fail(MAREX_ERR_UNSUPPORTED, "R_fill must be in 0..32");
   const MorphDisk d = morph_make_disk(R);
-  const int variant = (getenv("MAREX_MORPH_DISK") && atoi(getenv("MAREX_MORPH_DISK")) == 3) ? 3 : 2;  // tuning knob
+  const int env_variant = getenv("MAREX_MORPH_DISK") ? atoi(getenv("MAREX_MORPH_DISK")) : 2;  // tuning knob
+  const int variant = env_variant == 3 ? 3 : 2;
   const int Wpw = (int)((Wp + 31) >> 5);
   MAREX_REQUIRE(Hp * (int64_t)Wpw < (1LL << 31), "padded time step too large");
   const int64_t per_t = Hp * (int64_t)Wpw;
+  if (env_variant == 4 && R >= 1) {  // shared-memory tile variant (experiment); falls through when a tile does not fit
+    const MorphPlan pl = morph_make_plan(R);
+    const int TH = morph_tile_rows(Wpw, R, pl.nlev, 200 * 1024);
+    if (TH > 0) {
+      const size_t smem = (size_t)(1 + pl.nlev) * (TH + 2 * R) * Wpw * 4;
+      cudaError_t e = cudaFuncSetAttribute(morph_disk_tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(morph_disk_tile_kernel)");
+      for (int64_t t0 = 0; t0 < T; t0 += 65535) {
+        const dim3 grid((unsigned)((Hp + TH - 1) / TH), (unsigned)std::min<int64_t>(65535, T - t0));
+        morph_disk_tile_kernel<<<grid, 256, smem, (cudaStream_t)stream>>>(in + t0 * per_t, out + t0 * per_t, (int)Hp, Wpw,
+                                                                          morph_tailmask((int)Wp), pl, erode ? 1 : 0, TH);
+        MAREX_LAUNCH_CHECK("morph_disk_tile_kernel");
+      }
+      return MAREX_OK;
+    }
+  }
   for (int64_t t0 = 0; t0 < T; t0 += 65535) {  // gridDim.y <= 65535
     const dim3 grid((unsigned)((per_t + 255) / 256), (unsigned)std::min<int64_t>(65535, T - t0));
     morph_disk_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(in + t0 * per_t, out + t0 * per_t, (int)Hp, Wpw,

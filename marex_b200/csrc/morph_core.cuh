@@ -262,6 +262,51 @@ MAREX_HD uint32_t morph_disk_v_word(const uint32_t* in, const uint32_t* hb0, int
                : morph_disk_v_word_t<false>(in, hb0, lvl_stride, Hp, Wpw, tailmask, y, w, pl);
 }
 
+// ---- the separable pass inside ONE shared-memory tile (variant 4, MAREX_MORPH_DISK=4; host-checked, not yet measured) --------
+// A CTA owns TH output rows of one time step: it stages rows y0-R .. y0+TH+R-1 (complemented for erosion, rows outside the
+// slab as "False"), widens every staged row ONCE into one shared buffer per level (phase H), then ORs 2R+1 single words per
+// output word (phase V).  Each input row is widened once per tile instead of once per output row it feeds, and nothing
+// but the input and the output touches global memory.  The three per-item functions below are what both the kernel
+// (threads striding over items, __syncthreads between phases) and the host harness (plain loops) execute.
+MAREX_HD uint32_t morph_tile_load_item(const uint32_t* in, int Hp, int Wpw, int y0, int R, int item, uint32_t flip) {
+  const int row = item / Wpw, w = item - row * Wpw;
+  const int yy = y0 - R + row;
+  const uint32_t v = (yy >= 0 && yy < Hp) ? in[yy * Wpw + w] : 0u;
+  return v ^ flip;
+}
+
+MAREX_HD void morph_tile_h_item(const uint32_t* in_s, uint32_t* lvl_s, int lvl_stride, int Wpw, const MorphPlan& pl, int item,
+                                uint32_t flip) {
+  const int row = item / Wpw, w = item - row * Wpw;
+  uint32_t p = w > 0 ? in_s[item - 1] : flip;
+  uint32_t c = in_s[item];
+  uint32_t n = w + 1 < Wpw ? in_s[item + 1] : flip;
+  for (int s = 1; s <= pl.hmax; ++s) {
+    morph_h1(p, c, n);
+    const int j = pl.store_at[s];
+    if (j >= 0) lvl_s[j * lvl_stride + item] = c;
+  }
+}
+
+MAREX_HD uint32_t morph_tile_v_item(const uint32_t* in_s, const uint32_t* lvl_s, int lvl_stride, int Wpw, const MorphPlan& pl,
+                                    int orow, int w, uint32_t flip) {
+  uint32_t acc = 0;
+  const int ctr = (orow + pl.R) * Wpw + w;  // staged row of the output row
+  for (int a = 0; a <= pl.R; ++a) {
+    const int j = pl.row_lvl[a];
+    const uint32_t* src = j < 0 ? in_s : lvl_s + j * lvl_stride;
+    acc |= src[ctr - a * Wpw] | src[ctr + a * Wpw];
+  }
+  return acc ^ flip;
+}
+
+// Rows per tile that fit `smem_budget` bytes: (1 + nlev) buffers of (TH + 2R) x Wpw words; 0 = does not fit.
+inline int morph_tile_rows(int Wpw, int R, int nlev, int64_t smem_budget) {
+  for (int th = 32; th >= 4; th >>= 1)
+    if ((int64_t)(1 + nlev) * (th + 2 * R) * Wpw * 4 <= smem_budget) return th;
+  return 0;
+}
+
 // Chunk loop shared by the library (kernel launches) and the host test harness (plain loops): pass_h(t0, n, lvl_stride)
 // then pass_v(t0, n, lvl_stride) for consecutive chunks of n <= chunk time steps.
 template <class FH, class FV>

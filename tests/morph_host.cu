@@ -44,9 +44,36 @@ int marex_morph_pad_bits(const uint8_t* bytes, const uint32_t* bits, int64_t t_p
 int marex_morph_disk(const uint32_t* in, uint32_t* out, int64_t T, int64_t Hp, int64_t Wp, int32_t R, int32_t erode, void*) {
   if (R < 0 || R > MORPH_MAX_R) return -3;
   const MorphDisk d = morph_make_disk(R);
-  const int variant = (getenv("MAREX_MORPH_DISK") && atoi(getenv("MAREX_MORPH_DISK")) == 3) ? 3 : 2;  // as morph.cu
+  const int env_variant = getenv("MAREX_MORPH_DISK") ? atoi(getenv("MAREX_MORPH_DISK")) : 2;  // as morph.cu
+  const int variant = env_variant == 3 ? 3 : 2;
   const int Wpw = (int)((Wp + 31) >> 5);
   const int64_t per_t = Hp * Wpw;
+  if (env_variant == 4 && R >= 1) {  // morph_disk_tile_kernel: phases separated by __syncthreads() = three loops per tile
+    const MorphPlan pl = morph_make_plan(R);
+    const char* tb = getenv("MORPH_HOST_TILE_BUDGET");  // tests shrink the budget to force small tiles
+    const int TH = morph_tile_rows(Wpw, R, pl.nlev, tb ? atoll(tb) : 200 * 1024);
+    if (TH > 0) {
+      const int n_stage = (TH + 2 * R) * Wpw;
+      uint32_t* smem = new uint32_t[(size_t)(1 + pl.nlev) * n_stage];
+      uint32_t *in_s = smem, *lvl_s = smem + n_stage;
+      const uint32_t flip = erode ? 0xffffffffu : 0u;
+      for (int64_t t = 0; t < T; ++t)
+        for (int y0 = 0; y0 < Hp; y0 += TH) {  // blockIdx.x
+          for (int i = 0; i < (1 + pl.nlev) * n_stage; ++i) smem[i] = 0xdeadbeefu;  // shared memory starts undefined
+          for (int item = 0; item < n_stage; ++item) in_s[item] = morph_tile_load_item(in + t * per_t, (int)Hp, Wpw, y0, R, item, flip);
+          for (int item = 0; item < n_stage; ++item) morph_tile_h_item(in_s, lvl_s, n_stage, Wpw, pl, item, flip);
+          const int n_out = ((int)Hp - y0 < TH ? (int)Hp - y0 : TH) * Wpw;
+          for (int item = 0; item < n_out; ++item) {
+            const int orow = item / Wpw, w = item - orow * Wpw;
+            uint32_t res = morph_tile_v_item(in_s, lvl_s, n_stage, Wpw, pl, orow, w, flip);
+            if (w == Wpw - 1) res &= morph_tailmask((int)Wp);
+            out[t * per_t + (int64_t)(y0 + orow) * Wpw + w] = res;
+          }
+        }
+      delete[] smem;
+      return 0;
+    }
+  }
   for (int64_t t = 0; t < T; ++t)
     for (int y = 0; y < Hp; ++y)
       for (int w = 0; w < Wpw; ++w)

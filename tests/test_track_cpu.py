@@ -164,12 +164,18 @@ GRID_CASES = [
 ]
 
 
-@pytest.mark.parametrize("separable", [False, True, "disk3"])
+@pytest.mark.parametrize("separable", [False, True, "disk3", "disk4", "disk4_small_tiles"])
 @pytest.mark.parametrize("T,ny,nx,R,T_fill,regional,density,noise", GRID_CASES)
 def test_host_word_code_gridded(host_track, monkeypatch, T, ny, nx, R, T_fill, regional, density, noise, separable):
     ev, mask = events_field(T, ny, nx, seed=R + nx, density=density, noise=noise)
     if separable == "disk3":  # the third variant of the direct disk pass (MAREX_MORPH_DISK=3)
         monkeypatch.setenv("MAREX_MORPH_DISK", "3")
+        separable = False
+    elif separable in ("disk4", "disk4_small_tiles"):  # the shared-memory tile variant
+        monkeypatch.setenv("MAREX_MORPH_DISK", "4")
+        if separable == "disk4_small_tiles":  # 4- or 8-row tiles: several tiles per time step, a ragged last tile
+            nlev = max(1, host_track._lib.load().marex_morph_disk_levels(R))
+            monkeypatch.setenv("MORPH_HOST_TILE_BUDGET", str((1 + nlev) * (8 + 2 * R) * ((nx + 4 * R + 31) // 32) * 4))
         separable = False
     if separable:  # a scratch of two time steps' level buffers: the chunk loop runs several times, with a ragged tail
         nlev = max(1, host_track._lib.load().marex_morph_disk_levels(R))

@@ -118,11 +118,21 @@ def test_stage1_consumes_the_packed_mask_of_preprocess():
 
 
 @pytest.mark.skipif(os.environ.get("MAREX_TEST_EXPERIMENTAL") != "1", reason="round-2 experiment: set MAREX_TEST_EXPERIMENTAL=1")
+@pytest.mark.parametrize("variant", ["3", "4"])
 @pytest.mark.parametrize("T,ny,nx,R,T_fill,regional,density,noise", GRID_CASES)
-def test_gridded_fill_disk_variant_3(monkeypatch, T, ny, nx, R, T_fill, regional, density, noise):
-    """MAREX_MORPH_DISK=3: branch-free borders + funnel-shift widening (same bits, fewer instructions; checked on the host,
-    not yet run on a GPU)."""
+def test_gridded_fill_disk_variant_3(monkeypatch, T, ny, nx, R, T_fill, regional, density, noise, variant):
+    """MAREX_MORPH_DISK=3: branch-free borders + funnel-shift widening; =4: the separable pass inside one shared-memory
+    tile (same bits, fewer instructions; both checked on the host, not yet run on a GPU)."""
     track = _track()
-    monkeypatch.setenv("MAREX_MORPH_DISK", "3")
+    monkeypatch.setenv("MAREX_MORPH_DISK", variant)
     ev, mask = events_field(T, ny, nx, seed=R + nx, density=density, noise=noise)
     np.testing.assert_array_equal(track.MaskFiller(mask, R, T_fill, regional).run(ev), to.stage1(ev, mask, R, T_fill, regional))
+
+
+@pytest.mark.skipif(os.environ.get("MAREX_TEST_EXPERIMENTAL") != "1", reason="round-2 experiment: set MAREX_TEST_EXPERIMENTAL=1")
+@pytest.mark.parametrize("variant", ["3", "4"])
+def test_quarter_degree_slices_disk_variants(monkeypatch, variant):
+    track = _track()
+    monkeypatch.setenv("MAREX_MORPH_DISK", variant)
+    ev, mask = events_field(4, 720, 1440, seed=5, density=0.02, noise=0.0005)
+    np.testing.assert_array_equal(track.MaskFiller(mask, 8, 2).run(ev), to.stage1(ev, mask, 8, 2))
