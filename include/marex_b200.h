@@ -241,6 +241,8 @@ int marex_compare_global(const float* anom, int64_t T, int64_t N, int64_t pitch,
  *                        time steps outside [0, T_in) False: the temporal closing of track.py:1695-1719 is
  *                        a dilation (T_out = T + 2*half, off = -2*half) then an erosion (T_out = T, off = 0)
  *                        with K = T_fill + 1 = 2*half + 1.
+ *  marex_morph_pack_u8   bool bytes [T, N] (every byte 0 or 1) -> flattened bits, a word per thread (two 16-byte loads):
+ *                        the fast way into the bit layouts for callers that hold the reference's bool array.
  *  marex_morph_extract   source cells -> bool bytes [T, N] and / or flattened bits (+ count of True cells,
  *                        accumulated into a device uint64), the trim of track.py:1638-1643 + the mask.
  *
@@ -271,6 +273,8 @@ int marex_morph_extract(const uint8_t* src_bytes, const uint32_t* src_bits, int6
                         int64_t src_row_stride, int64_t src_origin, const uint32_t* mask_bits, int64_t T,
                         int64_t ny, int64_t nx, uint8_t* events, int64_t events_pitch, uint32_t* bits,
                         int64_t bits_pitch, unsigned long long* count, void* stream);
+int marex_morph_pack_u8(const uint8_t* events, int64_t T, int64_t N, int64_t pitch, uint32_t* bits, int64_t bits_pitch,
+                        void* stream);
 int64_t marex_morph_tpack_words(int64_t T);
 int marex_morph_tpack(const uint8_t* src_bytes, const uint32_t* src_bits, int64_t src_t_pitch, int64_t T,
                       int64_t N, uint32_t* packed, void* stream);

@@ -42,6 +42,7 @@ _SIGNATURES = {
     "marex_morph_disk_sep": ([_P, _P, c_int64, c_int64, c_int64, c_int32, c_int32, _P, c_int64, _P], ctypes.c_int),
     "marex_morph_time": ([_P, c_int64, c_int64, _P, c_int64, c_int32, c_int32, c_int32, _P], ctypes.c_int),
     "marex_morph_extract": ([_P, _P, c_int64, c_int64, c_int64, _P, c_int64, c_int64, c_int64, _P, c_int64, _P, c_int64, _P, _P], ctypes.c_int),
+    "marex_morph_pack_u8": ([_P, c_int64, c_int64, c_int64, _P, c_int64, _P], ctypes.c_int),
     "marex_morph_tpack_words": ([c_int64], c_int64),
     "marex_morph_tpack": ([_P, _P, c_int64, c_int64, c_int64, _P, _P], ctypes.c_int),
     "marex_morph_nbr": ([_P, _P, c_int64, c_int64, _P, c_int32, _P, c_int32, c_int32, _P], ctypes.c_int),

@@ -197,6 +197,17 @@ __global__ void __launch_bounds__(256) morph_extract_words_kernel(MorphSrc src, 
   }
 }
 
+// Bool bytes [T, N] -> flattened bits: thread = output word, two 16-byte loads, eight multiply-gathers.
+__global__ void __launch_bounds__(256) morph_pack_kernel(const uint8_t* __restrict__ events, int64_t T, int64_t N, int64_t pitch,
+                                                         uint32_t* __restrict__ bits, int64_t bits_pitch) {
+  const int64_t nwords = (N + 31) >> 5, total = T * nwords;
+  for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t t = idx / nwords, w = idx - t * nwords;
+    const int64_t c0 = w * 32;
+    bits[t * bits_pitch + w] = morph_pack_word(events + t * pitch + c0, (int)min((int64_t)32, N - c0));
+  }
+}
+
 // ---------------------------------------------------------------------------------------------------------
 // unstructured: cell-major, time-packed.  Word (c, k) holds time steps 32*(k-1) .. 32*(k-1)+31 of cell c: word 0 and
 // the last word of every cell are margins, so that the temporal closing can look 32 steps past either end.
@@ -411,6 +422,16 @@ extern "C" int marex_morph_extract(const uint8_t* src_bytes, const uint32_t* src
   morph_extract_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(src, T, (int)ny, (int)nx, events, events_pitch,
                                                                              bits, bits_pitch, count);
   MAREX_LAUNCH_CHECK("morph_extract_kernel");
+  return MAREX_OK;
+}
+
+extern "C" int marex_morph_pack_u8(const uint8_t* events, int64_t T, int64_t N, int64_t pitch, uint32_t* bits, int64_t bits_pitch,
+                                   void* stream) {
+  MAREX_REQUIRE(events && bits && T > 0 && N > 0 && pitch >= N && bits_pitch >= (N + 31) / 32, "bad arguments");
+  const int64_t items = T * ((N + 31) / 32);
+  const int64_t blocks = std::min<int64_t>((items + 255) / 256, (int64_t)sm_count() * 32);
+  morph_pack_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(events, T, N, pitch, bits, bits_pitch);
+  MAREX_LAUNCH_CHECK("morph_pack_kernel");
   return MAREX_OK;
 }
 

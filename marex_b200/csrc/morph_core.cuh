@@ -412,6 +412,21 @@ MAREX_HD uint32_t morph_extract_word(const MorphSrc& s, int64_t T, int64_t t, in
 // 4 bits -> 4 bool bytes (bit k -> byte k): the products b_j * 2^(7i) land on distinct bit positions, no carries.
 MAREX_HD uint32_t morph_expand4(uint32_t b) { return ((b & 0xfu) * 0x00204081u) & 0x01010101u; }
 
+// 32 bool bytes (each 0 or 1 -- the host mirror normalises other dtypes with `!= 0`) -> one word of the flattened bit mask.
+// 4 bytes at a time: (w * 0x01020408) >> 24 gathers b0 + 2 b1 + 4 b2 + 8 b3 (the partial products land on distinct bits).
+MAREX_HD uint32_t morph_nibble(uint32_t w) { return ((w & 0x01010101u) * 0x01020408u) >> 24; }
+MAREX_HD uint32_t morph_pack_word(const uint8_t* p, int n) {
+  uint32_t word = 0;
+  if (n == 32 && (reinterpret_cast<uintptr_t>(p) & 15) == 0) {
+    const uint4 a = reinterpret_cast<const uint4*>(p)[0], b = reinterpret_cast<const uint4*>(p)[1];
+    word = morph_nibble(a.x) | (morph_nibble(a.y) << 4) | (morph_nibble(a.z) << 8) | (morph_nibble(a.w) << 12) |
+           (morph_nibble(b.x) << 16) | (morph_nibble(b.y) << 20) | (morph_nibble(b.z) << 24) | (morph_nibble(b.w) << 28);
+  } else {
+    for (int j = 0; j < n; ++j) word |= (p[j] != 0 ? 1u : 0u) << j;
+  }
+  return word;
+}
+
 // ---- unstructured: cell-major, time-packed words (word k of a cell = time steps 32*(k-1) .. 32*(k-1)+31) ----------
 
 MAREX_HD uint32_t morph_tpack_word(const MorphSrc& src, int64_t T, int64_t c, int k, int Tw) {

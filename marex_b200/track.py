@@ -78,6 +78,7 @@ class MaskFiller:
     def __init__(self, mask, R_fill, T_fill: int = 2, regional_mode: bool = False, neighbours=None, device=None,
                  separable: Optional[bool] = None):
         self.separable = (os.environ.get("MAREX_MORPH_SEPARABLE", "0") == "1") if separable is None else bool(separable)
+        self.pack_input = os.environ.get("MAREX_MORPH_PACK", "0") == "1"
         self.R_fill = int(R_fill)
         self.T_fill = T_fill
         self.regional_mode = bool(regional_mode)
@@ -135,11 +136,17 @@ class MaskFiller:
         t = torch.from_numpy(np.ascontiguousarray(data_bin)) if as_numpy else data_bin
         if tuple(t.shape[1:]) != self.space:
             raise DataValidationError("data_bin does not match the mask", details=f"data {tuple(t.shape)} vs mask {self.space}")
-        if t.dtype not in (torch.bool, torch.uint8, torch.int8):
-            t = t != 0
-        t = t.to(self.device).reshape(t.shape[0], -1).contiguous()
-        t = t.view(torch.uint8) if t.dtype != torch.uint8 else t
-        return _Source(t, False, self.N, row_stride, 0), int(t.shape[0]), as_numpy
+        t = t.to(self.device)
+        if t.dtype != torch.bool:
+            t = t != 0  # any other dtype: "non-zero is True"; bool storage is exactly 0 / 1
+        t = t.reshape(t.shape[0], -1).contiguous().view(torch.uint8)
+        T = int(t.shape[0])
+        if self.pack_input:  # experiment: bool bytes -> flattened bits first (a word per thread), then the word-gather kernels
+            nw = (self.N + 31) // 32
+            bits = self._words(T, nw)
+            _call("marex_morph_pack_u8", _p(t), T, self.N, self.N, _p(bits), nw, _stream(self.device))
+            return _Source(bits, True, nw, row_stride, 0), T, as_numpy
+        return _Source(t, False, self.N, row_stride, 0), T, as_numpy
 
     def _output(self, T: int, packed: bool):
         count = torch.zeros(1, dtype=torch.int64, device=self.device)

@@ -152,6 +152,16 @@ int marex_morph_extract(const uint8_t* bytes, const uint32_t* bits_in, int64_t t
   return 0;
 }
 
+int marex_morph_pack_u8(const uint8_t* events, int64_t T, int64_t N, int64_t pitch, uint32_t* bits, int64_t bits_pitch, void*) {
+  const int64_t nwords = (N + 31) / 32;
+  for (int64_t t = 0; t < T; ++t)
+    for (int64_t w = 0; w < nwords; ++w) {
+      const int64_t c0 = w * 32;
+      bits[t * bits_pitch + w] = morph_pack_word(events + t * pitch + c0, (int)(N - c0 < 32 ? N - c0 : 32));
+    }
+  return 0;
+}
+
 int marex_morph_tpack(const uint8_t* bytes, const uint32_t* bits, int64_t t_pitch, int64_t T, int64_t N, uint32_t* dst, void*) {
   MorphSrc s{bytes, bits, t_pitch, 0, 0, nullptr};
   const int Tw = (int)marex_morph_tpack_words(T);

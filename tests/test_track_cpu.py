@@ -164,10 +164,13 @@ GRID_CASES = [
 ]
 
 
-@pytest.mark.parametrize("separable", [False, True, "disk3", "disk4", "disk4_small_tiles"])
+@pytest.mark.parametrize("separable", [False, True, "disk3", "disk4", "disk4_small_tiles", "pack"])
 @pytest.mark.parametrize("T,ny,nx,R,T_fill,regional,density,noise", GRID_CASES)
 def test_host_word_code_gridded(host_track, monkeypatch, T, ny, nx, R, T_fill, regional, density, noise, separable):
     ev, mask = events_field(T, ny, nx, seed=R + nx, density=density, noise=noise)
+    if separable == "pack":  # bool bytes -> bits first (MAREX_MORPH_PACK=1)
+        monkeypatch.setenv("MAREX_MORPH_PACK", "1")
+        separable = False
     if separable == "disk3":  # the third variant of the direct disk pass (MAREX_MORPH_DISK=3)
         monkeypatch.setenv("MAREX_MORPH_DISK", "3")
         separable = False
@@ -204,8 +207,11 @@ def test_host_word_code_gridded(host_track, monkeypatch, T, ny, nx, R, T_fill, r
     np.testing.assert_array_equal(out_bits.view(np.uint32), np.packbits(ref_bits, axis=1, bitorder="little").view(np.uint32))
 
 
+@pytest.mark.parametrize("pack", [False, True])
 @pytest.mark.parametrize("T,R,T_fill", [(7, 1, 2), (40, 2, 2), (70, 3, 4), (33, 0, 2), (9, 2, 0)])
-def test_host_word_code_unstructured(host_track, T, R, T_fill):
+def test_host_word_code_unstructured(host_track, monkeypatch, T, R, T_fill, pack):
+    if pack:
+        monkeypatch.setenv("MAREX_MORPH_PACK", "1")
     nb = mesh(10, seed=T)
     N = nb.shape[1]
     rng = np.random.default_rng(T)
@@ -341,3 +347,22 @@ def test_stage1_time_sharded_world2_gloo(harness, tmp_path):
     res = subprocess.run(cmd, capture_output=True, text=True, env=env, timeout=300)
     assert res.returncode == 0, res.stdout[-2000:] + res.stderr[-2000:]
     assert "STAGE1_GLOO_OK" in res.stdout
+
+
+def test_pack_word_aligned_and_ragged(harness):
+    """morph_pack_word: the 16-byte path (multiply-gather) and the byte path agree with numpy's packbits."""
+    rng = np.random.default_rng(1)
+    for N in (64, 96, 70, 31, 1):
+        T = 3
+        pitch = 112  # a multiple of 16: rows of the aligned case start on 16-byte boundaries
+        buf = np.zeros(T * pitch + 16, np.uint8)
+        off = (-buf.ctypes.data) % 16
+        ev = buf[off : off + T * pitch].reshape(T, pitch)
+        ev[:, :N] = rng.random((T, N)) < 0.4
+        nw = (N + 31) // 32
+        bits = np.zeros((T, nw), np.uint32)
+        rc = harness.marex_morph_pack_u8(ev.ctypes.data_as(ctypes.c_void_p), T, N, pitch, bits.ctypes.data_as(ctypes.c_void_p), nw, None)
+        assert rc == 0
+        padded = np.zeros((T, nw * 32), bool)
+        padded[:, :N] = ev[:, :N] != 0
+        np.testing.assert_array_equal(bits, np.packbits(padded, axis=1, bitorder="little").view(np.uint32))

@@ -136,3 +136,13 @@ def test_quarter_degree_slices_disk_variants(monkeypatch, variant):
     monkeypatch.setenv("MAREX_MORPH_DISK", variant)
     ev, mask = events_field(4, 720, 1440, seed=5, density=0.02, noise=0.0005)
     np.testing.assert_array_equal(track.MaskFiller(mask, 8, 2).run(ev), to.stage1(ev, mask, 8, 2))
+
+
+@pytest.mark.skipif(os.environ.get("MAREX_TEST_EXPERIMENTAL") != "1", reason="round-2 experiment: set MAREX_TEST_EXPERIMENTAL=1")
+def test_bool_input_through_the_pack_kernel(monkeypatch):
+    """MAREX_MORPH_PACK=1: bool bytes -> flattened bits (a word per thread) before the word-gather kernels."""
+    track = _track()
+    monkeypatch.setenv("MAREX_MORPH_PACK", "1")
+    for T, ny, nx, R in ((5, 20, 45, 3), (3, 48, 96, 4), (2, 720, 1440, 8)):
+        ev, mask = events_field(T, ny, nx, seed=R, density=0.05 if R > 4 else 0.12, noise=0.002)
+        np.testing.assert_array_equal(track.MaskFiller(mask, R, 2).run(ev), to.stage1(ev, mask, R, 2))

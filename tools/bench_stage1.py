@@ -47,6 +47,7 @@ def main():
     ap.add_argument("--T-fill", type=int, default=2)
     ap.add_argument("--density", type=float, default=0.05)
     ap.add_argument("--reps", type=int, default=5)
+    ap.add_argument("--input", default="bits", choices=["bits", "bool"], help="hand stage 1 the packed mask or the bool array")
     ap.add_argument("--out", default=None)
     a = ap.parse_args()
     assert torch.cuda.is_available(), "needs a CUDA device"
@@ -59,6 +60,13 @@ def main():
     mask[: ny // 12] = False  # a polar cap of land
     mask[ny // 3 : ny // 2, nx // 5 : nx // 3] = False
     bits = synthetic_bits(T, ny, nx, a.density, dev)
+    if a.input == "bool":  # the reference's layout: one byte per cell
+        shifts = torch.arange(32, device=dev, dtype=torch.int32).view(1, 1, 32)
+        events = torch.empty((T, ny, nx), dtype=torch.bool, device=dev)
+        for t0 in range(0, T, 64):
+            w = bits[t0 : t0 + 64]
+            events[t0 : t0 + 64] = (((w.unsqueeze(-1) >> shifts) & 1) != 0).reshape(w.shape[0], -1)[:, :N].reshape(-1, ny, nx)
+    run_kw = dict(from_bits=(bits, T)) if a.input == "bits" else dict(data_bin=events)
 
     # algorithmic bytes per call (read once + write once), from the arguments of the call itself
     def call_bytes(name, args):
@@ -71,6 +79,8 @@ def main():
             return 2 * v[2] * v[3] * ((v[4] + 31) // 32) * 4
         if name == "marex_morph_time":
             return (v[1] + v[4]) * v[2] * 4
+        if name == "marex_morph_pack_u8":
+            return v[1] * v[2] + v[1] * ((v[2] + 31) // 32) * 4
         if name == "marex_morph_extract":
             T_, ny_, nx_ = v[6], v[7], v[8]
             out = (T_ * ny_ * nx_ if v[9] else 0) + (T_ * ((ny_ * nx_ + 31) // 32) * 4 if v[11] else 0)
@@ -91,7 +101,7 @@ def main():
     for label, packed, separable in (("direct_packed_out", True, False), ("separable_packed_out", True, True),
                                      ("separable_bool_out", False, True)):
         f = track.MaskFiller(mask, R, a.T_fill, device=dev, separable=separable)
-        f.run(from_bits=(bits, T), packed=packed)  # warm-up (allocator, first launches)
+        f.run(packed=packed, **run_kw)  # warm-up (allocator, first launches)
         torch.cuda.synchronize()
         track._call = timed_call
         whole = []
@@ -100,7 +110,7 @@ def main():
             records.clear()
             s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             s0.record()
-            f.run(from_bits=(bits, T), packed=packed)
+            f.run(packed=packed, **run_kw)
             s1.record()
             torch.cuda.synchronize()
             whole.append(s0.elapsed_time(s1))
@@ -119,7 +129,8 @@ def main():
     line = {
         "metric": "gridpoint-days/s of tracker stage 1 (fill_holes + fill_time_gaps) on the bit-packed mask",
         "config": {"days": T, "grid": [ny, nx], "R_fill": R, "T_fill": a.T_fill, "density": a.density, "reps": a.reps,
-                   "input": "flattened bit mask on the device (the layout marex_compare_* writes)"},  # fmt: skip
+                   "input": "flattened bit mask on the device (the layout marex_compare_* writes)" if a.input == "bits" else "bool bytes on the device",
+                   "env": {k: v for k, v in os.environ.items() if k.startswith("MAREX_")}},  # fmt: skip
         "launches": int(_lib.launch_count()),
         "results": out,
     }
