@@ -1,6 +1,6 @@
 #!/usr/bin/env bash
 # One gpurun call that measures everything the previous round left unmeasured:
-#   /usr/local/graft/bin/gpurun --timeout 900 -- 'bash tools/gpu_first_call.sh'
+#   /usr/local/graft/bin/gpurun --timeout 1800 -- 'bash tools/gpu_first_call.sh'      (about 15 GPU-minutes when nothing hangs)
 # Every step is bounded by its own timeout and writes into gpurun_out/first/; nothing here runs under a profiler except
 # the two ncu passes at the end, whose printed numbers are never bench values.
 set -u
