@@ -58,14 +58,15 @@ def algorithmic_bytes_per_cell(T, T_out, hobday=True):
 # digitize kernel and the banded histogram kernel); scratch traffic is not algorithmic.
 def kernel_bytes_per_cell(T, T_out):
     return {
-        "marex_shift_anomaly_daily_f32": 4 * T + 4 * T_out + 1 + 4,
+        "marex_shift_anomaly_daily_f32": 4 * T + 4 * T_out + 1 + 4,  # (+ 2 * T_out of bin codes when fused: scratch, not algorithmic)
         "marex_shift_anomaly_f32": 4 * T + 4 * T_out + 1 + 4,
-        "marex_digitize_f32": 4 * T_out + 2 * T_out,
-        "marex_hobday_thresholds_pooled_f32": 4 * T_out + 4 * 366 + 4,
+        "marex_digitize_doy_f32": 4 * T_out + 2 * T_out,
+        "marex_hobday_thresholds_pooled_bins": 2 * T_out + 4 * 366 + 4,
         "marex_hobday_thresholds_hist": 2 * T_out + 4 * 366 + 4,
         "marex_hobday_thresholds_exact_f32": 4 * T_out + 4 * 366,
         "marex_transpose_f32": 2 * 4 * 366,
         "marex_compare_hobday": 4 * T_out + T_out + 4 * 366,
+        "marex_compare_hobday_bins": 2 * T_out + T_out + 4 * 366,
         "marex_detrend_coef_f64": 4 * T + 16,
         "marex_detrend_apply_f32": 8 * T + 16,
         "marex_doy_climatology_f32": 4 * T + 4 * 366,
@@ -79,8 +80,9 @@ def kernel_bytes_per_cell(T, T_out):
 
 STAGE_KERNELS = {
     "marex_shift_anomaly_daily_f32": ["shift_daily_kernel"],
-    "marex_hobday_thresholds_pooled_f32": ["digitize_ffff_kernel", "hobday_band_kernel", "hobday_pool_tile_kernel (fall-back list)"],
+    "marex_hobday_thresholds_pooled_bins": ["hobday_ring_kernel", "hobday_band_kernel (retry list)", "hobday_pool_tile_kernel (fall-back list)"],
     "marex_compare_hobday": ["compare_doy_kernel"],
+    "marex_compare_hobday_bins": ["compare_bins_kernel"],
 }
 
 
@@ -547,8 +549,7 @@ def main():
                 "days_out": T_out,
                 "halo_rows": halo,
                 "l2": "inputs (60 GB per GPU at 0.25 deg) are far larger than L2; no flush needed",
-                **({"shift_acc": os.environ["MAREX_SHIFT_ACC"]} if os.environ.get("MAREX_SHIFT_ACC") else {}),
-                **({"shift_lean": os.environ["MAREX_SHIFT_LEAN"]} if os.environ.get("MAREX_SHIFT_LEAN") else {}),
+                **({"tuning_env": {k: v for k, v in os.environ.items() if k.startswith("MAREX_")}} if any(k.startswith("MAREX_") for k in os.environ) else {}),
                 **kw,
             },
             "roofline": roofline,

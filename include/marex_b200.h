@@ -27,6 +27,8 @@
  *  - tidx[n_years*366] int32 row index of (year i, doy d) at [i*366 + d-1], or -1
  *  - out_row[T]  int32  output row of input row t, or -1 when the row is trimmed
  *  - doy_ptr[367], doy_rows[doy_ptr[366]] int32  CSR list of the rows of each day of year
+ *  - slot_row[366*NY] int32  row of (day of year d, k-th output year) at [d*NY + k], or -1: the
+ *    day-of-year-major "slot" order of the histogram bin codes
  */
 #ifndef MAREX_B200_H
 #define MAREX_B200_H
@@ -50,6 +52,10 @@ int marex_version(void);
 const char* marex_last_error(void);
 /* Number of kernel launches issued by this process so far (bench.py's gpu_launches). */
 long long marex_launch_count(void);
+/* Tuning / test knobs (kernel shapes, forced fall-backs; never changes a result): set != 0 pins `key` to `value`
+ * for this process, set == 0 removes the pin.  An unpinned key falls back to the environment variable
+ * MAREX_<KEY IN CAPITALS> (read once), then to the built-in default.  Keys: DESIGN.md section 9. */
+int marex_tune(const char* key, long long value, int32_t set);
 
 /* ---- (a) shifting baseline ------------------------------------------------------------
  * smoothed_rolling_climatology + anomaly + trim (detect.py:1511-1688, 1691-1816, 1819-1850,
@@ -69,22 +75,37 @@ int marex_shift_anomaly_f32(const float* x, int64_t T, int64_t N, int64_t pitch,
 
 /* Same stage, fast path for a GAP-FREE DAILY proleptic-Gregorian time axis whose row 0 is day
  * `doy0` (1..366) of calendar year `year0` (the kernel derives every calendar table itself).
- * One TMA box load per (32 gridpoints, day-of-year strip, year) stages the rows in shared
- * memory; requires x 16-byte aligned and pitch % 4 == 0.  Exact for gridpoints whose series is
+ * One TMA box load per (64 gridpoints, day-of-year strip, year) stages the rows in shared
+ * memory; requires x / out 16-byte aligned, N and the pitches multiples of 4, W <= 31.  Sums are float32
+ * (block sums + Kahan-compensated ring sum, within 1e-6 of the field scale of the float64 result;
+ * marex_tune("shift_f64", 1, 1) / MAREX_SHIFT_F64=1 selects float64 sums).  Exact for gridpoints whose series is
  * all finite or all NaN; `nonfinite` receives the per-gridpoint count of non-finite inputs and
  * marex_shift_anomaly_fixup_f32 must follow to recompute gridpoints with 0 < count < T.
- * Output row of input row t is t - (first row of year0 + W) for mode 0, t for mode 1. */
+ * Output row of input row t is t - (first row of year0 + W) for mode 0, t for mode 1.
+ * Fused np.digitize (detect.py:2622-2631), mode 0 only: when `bins` is non-NULL the kernel also writes the
+ * histogram bin code of every anomaly it stores (edges[n_edges] float32, edges[0] = -inf; NaN and
+ * a >= edges[n_edges-1] -> 0x7FFF) into the DAY-OF-YEAR-MAJOR bin array
+ *     bins[(doy0based * NY + k) * bins_pitch + c],  k = year index among the NY output years,
+ * and 0x7FFF into the slots of (day, year) pairs that have no row (day 366 of non-leap years, days after the
+ * end of the series): the layout marex_hobday_thresholds_pooled_bins / marex_compare_hobday_bins consume.
+ * MAREX_ERR_UNSUPPORTED when the windows do not fit shared memory (use marex_shift_anomaly_f32). */
 int marex_shift_anomaly_daily_f32(const float* x, int64_t T, int64_t N, int64_t pitch,
                                   int32_t year0, int32_t doy0, int32_t W, int32_t S, int32_t mode,
                                   float* out, int64_t out_pitch,
-                                  uint8_t* mask0, int32_t* nonfinite, void* stream);
+                                  uint8_t* mask0, int32_t* nonfinite,
+                                  const float* edges, int32_t n_edges, uint16_t* bins, int64_t bins_pitch,
+                                  void* stream);
 /* Recomputes, with the generic kernel of marex_shift_anomaly_f32 (same tables), the gridpoints
- * whose `nonfinite` count is strictly between 0 and T.  `work`: device scratch of N + 1 int32. */
+ * whose `nonfinite` count is strictly between 0 and T.  `work`: device scratch of N + 1 int32.
+ * With `bins` non-NULL (same arguments as above; T_out output rows starting on Jan 1 of `year_first`)
+ * the bin codes of those gridpoints are recomputed from the corrected anomalies as well. */
 int marex_shift_anomaly_fixup_f32(const float* x, int64_t T, int64_t N, int64_t pitch,
                                   const int32_t* tidx, const int32_t* year_val, int32_t n_years,
                                   int32_t W, int32_t S, const int32_t* out_row, int32_t mode,
                                   float* anom, int64_t anom_pitch,
-                                  uint8_t* mask0, int32_t* nonfinite, int32_t* work, void* stream);
+                                  uint8_t* mask0, int32_t* nonfinite, int32_t* work,
+                                  const float* edges, int32_t n_edges, uint16_t* bins, int64_t bins_pitch,
+                                  int64_t T_out, int32_t year_first, void* stream);
 
 /* ---- (a') fixed baseline ---------------------------------------------------------------
  * Per-day-of-year nanmean (flox nanmean, detect.py:2365-2373) over the rows listed in the CSR
@@ -128,16 +149,21 @@ int marex_div_doy_f32(const float* x, int64_t T, int64_t N, int64_t pitch, const
                       const float* sd, float* out, int64_t out_pitch, void* stream);
 
 /* ---- (b) thresholds --------------------------------------------------------------------
- * np.digitize(a, edges) - 1 as uint16 (detect.py:2622-2631): NaN and a >= edges[n_edges-1]
- * give n_edges-1 (dropped).  edges[0] must be -inf. */
-int marex_digitize_f32(const float* a, int64_t T, int64_t N, int64_t pitch,
-                       const float* edges, int32_t n_edges,
-                       uint16_t* bins, int64_t bins_pitch, void* stream);
+ * np.digitize(a, edges) - 1 as uint16 (detect.py:2622-2631) into the DAY-OF-YEAR-MAJOR bin array: slot
+ * s = doy0based * NY + k (k = index of the year among the NY output years) receives the codes of input row
+ * slot_row[s], or 0x7FFF when slot_row[s] < 0 (no row for that day and year).  NaN and a >= edges[n_edges-1]
+ * give 0x7FFF (not counted).  edges[0] must be -inf.  n_slots = 366 * NY. */
+int marex_digitize_doy_f32(const float* a, int64_t N, int64_t pitch,
+                           const int32_t* slot_row, int64_t n_slots,
+                           const float* edges, int32_t n_edges,
+                           uint16_t* bins, int64_t bins_pitch, void* stream);
 
 /* Approximate Hobday thresholds: (doy x bin) counts, ws x ws spatial pooling (periodic in x,
  * truncated in y), +-w/2 doy window (wrap 366), count-space interpolated quantile, NaN mask
  * from anom_row0, clamp to lower_bound (_compute_histogram_quantile_2d detect.py:2562-2734,
  * _rolling_histogram_quantile detect.py:2465-2559).  Unstructured: ny = 1, nx = N, ws = 1.
+ * `bins` rows are listed per day of year by the CSR (doy_ptr, doy_rows): for the day-of-year-major
+ * array doy_ptr[d] = d * NY and doy_rows[j] = j.  Codes >= nb are not counted.
  * thr[366, ny*nx] float32 doy-major.  stats[2] receives {min, max} of the thresholds before
  * the clamp, ignoring NaN (for the reference's two UserWarnings).  w odd, 3 <= w <= 365. */
 int marex_hobday_thresholds_hist(const uint16_t* bins, int64_t T, int64_t ny, int64_t nx,
@@ -146,19 +172,19 @@ int marex_hobday_thresholds_hist(const uint16_t* bins, int64_t T, int64_t ny, in
                                  int32_t w, int32_t ws, double q, const float* anom_row0,
                                  float lower_bound, float* thr, float* stats, void* stream);
 
-/* Same computation for gridded data with ws in {3, 5, 7}, straight from the float32 anomalies:
- * digitizes into `workspace` (edges[nb + 1] float32, edges[0] = -inf) and runs the banded
- * warp-cooperative kernel (pool_band.cu); tiles whose thresholds do not fit one band are
- * recomputed with full-range counters.  Requires nx >= 32, nb <= 1024.  `workspace`: device
- * scratch of at least marex_hobday_pooled_workspace_bytes(T, ny, nx) bytes.  The NaN mask is
- * taken from row 0 of `anom` (detect.py:2704-2705). */
-int64_t marex_hobday_pooled_workspace_bytes(int64_t T, int64_t ny, int64_t nx);
-int marex_hobday_thresholds_pooled_f32(const float* anom, int64_t T, int64_t ny, int64_t nx,
-                                       int64_t pitch, const int32_t* doy_ptr, const int32_t* doy_rows,
-                                       int32_t max_window_rows, const float* edges, const float* centers,
-                                       int32_t nb, int32_t w, int32_t ws, double q, float lower_bound,
-                                       float* thr, float* stats, void* workspace, int64_t workspace_bytes,
-                                       void* stream);
+/* Same computation for gridded data with ws in {3, 5, 7} from the day-of-year-major bin array
+ * (NY slots per day of year) with the banded warp-cooperative kernels (pool_band.cu); tiles whose
+ * thresholds do not fit one band are recomputed with full-range counters.  Requires nx >= 32, nb <= 1024,
+ * w * NY <= 65535.  (doy_ptr, doy_rows) as above.  `workspace`: device scratch of at least
+ * marex_hobday_pooled_workspace_bytes(ny, nx) bytes.  The NaN mask is row 0 of the anomalies
+ * (anom_row0[ny*nx], detect.py:2704-2705). */
+int64_t marex_hobday_pooled_workspace_bytes(int64_t ny, int64_t nx);
+int marex_hobday_thresholds_pooled_bins(const uint16_t* bins, int64_t NY, int64_t ny, int64_t nx,
+                                        int64_t bins_pitch, const int32_t* doy_ptr, const int32_t* doy_rows,
+                                        const float* centers, int32_t nb, int32_t w, int32_t ws, double q,
+                                        const float* anom_row0, float lower_bound,
+                                        float* thr, float* stats, void* workspace, int64_t workspace_bytes,
+                                        void* stream);
 
 /* Exact Hobday thresholds: np.nanpercentile (float32 'linear') over the +-w/2 doy window
  * (detect.py:1921-1956).  thr[366, N] doy-major, NaN where the window holds no valid sample.
@@ -207,6 +233,18 @@ int marex_compare_hobday(const float* anom, int64_t T, int64_t N, int64_t pitch,
                          uint8_t* events, int64_t events_pitch,
                          uint32_t* bits, int64_t bits_pitch,
                          unsigned long long* count, void* stream);
+/* The hobday compare from the day-of-year-major bin codes (2 bytes per sample instead of 4): a sample whose
+ * bin lies above / below the bin of its threshold is decided without the anomaly; the float anomaly
+ * (anom[row * pitch + c], row = slot_row[s]) is read only for samples in the threshold's own bin or with the
+ * invalid code.  Results are identical to marex_compare_hobday.  Needs N % 8 == 0, bins_pitch % 8 == 0,
+ * events_pitch % 8 == 0 and 16-byte aligned bases (MAREX_ERR_UNSUPPORTED otherwise). */
+int marex_compare_hobday_bins(const uint16_t* bins, int64_t NY, int64_t bins_pitch, const int32_t* slot_row,
+                              const float* anom, int64_t pitch, int64_t N,
+                              const float* thr, int64_t thr_pitch,
+                              const float* edges, int32_t n_edges,
+                              uint8_t* events, int64_t events_pitch,
+                              uint32_t* bits, int64_t bits_pitch,
+                              unsigned long long* count, void* stream);
 int marex_compare_global(const float* anom, int64_t T, int64_t N, int64_t pitch,
                          const double* thr,
                          uint8_t* events, int64_t events_pitch,

@@ -14,9 +14,10 @@ _SIGNATURES = {
     "marex_version": ([], ctypes.c_int),
     "marex_last_error": ([], c_char_p),
     "marex_launch_count": ([], c_longlong),
+    "marex_tune": ([c_char_p, c_longlong, c_int32], ctypes.c_int),
     "marex_shift_anomaly_f32": ([_P, c_int64, c_int64, c_int64, _P, _P, c_int32, c_int32, c_int32, _P, c_int32, _P, c_int64, _P, _P, _P], ctypes.c_int),
-    "marex_shift_anomaly_daily_f32": ([_P, c_int64, c_int64, c_int64, c_int32, c_int32, c_int32, c_int32, c_int32, _P, c_int64, _P, _P, _P], ctypes.c_int),
-    "marex_shift_anomaly_fixup_f32": ([_P, c_int64, c_int64, c_int64, _P, _P, c_int32, c_int32, c_int32, _P, c_int32, _P, c_int64, _P, _P, _P, _P], ctypes.c_int),
+    "marex_shift_anomaly_daily_f32": ([_P, c_int64, c_int64, c_int64, c_int32, c_int32, c_int32, c_int32, c_int32, _P, c_int64, _P, _P, _P, c_int32, _P, c_int64, _P], ctypes.c_int),
+    "marex_shift_anomaly_fixup_f32": ([_P, c_int64, c_int64, c_int64, _P, _P, c_int32, c_int32, c_int32, _P, c_int32, _P, c_int64, _P, _P, _P, _P, c_int32, _P, c_int64, c_int64, c_int32, _P], ctypes.c_int),
     "marex_doy_climatology_f32": ([_P, c_int64, c_int64, c_int64, _P, _P, _P, _P, _P], ctypes.c_int),
     "marex_sub_doy_climatology_f32": ([_P, c_int64, c_int64, c_int64, _P, _P, _P, _P, c_int64, _P, _P, _P], ctypes.c_int),
     "marex_detrend_coef_f64": ([_P, c_int64, c_int64, c_int64, _P, c_int32, _P, _P, _P, _P], ctypes.c_int),
@@ -24,15 +25,16 @@ _SIGNATURES = {
     "marex_doy_std_f32": ([_P, c_int64, c_int64, c_int64, _P, _P, _P, _P], ctypes.c_int),
     "marex_doy_rolling_rms_f32": ([_P, c_int64, c_int32, _P, _P], ctypes.c_int),
     "marex_div_doy_f32": ([_P, c_int64, c_int64, c_int64, _P, _P, _P, c_int64, _P], ctypes.c_int),
-    "marex_digitize_f32": ([_P, c_int64, c_int64, c_int64, _P, c_int32, _P, c_int64, _P], ctypes.c_int),
+    "marex_digitize_doy_f32": ([_P, c_int64, c_int64, _P, c_int64, _P, c_int32, _P, c_int64, _P], ctypes.c_int),
     "marex_hobday_thresholds_hist": ([_P, c_int64, c_int64, c_int64, c_int64, _P, _P, c_int32, _P, c_int32, c_int32, c_int32, c_double, _P, c_float, _P, _P, _P], ctypes.c_int),
-    "marex_hobday_pooled_workspace_bytes": ([c_int64, c_int64, c_int64], c_int64),
-    "marex_hobday_thresholds_pooled_f32": ([_P, c_int64, c_int64, c_int64, c_int64, _P, _P, c_int32, _P, _P, c_int32, c_int32, c_int32, c_double, c_float, _P, _P, _P, c_int64, _P], ctypes.c_int),
+    "marex_hobday_pooled_workspace_bytes": ([c_int64, c_int64], c_int64),
+    "marex_hobday_thresholds_pooled_bins": ([_P, c_int64, c_int64, c_int64, c_int64, _P, _P, _P, c_int32, c_int32, c_int32, c_double, _P, c_float, _P, _P, _P, c_int64, _P], ctypes.c_int),
     "marex_hobday_thresholds_exact_f32": ([_P, c_int64, c_int64, c_int64, _P, _P, c_int32, c_int32, c_int32, c_float, _P, _P], ctypes.c_int),
     "marex_global_threshold_hist_f64": ([_P, c_int64, c_int64, c_int64, _P, _P, c_int32, c_double, c_double, _P, _P, _P], ctypes.c_int),
     "marex_global_threshold_hist_fast_f64": ([_P, c_int64, c_int64, c_int64, _P, _P, c_float, _P, c_int32, c_double, c_double, _P, _P, _P, _P], ctypes.c_int),
     "marex_global_threshold_exact_f64": ([_P, c_int64, c_int64, c_int64, c_double, _P, _P], ctypes.c_int),
     "marex_compare_hobday": ([_P, c_int64, c_int64, c_int64, _P, _P, _P, _P, c_int64, _P, c_int64, _P, c_int64, _P, _P], ctypes.c_int),
+    "marex_compare_hobday_bins": ([_P, c_int64, c_int64, _P, _P, c_int64, c_int64, _P, c_int64, _P, c_int32, _P, c_int64, _P, c_int64, _P, _P], ctypes.c_int),
     "marex_memcpy2d_async": ([_P, c_int64, _P, c_int64, c_int64, c_int64, c_int32, _P], ctypes.c_int),
     "marex_compare_global": ([_P, c_int64, c_int64, c_int64, _P, _P, c_int64, _P, c_int64, _P, _P], ctypes.c_int),
     "marex_morph_slab_words": ([c_int64, c_int64, c_int32], c_int64),
@@ -52,6 +54,8 @@ _SIGNATURES = {
     "marex_synth_sst_f32": ([_P, c_int64, c_int64, c_int64, c_int64, c_int64, c_int64, _P, c_uint64, c_float, _P], ctypes.c_int),
 }
 EXPORTED = tuple(_SIGNATURES)
+
+ERR_INVALID_ARG, ERR_CUDA, ERR_UNSUPPORTED = -1, -2, -3  # MAREX_ERR_* of include/marex_b200.h
 
 _lib = None
 TRACE = None  # optional callable(name) invoked after every kernel-launching call (bench.py stage timing)
@@ -82,9 +86,16 @@ def call(name: str, *args) -> None:
     rc = getattr(lib, name)(*args)
     if rc != 0:
         msg = lib.marex_last_error().decode("utf-8", "replace")
-        raise ProcessingError(f"{name} failed (code {rc})", details=msg)
+        raise ProcessingError(f"{name} failed (code {rc})", details=msg, context={"code": int(rc)})
     if TRACE is not None:
         TRACE(name)
+
+
+def tune(**knobs) -> None:
+    """Pin (value) or release (None) tuning / test knobs of the library, e.g. ``tune(shift_v=4, pool_k=None)``."""
+    lib = load()
+    for key, value in knobs.items():
+        lib.marex_tune(key.encode(), 0 if value is None else int(value), 0 if value is None else 1)
 
 
 def launch_count() -> int:

@@ -147,6 +147,30 @@ def doy_csr(doy: np.ndarray, rows: Optional[np.ndarray] = None) -> Tuple[np.ndar
     return ptr, idx[order].astype(np.int32)
 
 
+def doy_slots(doy: np.ndarray, year: Optional[np.ndarray] = None) -> Tuple[int, np.ndarray]:
+    """Day-of-year-major slot table of an output time axis: ``NY`` slots per day of year and
+    ``slot_row[(doy - 1) * NY + k]`` = row of (doy, k) or -1.  With ``year`` given, k = year - first year (one slot
+    per calendar year, the order the fused shifting-baseline kernel writes its bin codes in); without it,
+    k = the running count of earlier rows with the same day of year."""
+    d = np.asarray(doy).astype(np.int64) - 1
+    if year is not None:
+        y = np.asarray(year).astype(np.int64)
+        k = y - y.min()
+    else:
+        order = np.argsort(d, kind="stable")
+        first = np.zeros(NDOY + 1, dtype=np.int64)
+        first[1:] = np.cumsum(np.bincount(d, minlength=NDOY))
+        k = np.empty(d.size, dtype=np.int64)
+        k[order] = np.arange(d.size) - first[d[order]]
+    ny = int(k.max()) + 1
+    slot = d * ny + k
+    if np.unique(slot).size != slot.size:
+        raise NotImplementedError("more than one time step per (year, dayofyear)")
+    slot_row = np.full(NDOY * ny, -1, dtype=np.int32)
+    slot_row[slot] = np.arange(d.size, dtype=np.int32)
+    return ny, slot_row
+
+
 def max_window_rows(doy_ptr: np.ndarray, w: int) -> int:
     """Largest number of rows any +-w//2 day-of-year window (wrap 366) holds."""
     counts = np.diff(doy_ptr.astype(np.int64))

@@ -15,6 +15,10 @@ namespace marex {
 extern thread_local std::string g_last_error;
 extern std::atomic<long long> g_launches;
 
+// Tuning / test knobs (not part of the computation's API): marex_tune("shift_v", 4) pins a value for this process;
+// unset keys fall back to the environment variable MAREX_<KEY IN CAPITALS>, read once, then to `dflt`.
+long long tune_get(const char* key, long long dflt);
+
 inline int fail(int code, const char* what, const char* detail = "") {
   g_last_error = std::string(what) + (detail[0] ? ": " : "") + detail;
   return code;

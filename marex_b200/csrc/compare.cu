@@ -1,11 +1,36 @@
 // (c) fused compare -> bool bytes and/or bit-packed extreme mask; utilities (transpose,
 // synthetic SST generator, library globals).
-#include "common.cuh"
+#include <climits>
+#include <cstdlib>
+#include <map>
+#include <mutex>
+
+#include "digitize.cuh"
 
 namespace marex {
 
 thread_local std::string g_last_error;
 std::atomic<long long> g_launches{0};
+
+namespace {
+std::mutex g_tune_mutex;
+std::map<std::string, long long> g_tune;      // pinned by marex_tune
+std::map<std::string, long long> g_tune_env;  // cached environment look-ups (LLONG_MIN = not set)
+}  // namespace
+
+long long tune_get(const char* key, long long dflt) {
+  std::lock_guard<std::mutex> lock(g_tune_mutex);
+  auto it = g_tune.find(key);
+  if (it != g_tune.end()) return it->second;
+  auto ie = g_tune_env.find(key);
+  if (ie == g_tune_env.end()) {
+    std::string name = "MAREX_";
+    for (const char* c = key; *c; ++c) name += (char)toupper((unsigned char)*c);
+    const char* v = getenv(name.c_str());
+    ie = g_tune_env.emplace(key, v ? atoll(v) : LLONG_MIN).first;
+  }
+  return ie->second == LLONG_MIN ? dflt : ie->second;
+}
 
 // events[t, c] = anom[t, c] >= thr.  A warp covers 32 consecutive gridpoints of one row, so the
 // packed word is one __ballot_sync (bit = lane = c & 31).  THR_GLOBAL: thr is float64[N] and the
@@ -85,6 +110,104 @@ __global__ void __launch_bounds__(128) compare_doy_kernel(const float* __restric
         w |= __shfl_xor_sync(0xffffffffu, w, 2);
         w |= __shfl_xor_sync(0xffffffffu, w, 4);
         if ((lane & 7) == 0 && live) bits[row[u] * bits_pitch + (c >> 5)] = w;
+      }
+    }
+  }
+  if (count) {
+    for (int o = 16; o; o >>= 1) local += __shfl_xor_sync(0xffffffffu, local, o);
+    if (lane == 0 && local) atomicAdd(count, (unsigned long long)local);
+  }
+}
+
+// Hobday compare from the 2-byte bin codes (the day-of-year-major array the anomaly / digitize kernels wrote for the
+// approximate thresholds) instead of the 4-byte anomalies: with bt = bin of the threshold under the same edge table,
+//   bin(a) > bt  =>  a >= edges[bin(a)] >= edges[bt + 1] > thr   : extreme
+//   bin(a) < bt  =>  a <  edges[bin(a) + 1] <= edges[bt] <= thr  : not extreme
+// so the float anomaly is only read where bin(a) == bt or where the sample carries the invalid code (NaN, or a beyond
+// the last edge) -- a fraction of a percent of the samples.  A CTA owns (1024 gridpoints, one day of year): the
+// threshold bins sit in registers, the rows of the day are consecutive slots of the bin array; 16-byte loads of 8
+// codes, 8-byte stores of 8 bool bytes.  slot_row[s] = output row of slot s, or -1.
+__global__ void __launch_bounds__(128) compare_bins_kernel(const uint16_t* __restrict__ bins, int NY, int64_t bins_pitch,
+                                                           const int32_t* __restrict__ slot_row,
+                                                           const float* __restrict__ anom, int64_t pitch, int64_t N,
+                                                           const float* __restrict__ thr, int64_t thr_pitch,
+                                                           const float* __restrict__ edges, int n_edges,
+                                                           uint8_t* __restrict__ events, int64_t events_pitch,
+                                                           uint32_t* __restrict__ bits, int64_t bits_pitch,
+                                                           unsigned long long* __restrict__ count) {
+  extern __shared__ float s_edges[];
+  for (int i = threadIdx.x; i < n_edges; i += blockDim.x) s_edges[i] = edges[i];
+  __syncthreads();
+  DigTable dig;
+  dig.init(s_edges, n_edges);
+  const int d = blockIdx.y;
+  const int64_t c = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * 8;  // N % 8 == 0: all eight live or none
+  const bool live = c < N;
+  const int64_t cc = live ? c : 0;
+  const int lane = threadIdx.x & 31;
+  float th[8];
+  {
+    const float4 t0 = __ldg(reinterpret_cast<const float4*>(thr + (int64_t)d * thr_pitch + cc));
+    const float4 t1 = __ldg(reinterpret_cast<const float4*>(thr + (int64_t)d * thr_pitch + cc + 4));
+    th[0] = t0.x; th[1] = t0.y; th[2] = t0.z; th[3] = t0.w; th[4] = t1.x; th[5] = t1.y; th[6] = t1.z; th[7] = t1.w;
+  }
+  // per gridpoint: with dd = bin - bt - 1 the sample is extreme iff (unsigned)dd < lim, and needs the float
+  // compare iff dd == -1 (same bin as the threshold) or dd == amb2 (invalid code); NaN threshold: never either
+  int nbt[8], lim[8], amb2[8];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    if (th[k] != th[k] || !live) { nbt[k] = -0x20000; lim[k] = 0; amb2[k] = -1; continue; }
+    const int bt = (int)dig(th[k]);
+    nbt[k] = -bt - 1;
+    lim[k] = bt < BIN_INV ? BIN_INV - bt - 1 : 0;
+    amb2[k] = bt < BIN_INV ? BIN_INV - bt - 1 : -1;
+  }
+  unsigned int local = 0;
+  const int64_t s0 = (int64_t)d * NY;
+  for (int j0 = 0; j0 < NY; j0 += 5) {
+    uint4 b[5];
+    int64_t row[5];
+#pragma unroll
+    for (int u = 0; u < 5; ++u) {
+      row[u] = (j0 + u < NY) ? (int64_t)__ldg(&slot_row[s0 + j0 + u]) : -1;
+      if (row[u] >= 0) b[u] = __ldcs(reinterpret_cast<const uint4*>(bins + (s0 + j0 + u) * bins_pitch + cc));
+    }
+#pragma unroll
+    for (int u = 0; u < 5; ++u) {
+      if (row[u] < 0) continue;
+      const unsigned int wv[4] = {b[u].x, b[u].y, b[u].z, b[u].w};
+      unsigned int e8 = 0;  // bit k: gridpoint k is extreme
+      bool amb = false;
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        const int bin = (int)((wv[k >> 1] >> ((k & 1) * 16)) & 0xFFFFu);
+        const int dd = bin + nbt[k];
+        e8 |= ((unsigned)dd < (unsigned)lim[k]) ? (1u << k) : 0u;
+        amb = amb || dd == -1 || dd == amb2[k];
+      }
+      if (amb) {  // rare: decide those samples on the float anomaly (detect.py:2001-2004)
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          const int bin = (int)((wv[k >> 1] >> ((k & 1) * 16)) & 0xFFFFu);
+          const int dd = bin + nbt[k];
+          if (dd == -1 || dd == amb2[k]) {
+            const float a = __ldg(anom + row[u] * pitch + cc + k);
+            if (a >= th[k]) e8 |= 1u << k;
+          }
+        }
+      }
+      local += __popc(e8);
+      if (events && live) {
+        // spread the 8 bits over 8 bytes: bit k -> byte k
+        const unsigned lo = e8 & 0xFu, hi = (e8 >> 4) & 0xFu;
+        const unsigned b0 = (lo * 0x00204081u) & 0x01010101u, b1 = (hi * 0x00204081u) & 0x01010101u;
+        __stcs(reinterpret_cast<uint2*>(events + row[u] * events_pitch + c), make_uint2(b0, b1));
+      }
+      if (bits) {  // 4 lanes x 8 gridpoints = one 32-bit word
+        unsigned w = e8 << ((lane & 3) * 8);
+        w |= __shfl_xor_sync(0xffffffffu, w, 1);
+        w |= __shfl_xor_sync(0xffffffffu, w, 2);
+        if ((lane & 3) == 0 && live) bits[row[u] * bits_pitch + (c >> 5)] = w;
       }
     }
   }
@@ -206,6 +329,13 @@ using namespace marex;
 extern "C" int marex_version(void) { return 100; }
 extern "C" const char* marex_last_error(void) { return g_last_error.c_str(); }
 extern "C" long long marex_launch_count(void) { return g_launches.load(); }
+extern "C" int marex_tune(const char* key, long long value, int32_t set) {
+  if (!key) return fail(MAREX_ERR_INVALID_ARG, "null key");
+  std::lock_guard<std::mutex> lock(g_tune_mutex);
+  if (set) g_tune[key] = value;
+  else g_tune.erase(key);
+  return MAREX_OK;
+}
 
 template <bool G>
 static int launch_compare(const float* anom, int64_t T, int64_t N, int64_t pitch, const int16_t* doy, const void* thr,
@@ -246,6 +376,30 @@ extern "C" int marex_compare_hobday(const float* anom, int64_t T, int64_t N, int
   }
   return launch_compare<false>(anom, T, N, pitch, doy, thr, thr_pitch, events, events_pitch, bits, bits_pitch, count,
                                (cudaStream_t)stream);
+}
+
+extern "C" int marex_compare_hobday_bins(const uint16_t* bins, int64_t NY, int64_t bins_pitch, const int32_t* slot_row,
+                                         const float* anom, int64_t pitch, int64_t N, const float* thr,
+                                         int64_t thr_pitch, const float* edges, int32_t n_edges, uint8_t* events,
+                                         int64_t events_pitch, uint32_t* bits, int64_t bits_pitch,
+                                         unsigned long long* count, void* stream) {
+  MAREX_REQUIRE(bins && slot_row && anom && thr && edges && (events || bits || count), "null pointer");
+  MAREX_REQUIRE(NY > 0 && N > 0 && pitch >= N && thr_pitch >= N && bins_pitch >= N, "bad shape");
+  MAREX_REQUIRE(n_edges >= 3 && n_edges <= 4096, "n_edges must be in 3..4096");
+  MAREX_REQUIRE(!events || events_pitch >= N, "events_pitch < N");
+  MAREX_REQUIRE(!bits || bits_pitch >= (N + 31) / 32, "bits_pitch < ceil(N/32)");
+  const bool aligned = (N % 8) == 0 && (bins_pitch % 8) == 0 && (thr_pitch % 4) == 0 &&
+                       (reinterpret_cast<uintptr_t>(bins) % 16) == 0 && (reinterpret_cast<uintptr_t>(thr) % 16) == 0 &&
+                       (!events || ((events_pitch % 8) == 0 && (reinterpret_cast<uintptr_t>(events) % 8) == 0)) &&
+                       (N % 32 == 0 || !bits);
+  if (!aligned) return fail(MAREX_ERR_UNSUPPORTED, "compare from bins needs N % 8 == 0 and 16-byte aligned rows");
+  const int threads = 128;
+  dim3 grid((unsigned)((N / 8 + threads - 1) / threads), NDOY);
+  compare_bins_kernel<<<grid, threads, n_edges * sizeof(float), (cudaStream_t)stream>>>(
+      bins, (int)NY, bins_pitch, slot_row, anom, pitch, N, thr, thr_pitch, edges, n_edges, events, events_pitch, bits,
+      bits_pitch, count);
+  MAREX_LAUNCH_CHECK("compare_bins_kernel");
+  return MAREX_OK;
 }
 
 extern "C" int marex_compare_global(const float* anom, int64_t T, int64_t N, int64_t pitch, const double* thr,

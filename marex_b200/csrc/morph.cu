@@ -329,12 +329,14 @@ extern "C" int marex_morph_disk(const uint32_t* in, uint32_t* out, int64_t T, in
   MAREX_REQUIRE(in && out && in != out && T > 0 && Hp > 0 && Wp > 0, "bad arguments");
   if (R < 0 || R > MORPH_MAX_R) return fail(MAREX_ERR_UNSUPPORTED, "R_fill must be in 0..32");
   const MorphDisk d = morph_make_disk(R);
-  const int env_variant = getenv("MAREX_MORPH_DISK") ? atoi(getenv("MAREX_MORPH_DISK")) : 2;  // tuning knob
-  const int variant = env_variant == 3 ? 3 : 2;
+  // measured on B200 (0.25 deg, R = 8, 2048 days, profiles/r02_first_call_parked_variants.json): shared-memory tile
+  // (4) 1.41 ms per pass, branch-free direct kernel (3) 1.45 / 1.62 ms, first direct kernel (2) 1.77 / 1.96 ms
+  const int env_variant = (int)tune_get("morph_disk", 4);
+  const int variant = env_variant == 2 ? 2 : 3;
   const int Wpw = (int)((Wp + 31) >> 5);
   MAREX_REQUIRE(Hp * (int64_t)Wpw < (1LL << 31), "padded time step too large");
   const int64_t per_t = Hp * (int64_t)Wpw;
-  if (env_variant == 4 && R >= 1) {  // shared-memory tile variant (experiment); falls through when a tile does not fit
+  if (env_variant == 4 && R >= 1) {  // shared-memory tile variant; falls through to the direct kernel when a tile does not fit
     const MorphPlan pl = morph_make_plan(R);
     const int TH = morph_tile_rows(Wpw, R, pl.nlev, 200 * 1024);
     if (TH > 0) {

@@ -27,7 +27,7 @@
 // (thresholds.cu), so exactness never depends on the band heuristic.
 #include <cstdlib>
 
-#include "common.cuh"
+#include "digitize.cuh"
 
 namespace marex {
 
@@ -62,7 +62,7 @@ __device__ __forceinline__ int pooled_row(const uint16_t* __restrict__ p, int la
   return s;
 }
 
-constexpr int BAND_INV = 0x7FFF;  // bin code of an invalid sample (NaN or >= last edge)
+constexpr int BAND_INV = BIN_INV;  // bin code of an invalid sample (NaN or >= last edge)
 constexpr int BAND_PRE = 26;       // entering samples prefetched into registers per step
 
 template <int P, int K, int OY>
@@ -385,59 +385,52 @@ __global__ void __launch_bounds__(OY * 32, (OY <= 16 && K <= 64) ? 2 : 1) hobday
   }
 }
 
-// np.digitize(a, edges) - 1 with the invalid class (NaN or a >= last edge) coded BAND_INV, which sorts
-// above every band: invalid samples travel through the event list like any sample that matters.
-__global__ void __launch_bounds__(256) digitize_ffff_kernel(const float* __restrict__ a, int64_t T, int64_t N,
-                                                            int64_t pitch, const float* __restrict__ edges, int n_edges,
-                                                            uint16_t* __restrict__ bins, int64_t bins_pitch,
-                                                            int rows_per_block) {
+// np.digitize(a, edges) - 1 (detect.py:2622-2631) into the DAY-OF-YEAR-MAJOR bin array the threshold and compare
+// kernels walk: slot s = doy * NY + (index of the year among the output years) holds the codes of input row
+// slot_row[s], or the invalid code when that (day, year) has no row (slot_row[s] < 0).  Invalid samples (NaN or
+// a >= last edge) are coded BIN_INV, which sorts above every band.  Four gridpoints x four slots in flight per thread.
+__global__ void __launch_bounds__(256) digitize_doy_kernel(const float* __restrict__ a, int64_t N, int64_t pitch,
+                                                           const int32_t* __restrict__ slot_row, int64_t n_slots,
+                                                           const float* __restrict__ edges, int n_edges,
+                                                           uint16_t* __restrict__ bins, int64_t bins_pitch,
+                                                           int slots_per_block) {
   extern __shared__ float s_edges[];
   for (int i = threadIdx.x; i < n_edges; i += blockDim.x) s_edges[i] = edges[i];
   __syncthreads();
-  const float e1 = s_edges[1];
-  const float inv_step = (n_edges > 2) ? 1.f / (s_edges[2] - s_edges[1]) : 1.f;
+  DigTable dig;
+  dig.init(s_edges, n_edges);
   const int64_t c = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * 4;  // four gridpoints per thread
   if (c >= N) return;
-  const bool quad = c + 3 < N && (pitch & 3) == 0 && (bins_pitch & 3) == 0;
-  const int64_t t0 = (int64_t)blockIdx.y * rows_per_block, t1 = min(T, t0 + rows_per_block);
-  auto dig = [&](float v) -> uint32_t {
-    // first guess from the near-uniform spacing, one branch-free correction each way against the real
-    // float32 edge table, and the (practically never taken) loops if the table is not near-uniform
-    float g = floorf((v - e1) * inv_step) + 1.f;
-    g = fminf(fmaxf(g, 0.f), (float)(n_edges - 2));  // NaN -> 0 (fmaxf drops it); the NaN test comes last
-    int i = (int)g;
-    i -= (v < s_edges[i]) ? 1 : 0;             // edges[0] = -inf: never below 0
-    i += (v >= s_edges[i + 1]) ? 1 : 0;
-    if (i < n_edges - 1 && (v < s_edges[i] || v >= s_edges[i + 1])) {
-      while (i > 0 && v < s_edges[i]) --i;
-      while (i < n_edges - 1 && v >= s_edges[i + 1]) ++i;
-    }
-    return (i >= n_edges - 1 || v != v) ? (uint32_t)BAND_INV : (uint32_t)i;
-  };
+  const bool quad = c + 3 < N && (pitch & 3) == 0 && (bins_pitch & 3) == 0 && (reinterpret_cast<uintptr_t>(a) & 15) == 0 &&
+                    (reinterpret_cast<uintptr_t>(bins) & 7) == 0;
+  const int64_t s0 = (int64_t)blockIdx.y * slots_per_block, s1 = min(n_slots, s0 + slots_per_block);
+  const uint32_t inv2 = (uint32_t)BIN_INV | ((uint32_t)BIN_INV << 16);
   if (quad) {
-    int64_t t = t0;
-    for (; t + 4 <= t1; t += 4) {  // four independent 16-byte loads in flight per thread
+    for (int64_t s = s0; s < s1; s += 4) {
       float4 v[4];
-#pragma unroll
-      for (int u = 0; u < 4; ++u) v[u] = __ldcs(reinterpret_cast<const float4*>(a + (t + u) * pitch + c));
+      int64_t row[4];
 #pragma unroll
       for (int u = 0; u < 4; ++u) {
-        uint2 o;
-        o.x = dig(v[u].x) | (dig(v[u].y) << 16);
-        o.y = dig(v[u].z) | (dig(v[u].w) << 16);
-        *reinterpret_cast<uint2*>(bins + (t + u) * bins_pitch + c) = o;
+        row[u] = (s + u < s1) ? (int64_t)__ldg(&slot_row[s + u]) : -2;
+        if (row[u] >= 0) v[u] = __ldcs(reinterpret_cast<const float4*>(a + row[u] * pitch + c));
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        if (row[u] == -2) continue;
+        uint2 o = make_uint2(inv2, inv2);
+        if (row[u] >= 0) {
+          o.x = dig(v[u].x) | (dig(v[u].y) << 16);
+          o.y = dig(v[u].z) | (dig(v[u].w) << 16);
+        }
+        *reinterpret_cast<uint2*>(bins + (s + u) * bins_pitch + c) = o;
       }
     }
-    for (; t < t1; ++t) {
-      const float4 v = __ldcs(reinterpret_cast<const float4*>(a + t * pitch + c));
-      uint2 o;
-      o.x = dig(v.x) | (dig(v.y) << 16);
-      o.y = dig(v.z) | (dig(v.w) << 16);
-      *reinterpret_cast<uint2*>(bins + t * bins_pitch + c) = o;
-    }
   } else {
-    for (int64_t t = t0; t < t1; ++t)
-      for (int k = 0; k < 4 && c + k < N; ++k) bins[t * bins_pitch + c + k] = (uint16_t)dig(a[t * pitch + c + k]);
+    for (int64_t s = s0; s < s1; ++s) {
+      const int64_t row = __ldg(&slot_row[s]);
+      for (int k = 0; k < 4 && c + k < N; ++k)
+        bins[s * bins_pitch + c + k] = row >= 0 ? (uint16_t)dig(a[row * pitch + c + k]) : (uint16_t)BIN_INV;
+    }
   }
 }
 
@@ -457,47 +450,53 @@ __global__ void init_band_kernel(float* stats, int32_t* list_a, int32_t* list_b)
 
 using namespace marex;
 
-extern "C" int64_t marex_hobday_pooled_workspace_bytes(int64_t T, int64_t ny, int64_t nx) {
-  // bins (uint16 [T][ny*nx], rows padded to an even count) + fail list
-  const int64_t N = ny * nx, pitch = (N + 3) & ~3LL;
-  const int64_t tiles = ((ny + 0) / 1 + 1) * ((nx + 27) / 28 + 1);  // generous upper bound on band tiles
-  return T * pitch * 2 + 2 * (2 * tiles + 8) * 4 + 512;
+extern "C" int marex_digitize_doy_f32(const float* a, int64_t N, int64_t pitch, const int32_t* slot_row, int64_t n_slots,
+                                      const float* edges, int32_t n_edges, uint16_t* bins, int64_t bins_pitch,
+                                      void* stream) {
+  MAREX_REQUIRE(a && slot_row && edges && bins, "null pointer");
+  MAREX_REQUIRE(N > 0 && n_slots > 0 && pitch >= N && bins_pitch >= N, "bad shape");
+  MAREX_REQUIRE(n_edges >= 3 && n_edges <= 4096, "n_edges must be in 3..4096");
+  const int threads = 256;
+  const int64_t bx = ((N + 3) / 4 + threads - 1) / threads;
+  int64_t by = (16LL * sm_count() + bx - 1) / bx;
+  by = by < 1 ? 1 : (by > n_slots ? n_slots : by);
+  if (by > 65535) by = 65535;
+  int slots_per_block = (int)((n_slots + by - 1) / by);
+  slots_per_block = (slots_per_block + 3) & ~3;
+  by = (n_slots + slots_per_block - 1) / slots_per_block;
+  digitize_doy_kernel<<<dim3((unsigned)bx, (unsigned)by), threads, n_edges * sizeof(float), (cudaStream_t)stream>>>(
+      a, N, pitch, slot_row, n_slots, edges, n_edges, bins, bins_pitch, slots_per_block);
+  MAREX_LAUNCH_CHECK("digitize_doy_kernel");
+  return MAREX_OK;
 }
 
-extern "C" int marex_hobday_thresholds_pooled_f32(const float* anom, int64_t T, int64_t ny, int64_t nx, int64_t pitch,
-                                                  const int32_t* doy_ptr, const int32_t* doy_rows,
-                                                  int32_t max_window_rows, const float* edges, const float* centers,
-                                                  int32_t nb, int32_t w, int32_t ws, double q, float lower_bound,
-                                                  float* thr, float* stats, void* workspace, int64_t workspace_bytes,
-                                                  void* stream) {
-  MAREX_REQUIRE(anom && doy_ptr && doy_rows && edges && centers && thr && workspace, "null pointer");
-  MAREX_REQUIRE(T > 0 && ny > 0 && nx > 0 && pitch >= ny * nx, "bad shape");
+extern "C" int64_t marex_hobday_pooled_workspace_bytes(int64_t ny, int64_t nx) {
+  // two tile lists (count + (y0, x0) pairs) for the band retries
+  const int64_t tiles = (ny + 1) * ((nx + 27) / 28 + 1);  // generous upper bound on band tiles
+  return 2 * (2 * tiles + 8) * 4 + 512;
+}
+
+extern "C" int marex_hobday_thresholds_pooled_bins(const uint16_t* bins, int64_t NY, int64_t ny, int64_t nx,
+                                                   int64_t bpitch, const int32_t* doy_ptr, const int32_t* doy_rows,
+                                                   const float* centers, int32_t nb, int32_t w, int32_t ws, double q,
+                                                   const float* anom_row0, float lower_bound, float* thr, float* stats,
+                                                   void* workspace, int64_t workspace_bytes, void* stream) {
+  MAREX_REQUIRE(bins && doy_ptr && doy_rows && centers && anom_row0 && thr && workspace, "null pointer");
+  MAREX_REQUIRE(NY > 0 && ny > 0 && nx > 0 && bpitch >= ny * nx, "bad shape");
   MAREX_REQUIRE(nb >= 2 && nb <= 1024, "nb must be in 2..1024");
   MAREX_REQUIRE(w >= 3 && w <= 365 && (w & 1), "window_days_hobday must be odd and in 3..365");
   MAREX_REQUIRE(ws == 3 || ws == 5 || ws == 7, "window_spatial_hobday must be 3, 5 or 7 for the pooled kernel");
-  MAREX_REQUIRE(max_window_rows <= 65535, "too many rows per day-of-year window for 16-bit counters");
+  MAREX_REQUIRE((int64_t)w * NY <= 65535, "too many rows per day-of-year window for 16-bit counters");
   MAREX_REQUIRE(nx >= 32 && ny <= 65535 * 4, "grid too small or too tall for the band tiles");
-  MAREX_REQUIRE(workspace_bytes >= marex_hobday_pooled_workspace_bytes(T, ny, nx), "workspace too small");
+  MAREX_REQUIRE(workspace_bytes >= marex_hobday_pooled_workspace_bytes(ny, nx), "workspace too small");
   cudaStream_t st = (cudaStream_t)stream;
-  const int64_t N = ny * nx, bpitch = (N + 3) & ~3LL;
-  uint16_t* bins = reinterpret_cast<uint16_t*>(workspace);
-  int32_t* fail_list = reinterpret_cast<int32_t*>(reinterpret_cast<unsigned char*>(workspace) +
-                                                  (((size_t)T * bpitch * 2 + 255) & ~(size_t)255));
-  {  // digitize (detect.py:2622-2631)
-    const int threads = 256;
-    const int64_t bx = ((N + 3) / 4 + threads - 1) / threads;
-    int64_t by = (16LL * sm_count() + bx - 1) / bx;
-    by = by < 1 ? 1 : (by > T ? T : by);
-    if (by > 65535) by = 65535;
-    const int rows_per_block = (int)((T + by - 1) / by);
-    by = (T + rows_per_block - 1) / rows_per_block;
-    digitize_ffff_kernel<<<dim3((unsigned)bx, (unsigned)by), threads, (nb + 1) * sizeof(float), st>>>(
-        anom, T, N, pitch, edges, nb + 1, bins, bpitch, rows_per_block);
-    MAREX_LAUNCH_CHECK("digitize_ffff_kernel");
-  }
+  const int64_t N = ny * nx;
+  (void)N;
+  int32_t* fail_list = reinterpret_cast<int32_t*>(workspace);
+  const float* anom = anom_row0;
   const int P = ws / 2;
-  const int env_k = getenv("MAREX_POOL_K") ? atoi(getenv("MAREX_POOL_K")) : 0;
-  const int env_ty = getenv("MAREX_POOL_TY") ? atoi(getenv("MAREX_POOL_TY")) : 0;
+  const int env_k = (int)tune_get("pool_k", 0);
+  const int env_ty = (int)tune_get("pool_ty", 0);
   MAREX_REQUIRE(env_k == 0 || env_k == 64 || env_k == 128, "MAREX_POOL_K must be 64 or 128");
   // 12 target rows (16 x 32 own gridpoints, two tiles per SM at 64 registers) measured best on B200:
   // 71.2 ms vs 74.6 (8 rows) and 74.1 (16 rows) for the threshold + compare stages at 0.25 deg.
@@ -513,9 +512,9 @@ extern "C" int marex_hobday_thresholds_pooled_f32(const float* anom, int64_t T, 
   bp.bins = bins; bp.ny = ny; bp.nx = nx; bp.pitch = bpitch;
   bp.doy_ptr = doy_ptr; bp.doy_rows = doy_rows; bp.centers = centers;
   bp.nb = nb; bp.w = w; bp.q = q;
-  bp.margin = getenv("MAREX_POOL_MARGIN") ? atoi(getenv("MAREX_POOL_MARGIN")) : 8;
+  bp.margin = (int)tune_get("pool_margin", 8);
   bp.anom_row0 = anom; bp.lower_bound = lower_bound; bp.thr = thr; bp.stats = stats;
-  bp.force_fail = getenv("MAREX_POOL_FORCE_FAIL") ? atoi(getenv("MAREX_POOL_FORCE_FAIL")) : 0;
+  bp.force_fail = (int)tune_get("pool_force_fail", 0);
   // One launch of the band kernel with K band bins over all tiles (tiles == nullptr) or over a list.
   auto launch_band = [&](int K, const int32_t* tiles, int32_t* fails) -> int {
     if (nb > 8 * K) return fail(MAREX_ERR_UNSUPPORTED, "nb too large for the coarse pass of this band width");

