@@ -136,31 +136,40 @@ __global__ void __launch_bounds__(128) compare_bins_kernel(const uint16_t* __res
                                                            uint32_t* __restrict__ bits, int64_t bits_pitch,
                                                            unsigned long long* __restrict__ count) {
   extern __shared__ float s_edges[];
-  for (int i = threadIdx.x; i < n_edges; i += blockDim.x) s_edges[i] = edges[i];
-  __syncthreads();
   DigTable dig;
-  dig.init(s_edges, n_edges);
+  dig.init_cta(edges, n_edges, s_edges);
   const int d = blockIdx.y;
   const int64_t c = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * 8;  // N % 8 == 0: all eight live or none
   const bool live = c < N;
   const int64_t cc = live ? c : 0;
   const int lane = threadIdx.x & 31;
-  float th[8];
+  const float* const thr_row = thr + (int64_t)d * thr_pitch + cc;
+  // Two codes per 32-bit word, decided with 16-bit-lane arithmetic (codes are < 0x8000):
+  //   extreme without looking at the anomaly:  bit 15 of (code | 0x8000) - (bt + 1)            [code > bt]
+  //   needs the float compare:                 code == bt, or code == invalid (zero-lane test of the XOR)
+  // NaN threshold (land) or a dead thread: bt + 1 := 0x8000 (never above), bt := 0xFFFF (never equal), invalid ignored.
+  unsigned p1[4], btp[4], mk[4];
   {
-    const float4 t0 = __ldg(reinterpret_cast<const float4*>(thr + (int64_t)d * thr_pitch + cc));
-    const float4 t1 = __ldg(reinterpret_cast<const float4*>(thr + (int64_t)d * thr_pitch + cc + 4));
-    th[0] = t0.x; th[1] = t0.y; th[2] = t0.z; th[3] = t0.w; th[4] = t1.x; th[5] = t1.y; th[6] = t1.z; th[7] = t1.w;
-  }
-  // per gridpoint: with dd = bin - bt - 1 the sample is extreme iff (unsigned)dd < lim, and needs the float
-  // compare iff dd == -1 (same bin as the threshold) or dd == amb2 (invalid code); NaN threshold: never either
-  int nbt[8], lim[8], amb2[8];
+    const float4 t0 = __ldg(reinterpret_cast<const float4*>(thr_row));
+    const float4 t1 = __ldg(reinterpret_cast<const float4*>(thr_row + 4));
+    const float th[8] = {t0.x, t0.y, t0.z, t0.w, t1.x, t1.y, t1.z, t1.w};
 #pragma unroll
-  for (int k = 0; k < 8; ++k) {
-    if (th[k] != th[k] || !live) { nbt[k] = -0x20000; lim[k] = 0; amb2[k] = -1; continue; }
-    const int bt = (int)dig(th[k]);
-    nbt[k] = -bt - 1;
-    lim[k] = bt < BIN_INV ? BIN_INV - bt - 1 : 0;
-    amb2[k] = bt < BIN_INV ? BIN_INV - bt - 1 : -1;
+    for (int j = 0; j < 4; ++j) {
+      unsigned a1 = 0, ab = 0, am = 0;
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const float t = th[2 * j + h];
+        unsigned q1 = 0x8000u, qb = 0xFFFFu, qm = 0u;
+        if (t == t && live) {
+          const unsigned bt = dig(t);  // BIN_INV when the threshold lies beyond the last edge
+          q1 = bt < (unsigned)BIN_INV ? bt + 1u : 0x8000u;
+          qb = bt;
+          qm = 0x8000u;
+        }
+        a1 |= q1 << (16 * h); ab |= qb << (16 * h); am |= qm << (16 * h);
+      }
+      p1[j] = a1; btp[j] = ab; mk[j] = am;
+    }
   }
   unsigned int local = 0;
   const int64_t s0 = (int64_t)d * NY;
@@ -175,36 +184,42 @@ __global__ void __launch_bounds__(128) compare_bins_kernel(const uint16_t* __res
 #pragma unroll
     for (int u = 0; u < 5; ++u) {
       if (row[u] < 0) continue;
-      const unsigned int wv[4] = {b[u].x, b[u].y, b[u].z, b[u].w};
-      unsigned int e8 = 0;  // bit k: gridpoint k is extreme
-      bool amb = false;
+      const unsigned wv[4] = {b[u].x, b[u].y, b[u].z, b[u].w};
+      unsigned g[4], am[4];
 #pragma unroll
-      for (int k = 0; k < 8; ++k) {
-        const int bin = (int)((wv[k >> 1] >> ((k & 1) * 16)) & 0xFFFFu);
-        const int dd = bin + nbt[k];
-        e8 |= ((unsigned)dd < (unsigned)lim[k]) ? (1u << k) : 0u;
-        amb = amb || dd == -1 || dd == amb2[k];
+      for (int j = 0; j < 4; ++j) {
+        g[j] = (((wv[j] | 0x80008000u) - p1[j]) >> 15) & 0x00010001u;          // bytes 0 and 2: code > bt
+        const unsigned x = wv[j] ^ btp[j], y = wv[j] ^ 0x7FFF7FFFu;
+        am[j] = ((x - 0x00010001u) & ~x & 0x80008000u) | ((y - 0x00010001u) & ~y & mk[j]);  // bits 15 / 31: ambiguous
       }
-      if (amb) {  // rare: decide those samples on the float anomaly (detect.py:2001-2004)
-#pragma unroll
-        for (int k = 0; k < 8; ++k) {
-          const int bin = (int)((wv[k >> 1] >> ((k & 1) * 16)) & 0xFFFFu);
-          const int dd = bin + nbt[k];
-          if (dd == -1 || dd == amb2[k]) {
-            const float a = __ldg(anom + row[u] * pitch + cc + k);
-            if (a >= th[k]) e8 |= 1u << k;
-          }
+      unsigned ex = __byte_perm(g[0], g[1], 0x6420), ey = __byte_perm(g[2], g[3], 0x6420);  // one bool byte per gridpoint
+      if ((am[0] | am[1]) | (am[2] | am[3])) {
+        // rare: decide those samples on the float anomaly (detect.py:2001-2004).  A zero-lane test may also flag
+        // the upper code of a word whose lower code matched: harmless, the float compare is the definition.
+        unsigned mx = __byte_perm((am[0] >> 15) & 0x00010001u, (am[1] >> 15) & 0x00010001u, 0x6420);
+        unsigned my = __byte_perm((am[2] >> 15) & 0x00010001u, (am[3] >> 15) & 0x00010001u, 0x6420);
+        const float* arow = anom + row[u] * pitch + cc;
+        while (mx) {
+          const int pos = __ffs(mx) - 1;  // 8 * k
+          mx &= mx - 1;
+          const int k = pos >> 3;
+          const unsigned e = __ldg(arow + k) >= __ldg(thr_row + k) ? 1u : 0u;
+          ex = (ex & ~(1u << pos)) | (e << pos);
+        }
+        while (my) {
+          const int pos = __ffs(my) - 1;
+          my &= my - 1;
+          const int k = pos >> 3;
+          const unsigned e = __ldg(arow + 4 + k) >= __ldg(thr_row + 4 + k) ? 1u : 0u;
+          ey = (ey & ~(1u << pos)) | (e << pos);
         }
       }
-      local += __popc(e8);
-      if (events && live) {
-        // spread the 8 bits over 8 bytes: bit k -> byte k
-        const unsigned lo = e8 & 0xFu, hi = (e8 >> 4) & 0xFu;
-        const unsigned b0 = (lo * 0x00204081u) & 0x01010101u, b1 = (hi * 0x00204081u) & 0x01010101u;
-        __stcs(reinterpret_cast<uint2*>(events + row[u] * events_pitch + c), make_uint2(b0, b1));
-      }
+      local += __popc(ex) + __popc(ey);
+      if (events && live) __stcs(reinterpret_cast<uint2*>(events + row[u] * events_pitch + c), make_uint2(ex, ey));
       if (bits) {  // 4 lanes x 8 gridpoints = one 32-bit word
-        unsigned w = e8 << ((lane & 3) * 8);
+        // bool bytes -> 8 bits: byte k -> bit k
+        const unsigned lo = (ex * 0x01020408u) >> 24, hi = (ey * 0x01020408u) >> 24;  // four 0/1 bytes gathered into a nibble
+        unsigned w = ((lo & 0xFu) | ((hi & 0xFu) << 4)) << ((lane & 3) * 8);
         w |= __shfl_xor_sync(0xffffffffu, w, 1);
         w |= __shfl_xor_sync(0xffffffffu, w, 2);
         if ((lane & 3) == 0 && live) bits[row[u] * bits_pitch + (c >> 5)] = w;

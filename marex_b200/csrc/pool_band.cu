@@ -25,9 +25,12 @@
 // coarse full-range pass over the current window picks the band).  A tile whose thresholds do
 // not fit one band is appended to `fail_list` and recomputed by the full-range tile kernel
 // (thresholds.cu), so exactness never depends on the band heuristic.
+#include <algorithm>
 #include <cstdlib>
+#include <cstring>
 
 #include "digitize.cuh"
+#include "tma.cuh"
 
 namespace marex {
 
@@ -385,6 +388,378 @@ __global__ void __launch_bounds__(OY * 32, (OY <= 16 && K <= 64) ? 2 : 1) hobday
   }
 }
 
+// ---------------------------------------------------------------------------------------------------------
+// Ring variant of the band kernel for the DAY-OF-YEAR-MAJOR bin array (slot s = doy * NY + year): every sample is read
+// from global memory ONCE.
+//   * the NY rows of the day of year that enters the window are one contiguous 3-D box {32 columns, OY rows, NY slots}
+//     of the bin array: a single cp.async.bulk.tensor.3d (TMA) stages it in shared memory behind an mbarrier while the
+//     tile answers the queries of the previous step (tiles on the longitude seam, or grids whose row pitch is not a
+//     multiple of 16 bytes, fill the same stage with plain loads),
+//   * a thread classifies its NY entering samples against the band and keeps the few that matter (inside / above the
+//     band, or invalid) as 1-byte codes in a per-gridpoint ring of the window's w days: when that day leaves the window
+//     w steps later, the thread replays its list with the opposite sign instead of loading and classifying the rows
+//     again (the second touch was 55 GB of DRAM traffic and half of the scan instructions of the first band kernel).
+// Counters, pooling, queries, re-centring and the fail list are those of hobday_band_kernel.
+// ---------------------------------------------------------------------------------------------------------
+struct RingParams {
+  BandParams b;      // bins = day-of-year-major array, pitch = its row pitch; doy_ptr / doy_rows unused
+  int NY;            // slots (years) per day of year
+  int use_tma;
+};
+
+constexpr int RING_ABOVE = 254, RING_INVALID = 255, RING_ALL_INVALID = 255;
+
+template <int P, int K, int OY>
+__global__ void __launch_bounds__(OY * 32, 1) hobday_ring_kernel(const __grid_constant__ CUtensorMap tmap,
+                                                                 const RingParams rp) {
+  const BandParams& p = rp.b;
+  constexpr int KB = K / 8;
+  constexpr int TY = OY - 2 * P, TX = 32 - 2 * P, CS = OY * 32;
+  extern __shared__ __align__(1024) unsigned char smem_ring[];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, tid = threadIdx.x;
+  const int NY = rp.NY, w = p.w, half = p.w / 2;
+  // carve-up: TMA stage first (1024-byte aligned), then counters, then the ring
+  uint16_t* const stage = reinterpret_cast<uint16_t*>(smem_ring);             // [NY][OY][32]
+  const size_t stage_bytes = (((size_t)NY * CS * 2 + 127) / 128) * 128;
+  uint16_t* const L0 = reinterpret_cast<uint16_t*>(smem_ring + stage_bytes);  // [K][CS]; the coarse pass reuses it as [nblk][CS]
+  uint16_t* const L1 = L0 + K * CS;                                           // [KB][CS]
+  uint16_t* const NTr = L1 + KB * CS;                                         // [CS] valid samples in the own window
+  uint16_t* const TBr = NTr + CS;                                             // [CS] of which >= Blo
+  uint8_t* const ring = reinterpret_cast<uint8_t*>(TBr + CS);                 // [w][NY][CS] codes of the samples that matter
+  uint8_t* const rlen = ring + (size_t)w * NY * CS;                           // [w][CS] list lengths (255: every sample invalid)
+  uint64_t* const bar = reinterpret_cast<uint64_t*>(rlen + (((size_t)w * CS + 15) / 16) * 16);
+  int* const s_misc = reinterpret_cast<int*>(bar + 1);                        // [0] violation flag, [1] min blk, [2] max blk
+
+  const int nb = p.nb;
+  const int nblk = (nb + 7) >> 3;
+  const int64_t nx = p.nx, ny = p.ny, N = nx * ny;
+  int64_t y0 = (int64_t)blockIdx.y * TY, x0 = (int64_t)blockIdx.x * TX;
+
+  // ---- own gridpoint of this thread (update role) ----
+  const int64_t gy = y0 - P + warp;
+  int64_t gx = (x0 - P + lane) % nx;
+  if (gx < 0) gx += nx;
+  const bool own_valid = gy >= 0 && gy < ny;
+  const uint16_t* const col = p.bins + (own_valid ? gy * nx + gx : 0);
+  const bool tma = rp.use_tma && x0 - P >= 0 && x0 - P + 32 <= nx;  // the box does not straddle the longitude seam
+  uint16_t* const myL0 = L0 + tid;
+  uint16_t* const myL1 = L1 + tid;
+  int NT = 0, TB = 0, Blo = 0;
+  bool dead = !own_valid;  // no valid sample in the own window: nothing to keep up to date
+
+  // ---- target of this lane (query role: warps 0..TY-1, lanes P..31-P) ----
+  const int64_t ty_g = y0 + warp, tx_g = x0 + lane - P;
+  const bool target_live = warp < TY && lane >= P && lane < 32 - P && ty_g < ny && tx_g < nx;
+  bool masked = true;
+  if (target_live) {
+    const float a0 = p.anom_row0[ty_g * nx + tx_g];
+    masked = a0 != a0;  // detect.py:2704-2705
+  }
+  float vmin = CUDART_INF_F, vmax = -CUDART_INF_F;
+
+  if (tid == 0) {
+    mbar_init(bar, 1);
+    mbar_fence_init();
+  }
+  uint32_t phase = 0;
+
+  auto slot_of = [&](int step_doy) { return ((step_doy % w) + w) % w; };  // ring slot of the day that entered at that step
+
+  // One code applied to the own counters.
+  auto apply = [&](int code, int sign) {
+    if (code == RING_INVALID) { NT -= sign; return; }  // invalid sample: only the valid count is corrected
+    TB += sign;
+    if (code != RING_ABOVE) {
+      const int s = code - 1;
+      myL0[s * CS] = (uint16_t)(myL0[s * CS] + sign);
+      myL1[(s >> 3) * CS] = (uint16_t)(myL1[(s >> 3) * CS] + sign);
+    }
+  };
+  auto code_of = [&](int v) -> int {  // 0: below the band (valid, not stored)
+    const int s = v - Blo;
+    const int c = (v == BAND_INV) ? RING_INVALID : (s < K ? s + 1 : RING_ABOVE);
+    return s < 0 ? 0 : c;
+  };
+  auto replay = [&](int slot, int sign) {
+    const int n = rlen[slot * CS + tid];
+    if (n == RING_ALL_INVALID) return;  // NY invalid samples: the valid count does not change
+    NT += sign * NY;
+    const uint8_t* r = ring + (size_t)slot * NY * CS + tid;
+    for (int j = 0; j < n; ++j) apply((int)r[j * CS], sign);
+  };
+
+  // ---- day `dd` of the year (0-based) into ring slot `slot` from global memory (rebuilds) ----
+  auto build_slot = [&](int dd, int slot) {
+    const uint16_t* src = col + (int64_t)dd * NY * p.pitch;
+    uint8_t* r = ring + (size_t)slot * NY * CS + tid;
+    int n = 0, all = BAND_INV;
+    for (int j = 0; j < NY; j += 5) {
+      int v[5];
+#pragma unroll
+      for (int u = 0; u < 5; ++u) v[u] = (j + u < NY) ? (int)src[(int64_t)(j + u) * p.pitch] : BAND_INV;
+#pragma unroll
+      for (int u = 0; u < 5; ++u) {
+        if (j + u >= NY) continue;
+        all &= v[u];
+        const int c = code_of(v[u]);
+        r[n] = (uint8_t)c;
+        n += c ? CS : 0;
+      }
+    }
+    n /= CS;
+    rlen[slot * CS + tid] = (uint8_t)((all == BAND_INV) ? RING_ALL_INVALID : n);
+  };
+
+  // ---- (re)build the counters and the ring of the window centred on step d ----
+  // returns false when the tile's thresholds do not fit one band (tile goes to the fail list)
+  auto rebuild = [&](int d) -> bool {
+    // 1. coarse pass: 8-bin block counts over the full range, own window
+    for (int i = tid; i < (K + KB) * CS; i += OY * 32) L0[i] = 0;  // L0 and L1 are contiguous
+    if (tid < 3) s_misc[tid] = tid == 1 ? 0x7fffffff : (tid == 2 ? -1 : 0);
+    __syncthreads();
+    NT = 0;
+    if (own_valid) {
+      for (int k = -half; k <= half; ++k) {
+        const int dd = ((d + k) % NDOY + NDOY) % NDOY;
+        const uint16_t* src = col + (int64_t)dd * NY * p.pitch;
+        for (int j = 0; j < NY; j += 5) {
+          int v[5];
+#pragma unroll
+          for (int u = 0; u < 5; ++u) v[u] = (j + u < NY) ? (int)src[(int64_t)(j + u) * p.pitch] : BAND_INV;
+#pragma unroll
+          for (int u = 0; u < 5; ++u)
+            if (v[u] != BAND_INV) {
+              ++NT;
+              if (K < 8 * nblk) myL0[(v[u] >> 3) * CS] = (uint16_t)(myL0[(v[u] >> 3) * CS] + 1);
+            }
+        }
+      }
+    }
+    dead = NT == 0;
+    NTr[tid] = (uint16_t)NT;
+    __syncthreads();
+    if (K >= 8 * nblk) {
+      Blo = 0;  // the band covers every bin: no coarse pass, no violation possible
+    } else {
+      if (warp < TY) {
+        const int ntot = pooled_row<P>(NTr + warp * 32 + lane, lane);
+        const bool livet = target_live && !masked && ntot > 0;
+        const int kk = (int)floor(__dmul_rn(p.q, (double)ntot));
+        int run = 0, jb = -1;
+        for (int j = 0; j < nblk; ++j) {
+          const int pj = pooled_row<P>(L0 + j * CS + warp * 32 + lane, lane);
+          if (jb < 0) { if (run + pj > kk) jb = j; else run += pj; }
+          if (__all_sync(0xffffffffu, jb >= 0 || !livet)) break;
+        }
+        if (livet) {
+          if (jb < 0) jb = nblk + K;  // rank beyond the last bin (q = 1): not representable in a band
+          atomicMin(&s_misc[1], jb);
+          atomicMax(&s_misc[2], jb);
+        }
+      }
+      __syncthreads();
+      const int jmin = s_misc[1], jmax = s_misc[2];
+      if (jmax >= 0) {
+        int lo = 8 * jmin - p.margin;
+        lo = lo < 0 ? 0 : (lo & ~7);
+        if (8 * jmax + 7 >= lo + K || p.force_fail) return false;
+        Blo = lo;
+      } else {
+        Blo = 0;
+        if (p.force_fail) return false;
+      }
+      for (int i = tid; i < (K + KB) * CS; i += OY * 32) L0[i] = 0;
+      __syncthreads();
+    }
+    // 2. ring lists and band counters of the window's days
+    TB = 0;
+    NT = 0;
+    if (own_valid) {
+      for (int k = -half; k <= half; ++k) {
+        const int dd = ((d + k) % NDOY + NDOY) % NDOY;
+        const int slot = slot_of(d + k);
+        build_slot(dd, slot);
+        replay(slot, +1);
+      }
+    }
+    dead = NT == 0;
+    NTr[tid] = (uint16_t)NT;
+    TBr[tid] = (uint16_t)TB;
+    __syncthreads();
+    return true;
+  };
+
+  // ---- the rows of the day entering at `step` into the stage ----
+  auto issue = [&](int step) {
+    const int dd = (step + half) % NDOY;
+    if (tma) {
+      if (tid == 0) {
+        fence_proxy_async();
+        mbar_expect_tx(bar, (uint32_t)NY * CS * 2u);
+        tma_load_3d(stage, &tmap, (int)(x0 - P), (int)(y0 - P), dd * NY, bar);
+      }
+    } else if (own_valid) {
+      const uint16_t* src = col + (int64_t)dd * NY * p.pitch;
+      for (int j = 0; j < NY; j += 5) {
+        uint16_t v[5];
+#pragma unroll
+        for (int u = 0; u < 5; ++u) v[u] = (j + u < NY) ? src[(int64_t)(j + u) * p.pitch] : (uint16_t)0;
+#pragma unroll
+        for (int u = 0; u < 5; ++u)
+          if (j + u < NY) stage[(j + u) * CS + tid] = v[u];
+      }
+    }
+  };
+
+  // ---- advance the own window by one day of year: the day that entered w steps ago leaves, the staged day enters ----
+  auto advance = [&](int step) {
+    if (tma) {
+      mbar_wait(bar, phase);
+      phase ^= 1u;
+    }
+    if (!own_valid) return;
+    const int slot = slot_of(step + half);
+    if (!dead) replay(slot, -1);  // a dead window holds invalid samples only: nothing to take out
+    // entering samples: classify, keep the ones that matter
+    const uint16_t* sv = stage + tid;
+    uint8_t* r = ring + (size_t)slot * NY * CS + tid;
+    int n = 0, all = BAND_INV;
+    for (int j = 0; j < NY; j += 5) {
+      int v[5];
+#pragma unroll
+      for (int u = 0; u < 5; ++u) v[u] = (j + u < NY) ? (int)sv[(j + u) * CS] : BAND_INV;
+#pragma unroll
+      for (int u = 0; u < 5; ++u) {
+        if (j + u >= NY) continue;
+        all &= v[u];
+        const int c = code_of(v[u]);
+        r[n] = (uint8_t)c;
+        n += c ? CS : 0;
+      }
+    }
+    n /= CS;
+    if (all == BAND_INV) {
+      rlen[slot * CS + tid] = (uint8_t)RING_ALL_INVALID;
+    } else {
+      rlen[slot * CS + tid] = (uint8_t)n;
+      dead = false;
+      NT += NY;
+      for (int j = 0; j < n; ++j) apply((int)r[j * CS], +1);
+    }
+    NTr[tid] = (uint16_t)NT;
+    TBr[tid] = (uint16_t)TB;
+  };
+
+  // ---- query of one day of year (as hobday_band_kernel) ----
+  auto query = [&](int d) {
+    const int rowoff = warp * 32 + lane;
+    const int ntot = pooled_row<P>(NTr + rowoff, lane);
+    const int tb = pooled_row<P>(TBr + rowoff, lane);
+    const bool livet = target_live && !masked && ntot > 0;
+    const double pos = __dmul_rn(p.q, (double)ntot);  // detect.py:2516
+    const int kk = (int)floor(pos);                   // cum > pos  <=>  cum >= kk + 1
+    const int below = ntot - tb;
+    bool viol = livet && below > kk;                  // quantile bin lies below the band
+    int run = below, jb = -1;
+    bool done = !livet || viol;
+    for (int j = 0; j < KB; ++j) {
+      if (__all_sync(0xffffffffu, done)) break;
+      const int pj = pooled_row<P>(L1 + j * CS + rowoff, lane);
+      if (!done) {
+        if (run + pj > kk) { jb = j; done = true; }
+        else run += pj;
+      }
+    }
+    int iu = -1, cl = 0, h = 0;
+    if (livet && !viol && jb < 0) {
+      // not found inside the band: either the band is too low, or (band = full range) the rank lies
+      // beyond the last bin and the reference clips iu to nb - 1 (detect.py:2530-2532)
+      if (K >= 8 * nblk) { iu = nb - 1; }
+      else viol = true;
+    }
+    const unsigned want = __ballot_sync(0xffffffffu, jb >= 0);
+    if (want) {
+      int jlo = jb >= 0 ? jb : KB, jhi = jb;
+      for (int o = 16; o; o >>= 1) {
+        jlo = min(jlo, __shfl_xor_sync(0xffffffffu, jlo, o));
+        jhi = max(jhi, __shfl_xor_sync(0xffffffffu, jhi, o));
+      }
+      for (int j = jlo; j <= jhi; ++j) {
+        if (!__any_sync(0xffffffffu, jb == j)) continue;
+#pragma unroll
+        for (int b = 0; b < 8; ++b) {
+          const int pb = pooled_row<P>(L0 + (8 * j + b) * CS + rowoff, lane);
+          if (jb == j && iu < 0) {
+            if (run + pb > kk) { iu = Blo + 8 * j + b; cl = run; h = pb; }
+            else run += pb;
+          }
+        }
+      }
+    }
+    if (iu == nb - 1 && jb < 0 && livet && !viol) {  // clipped rank (q = 1): cl = cum[nb - 2], h = hist[nb - 1]
+      h = pooled_row<P>(L0 + (nb - 1 - Blo) * CS + rowoff, lane);
+      cl = ntot - h;
+    }
+    if (__any_sync(0xffffffffu, viol)) {
+      if (lane == 0) s_misc[0] = 1;
+      return;
+    }
+    float res = CUDART_NAN_F;
+    if (livet) {
+      if (iu == 0) {
+        res = __ldg(&p.centers[0]);  // detect.py:2557
+      } else {
+        const float bl = __ldg(&p.centers[iu - 1]), bu = __ldg(&p.centers[iu]);
+        const double frac = (h > 0) ? __ddiv_rn(pos - (double)cl, (double)h) : 0.5;       // detect.py:2545-2547
+        res = (float)__dadd_rn((double)bl, __dmul_rn(frac, (double)__fsub_rn(bu, bl)));   // detect.py:2550 (no FMA)
+      }
+      vmin = fminf(vmin, res);
+      vmax = fmaxf(vmax, res);
+      if (res < p.lower_bound) res = p.lower_bound;  // detect.py:2722-2732
+    }
+    if (target_live) p.thr[(int64_t)d * N + ty_g * nx + tx_g] = res;
+  };
+
+  auto give_up = [&]() {
+    if (tid == 0) {
+      const int i = atomicAdd(&p.fail_list[0], 1);
+      p.fail_list[1 + 2 * i] = (int)y0;
+      p.fail_list[2 + 2 * i] = (int)x0;
+    }
+  };
+  // a TMA load still in flight must land before the CTA exits
+  auto drain = [&](bool pending) {
+    if (tma && pending) mbar_wait(bar, phase);
+  };
+
+  if (!rebuild(0)) { give_up(); return; }
+  issue(1);
+  for (int d = 0; d < NDOY; ++d) {
+    if (d > 0) {
+      advance(d);
+      __syncthreads();                 // every thread is done with the stage and the counters are up to date
+      if (d + 1 < NDOY) issue(d + 1);  // in flight while the queries run
+    }
+    if (warp < TY) query(d);
+    __syncthreads();
+    if (s_misc[0]) {  // a threshold left the band: re-centre the band on the current window and redo the day
+      __syncthreads();
+      if (!rebuild(d)) { drain(d + 1 < NDOY); give_up(); return; }
+      if (warp < TY) query(d);
+      __syncthreads();
+      if (s_misc[0]) { drain(d + 1 < NDOY); give_up(); return; }
+    }
+  }
+  if (warp < TY && p.stats) {
+    vmin = warp_min(vmin);
+    vmax = warp_max(vmax);
+    if (lane == 0) {
+      if (vmin != CUDART_INF_F) atomic_min_f(&p.stats[0], vmin);
+      if (vmax != -CUDART_INF_F) atomic_max_f(&p.stats[1], vmax);
+    }
+  }
+}
+
 // np.digitize(a, edges) - 1 (detect.py:2622-2631) into the DAY-OF-YEAR-MAJOR bin array the threshold and compare
 // kernels walk: slot s = doy * NY + (index of the year among the output years) holds the codes of input row
 // slot_row[s], or the invalid code when that (day, year) has no row (slot_row[s] < 0).  Invalid samples (NaN or
@@ -395,10 +770,8 @@ __global__ void __launch_bounds__(256) digitize_doy_kernel(const float* __restri
                                                            uint16_t* __restrict__ bins, int64_t bins_pitch,
                                                            int slots_per_block) {
   extern __shared__ float s_edges[];
-  for (int i = threadIdx.x; i < n_edges; i += blockDim.x) s_edges[i] = edges[i];
-  __syncthreads();
   DigTable dig;
-  dig.init(s_edges, n_edges);
+  dig.init_cta(edges, n_edges, s_edges);
   const int64_t c = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * 4;  // four gridpoints per thread
   if (c >= N) return;
   const bool quad = c + 3 < N && (pitch & 3) == 0 && (bins_pitch & 3) == 0 && (reinterpret_cast<uintptr_t>(a) & 15) == 0 &&
@@ -498,13 +871,28 @@ extern "C" int marex_hobday_thresholds_pooled_bins(const uint16_t* bins, int64_t
   const int env_k = (int)tune_get("pool_k", 0);
   const int env_ty = (int)tune_get("pool_ty", 0);
   MAREX_REQUIRE(env_k == 0 || env_k == 64 || env_k == 128, "MAREX_POOL_K must be 64 or 128");
-  // 12 target rows (16 x 32 own gridpoints, two tiles per SM at 64 registers) measured best on B200:
-  // 71.2 ms vs 74.6 (8 rows) and 74.1 (16 rows) for the threshold + compare stages at 0.25 deg.
-  // MAREX_POOL_TY < 8 selects 3-row tiles (exercised by the tests).
-  const int TY = (env_ty && env_ty < 8) ? 3 : 12;
-  const int OY = TY + 2 * P, TX = 32 - 2 * P;
+  const int TX = 32 - 2 * P;
+  // Ring kernel (every sample read once, TMA-staged): 64-bin band, OY = 14 own rows (one 448-thread tile per SM) or 10
+  // when the ring of w * NY codes per gridpoint does not fit; otherwise the first band kernel.
+  int ring_oy = 0;
+  size_t ring_smem = 0;
+  if (tune_get("pool_ring", 1) && env_k != 128 && !env_ty && nb <= 8 * 64 && NY <= 254) {
+    for (int oy : {14, 10}) {
+      if (oy - 2 * P < 1) continue;
+      const size_t cs = (size_t)oy * 32;
+      const size_t need = (((size_t)NY * cs * 2 + 127) / 128) * 128 + (size_t)(64 + 8 + 2) * cs * 2 + (size_t)w * NY * cs +
+                          (((size_t)w * cs + 15) / 16) * 16 + 64;
+      if (need <= 227 * 1024) { ring_oy = oy; ring_smem = need; break; }
+    }
+  }
+  // first band kernel: 12 target rows (16 x 32 own gridpoints, two tiles per SM at 64 registers); pool_ty < 8 selects
+  // 3-row tiles (exercised by the tests).  After the ring kernel it retries ring tiles (at most 12 rows) from their origin.
+  const int TY = (env_ty && env_ty < 8 && !ring_oy) ? 3 : 12;
+  const int OY = TY + 2 * P;
+  const int ring_ty = ring_oy ? ring_oy - 2 * P : TY;
   const dim3 grid_all((unsigned)((nx + TX - 1) / TX), (unsigned)((ny + TY - 1) / TY));
-  const int max_tiles = (int)(grid_all.x * grid_all.y);
+  const dim3 grid_ring((unsigned)((nx + TX - 1) / TX), (unsigned)((ny + ring_ty - 1) / ring_ty));
+  const int max_tiles = (int)std::max(grid_all.x * grid_all.y, grid_ring.x * grid_ring.y);
   int32_t* list_b = fail_list + 2 * ((ny + 1) * ((nx + 27) / 28 + 1)) + 8;
   init_band_kernel<<<1, 1, 0, st>>>(stats, fail_list, list_b);
   MAREX_LAUNCH_CHECK("init_band_kernel");
@@ -515,6 +903,34 @@ extern "C" int marex_hobday_thresholds_pooled_bins(const uint16_t* bins, int64_t
   bp.margin = (int)tune_get("pool_margin", 8);
   bp.anom_row0 = anom; bp.lower_bound = lower_bound; bp.thr = thr; bp.stats = stats;
   bp.force_fail = (int)tune_get("pool_force_fail", 0);
+  bp.tile_list = nullptr;
+  auto launch_ring = [&](int32_t* fails) -> int {
+    RingParams rp;
+    rp.b = bp;
+    rp.b.fail_list = fails;
+    rp.NY = (int)NY;
+    rp.use_tma = (nx % 8) == 0 && (bpitch % 8) == 0 && (reinterpret_cast<uintptr_t>(bins) % 16) == 0 &&
+                 tune_get("pool_tma", 1) && NDOY * NY < (1LL << 31);
+    CUtensorMap tmap;
+    memset(&tmap, 0, sizeof(tmap));
+    if (rp.use_tma) {
+      const int rc = make_tmap_3d(&tmap, bins, CU_TENSOR_MAP_DATA_TYPE_UINT16, 2, NDOY * NY, ny, nx, nx, bpitch, (int)NY,
+                                  ring_oy, 32);
+      if (rc) return rc;
+    }
+#define MAREX_RING(PP, OO)                                                                                       \
+  do {                                                                                                           \
+    cudaError_t e = cudaFuncSetAttribute(hobday_ring_kernel<PP, 64, OO>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+                                         (int)ring_smem);                                                        \
+    if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(hobday_ring)");                              \
+    hobday_ring_kernel<PP, 64, OO><<<grid_ring, OO * 32, ring_smem, st>>>(tmap, rp);                             \
+  } while (0)
+    if (ring_oy == 14) { if (P == 1) MAREX_RING(1, 14); else if (P == 2) MAREX_RING(2, 14); else MAREX_RING(3, 14); }
+    else { if (P == 1) MAREX_RING(1, 10); else if (P == 2) MAREX_RING(2, 10); else MAREX_RING(3, 10); }
+#undef MAREX_RING
+    MAREX_LAUNCH_CHECK("hobday_ring_kernel");
+    return MAREX_OK;
+  };
   // One launch of the band kernel with K band bins over all tiles (tiles == nullptr) or over a list.
   auto launch_band = [&](int K, const int32_t* tiles, int32_t* fails) -> int {
     if (nb > 8 * K) return fail(MAREX_ERR_UNSUPPORTED, "nb too large for the coarse pass of this band width");
@@ -544,7 +960,13 @@ extern "C" int marex_hobday_thresholds_pooled_bins(const uint16_t* bins, int64_t
   // 64-bin band (two tiles per SM) first; tiles whose thresholds spread wider retry with 128 bins;
   // what is left gets full-range counters.  MAREX_POOL_K pins a single width (tuning / tests).
   const int32_t* leftover = fail_list;
-  if (env_k) {
+  if (ring_oy) {
+    int rc = launch_ring(fail_list);
+    if (rc) return rc;
+    rc = launch_band(128, fail_list, list_b);
+    if (rc) return rc;
+    leftover = list_b;
+  } else if (env_k) {
     const int rc = launch_band(env_k, nullptr, fail_list);
     if (rc) return rc;
   } else if (nb > 8 * 64) {

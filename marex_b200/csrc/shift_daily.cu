@@ -153,11 +153,9 @@ __global__ void __launch_bounds__(512) shift_daily_kernel(const __grid_constant_
     const int db0 = days_before_year(p.year0) + p.doy0;
     for (int i = threadIdx.x; i <= p.n_years; i += blockDim.x) ybase[i] = days_before_year(p.year0 + i) - db0;
   }
-  if (DIG)
-    for (int i = threadIdx.x; i < p.n_edges; i += blockDim.x) s_edges[i] = p.edges[i];
   __syncthreads();
   DigTable dig;
-  if (DIG) dig.init(s_edges, p.n_edges);
+  if (DIG) dig.init_cta(p.edges, p.n_edges, s_edges);
 
   // producer state (thread 0): the box of the next year to issue
   int issue_year = 0, issue_st = 0;
@@ -434,10 +432,8 @@ __global__ void __launch_bounds__(128) redigitize_cells_kernel(const float* __re
                                                                uint16_t* __restrict__ bins, int64_t bins_pitch, int NY,
                                                                int year_first) {
   extern __shared__ float s_edges[];
-  for (int i = threadIdx.x; i < n_edges; i += blockDim.x) s_edges[i] = edges[i];
-  __syncthreads();
   DigTable dig;
-  dig.init(s_edges, n_edges);
+  dig.init_cta(edges, n_edges, s_edges);
   const int n = list[0];
   // output row 0 is Jan 1 of year_first (the trim keeps whole years)
   for (int k = blockIdx.y; k < n; k += gridDim.y) {
@@ -563,8 +559,11 @@ extern "C" int marex_shift_anomaly_daily_f32(const float* x, int64_t T, int64_t 
     else if (v == 2) rc = r == 2 ? MAREX_SD(2, 2, cps) : MAREX_SD(2, 4, cps);
     else rc = r == 1 ? MAREX_SD(1, 1, cps) : (r == 2 ? MAREX_SD(1, 2, cps) : MAREX_SD(1, 4, cps));
   } else {
-    rc = MAREX_SD(2, 4, 2);
-    if (rc == MAREX_ERR_UNSUPPORTED) rc = MAREX_SD(2, 4, 1);
+    // measured on B200 (0.25 deg, W = 15, S = 21, fused digitize; profiles/r02_shift_shapes.json): V = 1, R = 4, two CTAs
+    // per SM 68.8 ms; V = 2: 68.9 (R = 2) / 91.3 (R = 4); V = 4: 107 - 165 ms -- the ring's 60 bytes per (day, gridpoint)
+    // cap the resident threads, and fewer, fatter threads lose more to latency than they save in instructions.
+    rc = MAREX_SD(1, 4, 2);
+    if (rc == MAREX_ERR_UNSUPPORTED) rc = MAREX_SD(2, 2, 2);
     if (rc == MAREX_ERR_UNSUPPORTED) rc = MAREX_SD(1, 4, 1);
     if (rc == MAREX_ERR_UNSUPPORTED) rc = MAREX_SD(1, 1, 1);
   }
