@@ -86,14 +86,14 @@ STAGE_KERNELS = {
 }
 
 
-def ncu_traffic(kernel_stage):
-    """dram__bytes_read.sum + dram__bytes_write.sum per launch of the stage's kernels, from the ncu
-    --set full captures summarised in profiles/r01_ncu_traffic.json (same workload), or None."""
-    p = os.path.join(ROOT, "profiles", "r01_ncu_traffic.json")
+def ncu_traffic(workload, stage):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch, summed over ALL kernels the stage launches, from the
+    ncu --set full captures of this very workload summarised in profiles/r02_ncu_traffic.json ({workload: {stage:
+    bytes}}); None when no capture exists for the workload or the stage."""
+    p = os.path.join(ROOT, "profiles", "r02_ncu_traffic.json")
     if not os.path.exists(p):
         return None
-    d = json.load(open(p))
-    return d.get(kernel_stage)
+    return json.load(open(p)).get(workload, {}).get(stage)
 
 
 def host_memory_available():
@@ -159,24 +159,31 @@ def cpu_oracle_run(tiles, time, kw, cores):
     return _time.perf_counter() - t0
 
 
-def synth_host_tiles(time, n_tiles, tile=(6, 8), seed=2):
-    """numpy twin of the synthetic field's statistics for the CPU arms (the CPU baseline does not
-    need bit-identical inputs to be timed; the GPU arm's own tiles are used when available)."""
-    rng = np.random.default_rng(seed)
-    T = len(time)
-    frac = (time - time.astype("datetime64[Y]")).astype(float) / 365.25
-    tiles = []
-    for _ in range(n_tiles):
-        ny, nx = tile
-        amp = rng.uniform(0.5, 6, (ny, nx))
-        ph = rng.uniform(0, 1, (ny, nx))
-        x = 15 + amp * np.cos(2 * np.pi * (frac[:, None, None] - ph)) + 0.02 * np.arange(T)[:, None, None] / 365.25
-        ar = np.zeros((ny, nx))
-        for t in range(T):
-            ar = 0.9 * ar + 0.26 * rng.standard_normal((ny, nx))
-            x[t] += ar
-        tiles.append(x.astype(np.float32))
-    return tiles
+def sample_tile_origins(ny, nx, n_tiles, th, tw, unstructured):
+    """Where the CPU arms cut their tiles from the benchmark field: spread over the rows and columns, land included."""
+    out = []
+    for i in range(n_tiles):
+        if unstructured:
+            out.append((0, (i * 48 * 7) % (nx - 48)))
+        else:
+            out.append((((ny // 2) // th * th + (i // 32) * 3 * th) % (ny - th), (i * 5 * tw) % (nx - tw)))
+    return out
+
+
+def bench_config(args, ny, nx, T, T_out, halo, kw):
+    cfg = {
+        "workload": args.workload,
+        "per_gpu_grid": [ny, nx],
+        "days": T,
+        "days_out": T_out,
+        "halo_rows": halo,
+        "l2": "inputs (60 GB per GPU at 0.25 deg) are far larger than L2; no flush needed",
+    }
+    env = {k: v for k, v in os.environ.items() if k.startswith("MAREX_")}
+    if env:
+        cfg["tuning_env"] = env
+    cfg.update(kw)
+    return cfg
 
 
 # ------------------------------------------------------------------------------------------
@@ -230,22 +237,43 @@ class ClockSampler:
 
 # ------------------------------------------------------------------------------------------
 def run_reference(args, rank, world):
-    """Reference arm: the CPU restatement of marEx.preprocess_data on all host cores."""
+    """Reference arm: the CPU restatement of marEx.preprocess_data (the reference itself needs xarray / dask / flox /
+    xhistogram, absent from this image) on all host cores, on tiles cut from the SAME synthetic field as the GPU arm
+    (numpy twin of the counter-based generator: identical land blobs and random streams), same workload and config keys.
+    Imports neither torch nor the CUDA library."""
     if rank != 0:
         return
+    from marex_b200 import calendar as mcal
+    from marex_b200 import synthetic
+
     ny, nx, start, end, kw = WORKLOADS[args.workload]
     time = np.arange(np.datetime64(start), np.datetime64(end))
+    T = len(time)
+    cal = mcal.build_calendar(time)
+    shifting = kw.get("method_anomaly", "shifting_baseline") == "shifting_baseline"
+    T_out = int((cal.year >= cal.year_val[0] + kw.get("window_year_baseline", 15)).sum()) if shifting else T
+    unstructured = ny == 1
+    hobday_pooled = kw.get("method_extreme", "hobday_extreme") == "hobday_extreme" and kw.get("method_percentile", "approximate") == "approximate"
+    halo = 2 if (hobday_pooled and not unstructured) else 0
     cores = os.cpu_count() or 1
-    tiles = synth_host_tiles(time, 4 * cores, tile=(6, 8))  # four 48-cell tiles per core and step
-    cells = sum(t.shape[1] * t.shape[2] for t in tiles)
+    th, tw = (1, 48) if unstructured else (6, 8)
+    n_tiles = 4 * cores  # four 48-cell tiles per core and step
+    ny_g = ny * max(1, args.gpus)
+    origins = sample_tile_origins(ny, nx, n_tiles, th, tw, unstructured)
+    cells = np.stack([(r0 + np.arange(th))[:, None] * nx + (c0 + np.arange(tw))[None, :] for r0, c0 in origins])
+    field = synthetic.synth_sst_numpy(time, (ny_g, nx), cells, seed=2, land_fraction=0.0 if unstructured else 0.3)
+    tiles = [np.ascontiguousarray(field[:, i, 0] if unstructured else field[:, i]) for i in range(n_tiles)]
+    n_cells = n_tiles * th * tw
+    land = float(np.mean([np.isnan(t[0]).mean() for t in tiles]))
     for _ in range(args.warmup):
         cpu_oracle_run(tiles[: max(1, cores // 4)], time, kw, cores)
     t0 = _time.perf_counter()
     for _ in range(args.steps):
         cpu_oracle_run(tiles, time, kw, cores)
     dt = (_time.perf_counter() - t0) / args.steps
-    value = cells * len(time) / dt
-    sample = f"{len(tiles)} tiles of 6x8 cells x {len(time)} days per step (each tile its own periodic domain)"
+    value = n_cells * T / dt
+    sample = (f"{n_tiles} tiles of {th}x{tw} cells x {T} days per step, cut from the benchmark field "
+              f"(land fraction of the sample {land:.2f}; each tile its own periodic domain)")
     print(
         json.dumps(
             {
@@ -262,7 +290,7 @@ def run_reference(args, rank, world):
                 "vs_baseline": None,
                 "dtype": "f32",
                 "data": "synthetic",
-                "config": {"workload": args.workload, "grid": [ny, nx], "days": len(time), **kw},
+                "config": bench_config(args, ny, nx, T, T_out, halo, kw),
                 "cpu_baseline": {
                     "value": value,
                     "unit": "gridpoint-days/s",
@@ -288,6 +316,8 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-parity", action="store_true", help="skip the post-run tile check against the oracle")
+    ap.add_argument("--gather-thresholds", action="store_true", help="N > 1: also gather the thresholds on rank 0")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -319,9 +349,7 @@ def main():
     dev = torch.device("cuda", local)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        if os.environ.get("NCCL_DEBUG", "").upper() in ("VERSION", "INFO"):
-            os.environ["NCCL_DEBUG"] = "WARN"  # NCCL prints its banner on stdout; stdout carries one JSON line only
-        dist.init_process_group("nccl", device_id=dev)
+        dist.init_process_group("nccl", device_id=dev)  # NCCL_DEBUG output goes to stderr with everything else (dup2 above)
     ny, nx, start, end, kw = WORKLOADS[args.workload]
     time = np.arange(np.datetime64(start), np.datetime64(end))
     T = len(time)
@@ -363,13 +391,20 @@ def main():
             # every rank owns the same number of rows (weak scaling): the gathers need no size exchange and run
             # asynchronously on NCCL's stream, overlapping the first kernel of the next step; at most one step's
             # collectives are in flight, and the timed region ends only after the last one has completed
+            # The per-shard outputs stay where a sharded writer needs them: only the ocean mask is gathered
+            # (to rank 0) and the extreme count all-reduced.  Round 1 all-gathered the thresholds (1.5 GB per rank, 12 GB
+            # written into every HBM per step at N = 8) although no rank needs its peers' thresholds: that was the 4 %
+            # of lost scaling.  --gather-thresholds assembles them on rank 0.
             drain()
-            lay = out["thresholds_layout"]
-            w1, g1 = sharding.dist_gather(out["thresholds"].contiguous(), 1 if lay == "doy_first" else 0, equal=True, async_op=True)
-            w2, g2 = sharding.dist_gather(out["mask"], 0, equal=True, async_op=True)
+            m8 = out["mask"].to(torch.uint8).contiguous()
+            glist = [torch.empty_like(m8) for _ in range(world)] if rank == 0 else None
+            w2 = dist.gather(m8, glist, dst=0, async_op=True)
             w3 = dist.all_reduce(out["extreme_count"], async_op=True)
-            out["thresholds_global"], out["mask_global"] = g1[0], g2[0]
-            pending.extend([(w1, g1), (w2, g2), (w3, out["extreme_count"])])
+            pending.extend([(w2, (glist, m8)), (w3, out["extreme_count"])])
+            if args.gather_thresholds:
+                th = out["thresholds"].contiguous()
+                tlist = [torch.empty_like(th) for _ in range(world)] if rank == 0 else None
+                pending.append((dist.gather(th, tlist, dst=0, async_op=True), (tlist, th)))
         return out
 
     def barrier():
@@ -433,7 +468,10 @@ def main():
         "peak": peak,
         "unit": "GB/s",
         "frac": achieved / peak,
-        "traffic": ncu_traffic(dom),
+        "traffic": ncu_traffic(args.workload, dom),
+        "traffic_ratio": (ncu_traffic(args.workload, dom) / (kb[dom] * n_load)) if ncu_traffic(args.workload, dom) else None,
+        "traffic_source": "profiles/r02_ncu_traffic.json: ncu --set full capture of this workload, dram read + write bytes "
+                          "summed over every kernel the stage launches (null: no capture for this workload)",
         "algorithmic_bytes_per_launch": kb[dom] * n_load,
         "peak_source": peak_src,
         "ms_per_launch": stage_ms[dom],
@@ -441,6 +479,52 @@ def main():
     B = algorithmic_bytes_per_cell(T, T_out, hobday)
     pipe_gbs = B * n_own / (ms * 1e-3) / 1e9
     stages = {k: {"ms": v, "GBps": (kb[k] * n_load / (v * 1e-3) / 1e9) if k in kb and v > 0 else None} for k, v in stage_ms.items()}
+
+    # ---- parity: tiles of this very field and result against the oracle (oracle/tile_check.py) ----
+    parity = None
+    if rank == 0 and not args.no_parity:
+        from oracle.tile_check import check_tile
+
+        res = marex_b200.preprocess_arrays(x, time, output="torch", **kw)
+        torch.cuda.synchronize()
+        n_rows_loaded = x.shape[1] if not unstructured else 1
+        lay = res["thresholds_layout"]
+        tiles_done, compared, err = 0, 0, None
+        n = 12
+        if unstructured:
+            origins = [(0, 1000), (0, nx // 2 + 17), (0, nx - 48 - 5)]
+        else:
+            origins = [(n_rows_loaded // 7, nx // 5), (n_rows_loaded // 2 - 3, nx // 2 + 11), (n_rows_loaded - n - 4, nx - n - 9),
+                       (n_rows_loaded // 3, nx - n // 2)]  # the last tile straddles the longitude seam
+        try:
+            for r0, c0 in origins:
+                if unstructured:
+                    cols = torch.arange(c0, c0 + 48, device=dev)
+                    cut = lambda a, lead: a.index_select(lead, cols).cpu().numpy()  # noqa: E731
+                    sp = 0
+                else:
+                    rows_ = slice(r0, r0 + n)
+                    cols = torch.arange(c0, c0 + n, device=dev) % nx
+                    cut = lambda a, lead: a[(slice(None),) * lead + (rows_,)].index_select(lead + 1, cols).cpu().numpy()  # noqa: E731
+                    sp = 0
+                thr = res["thresholds"]
+                got = dict(
+                    dat_anomaly=cut(res["dat_anomaly"], 1), extreme_events=cut(res["extreme_events"], 1).astype(bool),
+                    mask=cut(res["mask"], 0).astype(bool), thresholds=cut(thr, 1 if lay == "doy_first" else sp),
+                )  # fmt: skip
+                compared += check_tile(cut(x, 1), time, got, **kw)
+                tiles_done += 1
+        except AssertionError as e:  # reported in the JSON line and as a non-zero exit code
+            err = str(e).strip().splitlines()[:6]
+        parity = {
+            "tiles": tiles_done, "ok": err is None, "thresholds_compared": compared,
+            "what": "12 x 12 tiles (48-cell runs for unstructured) of the benchmark field and of the result of one extra "
+                    "untimed step against the numpy oracle: anomalies within 1e-5 of the field scale, thresholds and "
+                    "events from the same anomalies bit for bit on the tile interior; the last tile straddles the seam",
+            **({"error": err} if err else {}),
+        }  # fmt: skip
+        del res
+        torch.cuda.empty_cache()
 
     # ---- end to end: host (pinned) buffers in, host buffers out, through the public array API ----
     e2e = None
@@ -506,16 +590,13 @@ def main():
         except Exception:
             pass
         cores = len(all_cpus) or os.cpu_count() or 1
-        th, tw = 6, 8
+        th, tw = (1, 48) if unstructured else (6, 8)
         tiles = []
-        r0 = 0 if unstructured else (x_sample_src.shape[1] // 2) // th * th
-        for i in range(cores * 8):  # ~15-30 s of CPU work on the box's cores
-            c0 = (i * 5 * tw) % (nx - tw)
-            rr = (r0 + (i // 32) * 3 * th) % (x_sample_src.shape[1] - th)
-            if unstructured:
-                tiles.append(np.ascontiguousarray(x_sample_src[:, (i * 48) % (nx - 48) : (i * 48) % (nx - 48) + 48].cpu().numpy()))
+        for r0, c0 in sample_tile_origins(x_sample_src.shape[1] if not unstructured else 1, nx, cores * 8, th, tw, unstructured):
+            if unstructured:  # ~15-30 s of CPU work on the box's cores
+                tiles.append(np.ascontiguousarray(x_sample_src[:, c0 : c0 + tw].cpu().numpy()))
             else:
-                tiles.append(np.ascontiguousarray(x_sample_src[:, rr : rr + th, c0 : c0 + tw].cpu().numpy()))
+                tiles.append(np.ascontiguousarray(x_sample_src[:, r0 : r0 + th, c0 : c0 + tw].cpu().numpy()))
         dtc = cpu_oracle_run(tiles, time, kw, cores)
         cells = len(tiles) * th * tw
         cpu = {
@@ -542,16 +623,7 @@ def main():
             "vs_baseline": None,
             "dtype": "f32",
             "data": "synthetic",
-            "config": {
-                "workload": args.workload,
-                "per_gpu_grid": [ny, nx],
-                "days": T,
-                "days_out": T_out,
-                "halo_rows": halo,
-                "l2": "inputs (60 GB per GPU at 0.25 deg) are far larger than L2; no flush needed",
-                **({"tuning_env": {k: v for k, v in os.environ.items() if k.startswith("MAREX_")}} if any(k.startswith("MAREX_") for k in os.environ) else {}),
-                **kw,
-            },
+            "config": bench_config(args, ny, nx, T, T_out, halo, kw),
             "roofline": roofline,
             "pipeline_roofline": {
                 "bytes_per_gridpoint": B,
@@ -563,6 +635,7 @@ def main():
             },
             "stages": stages,
             "cpu_baseline": cpu,
+            "parity": parity,
             "e2e": e2e,
             "gpu_launches": int(launches),
             "extreme_events": n_events,
@@ -574,6 +647,8 @@ def main():
         os.dup2(2, 1)
     if world > 1:
         dist.destroy_process_group()
+    if rank == 0 and parity is not None and not parity["ok"]:
+        sys.exit(3)
 
 
 def _ev(torch):

@@ -391,10 +391,10 @@ __global__ void __launch_bounds__(OY * 32, (OY <= 16 && K <= 64) ? 2 : 1) hobday
 // ---------------------------------------------------------------------------------------------------------
 // Ring variant of the band kernel for the DAY-OF-YEAR-MAJOR bin array (slot s = doy * NY + year): every sample is read
 // from global memory ONCE.
-//   * the NY rows of the day of year that enters the window are one contiguous 3-D box {32 columns, OY rows, NY slots}
-//     of the bin array: a single cp.async.bulk.tensor.3d (TMA) stages it in shared memory behind an mbarrier while the
-//     tile answers the queries of the previous step (tiles on the longitude seam, or grids whose row pitch is not a
-//     multiple of 16 bytes, fill the same stage with plain loads),
+//   * the NY rows of the day of year that enters the window are consecutive rows of the bin array: one 2-D TMA box
+//     {32 columns, NY slots} (cp.async.bulk.tensor.2d) per own row of the tile stages them in shared memory behind one
+//     mbarrier while the tile answers the queries of the previous step (tiles on the longitude seam, or bin arrays whose
+//     row pitch is not a multiple of 16 bytes, fill the same stage with plain loads),
 //   * a thread classifies its NY entering samples against the band and keeps the few that matter (inside / above the
 //     band, or invalid) as 1-byte codes in a per-gridpoint ring of the window's w days: when that day leaves the window
 //     w steps later, the thread replays its list with the opposite sign instead of loading and classifying the rows
@@ -419,8 +419,9 @@ __global__ void __launch_bounds__(OY * 32, 1) hobday_ring_kernel(const __grid_co
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, tid = threadIdx.x;
   const int NY = rp.NY, w = p.w, half = p.w / 2;
   // carve-up: TMA stage first (1024-byte aligned), then counters, then the ring
-  uint16_t* const stage = reinterpret_cast<uint16_t*>(smem_ring);             // [NY][OY][32]
-  const size_t stage_bytes = (((size_t)NY * CS * 2 + 127) / 128) * 128;
+  const int NYP = (NY + 1) & ~1;  // slots per own row of the stage: every row starts on a 128-byte boundary (TMA)
+  uint16_t* const stage = reinterpret_cast<uint16_t*>(smem_ring);             // [OY][NYP][32]
+  const size_t stage_bytes = (size_t)NYP * CS * 2;
   uint16_t* const L0 = reinterpret_cast<uint16_t*>(smem_ring + stage_bytes);  // [K][CS]; the coarse pass reuses it as [nblk][CS]
   uint16_t* const L1 = L0 + K * CS;                                           // [KB][CS]
   uint16_t* const NTr = L1 + KB * CS;                                         // [CS] valid samples in the own window
@@ -593,10 +594,12 @@ __global__ void __launch_bounds__(OY * 32, 1) hobday_ring_kernel(const __grid_co
   auto issue = [&](int step) {
     const int dd = (step + half) % NDOY;
     if (tma) {
-      if (tid == 0) {
+      if (tid == 0) {  // one 2-D box {32 columns, NY slots} per own row of the grid, all on the same mbarrier
         fence_proxy_async();
-        mbar_expect_tx(bar, (uint32_t)NY * CS * 2u);
-        tma_load_3d(stage, &tmap, (int)(x0 - P), (int)(y0 - P), dd * NY, bar);
+        const int oy0 = max(0, (int)(P - y0)), oy1 = min(OY, (int)(ny + P - y0));
+        mbar_expect_tx(bar, (uint32_t)(oy1 - oy0) * NY * 64u);
+        for (int oy = oy0; oy < oy1; ++oy)
+          tma_load_2d(stage + (size_t)oy * NYP * 32, &tmap, (int)((y0 - P + oy) * nx + x0 - P), dd * NY, bar);
       }
     } else if (own_valid) {
       const uint16_t* src = col + (int64_t)dd * NY * p.pitch;
@@ -606,7 +609,7 @@ __global__ void __launch_bounds__(OY * 32, 1) hobday_ring_kernel(const __grid_co
         for (int u = 0; u < 5; ++u) v[u] = (j + u < NY) ? src[(int64_t)(j + u) * p.pitch] : (uint16_t)0;
 #pragma unroll
         for (int u = 0; u < 5; ++u)
-          if (j + u < NY) stage[(j + u) * CS + tid] = v[u];
+          if (j + u < NY) stage[(warp * NYP + j + u) * 32 + lane] = v[u];
       }
     }
   };
@@ -621,13 +624,13 @@ __global__ void __launch_bounds__(OY * 32, 1) hobday_ring_kernel(const __grid_co
     const int slot = slot_of(step + half);
     if (!dead) replay(slot, -1);  // a dead window holds invalid samples only: nothing to take out
     // entering samples: classify, keep the ones that matter
-    const uint16_t* sv = stage + tid;
+    const uint16_t* sv = stage + (size_t)warp * NYP * 32 + lane;  // [OY][NYP][32]
     uint8_t* r = ring + (size_t)slot * NY * CS + tid;
     int n = 0, all = BAND_INV;
     for (int j = 0; j < NY; j += 5) {
       int v[5];
 #pragma unroll
-      for (int u = 0; u < 5; ++u) v[u] = (j + u < NY) ? (int)sv[(j + u) * CS] : BAND_INV;
+      for (int u = 0; u < 5; ++u) v[u] = (j + u < NY) ? (int)sv[(j + u) * 32] : BAND_INV;
 #pragma unroll
       for (int u = 0; u < 5; ++u) {
         if (j + u >= NY) continue;
@@ -880,7 +883,7 @@ extern "C" int marex_hobday_thresholds_pooled_bins(const uint16_t* bins, int64_t
     for (int oy : {14, 10}) {
       if (oy - 2 * P < 1) continue;
       const size_t cs = (size_t)oy * 32;
-      const size_t need = (((size_t)NY * cs * 2 + 127) / 128) * 128 + (size_t)(64 + 8 + 2) * cs * 2 + (size_t)w * NY * cs +
+      const size_t need = (size_t)((NY + 1) & ~1LL) * cs * 2 + (size_t)(64 + 8 + 2) * cs * 2 + (size_t)w * NY * cs +
                           (((size_t)w * cs + 15) / 16) * 16 + 64;
       if (need <= 227 * 1024) { ring_oy = oy; ring_smem = need; break; }
     }
@@ -909,13 +912,12 @@ extern "C" int marex_hobday_thresholds_pooled_bins(const uint16_t* bins, int64_t
     rp.b = bp;
     rp.b.fail_list = fails;
     rp.NY = (int)NY;
-    rp.use_tma = (nx % 8) == 0 && (bpitch % 8) == 0 && (reinterpret_cast<uintptr_t>(bins) % 16) == 0 &&
-                 tune_get("pool_tma", 1) && NDOY * NY < (1LL << 31);
+    rp.use_tma = (bpitch % 8) == 0 && (reinterpret_cast<uintptr_t>(bins) % 16) == 0 && tune_get("pool_tma", 1) &&
+                 NDOY * NY < (1LL << 31) && ny * nx < (1LL << 31);
     CUtensorMap tmap;
     memset(&tmap, 0, sizeof(tmap));
     if (rp.use_tma) {
-      const int rc = make_tmap_3d(&tmap, bins, CU_TENSOR_MAP_DATA_TYPE_UINT16, 2, NDOY * NY, ny, nx, nx, bpitch, (int)NY,
-                                  ring_oy, 32);
+      const int rc = make_tmap_2d(&tmap, bins, CU_TENSOR_MAP_DATA_TYPE_UINT16, 2, NDOY * NY, ny * nx, bpitch, (int)NY, 32);
       if (rc) return rc;
     }
 #define MAREX_RING(PP, OO)                                                                                       \

@@ -16,34 +16,11 @@ import pytest
 
 from oracle import marex_oracle as mo
 
-W, S, WD, WS, P = 15, 21, 11, 5, 95  # preprocess_data defaults (detect.py:287-313)
+from oracle.tile_check import check_tile as _check_tile  # noqa: E402
 
 
-def check_tile(x_tile, time, anom_tile, thr_tile, ev_tile, mask_tile):
-    """One (T, h, w) tile of the input against the matching tiles of a full-field result: ``anom_tile`` (T_out, h, w),
-    ``thr_tile`` (h, w, 366), ``ev_tile`` (T_out, h, w) bool, ``mask_tile`` (h, w) bool.  Returns the number of
-    threshold values compared."""
-    year, doy = mo.calendar_tables(time)
-    ref_anom, ref_mask, keep = mo.anomaly_shifting_baseline(x_tile, year, doy, W, S)
-    np.testing.assert_array_equal(mask_tile, ref_mask)
-    np.testing.assert_array_equal(np.isnan(anom_tile), np.isnan(ref_anom))
-    scale = float(np.nanmax(np.abs(x_tile))) if np.isfinite(x_tile).any() else 1.0
-    np.testing.assert_allclose(anom_tile, ref_anom, rtol=0, atol=1e-5 * scale, equal_nan=True)
-    # thresholds and events from the SAME anomalies; the interior of the tile pools over tile cells only
-    h, w = anom_tile.shape[1:]
-    half = WS // 2
-    doy_out = doy[keep]
-    a2 = np.ascontiguousarray(anom_tile.reshape(anom_tile.shape[0], -1))
-    thr_ref = mo.hobday_thresholds_approx(a2, doy_out, P / 100.0, WD, WS, (h, w)).reshape(h, w, 366)
-    inner = (slice(half, h - half), slice(half, w - half))
-    got, ref = thr_tile[inner], thr_ref[inner]
-    np.testing.assert_array_equal(np.isnan(got), np.isnan(ref))
-    ok = ~np.isnan(ref)
-    np.testing.assert_array_equal(np.ascontiguousarray(got)[ok].view(np.uint32), np.ascontiguousarray(ref)[ok].view(np.uint32))
-    with np.errstate(invalid="ignore"):
-        ev_ref = anom_tile >= np.moveaxis(thr_ref, -1, 0)[doy_out - 1]
-    np.testing.assert_array_equal(ev_tile[(slice(None),) + inner], ev_ref[(slice(None),) + inner])
-    return int(ok.sum())
+def check_tile(x_tile, time, anom_tile, thr_tile, ev_tile, mask_tile, **kw):
+    return _check_tile(x_tile, time, dict(dat_anomaly=anom_tile, thresholds=thr_tile, extreme_events=ev_tile, mask=mask_tile), **kw)
 
 
 def test_tile_check_is_consistent_with_the_oracle_pipeline():
@@ -68,7 +45,9 @@ def test_tile_check_is_consistent_with_the_oracle_pipeline():
         check_tile(args[0], time, args[2], bad, args[4], args[5])
 
 
-SIZES = [(180, 360)] + ([(720, 1440)] if os.environ.get("MAREX_TEST_FULLSIZE_025") == "1" else [])
+# 1 degree x 40 years (BASELINE configs[0]); a 48-row band of the 0.25 degree grid at full width (the 52 tile columns and
+# the longitude seam of configs[1] at 1/15 of the memory); the whole 0.25 degree field with MAREX_TEST_FULLSIZE_025=1
+SIZES = [(180, 360), (48, 1440)] + ([(720, 1440)] if os.environ.get("MAREX_TEST_FULLSIZE_025") == "1" else [])
 
 
 @pytest.mark.gpu
@@ -106,16 +85,17 @@ def test_full_size_properties(ny, nx):
     freq = n_bytes / (T_out * int(mask.sum()))
     assert 0.03 < freq < 0.08, freq
 
-    # tiles against the oracle
+    # tiles against the oracle; the last one straddles the longitude seam (its interior pools across the wrap)
     compared = 0
     n = 12
-    for y0, x0 in ((ny // 7, nx // 5), (ny // 2 - 3, nx // 2 + 11), (ny - n - 4, nx - n - 9)):
-        sl = (slice(y0, y0 + n), slice(x0, x0 + n))
-        tsl = (slice(None),) + sl
-        compared += check_tile(
-            x[tsl].cpu().numpy(), time, res["dat_anomaly"][tsl].cpu().numpy(), thr.reshape(ny, nx, 366)[sl].cpu().numpy(),
-            res["extreme_events"].reshape(T_out, ny, nx)[tsl].cpu().numpy().astype(bool), mask.reshape(ny, nx)[sl].cpu().numpy(),
-        )  # fmt: skip
+    thr3 = thr.reshape(ny, nx, 366)
+    ev3 = res["extreme_events"].reshape(T_out, ny, nx)
+    for y0, x0 in ((ny // 7, nx // 5), (ny // 2 - 3, nx // 2 + 11), (ny - n - 4, nx - n - 9), (ny // 3, nx - n // 2)):
+        rows = slice(y0, y0 + n)
+        cols = torch.arange(x0, x0 + n, device=x.device) % nx
+        cut = lambda a, lead: a[(slice(None),) * lead + (rows,)].index_select(lead + 1, cols).cpu().numpy()  # noqa: E731
+        compared += check_tile(cut(x, 1), time, cut(res["dat_anomaly"], 1), cut(thr3, 0), cut(ev3, 1).astype(bool),
+                               cut(mask.reshape(ny, nx), 0))  # fmt: skip
     assert compared > 0
 
     if (ny, nx) == (180, 360):  # longitude-roll equivariance (needs a second copy of the field: 1-degree size only)
