@@ -110,15 +110,17 @@ int launch_shift_generic(const float* x, int64_t T, int64_t N, int64_t pitch, co
                          int32_t mode, float* anom, int64_t anom_pitch, uint8_t* mask0, int32_t* nonfinite,
                          const int32_t* cell_list, const int32_t* n_list, int list_ctas, cudaStream_t st);
 
-inline int sm_count() {
-  static int n = 0;
-  if (!n) {
-    int dev = 0;
-    cudaGetDevice(&dev);
+inline int sm_count() {  // of the CURRENT device (cached per device: a process may drive several GPUs)
+  static int cache[64] = {0};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev < 0 || dev >= 64) dev = 0;
+  if (!cache[dev]) {
+    int n = 0;
     cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
-    if (n <= 0) n = 148;
+    cache[dev] = n > 0 ? n : 148;
   }
-  return n;
+  return cache[dev];
 }
 
 }  // namespace marex

@@ -54,6 +54,32 @@ def _device(device=None) -> torch.device:
     return torch.device(device)
 
 
+def _on_device(pick):
+    """Decorator: run the function with the CUDA device of its data made current, so that the library's launches,
+    torch's current stream and every scratch allocation agree with the device the pointers live on (a caller may pass
+    ``device="cuda:1"`` or tensors of a device that is not the current one).  ``pick(*args, **kwargs)`` returns the
+    device (or None for the current device)."""
+    import functools
+
+    def deco(fn):
+        @functools.wraps(fn)
+        def wrapper(*args, **kwargs):
+            dev = pick(*args, **kwargs)
+            dev = _device(dev) if not isinstance(dev, torch.device) else dev
+            if dev.type != "cuda":
+                return fn(*args, **kwargs)
+            with torch.cuda.device(dev):
+                return fn(*args, **kwargs)
+
+        return wrapper
+
+    return deco
+
+
+def _tensor_device(t):
+    return t.device if isinstance(t, torch.Tensor) and t.is_cuda else None
+
+
 def _up(a: np.ndarray, dtype, device) -> torch.Tensor:
     return torch.from_numpy(np.ascontiguousarray(a, dtype=dtype)).to(device)
 
@@ -528,6 +554,7 @@ def _shift_anomaly_call(h: "_Hold", xd: torch.Tensor, cal: Calendar, W: int, S: 
     return None
 
 
+@_on_device(lambda x, time, *a, device=None, **k: device if device is not None else _tensor_device(x))
 def rolling_climatology_arrays(x, time, window_year_baseline: int = 15, smooth_days_baseline: int = 1, device=None):
     """``rolling_climatology`` (S = 1, detect.py:1511-1688) / ``smoothed_rolling_climatology``
     (detect.py:1691-1816) at array level: the per-time-step climatology, NaN for the first
@@ -544,6 +571,7 @@ def rolling_climatology_arrays(x, time, window_year_baseline: int = 15, smooth_d
     return out.reshape((T,) + space)
 
 
+@_on_device(lambda x_dev, *a, **k: _tensor_device(x_dev))
 def compute_normalised_anomaly_arrays(
     x_dev: torch.Tensor,
     cal: Calendar,
@@ -697,6 +725,7 @@ def _warn_threshold_range(vmin: float, vmax: float, upper: float, lower: float, 
         )
 
 
+@_on_device(lambda anom, *a, **k: _tensor_device(anom))
 def identify_extremes_arrays(
     anom: torch.Tensor,
     doy: np.ndarray,
@@ -1150,6 +1179,7 @@ def _preprocess_host_streamed(xh: torch.Tensor, cal: Calendar, gridded: bool, de
 # --------------------------------------------------------------------------------------
 # full pipeline at array level
 # --------------------------------------------------------------------------------------
+@_on_device(lambda x, *a, device=None, **k: device if device is not None else _tensor_device(x))
 def preprocess_arrays(
     x,
     time,

@@ -151,10 +151,44 @@ def _fill_value(meta: Dict[str, Any], dt: np.dtype):
     return fv
 
 
-def read_array(store: str, name: str, out: Optional[np.ndarray] = None, dtype=None) -> np.ndarray:
+def _cf_decoder(attrs: Dict[str, Any], dt: np.dtype):
+    """xarray's ``mask_and_scale=True`` (what ``xr.open_zarr`` applies before marEx sees the data): values equal to
+    ``_FillValue`` / ``missing_value`` become NaN, then ``x * scale_factor + add_offset``.  Returns None when the
+    variable carries none of these attributes."""
+    fills = []
+    for key in ("_FillValue", "missing_value"):
+        v = attrs.get(key)
+        if v is None:
+            continue
+        for item in (v if isinstance(v, (list, tuple)) else [v]):
+            if isinstance(item, str):
+                item = {"NaN": np.nan, "Infinity": np.inf, "-Infinity": -np.inf}.get(item, item)
+            fills.append(np.array(item).astype(dt))
+    scale, offset = attrs.get("scale_factor"), attrs.get("add_offset")
+    if not fills and scale is None and offset is None:
+        return None
+
+    def decode(blk: np.ndarray) -> np.ndarray:
+        bad = np.zeros(blk.shape, dtype=bool)
+        for fv in fills:
+            bad |= np.isnan(blk) if (fv.dtype.kind == "f" and np.isnan(fv)) else (blk == fv)
+        val = blk.astype(np.float64 if dt.itemsize > 4 or scale is not None or offset is not None else np.float32)
+        if scale is not None:
+            val = val * np.float64(scale)
+        if offset is not None:
+            val = val + np.float64(offset)
+        val[bad] = np.nan
+        return val
+
+    return decode
+
+
+def read_array(store: str, name: str, out: Optional[np.ndarray] = None, dtype=None, decode_cf: bool = False) -> np.ndarray:
     """Read a whole array.  ``out`` (e.g. the numpy view of a page-locked torch tensor) receives the data,
     converted to its dtype chunk by chunk, so a float64 store lands as the float32 field the kernels read
-    (``da.astype(np.float32)``, detect.py:600) without a second full-size copy."""
+    (``da.astype(np.float32)``, detect.py:600) without a second full-size copy.  ``decode_cf`` applies the variable's
+    ``_FillValue`` / ``missing_value`` / ``scale_factor`` / ``add_offset`` attributes chunk by chunk (packed int16 SST,
+    land sentinels), as xarray does when it opens the store."""
     meta = array_meta(store, name)
     shape, chunks = tuple(meta["shape"]), tuple(meta["chunks"])
     dt = np.dtype(meta["dtype"])
@@ -163,6 +197,9 @@ def read_array(store: str, name: str, out: Optional[np.ndarray] = None, dtype=No
     if tuple(out.shape) != shape:
         raise ValueError(f"out has shape {out.shape}, the array has {shape}")
     fill = _fill_value(meta, dt)
+    decode = _cf_decoder(meta["attrs"], dt) if decode_cf else None
+    if decode is not None and out.dtype.kind != "f":
+        raise ValueError("decode_cf needs a floating-point destination")
     sep = meta["dimension_separator"]
     grid = [(s + c - 1) // c for s, c in zip(shape, chunks)] if shape else []
     chunk_bytes = int(np.prod(chunks)) * dt.itemsize if shape else dt.itemsize
@@ -170,12 +207,13 @@ def read_array(store: str, name: str, out: Optional[np.ndarray] = None, dtype=No
         sl = tuple(slice(i * c, min((i + 1) * c, s)) for i, c, s in zip(idx, chunks, shape))
         f = os.path.join(meta["path"], sep.join(str(i) for i in idx) if idx else "0")
         if not os.path.exists(f):
-            out[sl] = fill
+            out[sl] = decode(np.full((1,) * len(shape), fill, dtype=dt)) if decode is not None else fill
             continue
         with open(f, "rb") as fh:
             raw = _decode_chunk(fh.read(), meta.get("compressor"), chunk_bytes)
         blk = np.frombuffer(raw, dtype=dt).reshape(chunks if shape else ())
-        out[sl] = blk[tuple(slice(0, s.stop - s.start) for s in sl)]
+        blk = blk[tuple(slice(0, s.stop - s.start) for s in sl)]
+        out[sl] = decode(blk) if decode is not None else blk
     return out
 
 
@@ -221,7 +259,7 @@ def read_field(store: str, var: str, time_name: Optional[str] = None, pinned: bo
             out = np.empty(shape, dtype=np.float32)
     else:
         out = np.empty(shape, dtype=np.float32)
-    read_array(store, var, out=out)
+    read_array(store, var, out=out, decode_cf=True)
     tmeta = array_meta(store, tname)
     tvals = read_array(store, tname)
     units = tmeta["attrs"].get("units")

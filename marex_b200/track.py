@@ -35,6 +35,21 @@ def _device(device=None) -> torch.device:
     return torch.device(device)
 
 
+def _on_self_device(fn):
+    """Run a MaskFiller method with the filler's CUDA device made current (launches, streams and scratch allocations
+    must agree with the device the mask lives on, whatever the caller's current device is)."""
+    import functools
+
+    @functools.wraps(fn)
+    def wrapper(self, *args, **kwargs):
+        if self.device.type != "cuda":
+            return fn(self, *args, **kwargs)
+        with torch.cuda.device(self.device):
+            return fn(self, *args, **kwargs)
+
+    return wrapper
+
+
 def _stream(dev: torch.device):
     return ctypes.c_void_p(torch.cuda.current_stream(dev).cuda_stream) if dev.type == "cuda" else None
 
@@ -262,6 +277,7 @@ class MaskFiller:
         return self._finish(events, bits, count, T, as_numpy)
 
     # ------------------------------------------------------------------ the reference's methods
+    @_on_self_device
     def fill_holes(self, data_bin=None, R_fill: Optional[int] = None, packed: bool = False, from_bits=None):
         """``tracker.fill_holes`` (track.py:1520-1669)."""
         R = self.R_fill if R_fill is None else int(R_fill)
@@ -276,6 +292,7 @@ class MaskFiller:
         slab = self._close_open(self._pad(src, None, T, 2 * R), 2 * R, R)
         return self._extract(self._interior(slab, 2 * R), T, packed, as_numpy)
 
+    @_on_self_device
     def fill_time_gaps(self, data_bin=None, packed: bool = False, from_bits=None):
         """``tracker.fill_time_gaps`` (track.py:1671-1726): temporal closing, then ``fill_holes`` with ``R_fill // 2``."""
         src, T, as_numpy = self._input(data_bin, from_bits)
@@ -286,6 +303,7 @@ class MaskFiller:
             return self._tunpack(x, T, packed, as_numpy)
         return self._time_gaps_gridded(src, None, T, packed, as_numpy)
 
+    @_on_self_device
     def run(self, data_bin=None, packed: bool = False, from_bits=None):
         """``fill_time_gaps(fill_holes(data_bin))`` (track.py:1288-1297) without unpacking in between."""
         src, T, as_numpy = self._input(data_bin, from_bits)

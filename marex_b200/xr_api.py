@@ -95,20 +95,45 @@ def _is_dask(da) -> bool:
 
 
 def _space_dims(dimensions: Dict[str, str]) -> List[str]:
-    return [dimensions[k] for k in ("y", "x") if k in dimensions]
+    """[y,] x.  A mapping without "x" raises the bare ``KeyError: 'x'`` upstream's tests pin
+    (tests/test_error_handling.py:171-181)."""
+    return ([dimensions["y"]] if "y" in dimensions else []) + [dimensions["x"]]
 
 
 def _host_field(da, dimensions) -> np.ndarray:
-    """(time, [y,] x)-ordered numpy view of the DataArray (computes a dask-backed array)."""
+    """(time, [y,] x)-ordered numpy view of the DataArray (computes a dask-backed array in one piece: used by the
+    small sibling functions; ``preprocess_data`` streams, see ``_pinned_field``)."""
     order = [dimensions["time"]] + _space_dims(dimensions)
     return np.asarray(da.transpose(*order).values)
 
 
+def _pinned_field(da, dimensions):
+    """The dask-backed DataArray as a page-locked float32 host tensor (time, [y,] x), filled one TIME CHUNK at a time:
+    every dask block is computed, cast (``da.astype(np.float32)``, detect.py:600) and copied straight into the buffer
+    the host->device stream of ``preprocess_arrays`` reads from, so a 60 GB field is never materialised as a second,
+    pageable numpy array."""
+    import torch
+
+    tdim = dimensions["time"]
+    dat = da.transpose(tdim, *_space_dims(dimensions))
+    shape = tuple(int(n) for n in dat.shape)
+    buf = torch.empty(shape, dtype=torch.float32, pin_memory=torch.cuda.is_available())
+    view = buf.numpy()
+    t_chunks = dat.chunks[0] if dat.chunks is not None else (shape[0],)
+    t0 = 0
+    for n in t_chunks:
+        view[t0 : t0 + n] = np.asarray(dat.isel({tdim: slice(t0, t0 + n)}).values, dtype=np.float32)
+        t0 += n
+    return buf
+
+
 def _chunked(obj, chunks):
-    try:
-        return obj.chunk(chunks)
-    except Exception:  # dask not installed: hand back numpy-backed variables
-        return obj
+    """``ds.chunk(...)`` of detect.py:786-792: ``marEx.tracker`` rejects numpy-backed input (track.py:411-418), so a
+    failure to produce dask-backed variables is an error, not something to paper over."""
+    out = obj.chunk(chunks)
+    if getattr(out, "chunks", None) is None:
+        raise RuntimeError("DataArray.chunk() returned a numpy-backed variable: dask is required for the Dataset marEx.tracker consumes")
+    return out
 
 
 def preprocess_data(
@@ -170,7 +195,7 @@ def preprocess_data(
     sdims = _space_dims(dimensions)
     gridded = "y" in dimensions
     res = _d.preprocess_arrays(
-        _host_field(da, dimensions), da[coordinates["time"]].values, method_anomaly, method_extreme,
+        _pinned_field(da, dimensions), da[coordinates["time"]].values, method_anomaly, method_extreme,
         threshold_percentile, window_year_baseline, smooth_days_baseline, window_days_hobday, window_spatial_hobday,
         std_normalise, detrend_orders, force_zero_mean, reference_period, method_percentile, precision, max_anomaly,
         device=device, output="numpy", gridded=gridded,

@@ -828,3 +828,31 @@ def test_model_calendar_noleap(kw):
                                          95, kw.get("window_days_hobday", 11), None, "approximate", 0.01, 5.0)  # fmt: skip
     _ulp_equal(np.asarray(got["thresholds"]), thr)
     np.testing.assert_array_equal(np.asarray(got["extreme_events"]), ev)
+
+
+# ---------------------------------------------------------------- device argument
+def test_non_current_device_is_honoured():
+    """``device="cuda:1"`` (or tensors living on cuda:1) while cuda:0 is current: launches, streams and scratch buffers
+    must follow the data.  Needs two GPUs."""
+    mb = _cuda()
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two CUDA devices")
+    from oracle import track_oracle as to
+
+    x, time = _field(T1="2000-01-01", ny=6, nx=36, seed=8)
+    kw = dict(window_year_baseline=4, smooth_days_baseline=9, window_days_hobday=5)
+    torch.cuda.set_device(0)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        ref = mb.preprocess_arrays(x, time, device="cuda:0", **kw)
+        got = mb.preprocess_arrays(x, time, device="cuda:1", **kw)                       # host array, explicit device
+        got_t = mb.preprocess_arrays(torch.from_numpy(x).to("cuda:1"), time, output="torch", **kw)  # tensor on cuda:1
+    assert torch.cuda.current_device() == 0
+    assert got_t["dat_anomaly"].device == torch.device("cuda:1")
+    for k in ("dat_anomaly", "thresholds"):
+        _ulp_equal(got[k], ref[k])
+        _ulp_equal(got_t[k].cpu().numpy(), ref[k])
+    np.testing.assert_array_equal(got["extreme_events"], ref["extreme_events"])
+    ev, ocean = ref["extreme_events"].astype(bool), ref["mask"].astype(bool)
+    filled = mb.MaskFiller(ocean, 2, 2, device="cuda:1").run(ev)
+    np.testing.assert_array_equal(filled, to.stage1(ev, ocean, 2, 2))

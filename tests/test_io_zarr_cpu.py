@@ -113,3 +113,34 @@ def test_reads_the_reference_fixture_like_the_golden_subset(golden_dir):
     lat, lon = zio.read_array(store, "lat"), zio.read_array(store, "lon")
     np.testing.assert_allclose(lat, 35.125 + 0.25 * np.arange(20))
     np.testing.assert_allclose(lon, -39.875 + 0.25 * np.arange(40))
+
+
+def test_cf_mask_and_scale_is_applied_like_xarray(tmp_path):
+    """A packed, masked variable (int16 SST with scale_factor / add_offset and a land sentinel; a float variable with a
+    1e20 missing_value): ``read_field`` decodes it as ``xr.open_zarr(mask_and_scale=True)`` would, so land is NaN and
+    not a finite ocean value (the reference reads its input through xarray)."""
+    store = str(tmp_path / "packed.zarr")
+    os.makedirs(store)
+    json.dump({"zarr_format": 2}, open(os.path.join(store, ".zgroup"), "w"))
+    T, ny, nx = 7, 5, 9
+    rng = np.random.default_rng(0)
+    sst = rng.uniform(-1.8, 30, (T, ny, nx))
+    scale, offset, fv = 0.01, 15.0, -32768
+    packed = np.round((sst - offset) / scale).astype(np.int16)
+    packed[:, 1, 2] = fv  # land
+    zio.write_array(store, "sst", packed, (3, ny, nx), ["time", "lat", "lon"],
+                        {"scale_factor": scale, "add_offset": offset, "_FillValue": fv})  # fmt: skip
+    flt = sst.astype(np.float32)
+    flt[:, 3, 4] = np.float32(1e20)
+    zio.write_array(store, "sst_f", flt, (4, ny, nx), ["time", "lat", "lon"], {"missing_value": 1e20})
+    zio.write_array(store, "time", np.arange(T, dtype=np.int64), (T,), ["time"], {"units": "days since 2000-01-01"})
+    x, time, dims = zio.read_field(store, "sst", pinned=False)
+    assert x.dtype == np.float32 and dims == ["time", "lat", "lon"] and time[0] == np.datetime64("2000-01-01")
+    want = (packed.astype(np.float64) * scale + offset).astype(np.float32)
+    want[:, 1, 2] = np.nan
+    np.testing.assert_array_equal(np.isnan(x), np.isnan(want))
+    np.testing.assert_array_equal(x[~np.isnan(want)], want[~np.isnan(want)])
+    xf, _, _ = zio.read_field(store, "sst_f", pinned=False)
+    assert np.isnan(xf[:, 3, 4]).all() and np.isfinite(np.delete(xf.reshape(T, -1), 3 * nx + 4, axis=1)).all()
+    raw = zio.read_array(store, "sst")  # the raw stored values stay available
+    assert raw.dtype == np.int16 and raw[0, 1, 2] == fv
