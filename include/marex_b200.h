@@ -189,11 +189,13 @@ int marex_hobday_thresholds_pooled_bins(const uint16_t* bins, int64_t NY, int64_
 /* Exact Hobday thresholds: np.nanpercentile (float32 'linear') over the +-w/2 doy window
  * (detect.py:1921-1956).  thr[366, N] doy-major, NaN where the window holds no valid sample.
  * max_doy_rows = the largest number of rows of any single day of year (doy_ptr differences);
- * when the window (w * max_doy_rows samples per gridpoint) fits shared memory it is kept there. */
+ * when the window (w * max_doy_rows samples per gridpoint) fits shared memory it is kept there.
+ * `work` (optional device scratch of 2 * N float32): the per-gridpoint value range is then taken in a separate
+ * full-occupancy pass instead of inside the percentile kernel. */
 int marex_hobday_thresholds_exact_f32(const float* anom, int64_t T, int64_t N, int64_t pitch,
                                       const int32_t* doy_ptr, const int32_t* doy_rows,
                                       int32_t max_window_rows, int32_t max_doy_rows, int32_t w,
-                                      float percentile, float* thr, void* stream);
+                                      float percentile, float* thr, float* work, void* stream);
 
 /* Global (constant in time) thresholds, approximate: per-cell histogram with float64 edges
  * (last bin right-closed), pdf/cdf in float64 in the reference's order

@@ -29,7 +29,7 @@ _SIGNATURES = {
     "marex_hobday_thresholds_hist": ([_P, c_int64, c_int64, c_int64, c_int64, _P, _P, c_int32, _P, c_int32, c_int32, c_int32, c_double, _P, c_float, _P, _P, _P], ctypes.c_int),
     "marex_hobday_pooled_workspace_bytes": ([c_int64, c_int64], c_int64),
     "marex_hobday_thresholds_pooled_bins": ([_P, c_int64, c_int64, c_int64, c_int64, _P, _P, _P, c_int32, c_int32, c_int32, c_double, _P, c_float, _P, _P, _P, c_int64, _P], ctypes.c_int),
-    "marex_hobday_thresholds_exact_f32": ([_P, c_int64, c_int64, c_int64, _P, _P, c_int32, c_int32, c_int32, c_float, _P, _P], ctypes.c_int),
+    "marex_hobday_thresholds_exact_f32": ([_P, c_int64, c_int64, c_int64, _P, _P, c_int32, c_int32, c_int32, c_float, _P, _P, _P], ctypes.c_int),
     "marex_global_threshold_hist_f64": ([_P, c_int64, c_int64, c_int64, _P, _P, c_int32, c_double, c_double, _P, _P, _P], ctypes.c_int),
     "marex_global_threshold_hist_fast_f64": ([_P, c_int64, c_int64, c_int64, _P, _P, c_float, _P, c_int32, c_double, c_double, _P, _P, _P, _P], ctypes.c_int),
     "marex_global_threshold_exact_f64": ([_P, c_int64, c_int64, c_int64, c_double, _P, _P], ctypes.c_int),

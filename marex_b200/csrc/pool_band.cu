@@ -405,9 +405,12 @@ struct RingParams {
   BandParams b;      // bins = day-of-year-major array, pitch = its row pitch; doy_ptr / doy_rows unused
   int NY;            // slots (years) per day of year
   int use_tma;
+  int dbg;           // debug knob pool_dbg (bit 0: no drain before giving up; bit 1: land the staged day before a re-centre)
+  volatile int* dbg_ptr;  // debug: page-locked HOST buffer, 8 ints per tile (progress markers that survive a device fault)
 };
 
 constexpr int RING_ABOVE = 254, RING_INVALID = 255, RING_ALL_INVALID = 255;
+constexpr int RING_BW = 40;  // staged columns per own row: the 32 own columns inside a box that starts on a 16-byte boundary
 
 template <int P, int K, int OY>
 __global__ void __launch_bounds__(OY * 32, 1) hobday_ring_kernel(const __grid_constant__ CUtensorMap tmap,
@@ -419,17 +422,18 @@ __global__ void __launch_bounds__(OY * 32, 1) hobday_ring_kernel(const __grid_co
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, tid = threadIdx.x;
   const int NY = rp.NY, w = p.w, half = p.w / 2;
   // carve-up: TMA stage first (1024-byte aligned), then counters, then the ring
-  const int NYP = (NY + 1) & ~1;  // slots per own row of the stage: every row starts on a 128-byte boundary (TMA)
-  uint16_t* const stage = reinterpret_cast<uint16_t*>(smem_ring);             // [OY][NYP][32]
-  const size_t stage_bytes = (size_t)NYP * CS * 2;
-  uint16_t* const L0 = reinterpret_cast<uint16_t*>(smem_ring + stage_bytes);  // [K][CS]; the coarse pass reuses it as [nblk][CS]
+  const int NYP = (NY + 7) & ~7;  // slots per own row of the stage: every own row (NYP x 80 bytes) starts on a 128-byte boundary (TMA)
+  // carve-up: mbarrier + flags in the first 128 bytes, then the TMA stage (128-byte aligned), counters, ring
+  uint64_t* const bar = reinterpret_cast<uint64_t*>(smem_ring);
+  int* const s_misc = reinterpret_cast<int*>(smem_ring + 16);                 // [0] violation flag, [1] min blk, [2] max blk
+  uint16_t* const stage = reinterpret_cast<uint16_t*>(smem_ring + 128);       // [OY][NYP][RING_BW]
+  const size_t stage_bytes = (size_t)NYP * OY * RING_BW * 2;
+  uint16_t* const L0 = reinterpret_cast<uint16_t*>(smem_ring + 128 + stage_bytes);  // [K][CS]; the coarse pass reuses it as [nblk][CS]
   uint16_t* const L1 = L0 + K * CS;                                           // [KB][CS]
   uint16_t* const NTr = L1 + KB * CS;                                         // [CS] valid samples in the own window
   uint16_t* const TBr = NTr + CS;                                             // [CS] of which >= Blo
   uint8_t* const ring = reinterpret_cast<uint8_t*>(TBr + CS);                 // [w][NY][CS] codes of the samples that matter
   uint8_t* const rlen = ring + (size_t)w * NY * CS;                           // [w][CS] list lengths (255: every sample invalid)
-  uint64_t* const bar = reinterpret_cast<uint64_t*>(rlen + (((size_t)w * CS + 15) / 16) * 16);
-  int* const s_misc = reinterpret_cast<int*>(bar + 1);                        // [0] violation flag, [1] min blk, [2] max blk
 
   const int nb = p.nb;
   const int nblk = (nb + 7) >> 3;
@@ -442,7 +446,11 @@ __global__ void __launch_bounds__(OY * 32, 1) hobday_ring_kernel(const __grid_co
   if (gx < 0) gx += nx;
   const bool own_valid = gy >= 0 && gy < ny;
   const uint16_t* const col = p.bins + (own_valid ? gy * nx + gx : 0);
-  const bool tma = rp.use_tma && x0 - P >= 0 && x0 - P + 32 <= nx;  // the box does not straddle the longitude seam
+  // TMA boxes start on a 16-byte boundary of global memory (8 codes): the box of an own row is the RING_BW columns from
+  // xs0 = (x0 - P) rounded down to a multiple of 8, and must not straddle the longitude seam
+  const int64_t xs0 = (x0 - P) & ~(int64_t)7;
+  const bool tma = rp.use_tma && x0 - P >= 0 && xs0 + RING_BW <= nx;
+  const int xoff = tma ? (int)(x0 - P - xs0) : 0;  // column of lane 0 inside a staged row
   uint16_t* const myL0 = L0 + tid;
   uint16_t* const myL1 = L1 + tid;
   int NT = 0, TB = 0, Blo = 0;
@@ -597,9 +605,9 @@ __global__ void __launch_bounds__(OY * 32, 1) hobday_ring_kernel(const __grid_co
       if (tid == 0) {  // one 2-D box {32 columns, NY slots} per own row of the grid, all on the same mbarrier
         fence_proxy_async();
         const int oy0 = max(0, (int)(P - y0)), oy1 = min(OY, (int)(ny + P - y0));
-        mbar_expect_tx(bar, (uint32_t)(oy1 - oy0) * NY * 64u);
+        mbar_expect_tx(bar, (uint32_t)(oy1 - oy0) * NY * (RING_BW * 2u));
         for (int oy = oy0; oy < oy1; ++oy)
-          tma_load_2d(stage + (size_t)oy * NYP * 32, &tmap, (int)((y0 - P + oy) * nx + x0 - P), dd * NY, bar);
+          tma_load_2d(stage + (size_t)oy * NYP * RING_BW, &tmap, (int)((y0 - P + oy) * nx + xs0), dd * NY, bar);
       }
     } else if (own_valid) {
       const uint16_t* src = col + (int64_t)dd * NY * p.pitch;
@@ -609,28 +617,30 @@ __global__ void __launch_bounds__(OY * 32, 1) hobday_ring_kernel(const __grid_co
         for (int u = 0; u < 5; ++u) v[u] = (j + u < NY) ? src[(int64_t)(j + u) * p.pitch] : (uint16_t)0;
 #pragma unroll
         for (int u = 0; u < 5; ++u)
-          if (j + u < NY) stage[(warp * NYP + j + u) * 32 + lane] = v[u];
+          if (j + u < NY) stage[(warp * NYP + j + u) * RING_BW + lane] = v[u];
       }
     }
   };
 
   // ---- advance the own window by one day of year: the day that entered w steps ago leaves, the staged day enters ----
+  bool landed = false;  // the staged day has already been waited for
   auto advance = [&](int step) {
-    if (tma) {
+    if (tma && !landed) {
       mbar_wait(bar, phase);
       phase ^= 1u;
     }
+    landed = false;
     if (!own_valid) return;
     const int slot = slot_of(step + half);
     if (!dead) replay(slot, -1);  // a dead window holds invalid samples only: nothing to take out
     // entering samples: classify, keep the ones that matter
-    const uint16_t* sv = stage + (size_t)warp * NYP * 32 + lane;  // [OY][NYP][32]
+    const uint16_t* sv = stage + (size_t)warp * NYP * RING_BW + xoff + lane;  // [OY][NYP][RING_BW]
     uint8_t* r = ring + (size_t)slot * NY * CS + tid;
     int n = 0, all = BAND_INV;
     for (int j = 0; j < NY; j += 5) {
       int v[5];
 #pragma unroll
-      for (int u = 0; u < 5; ++u) v[u] = (j + u < NY) ? (int)sv[(j + u) * 32] : BAND_INV;
+      for (int u = 0; u < 5; ++u) v[u] = (j + u < NY) ? (int)sv[(j + u) * RING_BW] : BAND_INV;
 #pragma unroll
       for (int u = 0; u < 5; ++u) {
         if (j + u >= NY) continue;
@@ -732,25 +742,42 @@ __global__ void __launch_bounds__(OY * 32, 1) hobday_ring_kernel(const __grid_co
   };
   // a TMA load still in flight must land before the CTA exits
   auto drain = [&](bool pending) {
-    if (tma && pending) mbar_wait(bar, phase);
+    if (tma && pending && !landed && !(rp.dbg & 1)) mbar_wait(bar, phase);
   };
 
-  if (!rebuild(0)) { give_up(); return; }
+  volatile int* const mark = rp.dbg_ptr ? rp.dbg_ptr + 8 * (blockIdx.y * gridDim.x + blockIdx.x) : nullptr;
+  auto note = [&](int k, int v) {
+    if (mark && tid == 0) { mark[k] = v; __threadfence_system(); }
+  };
+  note(0, 1 + (tma ? 1 : 0));
+  if (!rebuild(0)) { note(1, -1); give_up(); return; }
+  note(1, 1);
   issue(1);
+  note(2, 1);
   for (int d = 0; d < NDOY; ++d) {
     if (d > 0) {
+      note(3, d);
       advance(d);
+      note(4, d);
       __syncthreads();                 // every thread is done with the stage and the counters are up to date
       if (d + 1 < NDOY) issue(d + 1);  // in flight while the queries run
     }
     if (warp < TY) query(d);
     __syncthreads();
+    note(5, d);
     if (s_misc[0]) {  // a threshold left the band: re-centre the band on the current window and redo the day
       __syncthreads();
-      if (!rebuild(d)) { drain(d + 1 < NDOY); give_up(); return; }
+      if ((rp.dbg & 2) && tma && d + 1 < NDOY && !landed) {
+        mbar_wait(bar, phase);
+        phase ^= 1u;
+        landed = true;
+      }
+      note(6, d);
+      if (!rebuild(d)) { note(7, -d - 1); drain(d + 1 < NDOY); give_up(); return; }
       if (warp < TY) query(d);
       __syncthreads();
-      if (s_misc[0]) { drain(d + 1 < NDOY); give_up(); return; }
+      if (s_misc[0]) { note(7, -1000 - d); drain(d + 1 < NDOY); give_up(); return; }
+      note(7, d);
     }
   }
   if (warp < TY && p.stats) {
@@ -883,8 +910,8 @@ extern "C" int marex_hobday_thresholds_pooled_bins(const uint16_t* bins, int64_t
     for (int oy : {14, 10}) {
       if (oy - 2 * P < 1) continue;
       const size_t cs = (size_t)oy * 32;
-      const size_t need = (size_t)((NY + 1) & ~1LL) * cs * 2 + (size_t)(64 + 8 + 2) * cs * 2 + (size_t)w * NY * cs +
-                          (((size_t)w * cs + 15) / 16) * 16 + 64;
+      const size_t need = (size_t)((NY + 7) & ~7LL) * oy * RING_BW * 2 + (size_t)(64 + 8 + 2) * cs * 2 + (size_t)w * NY * cs +
+                          (((size_t)w * cs + 15) / 16) * 16 + 128;
       if (need <= 227 * 1024) { ring_oy = oy; ring_smem = need; break; }
     }
   }
@@ -912,12 +939,14 @@ extern "C" int marex_hobday_thresholds_pooled_bins(const uint16_t* bins, int64_t
     rp.b = bp;
     rp.b.fail_list = fails;
     rp.NY = (int)NY;
-    rp.use_tma = (bpitch % 8) == 0 && (reinterpret_cast<uintptr_t>(bins) % 16) == 0 && tune_get("pool_tma", 1) &&
-                 NDOY * NY < (1LL << 31) && ny * nx < (1LL << 31);
+    rp.dbg = (int)tune_get("pool_dbg", 0);
+    rp.dbg_ptr = reinterpret_cast<volatile int*>((uintptr_t)tune_get("pool_dbg_ptr", 0));
+    rp.use_tma = (nx % 8) == 0 && (bpitch % 8) == 0 && (reinterpret_cast<uintptr_t>(bins) % 16) == 0 &&
+                 tune_get("pool_tma", 1) && NDOY * NY < (1LL << 31) && ny * nx < (1LL << 31);
     CUtensorMap tmap;
     memset(&tmap, 0, sizeof(tmap));
     if (rp.use_tma) {
-      const int rc = make_tmap_2d(&tmap, bins, CU_TENSOR_MAP_DATA_TYPE_UINT16, 2, NDOY * NY, ny * nx, bpitch, (int)NY, 32);
+      const int rc = make_tmap_2d(&tmap, bins, CU_TENSOR_MAP_DATA_TYPE_UINT16, 2, NDOY * NY, ny * nx, bpitch, (int)NY, RING_BW);
       if (rc) return rc;
     }
 #define MAREX_RING(PP, OO)                                                                                       \

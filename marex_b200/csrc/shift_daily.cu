@@ -188,6 +188,8 @@ __global__ void __launch_bounds__(512) shift_daily_kernel(const __grid_constant_
   float* ringp = ring + (size_t)rbase * CW + lane * V;  // this thread's first day in ring slot 0
   float* const outc = p.out + c;                        // column of these gridpoints (dead lanes never store)
   const uint32_t leave_bit = 1u << (W - 1);
+  const int64_t bin_stride = DIG ? (int64_t)p.NY * p.bins_pitch : 0;  // one day of year further
+  uint16_t* const bin0 = DIG ? p.bins + (int64_t)(d0 + rbase) * bin_stride + c : nullptr;
 
   for (int i = 0; i < p.n_years; ++i) {
     const int base = ybase[i], ylen = ybase[i + 1] - base;
@@ -204,12 +206,7 @@ __global__ void __launch_bounds__(512) shift_daily_kernel(const __grid_constant_
       }
     }
     float* outp = outc + (int64_t)(t0 - p.out_off) * p.out_pitch;  // only dereferenced for target years
-    uint16_t* binp = nullptr;
-    int64_t bin_stride = 0;
-    if (DIG) {
-      bin_stride = (int64_t)p.NY * p.bins_pitch;
-      binp = p.bins + ((int64_t)(d0 + rbase) * p.NY + (i - W)) * p.bins_pitch + c;
-    }
+    uint16_t* const binp = DIG ? bin0 + (int64_t)(i - W) * p.bins_pitch : nullptr;  // slot (first day, output year i - W)
 
     // ring turnover of one day: year i - W leaves (if it had a value), year i enters (if it has one)
     auto turnover = [&](int r, const Pack<float, V>& s, bool valid_now) {

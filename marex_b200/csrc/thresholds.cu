@@ -551,7 +551,8 @@ template <typename CT>
 __global__ void __launch_bounds__(32) hobday_exact_win_kernel(const float* __restrict__ anom, int64_t T, int64_t N,
                                                               int64_t pitch, const int32_t* __restrict__ doy_ptr,
                                                               const int32_t* __restrict__ doy_rows, int w, int rowcap,
-                                                              float qf, float* __restrict__ thr) {
+                                                              float qf, float* __restrict__ thr,
+                                                              const float* __restrict__ minmax) {
   extern __shared__ unsigned char smem_raw[];
   CT* hist = reinterpret_cast<CT*>(smem_raw);                                     // [NBX][32]
   float* win = reinterpret_cast<float*>(smem_raw + (size_t)NBX * 32 * sizeof(CT)); // [w][rowcap][32]
@@ -562,12 +563,17 @@ __global__ void __launch_bounds__(32) hobday_exact_win_kernel(const float* __res
   const float* col = anom + (live ? c : N - 1);
   for (int b = 0; b < NBX; ++b) hist[b * 32 + lane] = 0;
   float mn = CUDART_INF_F, mx = -CUDART_INF_F;
-  for (int64_t t0 = 0; t0 < T; t0 += 8) {
-    float v[8];
+  if (minmax) {  // finite range of the series, from col_minmax_kernel (this kernel runs 4 warps per SM: a poor place for a full pass)
+    mn = minmax[live ? c : N - 1];
+    mx = minmax[N + (live ? c : N - 1)];
+  } else {
+    for (int64_t t0 = 0; t0 < T; t0 += 8) {
+      float v[8];
 #pragma unroll
-    for (int u = 0; u < 8; ++u) v[u] = (t0 + u < T) ? __ldg(col + (t0 + u) * pitch) : CUDART_NAN_F;
+      for (int u = 0; u < 8; ++u) v[u] = (t0 + u < T) ? __ldg(col + (t0 + u) * pitch) : CUDART_NAN_F;
 #pragma unroll
-    for (int u = 0; u < 8; ++u) if (is_finite_f(v[u])) { mn = fminf(mn, v[u]); mx = fmaxf(mx, v[u]); }
+      for (int u = 0; u < 8; ++u) if (is_finite_f(v[u])) { mn = fminf(mn, v[u]); mx = fmaxf(mx, v[u]); }
+    }
   }
   BinMap bm;
   bm.mn = (mn <= mx) ? mn : 0.f;
@@ -927,6 +933,31 @@ __global__ void __launch_bounds__(256) global_hist_fast_kernel(const float* __re
   }
 }
 
+// Finite minimum / maximum of every gridpoint's series: mm[c] = min, mm[N + c] = max (+inf / -inf when no sample is finite).
+// Thread = gridpoint, rows split over blockIdx.y and merged with float atomics.
+__global__ void __launch_bounds__(256) col_minmax_kernel(const float* __restrict__ a, int64_t T, int64_t N, int64_t pitch,
+                                                         float* __restrict__ mm, int rows_per_block) {
+  const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= N) return;
+  const int64_t t0 = (int64_t)blockIdx.y * rows_per_block, t1 = min(T, t0 + rows_per_block);
+  float mn = CUDART_INF_F, mx = -CUDART_INF_F;
+  for (int64_t t = t0; t < t1; t += 8) {
+    float v[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) v[u] = (t + u < t1) ? ld_stream(a + (t + u) * pitch + c) : CUDART_NAN_F;
+#pragma unroll
+    for (int u = 0; u < 8; ++u) if (is_finite_f(v[u])) { mn = fminf(mn, v[u]); mx = fmaxf(mx, v[u]); }
+  }
+  if (mn <= mx) {
+    atomic_min_f(&mm[c], mn);
+    atomic_max_f(&mm[N + c], mx);
+  }
+}
+__global__ void init_minmax_kernel(float* mm, int64_t N) {
+  const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (c < N) { mm[c] = CUDART_INF_F; mm[N + c] = -CUDART_INF_F; }
+}
+
 template <typename F>
 __global__ void init_stats_kernel(F* stats) {
   stats[0] = (F)CUDART_INF;
@@ -1032,7 +1063,8 @@ extern "C" int marex_hobday_thresholds_hist(const uint16_t* bins, int64_t T, int
   }
   const long long max_count = (long long)max_window_rows * ws * ws;
   const bool wide = max_count > 65535;
-  const size_t smem = (size_t)nb * 32 * (wide ? 4 : 2);
+  const bool narrow = max_count <= 255 && !tune_get("hist_u16", 0);  // byte counters: half the shared memory, twice the warps per SM
+  const size_t smem = (size_t)nb * 32 * (wide ? 4 : (narrow ? 1 : 2));
   MAREX_REQUIRE(smem <= 220 * 1024, "histogram does not fit shared memory");
   dim3 grid((unsigned)((nx + 31) / 32), (unsigned)ny);
 #define MAREX_HH(CT, P)                                                                                           \
@@ -1042,8 +1074,8 @@ extern "C" int marex_hobday_thresholds_hist(const uint16_t* bins, int64_t T, int
     hobday_hist_kernel<CT, P><<<grid, 32, smem, st>>>(bins, ny, nx, pitch, doy_ptr, doy_rows, centers, nb, w, ws, \
                                                       q, anom_row0, lower_bound, thr, stats);                     \
   } while (0)
-  if (ws > 1) { if (wide) MAREX_HH(uint32_t, true); else MAREX_HH(uint16_t, true); }
-  else        { if (wide) MAREX_HH(uint32_t, false); else MAREX_HH(uint16_t, false); }
+  if (ws > 1) { if (wide) MAREX_HH(uint32_t, true); else if (narrow) MAREX_HH(uint8_t, true); else MAREX_HH(uint16_t, true); }
+  else        { if (wide) MAREX_HH(uint32_t, false); else if (narrow) MAREX_HH(uint8_t, false); else MAREX_HH(uint16_t, false); }
 #undef MAREX_HH
   MAREX_LAUNCH_CHECK("hobday_hist_kernel");
   return MAREX_OK;
@@ -1052,7 +1084,7 @@ extern "C" int marex_hobday_thresholds_hist(const uint16_t* bins, int64_t T, int
 extern "C" int marex_hobday_thresholds_exact_f32(const float* anom, int64_t T, int64_t N, int64_t pitch,
                                                  const int32_t* doy_ptr, const int32_t* doy_rows,
                                                  int32_t max_window_rows, int32_t max_doy_rows, int32_t w,
-                                                 float percentile, float* thr, void* stream) {
+                                                 float percentile, float* thr, float* work, void* stream) {
   MAREX_REQUIRE(anom && doy_ptr && doy_rows && thr, "null pointer");
   MAREX_REQUIRE(T > 0 && N > 0 && pitch >= N, "bad shape");
   MAREX_REQUIRE(w >= 1 && w <= 365 && (w & 1), "window_days_hobday must be odd and in 1..365");
@@ -1067,8 +1099,20 @@ extern "C" int marex_hobday_thresholds_exact_f32(const float* anom, int64_t T, i
   if (!wide && max_doy_rows > 0 && smem_win <= 200 * 1024 && !tune_get("exact_v1", 0)) {
     int rc = set_smem(hobday_exact_win_kernel<uint16_t>, smem_win);
     if (rc) return rc;
+    if (work) {  // per-gridpoint finite range at full occupancy (optional scratch of 2 * N floats)
+      init_minmax_kernel<<<(unsigned)((N + 255) / 256), 256, 0, st>>>(work, N);
+      MAREX_LAUNCH_CHECK("init_minmax_kernel");
+      const int64_t bx = (N + 255) / 256;
+      int64_t by = (16LL * sm_count() + bx - 1) / bx;
+      by = by < 1 ? 1 : (by > T ? T : by);
+      if (by > 65535) by = 65535;
+      const int rpb = (int)((T + by - 1) / by);
+      by = (T + rpb - 1) / rpb;
+      col_minmax_kernel<<<dim3((unsigned)bx, (unsigned)by), 256, 0, st>>>(anom, T, N, pitch, work, rpb);
+      MAREX_LAUNCH_CHECK("col_minmax_kernel");
+    }
     hobday_exact_win_kernel<uint16_t><<<grid, 32, smem_win, st>>>(anom, T, N, pitch, doy_ptr, doy_rows, w, rowcap_day,
-                                                                  qf, thr);
+                                                                  qf, thr, work);
     MAREX_LAUNCH_CHECK("hobday_exact_win_kernel");
     return MAREX_OK;
   }

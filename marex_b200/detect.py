@@ -784,9 +784,11 @@ def identify_extremes_arrays(
             ptr, rows = doy_csr(doy)
             mwr = max_window_rows(ptr, w)
             ptr_d, rows_d = _up(ptr, np.int32, dev), _up(rows, np.int32, dev)
+            mm = torch.empty(2 * N, dtype=torch.float32, device=dev)
+            h.append(mm)
             _lib.call(
                 "marex_hobday_thresholds_exact_f32", _p(anom), T, N, N, _p(ptr_d), _p(rows_d), mwr,
-                int(np.diff(ptr).max()), w, float(threshold_percentile), _p(thr), st,
+                int(np.diff(ptr).max()), w, float(threshold_percentile), _p(thr), _p(mm), st,
             )  # fmt: skip
             out["thresholds"] = thr if not gridded else thr.reshape((NDOY,) + tuple(grid))
             out["thresholds_layout"] = "doy_first"

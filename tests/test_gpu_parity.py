@@ -856,3 +856,49 @@ def test_non_current_device_is_honoured():
     ev, ocean = ref["extreme_events"].astype(bool), ref["mask"].astype(bool)
     filled = mb.MaskFiller(ocean, 2, 2, device="cuda:1").run(ev)
     np.testing.assert_array_equal(filled, to.stage1(ev, ocean, 2, 2))
+
+
+def test_ring_kernel_tma_path_runs_and_is_bit_exact(tune):
+    """The TMA-staged ring kernel on grids whose rows are TMA-eligible (nx % 8 == 0): homogeneous variance with a seasonal
+    drift, so tiles keep their band (with re-centres) instead of falling back.  The kernel's progress markers (a
+    page-locked host buffer, debug knob pool_dbg_ptr) prove that TMA tiles ran through all 366 days."""
+    mb = _cuda()
+    rng = np.random.default_rng(5)
+    for ny, nx, T1, w in ((24, 72, "1998-01-01", 5), (13, 360, "2001-01-01", 11)):
+        time = np.arange(np.datetime64("1990-01-01"), np.datetime64(T1))
+        year, doy = mo.calendar_tables(time)
+        season = 0.5 + 0.25 * np.cos(2 * np.pi * doy / 366.0)
+        a = (rng.standard_normal((len(time), ny, nx)) * season[:, None, None]).astype(np.float32)
+        f = a.reshape(len(time), -1)
+        f[:, 5] = np.nan
+        f[:, nx * 3 + 40] = np.nan
+        f[::4, nx * 6 + 50] = 9.0
+        dbg = torch.zeros(8 * 256, dtype=torch.int32).pin_memory()
+        tune(pool_dbg_ptr=dbg.data_ptr())
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            res = mb.identify_extremes_arrays(torch.from_numpy(f.copy()).cuda(), doy, (ny, nx), "hobday_extreme", 95, w, 5, year=year)
+            torch.cuda.synchronize()
+        tune(pool_dbg_ptr=None)
+        m = dbg.view(-1, 8).numpy()
+        ran = (m[:, 0] == 2) & (m[:, 1] == 1) & (m[:, 5] == 365)
+        assert ran.any(), m[:16]
+        ref = mo.hobday_thresholds_approx(f, doy, 0.95, w, 5, (ny, nx))
+        _ulp_equal(res["thresholds"].cpu().numpy().reshape(-1, 366), ref)
+        np.testing.assert_array_equal(res["extreme_events"].cpu().numpy(), mo.compare_hobday(f, doy, np.ascontiguousarray(ref.T)))
+
+
+def test_synthetic_field_numpy_twin_matches_the_cuda_generator():
+    """bench.py's CPU arms cut their tiles from the SAME synthetic field as the GPU arm through a numpy twin of the
+    counter-based generator: identical land cells, values equal up to the float32 fast-math intrinsics of the kernel."""
+    _cuda()
+    from marex_b200 import synthetic
+
+    time = synthetic.daily_time_axis("1991-01-01", "1993-03-01")
+    ny, nx = 48, 80
+    dev = synthetic.synth_sst(time, (ny, nx), rows=(8, 40), seed=2).cpu().numpy()
+    cells = (np.arange(8, 40)[:, None] * nx + np.arange(nx)[None, :])
+    host = synthetic.synth_sst_numpy(time, (ny, nx), cells, seed=2)
+    np.testing.assert_array_equal(np.isnan(dev), np.isnan(host))
+    assert 0.1 < np.isnan(host[0]).mean() < 0.5
+    np.testing.assert_allclose(dev, host, rtol=0, atol=2e-3, equal_nan=True)
