@@ -906,7 +906,10 @@ extern "C" int marex_hobday_thresholds_pooled_bins(const uint16_t* bins, int64_t
   // when the ring of w * NY codes per gridpoint does not fit; otherwise the first band kernel.
   int ring_oy = 0;
   size_t ring_smem = 0;
-  if (tune_get("pool_ring", 1) && env_k != 128 && !env_ty && nb <= 8 * 64 && NY <= 254) {
+  // measured on B200 (0.25 deg, 25 output years, w = 11; profiles/r02_band_kernels.json): the ring kernel halves the DRAM
+  // traffic (34.7 GB against 75 GB) but one 448-thread tile per SM runs 65.1 ms against 50.5 ms for two 512-thread
+  // tiles of the first band kernel, so it is opt-in (marex_tune("pool_ring", 1) / MAREX_POOL_RING=1)
+  if (tune_get("pool_ring", 0) && env_k != 128 && !env_ty && nb <= 8 * 64 && NY <= 254) {
     for (int oy : {14, 10}) {
       if (oy - 2 * P < 1) continue;
       const size_t cs = (size_t)oy * 32;

@@ -28,6 +28,7 @@
 // series is all finite or all NaN (land).  It counts the non-finite inputs per gridpoint (the
 // same numbers _validate_data_values needs, detect.py:205-279); marex_shift_anomaly_fixup_f32
 // then recomputes the few gridpoints with 0 < count < T with the generic kernel (anomaly.cu).
+#include <algorithm>
 #include <cstdlib>
 #include <type_traits>
 
@@ -113,7 +114,7 @@ struct RingSum<float> {
 constexpr int SD_MAX_YEARS = 1024;
 
 template <int V, int R, int NST, int MODE, typename Acc, bool DIG>
-__global__ void __launch_bounds__(512) shift_daily_kernel(const __grid_constant__ CUtensorMap tmap,
+__global__ void __launch_bounds__(384, 2) shift_daily_kernel(const __grid_constant__ CUtensorMap tmap,
                                                           const __grid_constant__ DailyParams p) {
   constexpr int CW = 32 * V;  // gridpoints per CTA
   extern __shared__ __align__(1024) unsigned char smem_raw[];
@@ -519,7 +520,7 @@ extern "C" int marex_shift_anomaly_daily_f32(const float* x, int64_t T, int64_t 
              (size_t)((D + S - 1 + R - 1) / R) * 32 * V * acc_bytes;
     };
     const size_t budget = (size_t)(227 * 1024) / cps - (cps > 1 ? 1024 : 0);
-    int NW = env.nw ? env.nw : 16;
+    int NW = env.nw ? std::min(env.nw, 12) : 12;  // __launch_bounds__(384, 2): two CTAs per SM keep <= 85 registers per thread
     for (; NW >= 1; --NW) {
       const int D = R * NW;
       if (D + S - 1 <= 256 && D <= NDOY + R && smem_of(D) <= budget) break;
@@ -551,14 +552,14 @@ extern "C" int marex_shift_anomaly_daily_f32(const float* x, int64_t T, int64_t 
 #define MAREX_SD(V_, R_, CPS_) (f64 ? MAREX_SD3(V_, R_, CPS_, double) : MAREX_SD3(V_, R_, CPS_, float))
   int rc = MAREX_ERR_UNSUPPORTED;
   if (env.v || env.r) {
-    const int v = env.v ? env.v : 2, r = env.r ? env.r : 4, cps = env.cps ? env.cps : 2;
-    if (v == 4) rc = r == 2 ? MAREX_SD(4, 2, cps) : MAREX_SD(4, 4, cps);
-    else if (v == 2) rc = r == 2 ? MAREX_SD(2, 2, cps) : MAREX_SD(2, 4, cps);
+    const int v = env.v ? env.v : 1, r = env.r ? env.r : 4, cps = env.cps ? env.cps : 2;
+    if (v >= 2) rc = r == 2 ? MAREX_SD(2, 2, cps) : MAREX_SD(2, 4, cps);
     else rc = r == 1 ? MAREX_SD(1, 1, cps) : (r == 2 ? MAREX_SD(1, 2, cps) : MAREX_SD(1, 4, cps));
   } else {
     // measured on B200 (0.25 deg, W = 15, S = 21, fused digitize; profiles/r02_shift_shapes.json): V = 1, R = 4, two CTAs
-    // per SM 68.8 ms; V = 2: 68.9 (R = 2) / 91.3 (R = 4); V = 4: 107 - 165 ms -- the ring's 60 bytes per (day, gridpoint)
-    // cap the resident threads, and fewer, fatter threads lose more to latency than they save in instructions.
+    // per SM 65.9 ms; V = 2: 68.9 (R = 2) / 91.3 (R = 4); V = 4: 107 - 165 ms (removed) -- the ring's 60 bytes per
+    // (day, gridpoint) cap the resident threads, and fewer, fatter threads lose more to latency than they save in
+    // instructions.
     rc = MAREX_SD(1, 4, 2);
     if (rc == MAREX_ERR_UNSUPPORTED) rc = MAREX_SD(2, 2, 2);
     if (rc == MAREX_ERR_UNSUPPORTED) rc = MAREX_SD(1, 4, 1);

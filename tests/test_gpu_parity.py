@@ -128,13 +128,13 @@ DAILY_SHAPES = [
     ("1982-01-01", "2002-03-05", 8, 36, 15, 21, {}),                         # the benchmark's windows
     ("1988-02-29", "2001-03-01", 8, 36, 2, 3, {}),                           # starts on a leap day, W = 2
     ("1990-01-01", "2001-07-01", 8, 36, 5, 11, {"shift_v": 1, "shift_r": 4}),
-    ("1990-01-01", "2001-07-01", 8, 36, 5, 11, {"shift_v": 4, "shift_r": 4}),
-    ("1990-03-17", "2001-07-01", 8, 36, 5, 11, {"shift_v": 4, "shift_r": 2}),
+    ("1990-01-01", "2001-07-01", 8, 36, 5, 11, {"shift_v": 2, "shift_r": 4}),
+    ("1990-03-17", "2001-07-01", 8, 36, 5, 11, {"shift_v": 2, "shift_r": 4, "shift_cps": 1}),
     ("1990-03-17", "2001-07-01", 8, 36, 5, 11, {"shift_v": 2, "shift_r": 2, "shift_cps": 1}),
     ("1990-01-01", "2001-07-01", 8, 36, 5, 11, {"shift_v": 1, "shift_r": 1}),
     ("1990-01-01", "2001-07-01", 8, 36, 5, 11, {"shift_v": 1, "shift_r": 2, "shift_nw": 3}),
     ("1990-01-01", "2001-07-01", 8, 36, 5, 11, {"shift_f64": 1}),
-    ("1982-01-01", "2002-03-05", 4, 36, 15, 21, {"shift_f64": 1, "shift_v": 4, "shift_r": 4}),
+    ("1982-01-01", "2002-03-05", 4, 36, 15, 21, {"shift_f64": 1, "shift_v": 2, "shift_r": 4}),
 ]
 
 
@@ -556,8 +556,9 @@ def _hetero_anoms(ny=13, nx=70, T1="2001-01-01", seed=11):
         ({"pool_k": 128, "pool_ty": 3}, 7, 11, 99),
         ({"pool_force_fail": 1}, 5, 11, 95),
         ({"pool_ty": 1}, 5, 31, 80),
-        ({"pool_ring": 0}, 5, 11, 95),
-        ({"pool_ring": 0, "pool_force_fail": 1}, 3, 5, 90),
+        ({"pool_ring": 1}, 5, 11, 95),
+        ({"pool_ring": 1, "pool_tma": 0}, 7, 11, 99),
+        ({"pool_ring": 1, "pool_force_fail": 1}, 3, 5, 90),
     ],
 )
 def test_banded_pooled_kernel_bit_exact(tune, env, ws, w, p):
@@ -874,7 +875,7 @@ def test_ring_kernel_tma_path_runs_and_is_bit_exact(tune):
         f[:, nx * 3 + 40] = np.nan
         f[::4, nx * 6 + 50] = 9.0
         dbg = torch.zeros(8 * 256, dtype=torch.int32).pin_memory()
-        tune(pool_dbg_ptr=dbg.data_ptr())
+        tune(pool_dbg_ptr=dbg.data_ptr(), pool_ring=1)
         with warnings.catch_warnings():
             warnings.simplefilter("ignore")
             res = mb.identify_extremes_arrays(torch.from_numpy(f.copy()).cuda(), doy, (ny, nx), "hobday_extreme", 95, w, 5, year=year)

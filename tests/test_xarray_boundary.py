@@ -38,7 +38,8 @@ def _sst(T0="1990-01-01", T1="2001-01-01", ny=6, nx=40, seed=0):
     time = np.arange(np.datetime64(T0), np.datetime64(T1))
     frac = (time - time.astype("datetime64[Y]")).astype(float) / 365.25
     x = (15 + 4 * np.cos(2 * np.pi * frac)[:, None, None] + rng.standard_normal((len(time), ny, nx))).astype(np.float32)
-    x[:, 1, 1] = np.nan  # the NaN column the reference's tests inject (tests/test_gridded_preprocessing.py:22-25)
+    if ny > 1:
+        x[:, 1, 1] = np.nan  # the NaN column the reference's tests inject (tests/test_gridded_preprocessing.py:22-25)
     return x, time
 
 
