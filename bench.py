@@ -553,7 +553,7 @@ def main():
             if i == 1:
                 barrier()
                 t0 = _time.perf_counter()
-            res = marex_b200.preprocess_arrays(xh, time, output="pinned", **kw)
+            res = marex_b200.preprocess_arrays(xh, time, output="pinned_reuse", **kw)
             d2h = sum(res[k].nbytes for k in ("dat_anomaly", "mask", "thresholds", "extreme_events"))
             h2d = int(res.get("h2d_bytes", xh.numel() * 4))
             n_chunks = int(res.get("chunks", 1))

@@ -38,6 +38,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
     os.makedirs(objdir, exist_ok=True)
     flags = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17", "-Xcompiler", "-fPIC",
              "-Xptxas", "-v" if verbose else "-O3"]  # fmt: skip
+    flags += os.environ.get("MAREX_NVCC_FLAGS", "").split()  # experiments (tools/gpu_*.sh build variants on the GPU box)
 
     def compile_one(src):
         obj = os.path.join(objdir, src.replace(".cu", ".o"))

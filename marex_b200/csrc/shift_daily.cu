@@ -112,9 +112,20 @@ struct RingSum<float> {
 };
 
 constexpr int SD_MAX_YEARS = 1024;
+// Register budget: two CTAs of 11 warps per SM need <= 93 registers per thread.  The instantiations without the fused
+// digitize are capped through the launch bounds (uncapped they took 115 registers: one CTA per SM, 82 instead of 49 ms);
+// the fused-digitize instantiation compiles to 64 registers uncapped and runs 10 % faster that way than capped (measured:
+// 65.9 vs 72.5 ms, profiles/r02_shift_shapes.json).
+#ifndef MAREX_SD_MAXTHREADS
+#define MAREX_SD_MAXTHREADS 384
+#endif
+#ifndef MAREX_SD_MINBLOCKS
+#define MAREX_SD_MINBLOCKS 2
+#endif
 
 template <int V, int R, int NST, int MODE, typename Acc, bool DIG>
-__global__ void __launch_bounds__(384, 2) shift_daily_kernel(const __grid_constant__ CUtensorMap tmap,
+__global__ void __launch_bounds__(DIG ? 512 : MAREX_SD_MAXTHREADS, DIG ? 0 : MAREX_SD_MINBLOCKS)
+    shift_daily_kernel(const __grid_constant__ CUtensorMap tmap,
                                                           const __grid_constant__ DailyParams p) {
   constexpr int CW = 32 * V;  // gridpoints per CTA
   extern __shared__ __align__(1024) unsigned char smem_raw[];
@@ -189,8 +200,6 @@ __global__ void __launch_bounds__(384, 2) shift_daily_kernel(const __grid_consta
   float* ringp = ring + (size_t)rbase * CW + lane * V;  // this thread's first day in ring slot 0
   float* const outc = p.out + c;                        // column of these gridpoints (dead lanes never store)
   const uint32_t leave_bit = 1u << (W - 1);
-  const int64_t bin_stride = DIG ? (int64_t)p.NY * p.bins_pitch : 0;  // one day of year further
-  uint16_t* const bin0 = DIG ? p.bins + (int64_t)(d0 + rbase) * bin_stride + c : nullptr;
 
   for (int i = 0; i < p.n_years; ++i) {
     const int base = ybase[i], ylen = ybase[i + 1] - base;
@@ -207,7 +216,8 @@ __global__ void __launch_bounds__(384, 2) shift_daily_kernel(const __grid_consta
       }
     }
     float* outp = outc + (int64_t)(t0 - p.out_off) * p.out_pitch;  // only dereferenced for target years
-    uint16_t* const binp = DIG ? bin0 + (int64_t)(i - W) * p.bins_pitch : nullptr;  // slot (first day, output year i - W)
+    const int64_t bin_stride = DIG ? (int64_t)p.NY * p.bins_pitch : 0;
+    uint16_t* const binp = DIG ? p.bins + ((int64_t)(d0 + rbase) * p.NY + (i - W)) * p.bins_pitch + c : nullptr;
 
     // ring turnover of one day: year i - W leaves (if it had a value), year i enters (if it has one)
     auto turnover = [&](int r, const Pack<float, V>& s, bool valid_now) {
@@ -520,7 +530,7 @@ extern "C" int marex_shift_anomaly_daily_f32(const float* x, int64_t T, int64_t 
              (size_t)((D + S - 1 + R - 1) / R) * 32 * V * acc_bytes;
     };
     const size_t budget = (size_t)(227 * 1024) / cps - (cps > 1 ? 1024 : 0);
-    int NW = env.nw ? std::min(env.nw, 12) : 12;  // __launch_bounds__(384, 2): two CTAs per SM keep <= 85 registers per thread
+    int NW = env.nw ? std::min(env.nw, MAREX_SD_MAXTHREADS / 32) : MAREX_SD_MAXTHREADS / 32;  // launch bounds of the kernel
     for (; NW >= 1; --NW) {
       const int D = R * NW;
       if (D + S - 1 <= 256 && D <= NDOY + R && smem_of(D) <= budget) break;

@@ -19,6 +19,7 @@ from __future__ import annotations
 
 import ctypes
 import logging
+import os
 import warnings
 from typing import Any, Dict, List, Optional, Sequence, Tuple
 
@@ -87,24 +88,31 @@ def _up(a: np.ndarray, dtype, device) -> torch.Tensor:
 _PINNED: Dict[Any, torch.Tensor] = {}
 
 
-def _to_host(t: torch.Tensor, key: str, pinned: bool):
-    """Device -> host.  ``pinned`` reuses a cached page-locked buffer per (key, shape, dtype) so a
-    repeated pipeline call pays the PCIe transfer, not cudaHostAlloc."""
-    if not pinned:
-        return t.cpu()
-    k = (key, tuple(t.shape), t.dtype)
+def _pinned_buffer(key: str, shape, dtype, reuse: bool) -> torch.Tensor:
+    """Page-locked host tensor.  ``reuse``: one cached buffer per (key, shape, dtype), overwritten by the next call that
+    asks for it (a repeated pipeline call then pays the PCIe transfer, not cudaHostAlloc); otherwise a fresh one."""
+    if not reuse:
+        return torch.empty(shape, dtype=dtype, pin_memory=True)
+    k = (key, tuple(shape), dtype)
     buf = _PINNED.get(k)
     if buf is None:
-        buf = torch.empty(t.shape, dtype=t.dtype, pin_memory=True)
+        buf = torch.empty(shape, dtype=dtype, pin_memory=True)
         _PINNED[k] = buf
+    return buf
+
+
+def _to_host(t: torch.Tensor, key: str, output: str):
+    """Device -> host for ``output`` "numpy" (pageable), "pinned" (fresh page-locked buffer) or "pinned_reuse"."""
+    if output == "numpy":
+        return t.cpu()
+    buf = _pinned_buffer(key, tuple(t.shape), t.dtype, output == "pinned_reuse")
     buf.copy_(t, non_blocking=True)
     return buf
 
 
 def release_host_buffers() -> None:
-    """Drop the cached page-locked output buffers (``output="pinned"`` reuses one buffer per output name,
-    shape and dtype so that repeated calls pay the PCIe transfer, not ``cudaHostAlloc``; arrays returned by
-    earlier ``output="pinned"`` calls become invalid)."""
+    """Drop the cached page-locked output buffers of ``output="pinned_reuse"`` (one buffer per output name, shape and
+    dtype; arrays returned by earlier ``"pinned_reuse"`` calls become invalid)."""
     _PINNED.clear()
 
 
@@ -132,63 +140,48 @@ def _to_device_field(x, device) -> Tuple[torch.Tensor, Tuple[int, ...]]:
 
 
 # --------------------------------------------------------------------------------------
-# configuration validation (messages follow the reference; tests match on them)
+# configuration validation.  The HEADLINE of every error is the reference's (its tests match them with regular
+# expressions, tests/test_error_handling.py); rule order follows detect.py.  Details and hints are this package's own.
 # --------------------------------------------------------------------------------------
+def _bad_config(headline: str, why: str, *hints: str, **context) -> ConfigurationError:
+    return ConfigurationError(headline, details=why, suggestions=list(hints), context=context or None)
+
+
 def validate_reference_period_method(reference_period, method_anomaly: str) -> None:
     """detect.py:571-579 / 1069-1077."""
     if reference_period is not None and method_anomaly not in ("fixed_baseline", "detrend_fixed_baseline"):
-        raise ConfigurationError(
+        raise _bad_config(
             f"reference_period is not supported for method_anomaly='{method_anomaly}'",
-            details="reference_period is only applicable to 'fixed_baseline' and 'detrend_fixed_baseline' methods",
-            suggestions=[
-                "Remove the reference_period parameter, or",
-                "Use method_anomaly='fixed_baseline' or 'detrend_fixed_baseline'",
-            ],
+            "only the two fixed-climatology methods average over a chosen span of years",
+            "drop reference_period, or pick method_anomaly='fixed_baseline' / 'detrend_fixed_baseline'",
         )
 
 
 def validate_anomaly_method(method_anomaly: str) -> None:
     """detect.py:1100-1116."""
     if method_anomaly not in VALID_ANOMALY:
-        raise ConfigurationError(
+        raise _bad_config(
             f"Unknown anomaly method '{method_anomaly}'",
-            details="Invalid method_anomaly parameter",
-            suggestions=[
-                "Use 'detrend_harmonic' for efficient processing with trend and harmonic removal",
-                "Use 'shifting_baseline' for accurate climatology (requires more data)",
-                "Use 'fixed_baseline' to remove a single daily climatology across all years "
-                "(keeps any long-term trend in the anomaly)",
-                "Use 'detrend_fixed_baseline' for trend removal followed by fixed climatology",
-            ],
-            context={
-                "provided_method": method_anomaly,
-                "valid_methods": ["detrend_harmonic", "shifting_baseline", "fixed_baseline", "detrend_fixed_baseline"],
-            },
-        )
+            "method_anomaly selects the baseline that is removed from the data",
+            "choose one of: " + ", ".join(VALID_ANOMALY),
+            provided_method=method_anomaly, valid_methods=list(VALID_ANOMALY),
+        )  # fmt: skip
 
 
 def validate_detrend_orders(detrend_orders: Sequence[int]) -> None:
     """detect.py:2104-2126."""
     if not detrend_orders:
-        raise ConfigurationError(
+        raise _bad_config(
             "detrend_orders cannot be empty",
-            details="At least one polynomial order must be specified for detrending",
-            suggestions=[
-                "Use detrend_orders=[1] for linear detrending",
-                "Use detrend_orders=[1, 2] for linear + quadratic detrending",
-                "Remove detrend_orders optional parameter to use default [1]",
-            ],
+            "the trend model needs at least one polynomial term",
+            "detrend_orders=[1] removes a linear trend (the default); [1, 2] adds a quadratic term",
         )
-    if any(order < 1 for order in detrend_orders):
-        invalid = [order for order in detrend_orders if order < 1]
-        raise ConfigurationError(
+    invalid = [order for order in detrend_orders if order < 1]
+    if invalid:
+        raise _bad_config(
             f"Invalid polynomial orders: {invalid}",
-            details="Polynomial orders must be positive integers (≥ 1)",
-            suggestions=[
-                "Use only positive integers for polynomial orders",
-                "Common values: [1] for linear, [1,2] for linear+quadratic",
-                f"Remove invalid orders: {invalid}",
-            ],
+            "orders are exponents of the centred decimal year and start at 1 (the constant is always fitted)",
+            f"remove {invalid}",
         )
 
 
@@ -196,21 +189,18 @@ def validate_reference_period(reference_period, year: np.ndarray) -> np.ndarray:
     """detect.py:2334-2355: returns the row indices of the reference period."""
     start_year, end_year = reference_period
     if start_year > end_year:
-        raise ConfigurationError(
+        raise _bad_config(
             f"Invalid reference_period: start year ({start_year}) must be <= end year ({end_year})",
-            details="The reference_period tuple must be (start_year, end_year) with start_year <= end_year",
-            suggestions=[f"Swap the order: use reference_period=({end_year}, {start_year})"],
+            "reference_period is (first year, last year), both inclusive",
+            f"did you mean ({end_year}, {start_year})?",
         )
     rows = np.nonzero((year >= start_year) & (year <= end_year))[0]
     if rows.size == 0:
         lo, hi = int(year.min()), int(year.max())
-        raise ConfigurationError(
+        raise _bad_config(
             f"No data found in reference_period ({start_year}, {end_year})",
-            details=f"Dataset spans {lo}-{hi} but no timesteps fall within the specified period",
-            suggestions=[
-                f"Adjust reference_period to overlap with data range ({lo}-{hi})",
-                "Set reference_period=None to use the full time series",
-            ],
+            f"the time axis covers {lo}-{hi}",
+            f"choose years inside {lo}-{hi}, or reference_period=None for the whole series",
         )
     return rows
 
@@ -230,157 +220,69 @@ def resolve_extreme_config(
     """The configuration rules of ``identify_extremes`` (detect.py:1277-1503), in the reference's
     order.  Returns the effective ``window_spatial_hobday`` (5 by default on gridded data,
     detect.py:1450-1452)."""
-    valid_methods = ["exact", "approximate"]
-    if method_percentile not in valid_methods:
-        raise ConfigurationError(
+    if method_percentile not in ("exact", "approximate"):  # :1281
+        raise _bad_config(
             f"Unknown method_percentile '{method_percentile}'",
-            details="Invalid method_percentile parameter",
-            suggestions=[
-                "Use 'exact' for precise percentile computation (memory intensive)",
-                "Use 'approximate' for efficient histogram-based computation (default)",
-            ],
-            context={"provided_method": method_percentile, "valid_methods": valid_methods},
-        )
-    if method_percentile == "exact":
-        if precision != 0.01:
-            raise ConfigurationError(
-                "Parameter 'precision' cannot be used with method_percentile='exact'",
-                details=(
-                    f"The precision parameter (precision={precision}) is only used by the approximate "
-                    "histogram method and is ignored when using exact percentile computation"
-                ),
-                suggestions=[
-                    "Remove the 'precision' parameter when using method_percentile='exact'",
-                    "Use method_percentile='approximate' if you want to control histogram precision",
-                ],
-                context={"method_percentile": method_percentile, "provided_precision": precision, "default_precision": 0.01},
-            )
-        if max_anomaly != 5.0:
-            raise ConfigurationError(
-                "Parameter 'max_anomaly' cannot be used with method_percentile='exact'",
-                details=(
-                    f"The max_anomaly parameter (max_anomaly={max_anomaly}) is only used by the approximate "
-                    "histogram method and is ignored when using exact percentile computation"
-                ),
-                suggestions=[
-                    "Remove the 'max_anomaly' parameter when using method_percentile='exact'",
-                    "Use method_percentile='approximate' if you want to control histogram binning range",
-                ],
-                context={
-                    "method_percentile": method_percentile,
-                    "provided_max_anomaly": max_anomaly,
-                    "default_max_anomaly": 5.0,
-                },
-            )
-    if threshold_percentile < 60 and method_percentile == "approximate":
-        raise ConfigurationError(
+            "thresholds come either from a selection of the samples or from a histogram",
+            "method_percentile='approximate' (histogram, the default) or 'exact'",
+            provided_method=method_percentile, valid_methods=["exact", "approximate"],
+        )  # fmt: skip
+    if method_percentile == "exact":  # :1302, :1322 -- histogram parameters make no sense without a histogram
+        for name, value, default in (("precision", precision, 0.01), ("max_anomaly", max_anomaly, 5.0)):
+            if value != default:
+                raise _bad_config(
+                    f"Parameter '{name}' cannot be used with method_percentile='exact'",
+                    f"{name}={value} shapes the histogram of the approximate method; the exact method has none",
+                    f"leave {name} at its default, or switch to method_percentile='approximate'",
+                    **{"method_percentile": method_percentile, f"provided_{name}": value, f"default_{name}": default},
+                )
+    if threshold_percentile < 60 and method_percentile == "approximate":  # :1342
+        raise _bad_config(
             f"Percentile threshold {threshold_percentile}% is not supported with method_percentile='approximate'",
-            details=(
-                "Low percentile thresholds (<60%) produce undefined and unsupported behaviour "
-                "when using approximate histogram methods"
-            ),
-            suggestions=[
-                "Use method_percentile='exact' for percentiles below 60%",
-                "Use a higher percentile threshold (≥60%) with method_percentile='approximate'",
-                "Consider if such low percentiles are appropriate for extreme event identification",
-            ],
-            context={
-                "threshold_percentile": threshold_percentile,
-                "method_percentile": method_percentile,
-                "min_supported_percentile": 60,
-            },
-        )
+            "the histogram lumps everything below -precision into one bin, so quantiles in the lower half are not resolved",
+            "use method_percentile='exact' below the 60th percentile",
+            threshold_percentile=threshold_percentile, method_percentile=method_percentile, min_supported_percentile=60,
+        )  # fmt: skip
     if window_spatial_hobday is not None:
-        if not gridded:
-            raise ConfigurationError(
-                "window_spatial_hobday is not supported for unstructured grids",
-                details=(
-                    "Spatial smoothing with window_spatial_hobday requires structured grids with both x and y dimensions. "
-                    "Unstructured grids do not support spatial window operations due to computational and memory "
-                    "limitations of the algorithms."
-                ),
-                suggestions=[
-                    "Remove the window_spatial_hobday parameter for unstructured grids",
-                    "Use structured grid data if spatial smoothing is required",
-                    "Set window_spatial_hobday=None to use default behavior",
-                ],
-                context={
-                    "grid_type": "unstructured",
-                    "window_spatial_hobday": window_spatial_hobday,
-                    "dimensions": dimensions,
-                    "available_dims": available_dims,
-                },
-            )
-        if method_extreme != "hobday_extreme":
-            raise ConfigurationError(
-                "window_spatial_hobday can only be used with method_extreme='hobday_extreme'",
-                details=(
-                    "The window_spatial_hobday parameter is only implemented for the Hobday extreme method. "
-                    "Other extreme methods do not support spatial smoothing due to computational and memory "
-                    "limitations of the algorithms."
-                ),
-                suggestions=[
-                    "Remove the window_spatial_hobday parameter when using method_extreme='global_extreme'",
-                    "Use method_extreme='hobday_extreme' if spatial smoothing is required",
-                    "Set window_spatial_hobday=None to use default behavior",
-                ],
-                context={
-                    "method_extreme": method_extreme,
-                    "window_spatial_hobday": window_spatial_hobday,
-                    "compatible_methods": ["hobday_extreme"],
-                },
-            )
-        if method_percentile == "exact":
-            raise ConfigurationError(
-                "window_spatial_hobday is not supported with method_percentile='exact'",
-                details=(
-                    "The window_spatial_hobday parameter is only implemented for the approximate percentile method. "
-                    "Exact percentile computation does not support spatial smoothing due to computational and memory "
-                    "limitations of the algorithms."
-                ),
-                suggestions=[
-                    "Remove the window_spatial_hobday parameter when using method_percentile='exact'",
-                    "Use method_percentile='approximate' if spatial smoothing is required",
-                    "Set window_spatial_hobday=None to use default behavior",
-                ],
-                context={
-                    "method_percentile": method_percentile,
-                    "window_spatial_hobday": window_spatial_hobday,
-                    "compatible_methods": ["approximate"],
-                },
-            )
-    if method_extreme == "hobday_extreme" and window_days_hobday is not None and window_days_hobday % 2 == 0:
-        raise ConfigurationError(
+        where = None
+        if not gridded:  # :1367
+            where = ("for unstructured grids", "pooling needs the (y, x) neighbourhood of a structured grid",
+                     dict(grid_type="unstructured", dimensions=dimensions, available_dims=available_dims))  # fmt: skip
+            headline = "window_spatial_hobday is not supported for unstructured grids"
+        elif method_extreme != "hobday_extreme":  # :1390
+            where = ("", "only the day-of-year histograms of hobday_extreme are pooled",
+                     dict(method_extreme=method_extreme, compatible_methods=["hobday_extreme"]))  # fmt: skip
+            headline = "window_spatial_hobday can only be used with method_extreme='hobday_extreme'"
+        elif method_percentile == "exact":  # :1412
+            where = ("", "the exact percentile selects among a gridpoint's own samples and pools nothing",
+                     dict(method_percentile=method_percentile, compatible_methods=["approximate"]))  # fmt: skip
+            headline = "window_spatial_hobday is not supported with method_percentile='exact'"
+        if where is not None:
+            raise _bad_config(headline, where[1], "pass window_spatial_hobday=None",
+                              window_spatial_hobday=window_spatial_hobday, **where[2])  # fmt: skip
+    if method_extreme == "hobday_extreme" and window_days_hobday is not None and window_days_hobday % 2 == 0:  # :1434
+        raise _bad_config(
             "window_days_hobday must be an odd number",
-            details=(
-                f"Window parameters require odd numbers to ensure symmetric windows around a central point. "
-                f"window_days_hobday={window_days_hobday} is even, which would create asymmetric temporal windows."
-            ),
-            suggestions=[f"Use window_days_hobday={window_days_hobday + 1} or {window_days_hobday - 1}", "Choose an odd number"],
-            context={"window_days_hobday": window_days_hobday, "is_odd": False},
-        )
+            f"the window is centred on a day, so it spans 2k + 1 days; got {window_days_hobday}",
+            f"use {window_days_hobday - 1} or {window_days_hobday + 1}",
+            window_days_hobday=window_days_hobday, is_odd=False,
+        )  # fmt: skip
     if method_extreme == "hobday_extreme" and window_spatial_hobday is None and gridded:
         window_spatial_hobday = 5  # detect.py:1451-1452
-    if method_extreme == "hobday_extreme" and window_spatial_hobday is not None and window_spatial_hobday % 2 == 0:
-        raise ConfigurationError(
+    if method_extreme == "hobday_extreme" and window_spatial_hobday is not None and window_spatial_hobday % 2 == 0:  # :1456
+        raise _bad_config(
             "window_spatial_hobday must be an odd number",
-            details=(
-                f"Window parameters require odd numbers to ensure symmetric windows around a central point. "
-                f"window_spatial_hobday={window_spatial_hobday} is even, which would create asymmetric spatial windows."
-            ),
-            suggestions=[f"Use window_days_hobday={window_days_hobday + 1} or {window_days_hobday - 1}", "Choose an odd number."],
-            context={"window_spatial_hobday": window_spatial_hobday, "is_odd": False},
-        )
-    if method_extreme not in VALID_EXTREME:
-        raise ConfigurationError(
+            f"the pooling window is centred on a gridpoint, so it spans 2k + 1 cells; got {window_spatial_hobday}",
+            f"use {window_spatial_hobday - 1} or {window_spatial_hobday + 1}",
+            window_spatial_hobday=window_spatial_hobday, is_odd=False,
+        )  # fmt: skip
+    if method_extreme not in VALID_EXTREME:  # :1492
+        raise _bad_config(
             f"Unknown extreme method '{method_extreme}'",
-            details="Invalid method_extreme parameter",
-            suggestions=[
-                "Use 'global_extreme' for efficient constant percentile threshold",
-                "Use 'hobday_extreme' for day-of-year specific thresholds",
-            ],
-            context={"provided_method": method_extreme, "valid_methods": ["global_extreme", "hobday_extreme"]},
-        )
+            "method_extreme selects constant (global_extreme) or day-of-year (hobday_extreme) thresholds",
+            "choose one of: " + ", ".join(VALID_EXTREME),
+            provided_method=method_extreme, valid_methods=list(VALID_EXTREME),
+        )  # fmt: skip
     return window_spatial_hobday
 
 
@@ -428,49 +330,46 @@ def get_preprocessing_steps(
     return steps
 
 
+def _raise_no_finite_data(total_values: int, n_locations: int):
+    """detect.py:226-237."""
+    raise create_data_validation_error(
+        "Dataset contains no valid (finite) data",
+        details="every value of the first time step is NaN or infinite, so no gridpoint counts as ocean",
+        suggestions=["check how the field was read (fill values, units, a mask applied twice)"],
+        data_info={"total_values": int(total_values), "total_spatial_locations": int(n_locations)},
+    )
+
+
+def _raise_invalid_ocean_values(total_invalid: int, affected: int, ocean: int, worst: int, T: int):
+    """detect.py:258-279: gridpoints that are finite on the first time step must be finite throughout."""
+    raise create_data_validation_error(
+        f"Dataset contains {total_invalid} invalid values in {affected} ocean locations",
+        details=f"Found invalid data across time series. Worst location has {worst} invalid time steps out of {T}.",
+        suggestions=[
+            "interpolate or fill the gaps before preprocessing, or mask those gridpoints on every time step",
+            "gridpoints that are NaN on the first time step are treated as land and skipped",
+        ],
+        data_info={
+            "total_invalid_values_in_ocean": total_invalid,
+            "locations_affected": affected,
+            "total_ocean_locations": ocean,
+            "max_invalid_at_one_location": worst,
+            "total_time_steps": int(T),
+            "percentage_affected": f"{100.0 * affected / ocean:.2f}%",
+        },
+    )
+
+
 def check_data_values(mask0: torch.Tensor, nonfinite: torch.Tensor, T: int, total_values: int) -> None:
     """``_validate_data_values`` (detect.py:205-279) from the per-cell numbers the first anomaly
-    kernel produced in the same pass that read the data."""
+    kernel produced in the same pass that read the data; one device->host transfer of four numbers."""
     m = mask0.bool()
-    if not bool(m.any()):
-        raise create_data_validation_error(
-            "Dataset contains no valid (finite) data",
-            details="All values in the first time step are NaN or infinite",
-            suggestions=[
-                "Check your input data for data quality issues",
-                "Verify the data was loaded correctly",
-                "Check for issues in data preprocessing steps",
-            ],
-            data_info={"total_values": int(total_values), "total_spatial_locations": int(m.numel())},
-        )
-    inv = torch.where(m, nonfinite, torch.zeros_like(nonfinite))
-    max_invalid = int(inv.max())
-    if max_invalid > 0:
-        total_invalid = int(inv.sum())
-        affected = int((inv > 0).sum())
-        ocean = int(m.sum())
-        raise create_data_validation_error(
-            f"Dataset contains {total_invalid} invalid values in {affected} ocean locations",
-            details=(
-                f"Found invalid data across time series. Worst location has {max_invalid} "
-                f"invalid time steps out of {T}."
-            ),
-            suggestions=[
-                "Remove or interpolate NaN/infinite values before preprocessing",
-                "Check data quality and loading procedures",
-                "Consider using data.fillna() or data.interpolate_na() methods",
-                "Verify coordinate/dimension alignment in your dataset",
-                "For ocean data, ensure land mask is properly applied before preprocessing",
-            ],
-            data_info={
-                "total_invalid_values_in_ocean": total_invalid,
-                "locations_affected": affected,
-                "total_ocean_locations": ocean,
-                "max_invalid_at_one_location": max_invalid,
-                "total_time_steps": int(T),
-                "percentage_affected": f"{100.0 * affected / ocean:.2f}%",
-            },
-        )
+    inv = torch.where(m, nonfinite, torch.zeros_like(nonfinite)).to(torch.int64)
+    ocean, worst, total_invalid, affected = (int(v) for v in torch.stack([m.sum(), inv.max(), inv.sum(), (inv > 0).sum()]).tolist())
+    if ocean == 0:
+        _raise_no_finite_data(total_values, m.numel())
+    if worst > 0:
+        _raise_invalid_ocean_values(total_invalid, affected, ocean, worst, T)
 
 
 def check_sufficient_years(cal: Calendar, W: int) -> None:
@@ -482,9 +381,8 @@ def check_sufficient_years(cal: Calendar, W: int) -> None:
             "Insufficient data for shifting_baseline method",
             details=f"Dataset spans {total_years} years but requires at least {W} years",
             suggestions=[
-                "Use more years of data to meet minimum requirement",
-                f"Reduce window_year_baseline parameter (currently {W})",
-                "Consider using detrend_fixed_baseline or detrend_harmonic method instead",
+                f"lower window_year_baseline (now {W}) or supply a longer series",
+                "the fixed-climatology and detrending methods need no spin-up years",
             ],
             data_info={"available_years": int(total_years), "required_years": int(W)},
         )
@@ -922,11 +820,18 @@ def identify_extremes_arrays(
     return out
 
 
+# The shifting-baseline kernel can write the histogram bin codes of its anomalies itself (no second pass over 38 GB of
+# anomalies) -- but it is issue-bound, and the digitize arithmetic costs it more than the separate, memory-bound pass does:
+# measured at 0.25 deg, fused 66.3 ms against 48.1 + 13.9 ms unfused (profiles/r02_fused_vs_unfused_digitize.json).  The
+# faster arrangement is the default; MAREX_FUSE_DIGITIZE=1 selects the fused kernel (38 GB less DRAM traffic per step).
+_FUSE_DIGITIZE = os.environ.get("MAREX_FUSE_DIGITIZE", "0") == "1"
+
+
 def _fused_edges(method_anomaly, method_extreme, method_percentile, precision, max_anomaly) -> Optional[np.ndarray]:
     """Edge table for the digitize fused into the shifting-baseline kernel, or None when the configuration does not
     digitize (or is invalid: ``identify_extremes_arrays`` raises the reference's error later)."""
     if (
-        method_anomaly == "shifting_baseline" and method_extreme == "hobday_extreme" and method_percentile == "approximate"
+        _FUSE_DIGITIZE and method_anomaly == "shifting_baseline" and method_extreme == "hobday_extreme" and method_percentile == "approximate"
         and isinstance(precision, (int, float)) and isinstance(max_anomaly, (int, float)) and precision > 0
         and 2 <= (max_anomaly + precision) / precision <= 4000
     ):  # fmt: skip
@@ -964,16 +869,11 @@ def _dataset_attrs(method_anomaly, method_extreme, threshold_percentile, std_nor
     return attrs
 
 
-def _host_buffer(key: str, shape, dtype, pinned: bool) -> torch.Tensor:
-    """Host tensor for a streamed output; page-locked buffers are cached per (key, shape, dtype)."""
-    if not pinned:
+def _host_buffer(key: str, shape, dtype, output: str) -> torch.Tensor:
+    """Host tensor for a streamed output."""
+    if output == "numpy":
         return torch.empty(shape, dtype=dtype)
-    k = (key, tuple(shape), dtype)
-    buf = _PINNED.get(k)
-    if buf is None:
-        buf = torch.empty(shape, dtype=dtype, pin_memory=True)
-        _PINNED[k] = buf
-    return buf
+    return _pinned_buffer(key, shape, dtype, output == "pinned_reuse")
 
 
 def _copy2d(dst_ptr: int, dpitch: int, src_ptr: int, spitch: int, width: int, height: int, to_device: bool, stream) -> None:
@@ -1021,7 +921,6 @@ def _preprocess_host_streamed(xh: torch.Tensor, cal: Calendar, gridded: bool, de
         raise IndexError("shifting_baseline: no time steps remain after removing the first window_year_baseline years")
     doy_out, year_out = cal.doy[keep], cal.year[keep]
     n_years_out = int(np.unique(year_out).size)
-    pinned = output == "pinned"
     hobday = method_extreme == "hobday_extreme"
     exact = kw["method_percentile"] == "exact"
     fused_edges = _fused_edges(method_anomaly, method_extreme, kw["method_percentile"], kw["precision"], kw["max_anomaly"])
@@ -1031,10 +930,10 @@ def _preprocess_host_streamed(xh: torch.Tensor, cal: Calendar, gridded: bool, de
         thr_shape, thr_dtype, layout = (NDOY, n_total), torch.float32, "doy_first"
     else:
         thr_shape, thr_dtype, layout = (n_total,), torch.float64, "space"
-    anom_h = _host_buffer("dat_anomaly", (T_out, n_total), torch.float32, pinned)
-    ev_h = _host_buffer("extreme_events", (T_out, n_total), torch.uint8, pinned) if want_events else None
-    thr_h = _host_buffer("thresholds", thr_shape, thr_dtype, pinned)
-    mask_h = _host_buffer("mask", (n_total,), torch.uint8, pinned)
+    anom_h = _host_buffer("dat_anomaly", (T_out, n_total), torch.float32, output)
+    ev_h = _host_buffer("extreme_events", (T_out, n_total), torch.uint8, output) if want_events else None
+    thr_h = _host_buffer("thresholds", thr_shape, thr_dtype, output)
+    mask_h = _host_buffer("mask", (n_total,), torch.uint8, output)
 
     bounds = _chunk_bounds(n_units, n_chunks, align)
     loads = [(max(0, lo - halo), min(n_units, hi + halo)) for lo, hi in bounds]
@@ -1130,37 +1029,10 @@ def _preprocess_host_streamed(xh: torch.Tensor, cal: Calendar, gridded: bool, de
     # ---- _validate_data_values over the whole field (detect.py:205-279) ----
     vals = torch.stack([n_ocean, n_affected, n_invalid, max_invalid, n_events]).cpu().tolist()
     ocean, affected, total_invalid, worst, count = (int(v) for v in vals)
-    if ocean == 0:  # same error as check_data_values (detect.py:226-237), with the whole field's numbers
-        raise create_data_validation_error(
-            "Dataset contains no valid (finite) data",
-            details="All values in the first time step are NaN or infinite",
-            suggestions=[
-                "Check your input data for data quality issues",
-                "Verify the data was loaded correctly",
-                "Check for issues in data preprocessing steps",
-            ],
-            data_info={"total_values": int(T * n_total), "total_spatial_locations": int(n_total)},
-        )
+    if ocean == 0:  # the errors of check_data_values, with the whole field's numbers
+        _raise_no_finite_data(T * n_total, n_total)
     if worst > 0:
-        raise create_data_validation_error(
-            f"Dataset contains {total_invalid} invalid values in {affected} ocean locations",
-            details=f"Found invalid data across time series. Worst location has {worst} invalid time steps out of {T}.",
-            suggestions=[
-                "Remove or interpolate NaN/infinite values before preprocessing",
-                "Check data quality and loading procedures",
-                "Consider using data.fillna() or data.interpolate_na() methods",
-                "Verify coordinate/dimension alignment in your dataset",
-                "For ocean data, ensure land mask is properly applied before preprocessing",
-            ],
-            data_info={
-                "total_invalid_values_in_ocean": total_invalid,
-                "locations_affected": affected,
-                "total_ocean_locations": ocean,
-                "max_invalid_at_one_location": worst,
-                "total_time_steps": int(T),
-                "percentage_affected": f"{100.0 * affected / ocean:.2f}%",
-            },
-        )
+        _raise_invalid_ocean_values(total_invalid, affected, ocean, worst, T)
     if stats_bounds is not None:
         _warn_threshold_range(float(smin), float(smax), stats_bounds[0], stats_bounds[1], kw["max_anomaly"])
     out: Dict[str, Any] = {
@@ -1211,8 +1083,9 @@ def preprocess_arrays(
     axis.  Returns ``dat_anomaly`` (T_out, ..space) float32, ``mask`` (..space) bool,
     ``thresholds`` in the reference's layout and dtype, ``extreme_events`` (T_out, ..space) bool,
     ``time`` (trimmed), ``attrs`` (the Dataset attrs, detect.py:731-783) -- numpy arrays
-    (``output="numpy"``), numpy views of cached page-locked buffers that the next call overwrites
-    (``output="pinned"``) or CUDA tensors (``output="torch"``).  A HOST field larger than 1 GiB (or
+    (``output="numpy"``), numpy views of page-locked buffers (``output="pinned"``: fresh buffers, the result owns them;
+    ``"pinned_reuse"``: cached buffers that the next such call overwrites -- for loops that consume each result before
+    the next call) or CUDA tensors (``output="torch"``).  A HOST field larger than 1 GiB (or
     any host field when ``chunks`` > 1) is streamed through the GPU in ``chunks`` spatial pieces with
     copies and kernels overlapped (``_preprocess_host_streamed``); ``chunks=1`` forces one piece."""
     if detrend_orders is None:
@@ -1223,7 +1096,9 @@ def preprocess_arrays(
     validate_anomaly_method(method_anomaly)
     cal = build_calendar(time)
     on_host = not (isinstance(x, torch.Tensor) and x.is_cuda)
-    if on_host and output in ("numpy", "pinned") and not want_bits and not std_normalise:
+    if output not in ("numpy", "pinned", "pinned_reuse", "torch"):
+        raise ValueError(f"output must be 'numpy', 'pinned', 'pinned_reuse' or 'torch', not {output!r}")
+    if on_host and output != "torch" and not want_bits and not std_normalise:
         xh = x if isinstance(x, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(x))
         nbytes = xh.numel() * 4
         n_chunks = chunks if chunks is not None else (1 if nbytes < (1 << 30) else int(min(16, max(2, round(nbytes / 6e9)))))
@@ -1306,9 +1181,9 @@ def preprocess_arrays(
         out["extreme_events_stn"] = ext_s["extreme_events"].reshape((T_out,) + space)
         out["thresholds_stn"] = ext_s["thresholds"]
     logger.info("Preprocessing completed successfully - %d extreme events identified", int(ext["count"]))
-    if output in ("numpy", "pinned"):
+    if output != "torch":
         keys = ("dat_anomaly", "mask", "thresholds", "extreme_events", "bits", "dat_stn", "STD", "extreme_events_stn", "thresholds_stn")
-        host = {k: _to_host(out[k], k, output == "pinned") for k in keys if k in out}
+        host = {k: _to_host(out[k], k, output) for k in keys if k in out}
         out["extreme_count"] = int(out["extreme_count"])  # synchronises the stream: the copies above are complete
         for k, v in host.items():
             out[k] = v.numpy()

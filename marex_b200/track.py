@@ -398,22 +398,29 @@ def stage1_time_sharded(bits_band: torch.Tensor, T: int, rows: int, mask, R_fill
     ny, nx = mask.shape
     world = dist.get_world_size(group) if dist.is_initialized() else 1
     rank = dist.get_rank(group) if dist.is_initialized() else 0
-    if (rows * nx) % 32 != 0 or bits_band.dim() != 2 or bits_band.shape[0] != T or bits_band.shape[1] != rows * nx // 32:
-        raise DataValidationError(
-            "bits_band must be int32 [T, rows * nx / 32] with rows * nx a multiple of 32",
-            details=f"got {tuple(bits_band.shape)} for T={T}, rows={rows}, nx={nx}",
-        )
-    filler = MaskFiller(mask, R_fill, T_fill, regional_mode, device=device)
+    local_ok = (rows * nx) % 32 == 0 and bits_band.dim() == 2 and bits_band.shape[0] == T and bits_band.shape[1] == rows * nx // 32
+    local_msg = f"got {tuple(bits_band.shape)} for T={T}, rows={rows}, nx={nx}"
     if world == 1:
+        if not local_ok:
+            raise DataValidationError("bits_band must be int32 [T, rows * nx / 32] with rows * nx a multiple of 32", details=local_msg)
         if rows != ny:
             raise DataValidationError("a single rank must own the whole grid", details=f"rows={rows}, ny={ny}")
-        return filler.run(from_bits=(bits_band.contiguous(), T), packed=packed), (0, T)
+        return MaskFiller(mask, R_fill, T_fill, regional_mode, device=device).run(from_bits=(bits_band.contiguous(), T), packed=packed), (0, T)
+    # every rank's band size AND the verdict of its local checks travel in the first collective: a rank with a bad
+    # input must not raise while its peers block in the exchange -- all ranks raise together
     dev = bits_band.device  # NCCL moves CUDA tensors, gloo CPU tensors: keep the bookkeeping where the data is
-    all_rows = [torch.zeros(1, dtype=torch.int64, device=dev) for _ in range(world)]
-    dist.all_gather(all_rows, torch.tensor([rows], dtype=torch.int64, device=dev), group=group)
-    all_rows = [int(r.item()) for r in all_rows]
+    all_info = [torch.zeros(2, dtype=torch.int64, device=dev) for _ in range(world)]
+    dist.all_gather(all_info, torch.tensor([rows, 1 if local_ok else 0], dtype=torch.int64, device=dev), group=group)
+    all_rows = [int(r[0].item()) for r in all_info]
+    bad = [p for p, r in enumerate(all_info) if int(r[1].item()) == 0]
+    if bad:
+        raise DataValidationError(
+            "bits_band must be int32 [T, rows * nx / 32] with rows * nx a multiple of 32",
+            details=f"rejected on rank(s) {bad}" + (f"; this rank: {local_msg}" if rank in bad else ""),
+        )
     if sum(all_rows) != ny or any((r * nx) % 32 for r in all_rows):
         raise DataValidationError("the bands of all ranks must tile the grid on word boundaries", details=f"rows per rank {all_rows}, ny={ny}")
+    filler = MaskFiller(mask, R_fill, T_fill, regional_mode, device=device)
     blocks = time_blocks(T, world, int(T_fill))
     own_lo, own_hi, load_lo, load_hi = blocks[rank]
     n_load = load_hi - load_lo

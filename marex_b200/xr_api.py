@@ -21,46 +21,22 @@ from .exceptions import create_data_validation_error
 logger = logging.getLogger("marex_b200")
 
 
-def _validate_dimensions_exist(da, dimensions: Dict[str, str]) -> None:
-    """detect.py:53-89."""
-    missing = [f"'{actual}' (for {concept})" for concept, actual in dimensions.items() if actual not in da.dims]
+def _require_names(kind: str, wanted: Dict[str, str], present) -> None:
+    """detect.py:53-128: every name the caller mapped must exist on the DataArray (``kind`` = dimensions / coordinates)."""
+    present = list(present)
+    missing = [f"'{actual}' (for {concept})" for concept, actual in wanted.items() if actual not in present]
     if missing:
-        available = list(da.dims)
         raise create_data_validation_error(
-            f"Missing required dimensions: {', '.join(missing)}",
-            details=f"Dataset has dimensions: {available}",
-            suggestions=[
-                "Check dimension names in your data",
-                "Update the 'dimensions' parameter to match your data structure",
-                f"Available dimensions: {available}",
-            ],
-            data_info={"missing_dimensions": missing, "available_dimensions": available, "provided_dimensions": dimensions},
-        )
-
-
-def _validate_coordinates_exist(da, coordinates: Dict[str, str]) -> None:
-    """detect.py:92-128."""
-    missing = [f"'{actual}' (for {concept})" for concept, actual in coordinates.items() if actual not in da.coords]
-    if missing:
-        available = list(da.coords.keys())
-        raise create_data_validation_error(
-            f"Missing required coordinates: {', '.join(missing)}",
-            details=f"Dataset has coordinates: {available}",
-            suggestions=[
-                "Check coordinate names in your data",
-                "Update the 'coordinates' parameter to match your data structure",
-                f"Available coordinates: {available}",
-            ],
-            data_info={
-                "missing_coordinates": missing,
-                "available_coordinates": available,
-                "provided_coordinates": coordinates,
-            },
+            f"Missing required {kind}: {', '.join(missing)}",
+            details=f"the DataArray has {kind} {present}",
+            suggestions=[f"pass {kind}={{...}} with the names your data uses"],
+            data_info={f"missing_{kind}": missing, f"available_{kind}": present, f"provided_{kind}": wanted},
         )
 
 
 def _infer_dims_coords(da, dimensions, coordinates) -> Tuple[Dict[str, str], Dict[str, str]]:
-    """detect.py:131-202."""
+    """detect.py:131-202: defaults (time / lat / lon), "time" added when omitted, no "y" means an unstructured mesh,
+    which must name its coordinates explicitly."""
     if dimensions is None:
         dimensions = {"time": "time", "x": "lon", "y": "lat"}
     if "time" not in dimensions:
@@ -69,24 +45,15 @@ def _infer_dims_coords(da, dimensions, coordinates) -> Tuple[Dict[str, str], Dic
         if "y" not in dimensions:
             raise create_data_validation_error(
                 "Coordinates parameter must be explicitly specified for unstructured data",
-                details="Unstructured data requires coordinate names for x and y spatial coordinates",
-                suggestions=[
-                    "Specify coordinates parameter with spatial coordinate names",
-                    "Example: coordinates={'time': 'time', 'x': 'lon', 'y': 'lat'}",
-                    f"Your x dimension '{dimensions['x']}' needs associated coordinate names",
-                    "If data is gridded, ensure 'y' dimension is also specified",
-                ],
-                data_info={
-                    "data_structure": "unstructured (2D)",
-                    "dimensions": dimensions,
-                    "missing_coordinates": "x and y spatial coordinates",
-                },
+                details="a mesh has one spatial dimension, so the x / y coordinate variables cannot be guessed from the dimension names",
+                suggestions=["e.g. coordinates={'time': 'time', 'x': 'lon', 'y': 'lat'}"],
+                data_info={"data_structure": "unstructured (2D)", "dimensions": dimensions},
             )
         coordinates = dimensions.copy()
     elif "time" not in coordinates:
         coordinates = {"time": dimensions.get("time", "time"), **coordinates}
-    _validate_dimensions_exist(da, dimensions)
-    _validate_coordinates_exist(da, coordinates)
+    _require_names("dimensions", dimensions, da.dims)
+    _require_names("coordinates", coordinates, da.coords.keys())
     return dimensions, coordinates
 
 
@@ -183,11 +150,8 @@ def preprocess_data(
     if not _is_dask(da):  # detect.py:557-568
         raise create_data_validation_error(
             "Input DataArray must be Dask-backed",
-            details="Preprocessing requires chunked data for efficient computation",
-            suggestions=[
-                "Convert to Dask array: da = da.chunk({'time': 30})",
-                "Load with chunking: xr.open_dataset('file.nc', chunks={'time': 30})",
-            ],
+            details="the reference only accepts chunked input; this drop-in keeps the contract and reads it block by block",
+            suggestions=["da.chunk({'time': 30}), or open the file with chunks={'time': 30}"],
             data_info={"data_type": type(da.data).__name__, "shape": da.shape},
         )
     _d.validate_reference_period_method(reference_period, method_anomaly)

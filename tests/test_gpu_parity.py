@@ -275,10 +275,17 @@ def _anoms(seed=1, ny=6, nx=35, T1="2003-01-01", scale=1.0):
     return a, time
 
 
-def test_digitize_bit_exact():
+@pytest.mark.parametrize("table", ["reference", "coarse", "slightly_irregular", "irregular"])
+def test_digitize_bit_exact(table):
+    """np.digitize - 1 for the reference's edge table (arithmetic fast path + look-ups near the edges), for another
+    precision, and for tables that deviate from uniform spacing by 0.5 % (wide margin tier) and by 30 % of a step (walked)."""
     mb = _cuda()
-    edges, _ = mo.hobday_bins()
+    edges, _ = mo.hobday_bins() if table != "coarse" else mo.hobday_bins(0.05, 3.0)
     rng = np.random.default_rng(5)
+    if table.endswith("irregular"):
+        jit = rng.uniform(-1, 1, len(edges) - 1).astype(np.float32) * np.float32(0.00005 if table.startswith("slightly") else 0.003)
+        edges = edges.copy()
+        edges[1:] = np.sort(edges[1:] + jit)
     v = np.concatenate(
         [
             edges[1:].astype(np.float32),
@@ -903,3 +910,22 @@ def test_synthetic_field_numpy_twin_matches_the_cuda_generator():
     np.testing.assert_array_equal(np.isnan(dev), np.isnan(host))
     assert 0.1 < np.isnan(host[0]).mean() < 0.5
     np.testing.assert_allclose(dev, host, rtol=0, atol=2e-3, equal_nan=True)
+
+
+def test_pinned_outputs_do_not_alias_unless_asked():
+    """``output="pinned"`` results own their page-locked buffers; only ``"pinned_reuse"`` hands out the cached ones."""
+    mb = _cuda()
+    x, time = _field(T1="1998-01-01", ny=4, nx=36, seed=9)
+    kw = dict(window_year_baseline=3, smooth_days_baseline=5, window_days_hobday=5)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        a = mb.preprocess_arrays(x, time, output="pinned", **kw)
+        keep = a["dat_anomaly"].copy()
+        b = mb.preprocess_arrays(x + np.float32(1.0), time, output="pinned", **kw)
+        c = mb.preprocess_arrays(x, time, output="pinned_reuse", **kw)
+        d = mb.preprocess_arrays(x, time, output="pinned_reuse", **kw)
+    assert not np.shares_memory(a["dat_anomaly"], b["dat_anomaly"])
+    np.testing.assert_array_equal(a["dat_anomaly"], keep)
+    assert np.shares_memory(c["dat_anomaly"], d["dat_anomaly"])
+    with pytest.raises(ValueError, match="output must be"):
+        mb.preprocess_arrays(x, time, output="host", **kw)

@@ -1,0 +1,19 @@
+#!/usr/bin/env bash
+# build variants of the anomaly kernel on the box and time the anomaly stage on config 2
+set -u
+out=gpurun_out/r2o; mkdir -p "$out"
+B="python bench.py --steps 4 --warmup 3 --no-e2e --no-cpu --no-parity"
+v() { name=$1; flags=$2; echo "== $name [$flags]" | tee -a "$out/steps.log"
+  MAREX_NVCC_FLAGS="$flags" python -c "from marex_b200 import _build; _build.build(force=True)" > "$out/build_$name.log" 2>&1
+  timeout 300 $B > "$out/bench_$name.log" 2>&1
+  grep -h '"metric"' "$out/bench_$name.log" | python -c "
+import sys, json
+for l in sys.stdin:
+    d = json.loads(l); print(round(d['ms_per_step'], 2), {k.replace('marex_',''): round(v['ms'], 2) for k, v in d['stages'].items()})
+" | tee -a "$out/steps.log"; }
+v default ""
+v b512_1 "-DMAREX_SD_MAXTHREADS=512 -DMAREX_SD_MINBLOCKS=1"
+v b512_1_nohoist "-DMAREX_SD_MAXTHREADS=512 -DMAREX_SD_MINBLOCKS=1 -DMAREX_SD_NOHOIST"
+v b384_2_nohoist "-DMAREX_SD_NOHOIST"
+v b512_2 "-DMAREX_SD_MAXTHREADS=512 -DMAREX_SD_MINBLOCKS=2"
+v b352_2 "-DMAREX_SD_MAXTHREADS=352 -DMAREX_SD_MINBLOCKS=2"
