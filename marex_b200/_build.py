@@ -9,7 +9,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libmarex_b200.so")
 SOURCES = ["anomaly.cu", "shift_daily.cu", "thresholds.cu", "pool_band.cu", "compare.cu", "morph.cu"]
-HEADERS = ["common.cuh", "tma.cuh", "digitize.cuh", "morph_core.cuh", os.path.join("..", "..", "include", "marex_b200.h")]
+HEADERS = ["common.cuh", "tma.cuh", "digitize.cuh", "exact_queue.cuh", "morph_core.cuh", os.path.join("..", "..", "include", "marex_b200.h")]
 
 
 def _nvcc() -> str:

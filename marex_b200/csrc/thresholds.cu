@@ -7,6 +7,7 @@
 #include <cstdlib>
 
 #include "common.cuh"
+#include "exact_queue.cuh"
 
 namespace marex {
 
@@ -552,13 +553,16 @@ __global__ void __launch_bounds__(32) hobday_exact_win_kernel(const float* __res
                                                               int64_t pitch, const int32_t* __restrict__ doy_ptr,
                                                               const int32_t* __restrict__ doy_rows, int w, int rowcap,
                                                               float qf, float* __restrict__ thr,
-                                                              const float* __restrict__ minmax) {
+                                                              const float* __restrict__ minmax,
+                                                              const int32_t* __restrict__ warp_list) {
   extern __shared__ unsigned char smem_raw[];
   CT* hist = reinterpret_cast<CT*>(smem_raw);                                     // [NBX][32]
   float* win = reinterpret_cast<float*>(smem_raw + (size_t)NBX * 32 * sizeof(CT)); // [w][rowcap][32]
   int* nrow = reinterpret_cast<int*>(win + (size_t)w * rowcap * 32);              // [w] rows held by each slot
   const int lane = threadIdx.x;
-  const int64_t c = (int64_t)blockIdx.x * 32 + lane;
+  // all groups of 32 gridpoints, or (list mode) the groups warp_list[1 .. 1 + warp_list[0]) the queue kernel gave up on
+  if (warp_list && (int)blockIdx.x >= __ldg(&warp_list[0])) return;
+  const int64_t c = (int64_t)(warp_list ? __ldg(&warp_list[1 + blockIdx.x]) : (int)blockIdx.x) * 32 + lane;
   const bool live = c < N;
   const float* col = anom + (live ? c : N - 1);
   for (int b = 0; b < NBX; ++b) hist[b * 32 + lane] = 0;
@@ -679,6 +683,72 @@ __global__ void __launch_bounds__(32) hobday_exact_win_kernel(const float* __res
     }
     if (live) thr[(int64_t)d * N + c] = res;
   }
+}
+
+// Queue variant (exact_queue.cuh): per gridpoint a first-in first-out queue of the samples above a pivot instead of
+// the window and its histogram -- 8.3 KB of shared memory per warp instead of 51 KB, four warps per CTA.
+struct XqDevEnv {
+  const char* col;   // the lane's gridpoint in row 0 (bytes)
+  uint32_t pitch4;   // row pitch in bytes: one 32 x 32 + 64 bit multiply-add per sample address
+  const int32_t* doy_ptr;
+  const int32_t* doy_rows;
+  float* que_;    // [Q][32] of this warp, already offset by the lane
+  uint8_t* cnt_;  // [3][w][32] of this warp, already offset by the lane
+  int w;
+  static __device__ __forceinline__ float inf() { return CUDART_INF_F; }
+  static __device__ __forceinline__ float nan() { return CUDART_NAN_F; }
+  static __device__ __forceinline__ bool finite(float v) { return is_finite_f(v); }
+  static __device__ __forceinline__ float fmin(float a, float b) { return fminf(a, b); }
+  static __device__ __forceinline__ float fmax(float a, float b) { return fmaxf(a, b); }
+  static __device__ __forceinline__ float level(float lob, float top, int j) {
+    return j == 7 ? top : lob + (top - lob) * ((float)(j + 1) * 0.125f);
+  }
+  static __host__ __device__ __forceinline__ void rank(int n, float qf, int& r0, int& r1, float& g) {
+#ifdef __CUDA_ARCH__
+    f32_rank(n, qf, r0, r1, g);
+#else
+    const float vi = (float)(n - 1) * qf;  // host copy of f32_rank for the dispatch rule
+    if (vi >= (float)(n - 1)) { r0 = r1 = n - 1; g = 0.f; return; }
+    if (vi < 0.f) { r0 = r1 = 0; g = 0.f; return; }
+    r0 = (int)floorf(vi); r1 = r0 + 1; g = vi - floorf(vi);
+#endif
+  }
+  static __device__ __forceinline__ float lerp(float a, float b, float g) { return f32_lerp(a, b, g); }
+  __device__ __forceinline__ float load(int j) const {
+    return __ldg(reinterpret_cast<const float*>(col + (uint64_t)(uint32_t)__ldg(&doy_rows[j]) * pitch4));
+  }
+  __device__ __forceinline__ int doy_begin(int dd) const { return __ldg(&doy_ptr[dd]); }
+  __device__ __forceinline__ float& que(int pos) { return *reinterpret_cast<float*>(reinterpret_cast<char*>(que_) + (pos << 7)); }
+  __device__ __forceinline__ uint8_t& cnt(int s) { return cnt_[s * 32]; }
+  __device__ __forceinline__ uint8_t& eqc(int s) { return cnt_[(w + s) * 32]; }
+  __device__ __forceinline__ uint8_t& nvc(int s) { return cnt_[(2 * w + s) * 32]; }
+  __device__ __forceinline__ int wmax(int v) { return __reduce_max_sync(0xffffffffu, v); }
+  __device__ __forceinline__ bool any(bool p) { return __any_sync(0xffffffffu, p); }
+  __device__ __forceinline__ bool all(bool p) { return __all_sync(0xffffffffu, p); }
+};
+
+constexpr int XQ_WARPS = 4;
+
+template <int Q>
+__global__ void __launch_bounds__(XQ_WARPS * 32, 6) hobday_exact_queue_kernel(const float* __restrict__ anom, int64_t N, int64_t pitch,
+                                                                          const int32_t* __restrict__ doy_ptr,
+                                                                          const int32_t* __restrict__ doy_rows, int w, float qf,
+                                                                          float* __restrict__ thr, int32_t* __restrict__ fail_list,
+                                                                          int force_fail) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int lane = threadIdx.x & 31, wi = threadIdx.x >> 5;
+  const int64_t group = (int64_t)blockIdx.x * XQ_WARPS + wi;  // 32 adjacent gridpoints; no CTA-wide barrier below
+  if (group * 32 >= N) return;
+  const int64_t c = group * 32 + lane;
+  const bool live = c < N;
+  const size_t per_warp = (size_t)Q * 128 + (size_t)3 * w * 32;
+  unsigned char* base = smem_raw + wi * per_warp;
+  XqDevEnv env{reinterpret_cast<const char*>(anom + (live ? c : N - 1)), (uint32_t)(pitch * 4), doy_ptr, doy_rows, reinterpret_cast<float*>(base) + lane,
+               base + (size_t)Q * 128 + lane, w};
+  ExactQueue<Q, XqDevEnv> lane_q(env, w, qf);
+  bool ok = !(force_fail == 1 || (force_fail == 2 && (group & 1)));
+  if (ok) ok = lane_q.run([&](int d, float v) { if (live) thr[(int64_t)d * N + c] = v; });
+  if (!ok && lane == 0) fail_list[1 + atomicAdd(&fail_list[0], 1)] = (int32_t)group;
 }
 
 // np.nanquantile(a, float64 q) 'linear' (xarray .quantile, detect.py:2899): float64 virtual
@@ -1099,6 +1169,34 @@ extern "C" int marex_hobday_thresholds_exact_f32(const float* anom, int64_t T, i
   if (!wide && max_doy_rows > 0 && smem_win <= 200 * 1024 && !tune_get("exact_v1", 0)) {
     int rc = set_smem(hobday_exact_win_kernel<uint16_t>, smem_win);
     if (rc) return rc;
+    // Queue kernel (exact_queue.cuh) when the kk largest samples of any window plus the pivot's room fit a queue of 64
+    // or 128 floats per gridpoint; the groups of 32 gridpoints it gives up on are listed in `work` and recomputed by
+    // the histogram kernel.  marex_tune("exact_queue", 0) selects the histogram kernel for everything;
+    // "exact_force_fail" = 1 / 2 sends every / every other group through the list (tests).
+    const int kk_max = xq_kk_max<XqDevEnv>(max_window_rows, qf);
+    const int qcap = kk_max + XQ_ROOM <= 64 - XQ_HEAD ? 64 : (kk_max + XQ_ROOM <= 128 - XQ_HEAD ? 128 : 0);
+    const size_t smem_q = (size_t)XQ_WARPS * ((size_t)qcap * 128 + (size_t)3 * w * 32);
+    if (work && qcap && max_doy_rows <= 255 && pitch < (1LL << 30) && smem_q <= 200 * 1024 && tune_get("exact_queue", 1)) {
+      int32_t* fail_list = reinterpret_cast<int32_t*>(work);  // [0] = count, then group indices (2 * N floats of room)
+      cudaError_t e = cudaMemsetAsync(fail_list, 0, sizeof(int32_t), st);
+      MAREX_REQUIRE(e == cudaSuccess, "cudaMemsetAsync failed");
+      const int ff = (int)tune_get("exact_force_fail", 0);
+      const unsigned qgrid = (unsigned)((grid + XQ_WARPS - 1) / XQ_WARPS);
+      if (qcap == 64) {
+        rc = set_smem(hobday_exact_queue_kernel<64>, smem_q);
+        if (rc) return rc;
+        hobday_exact_queue_kernel<64><<<qgrid, XQ_WARPS * 32, smem_q, st>>>(anom, N, pitch, doy_ptr, doy_rows, w, qf, thr, fail_list, ff);
+      } else {
+        rc = set_smem(hobday_exact_queue_kernel<128>, smem_q);
+        if (rc) return rc;
+        hobday_exact_queue_kernel<128><<<qgrid, XQ_WARPS * 32, smem_q, st>>>(anom, N, pitch, doy_ptr, doy_rows, w, qf, thr, fail_list, ff);
+      }
+      MAREX_LAUNCH_CHECK("hobday_exact_queue_kernel");
+      hobday_exact_win_kernel<uint16_t><<<grid, 32, smem_win, st>>>(anom, T, N, pitch, doy_ptr, doy_rows, w, rowcap_day,
+                                                                    qf, thr, nullptr, fail_list);
+      MAREX_LAUNCH_CHECK("hobday_exact_win_kernel (list)");
+      return MAREX_OK;
+    }
     if (work) {  // per-gridpoint finite range at full occupancy (optional scratch of 2 * N floats)
       init_minmax_kernel<<<(unsigned)((N + 255) / 256), 256, 0, st>>>(work, N);
       MAREX_LAUNCH_CHECK("init_minmax_kernel");
@@ -1112,7 +1210,7 @@ extern "C" int marex_hobday_thresholds_exact_f32(const float* anom, int64_t T, i
       MAREX_LAUNCH_CHECK("col_minmax_kernel");
     }
     hobday_exact_win_kernel<uint16_t><<<grid, 32, smem_win, st>>>(anom, T, N, pitch, doy_ptr, doy_rows, w, rowcap_day,
-                                                                  qf, thr, work);
+                                                                  qf, thr, work, nullptr);
     MAREX_LAUNCH_CHECK("hobday_exact_win_kernel");
     return MAREX_OK;
   }

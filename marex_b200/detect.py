@@ -690,6 +690,7 @@ def identify_extremes_arrays(
             )  # fmt: skip
             out["thresholds"] = thr if not gridded else thr.reshape((NDOY,) + tuple(grid))
             out["thresholds_layout"] = "doy_first"
+            out["exact_scratch"] = mm  # int32 view: [0] = groups of 32 gridpoints the queue kernel handed to the histogram kernel
         else:
             if w < 3:
                 raise ConfigurationError(

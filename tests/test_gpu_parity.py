@@ -4,6 +4,7 @@ marex_b200/_lib.py), against the numpy oracle on the same seeded inputs.
 Bars (north_star): histogram counts / masks / thresholds-from-identical-anomalies BIT-EXACT;
 anomalies and end-to-end thresholds within 1e-5 relative of the field scale in float32.
 """
+import functools
 import os
 import warnings
 
@@ -363,6 +364,43 @@ def test_hobday_exact_thresholds_bit_exact(w, p):
     np.testing.assert_array_equal(res["extreme_events"].cpu().numpy(), mo.compare_hobday(a2, doy, ref))
 
 
+@functools.lru_cache(maxsize=None)
+def _exact_case(kind):
+    from test_exact_queue_host import _field
+
+    a, doy = _field(11, 25, 203, kind)  # 6 full groups of 32 gridpoints and a ragged one
+    return a, doy, mo.hobday_thresholds_exact(a, doy, 95.0, 11)
+
+
+@pytest.mark.parametrize("kind", ["plain", "seasonal", "special"])
+@pytest.mark.parametrize("mode", ["queue", "all_listed", "half_listed", "histogram"])
+def test_hobday_exact_queue_kernel_bit_exact(tune, kind, mode):
+    """The queue kernel (exact_queue.cuh) on 25 years of windows with ties, gaps, infinities and a moving threshold; the
+    groups it gives up on (here: forced) recomputed by the histogram kernel in list mode; and the histogram kernel alone."""
+    mb = _cuda()
+    a, doy, ref = _exact_case(kind)
+    tune(exact_queue=0 if mode == "histogram" else 1, exact_force_fail={"all_listed": 1, "half_listed": 2}.get(mode, 0))
+    n0 = mb._lib.launch_count()
+    res = mb.identify_extremes_arrays(torch.from_numpy(a).cuda(), doy, None, "hobday_extreme", 95.0, 11, None, method_percentile="exact")
+    got = res["thresholds"].cpu().numpy().reshape(366, -1)
+    launched = mb._lib.launch_count() - n0
+    _ulp_equal(got, ref)
+    assert (np.isnan(got) == np.isnan(ref)).all()
+    np.testing.assert_array_equal(got[~np.isnan(ref)], ref[~np.isnan(ref)])
+    listed = int(res["exact_scratch"][:1].view(torch.int32).item())  # [0] of the queue kernel's list of groups it gave up on
+    groups = (a.shape[1] + 31) // 32
+    if mode == "histogram":
+        assert launched >= 3  # range pass (2 kernels) + histogram kernel (+ compare)
+    elif mode == "all_listed":
+        assert listed == groups
+    elif mode == "half_listed":
+        assert listed >= groups // 2
+    elif kind != "special":
+        assert listed == 0
+    else:
+        assert listed <= 1  # the group with the columns that are mostly infinities may be listed
+
+
 def test_hobday_exact_matches_reference_golden(golden_dir):
     """Against outputs of the reference's own _doy_percentiles (detect.py:1936-1942)."""
     mb = _cuda()
@@ -586,9 +624,9 @@ def test_banded_pooled_kernel_bit_exact(tune, env, ws, w, p):
     )
 
 
-def test_digitize_ffff_matches_numpy_digitize():
-    """The pooled path digitizes internally (invalid class coded 0x7FFF); its counts feed the same
-    thresholds as np.digitize - checked here through a band wide enough that nothing is pooled away."""
+def test_pooled_path_digitize_matches_numpy_digitize():
+    """The pooled path digitizes with the invalid class coded 0x7FFF; its counts feed the same thresholds as
+    np.digitize (samples exactly on an edge, one ulp below it, on the last edge, +-inf)."""
     mb = _cuda()
     rng = np.random.default_rng(3)
     time = np.arange(np.datetime64("1995-01-01"), np.datetime64("2001-01-01"))
