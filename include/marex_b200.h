@@ -188,10 +188,13 @@ int marex_hobday_thresholds_pooled_bins(const uint16_t* bins, int64_t NY, int64_
 
 /* Exact Hobday thresholds: np.nanpercentile (float32 'linear') over the +-w/2 doy window
  * (detect.py:1921-1956).  thr[366, N] doy-major, NaN where the window holds no valid sample.
- * max_doy_rows = the largest number of rows of any single day of year (doy_ptr differences);
- * when the window (w * max_doy_rows samples per gridpoint) fits shared memory it is kept there.
- * `work` (optional device scratch of 2 * N float32): the per-gridpoint value range is then taken in a separate
- * full-occupancy pass instead of inside the percentile kernel. */
+ * max_window_rows / max_doy_rows = the largest number of rows of any doy window / of any single day of year
+ * (doy_ptr differences).  `work`: optional device scratch of 2 * N float32.  With it, and when the samples that decide
+ * the percentile (the n - floor(q (n - 1)) largest of a window, plus room) fit a queue of 64 or 128 floats per
+ * gridpoint, the queue kernel runs (csrc/exact_queue.cuh) and `work` holds, as int32, the number of groups of 32
+ * gridpoints it handed to the histogram kernel ([0]) and their indices; otherwise the histogram kernel runs for every
+ * gridpoint (window in shared memory when w * max_doy_rows samples fit) and `work` receives the per-gridpoint value
+ * range taken in a separate full-occupancy pass.  The result does not depend on which kernel ran. */
 int marex_hobday_thresholds_exact_f32(const float* anom, int64_t T, int64_t N, int64_t pitch,
                                       const int32_t* doy_ptr, const int32_t* doy_rows,
                                       int32_t max_window_rows, int32_t max_doy_rows, int32_t w,
