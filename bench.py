@@ -317,6 +317,7 @@ def main():
     ap.add_argument("--workload", default="0.25deg_40yr_shifting_hobday_approx", choices=sorted(WORKLOADS))
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--e2e-chunks", type=int, default=None, help="spatial pieces of the streamed host path (default: the library's own rule)")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-parity", action="store_true", help="skip the post-run tile check against the oracle")
     ap.add_argument("--gather-thresholds", action="store_true", help="N > 1: also gather the thresholds on rank 0")
@@ -555,7 +556,7 @@ def main():
             if i == 1:
                 barrier()
                 t0 = _time.perf_counter()
-            res = marex_b200.preprocess_arrays(xh, time, output="pinned_reuse", **kw)
+            res = marex_b200.preprocess_arrays(xh, time, output="pinned_reuse", chunks=args.e2e_chunks, **kw)
             d2h = sum(res[k].nbytes for k in ("dat_anomaly", "mask", "thresholds", "extreme_events"))
             h2d = int(res.get("h2d_bytes", xh.numel() * 4))
             n_chunks = int(res.get("chunks", 1))

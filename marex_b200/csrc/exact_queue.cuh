@@ -26,8 +26,12 @@
 //     (hobday_exact_win_kernel, list mode).
 //
 // The lane algorithm is written against an environment `Env` (row loads, queue / counter storage, warp votes, the
-// float32 rank and interpolation rules) so that the very same code runs per lane in the CUDA kernel and, with a
-// one-lane environment, on the host for tests/test_exact_queue_host.py.
+// rank rule `rank(n, r0, r1, g)` -- ascending 0-based ranks of the two order statistics and the interpolation weight
+// -- and `finish(a, b, g)`, which interpolates) so that the very same code runs per lane in the CUDA kernel and, with
+// a one-lane environment, on the host for tests/test_exact_queue_host.py.
+// (The same queue on uint16 bin codes for the approximate path without pooling was built and checked on the host: it
+// needs a second selection pass per day for the bin's count, ~3,700 warp instructions per warp and day against the
+// 1,230 of hobday_hist_kernel's byte histogram -- not pursued.)
 #pragma once
 #include <cstdint>
 
@@ -72,26 +76,16 @@ constexpr int XQ_DEPTH = XQ_DEPTH_V;  // neighbours of the guess a selection pas
 constexpr int XQ_NDOY = 366;
 constexpr int XQ_PASSES = 24;  // bracketing passes before a lane gives up
 
-// Largest kk any window of at most `rows` samples can ask for (kk is non-decreasing in n).
-template <class Env>
-inline int xq_kk_max(int rows, float qf) {
-  int r0, r1;
-  float g;
-  Env::rank(rows < 1 ? 1 : rows, qf, r0, r1, g);
-  return (rows < 1 ? 1 : rows) - r0;
-}
-
 template <int Q, class Env>
 struct ExactQueue {
   Env& e;
   const int w, half;
-  const float qf;
   float pivot, x;  // x: the previous answer (lower order statistic), the guess of the next selection
   float scale;     // window maximum - pivot when the pivot was last bracketed: the step of a lowering
   int h, m_gt, m_eq, n;
 
-  XQ_HD ExactQueue(Env& env, int w_, float qf_)
-      : e(env), w(w_), half(w_ / 2), qf(qf_), pivot(-Env::inf()), x(-Env::inf()), scale(0.f), h(0), m_gt(0), m_eq(0), n(0) {}
+  XQ_HD ExactQueue(Env& env, int w_)
+      : e(env), w(w_), half(w_ / 2), pivot(-Env::inf()), x(-Env::inf()), scale(0.f), h(0), m_gt(0), m_eq(0), n(0) {}
 
   static XQ_HD int wrap(int d) { return ((d % XQ_NDOY) + XQ_NDOY) % XQ_NDOY; }
 
@@ -196,7 +190,7 @@ struct ExactQueue {
     if (mine && nn > 0) {
       int r0, r1;
       float g;
-      Env::rank(nn, qf, r0, r1, g);
+      e.rank(nn, r0, r1, g);
       kk = nn - r0;
       need = kk + XQ_SLACK;
       mhi = kk + XQ_ROOM;
@@ -207,19 +201,26 @@ struct ExactQueue {
     }
     for (int it = 0; it < XQ_PASSES && e.any(!done); ++it) {
       XQ_EVENT(3);
-      const float lob = (lo == -Env::inf()) ? mn : lo, top = hi_real ? hi : mx;
+      // levels lob + (top - lob) * k / 8: k = 1..8 above a pivot candidate that already qualifies, k = 0..7 (the
+      // minimum itself included: a block of equal values at the bottom) while none does
+      const bool open = lo == -Env::inf();
+      const float lob = open ? mn : lo, top = hi_real ? hi : mx;
       float f[8];
       int cge[8];
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
-        f[j] = Env::level(lob, top, j);
+        f[j] = Env::level(lob, top, open ? j : j + 1);
         cge[j] = 0;
       }
+      int cgt = 0;  // samples strictly above the qualifying candidate
       scan_window(d, !done, [&](float v) {
+        cgt += (v > lob) ? 1 : 0;
 #pragma unroll
         for (int j = 0; j < 8; ++j) cge[j] += (v >= f[j]) ? 1 : 0;
       });
-      if (!done) {
+      if (!done && !open && cgt < need) {
+        done = true;  // a block of equal values at lo holds the rank: the tie counter absorbs it
+      } else if (!done) {
         int jq = -1;
 #pragma unroll
         for (int j = 0; j < 8; ++j)
@@ -238,8 +239,7 @@ struct ExactQueue {
         else if (!progress) done = true;  // equal values at lo (checked below) or nothing to find
       }
     }
-    if (!done) ok = false;
-    if (mine) {
+    if (mine) {  // (a lane that ran out of passes keeps its best candidate: the counts below decide)
       pivot = lo;
       scale = (mn <= mx && lo != -Env::inf()) ? mx - lo : 0.f;
     }
@@ -321,7 +321,7 @@ struct ExactQueue {
       float gw = 0.f;
       const bool has = n > 0;
       if (has) {
-        Env::rank(n, qf, r0, r1, gw);
+        e.rank(n, r0, r1, gw);
         kk = n - r0;
         kk1 = n - r1;
       }
@@ -347,7 +347,7 @@ struct ExactQueue {
       float res = Env::nan(), a = res, b = res;
       select(has, kk, kk1, a, b);
       if (has) {
-        res = Env::lerp(a, b, gw);
+        res = e.finish(a, b, gw);
         x = a;
       }
       out(d, res);

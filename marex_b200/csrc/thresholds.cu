@@ -56,6 +56,24 @@ __global__ void __launch_bounds__(32) hobday_hist_kernel(
 
   auto apply_doy = [&](int d, int sign) {
     const int b0 = __ldg(&doy_ptr[d]), b1 = __ldg(&doy_ptr[d + 1]);
+    if (!POOLED) {  // batches of 8 independent loads (the kernel runs 13 warps per SM: latency is what it waits for)
+      const uint16_t* colp = bins + y * nx + xx;
+      auto count = [&](int v) {
+        if (v < nb) {
+          hist[v * 32 + lane] += (CT)sign;
+          ntot += sign;
+          if (v < iu) cl += sign;
+        }
+      };
+      for (int j = b0; j < b1; j += 8) {
+        int v[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) v[u] = (j + u < b1) ? (int)colp[(int64_t)__ldg(&doy_rows[j + u]) * pitch] : 0xFFFF;
+#pragma unroll
+        for (int u = 0; u < 8; ++u) count(v[u]);
+      }
+      return;
+    }
     for (int j = b0; j < b1; ++j) {
       const uint16_t* row = bins + (int64_t)__ldg(&doy_rows[j]) * pitch;
       if (POOLED) {
@@ -700,20 +718,12 @@ struct XqDevEnv {
   static __device__ __forceinline__ bool finite(float v) { return is_finite_f(v); }
   static __device__ __forceinline__ float fmin(float a, float b) { return fminf(a, b); }
   static __device__ __forceinline__ float fmax(float a, float b) { return fmaxf(a, b); }
-  static __device__ __forceinline__ float level(float lob, float top, int j) {
-    return j == 7 ? top : lob + (top - lob) * ((float)(j + 1) * 0.125f);
+  static __device__ __forceinline__ float level(float lob, float top, int k) {
+    return k == 8 ? top : (k == 0 ? lob : lob + (top - lob) * ((float)k * 0.125f));
   }
-  static __host__ __device__ __forceinline__ void rank(int n, float qf, int& r0, int& r1, float& g) {
-#ifdef __CUDA_ARCH__
-    f32_rank(n, qf, r0, r1, g);
-#else
-    const float vi = (float)(n - 1) * qf;  // host copy of f32_rank for the dispatch rule
-    if (vi >= (float)(n - 1)) { r0 = r1 = n - 1; g = 0.f; return; }
-    if (vi < 0.f) { r0 = r1 = 0; g = 0.f; return; }
-    r0 = (int)floorf(vi); r1 = r0 + 1; g = vi - floorf(vi);
-#endif
-  }
-  static __device__ __forceinline__ float lerp(float a, float b, float g) { return f32_lerp(a, b, g); }
+  float qf;
+  __device__ __forceinline__ void rank(int n, int& r0, int& r1, float& g) const { f32_rank(n, qf, r0, r1, g); }
+  __device__ __forceinline__ float finish(float a, float b, float g) const { return f32_lerp(a, b, g); }
   __device__ __forceinline__ float load(int j) const {
     return __ldg(reinterpret_cast<const float*>(col + (uint64_t)(uint32_t)__ldg(&doy_rows[j]) * pitch4));
   }
@@ -744,8 +754,8 @@ __global__ void __launch_bounds__(XQ_WARPS * 32, 6) hobday_exact_queue_kernel(co
   const size_t per_warp = (size_t)Q * 128 + (size_t)3 * w * 32;
   unsigned char* base = smem_raw + wi * per_warp;
   XqDevEnv env{reinterpret_cast<const char*>(anom + (live ? c : N - 1)), (uint32_t)(pitch * 4), doy_ptr, doy_rows, reinterpret_cast<float*>(base) + lane,
-               base + (size_t)Q * 128 + lane, w};
-  ExactQueue<Q, XqDevEnv> lane_q(env, w, qf);
+               base + (size_t)Q * 128 + lane, w, qf};
+  ExactQueue<Q, XqDevEnv> lane_q(env, w);
   bool ok = !(force_fail == 1 || (force_fail == 2 && (group & 1)));
   if (ok) ok = lane_q.run([&](int d, float v) { if (live) thr[(int64_t)d * N + c] = v; });
   if (!ok && lane == 0) fail_list[1 + atomicAdd(&fail_list[0], 1)] = (int32_t)group;
@@ -1173,7 +1183,13 @@ extern "C" int marex_hobday_thresholds_exact_f32(const float* anom, int64_t T, i
     // or 128 floats per gridpoint; the groups of 32 gridpoints it gives up on are listed in `work` and recomputed by
     // the histogram kernel.  marex_tune("exact_queue", 0) selects the histogram kernel for everything;
     // "exact_force_fail" = 1 / 2 sends every / every other group through the list (tests).
-    const int kk_max = xq_kk_max<XqDevEnv>(max_window_rows, qf);
+    int kk_max;  // largest kk = n - r0 any window can ask for (non-decreasing in n): f32_rank on the host
+    {
+      const int n = max_window_rows < 1 ? 1 : max_window_rows;
+      const float vi = (float)(n - 1) * qf;
+      const int r0 = vi >= (float)(n - 1) ? n - 1 : (vi < 0.f ? 0 : (int)floorf(vi));
+      kk_max = n - r0;
+    }
     const int qcap = kk_max + XQ_ROOM <= 64 - XQ_HEAD ? 64 : (kk_max + XQ_ROOM <= 128 - XQ_HEAD ? 128 : 0);
     const size_t smem_q = (size_t)XQ_WARPS * ((size_t)qcap * 128 + (size_t)3 * w * 32);
     if (work && qcap && max_doy_rows <= 255 && pitch < (1LL << 30) && smem_q <= 200 * 1024 && tune_get("exact_queue", 1)) {

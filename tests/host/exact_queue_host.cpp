@@ -25,13 +25,16 @@ struct HostEnv {
   int w;
   std::vector<float> q;
   std::vector<uint8_t> c;
+  HostEnv(const float* col_, int64_t pitch_, const int32_t* p_, const int32_t* r_, int w_, int Q, float qf_)
+      : col(col_), pitch(pitch_), doy_ptr(p_), doy_rows(r_), w(w_), q(Q, -1234.f), c(3 * w_, 0), qf(qf_) {}
   static float inf() { return std::numeric_limits<float>::infinity(); }
   static float nan() { return std::numeric_limits<float>::quiet_NaN(); }
   static bool finite(float v) { return std::fabs(v) < inf(); }
   static float fmin(float a, float b) { return std::fmin(a, b); }
   static float fmax(float a, float b) { return std::fmax(a, b); }
-  static float level(float lob, float top, int j) { return j == 7 ? top : lob + (top - lob) * ((float)(j + 1) * 0.125f); }
-  static void rank(int n, float qf, int& r0, int& r1, float& g) {  // as f32_rank (thresholds.cu)
+  static float level(float lob, float top, int k) { return k == 8 ? top : (k == 0 ? lob : lob + (top - lob) * ((float)k * 0.125f)); }
+  float qf;
+  void rank(int n, int& r0, int& r1, float& g) const {  // as f32_rank (thresholds.cu)
     const float vi = (float)(n - 1) * qf;
     if (vi >= (float)(n - 1)) { r0 = r1 = n - 1; g = 0.f; return; }
     if (vi < 0.f) { r0 = r1 = 0; g = 0.f; return; }
@@ -40,7 +43,7 @@ struct HostEnv {
     r1 = r0 + 1;
     g = vi - lo;
   }
-  static float lerp(float a, float b, float g) {  // as f32_lerp (thresholds.cu)
+  float finish(float a, float b, float g) const {  // as f32_lerp (thresholds.cu)
     const float diff = b - a;
     volatile float t = diff * g;
     float r = a + t;
@@ -63,8 +66,8 @@ static int run_all(const float* anom, int64_t N, int64_t pitch, const int32_t* d
                    float qf, float* thr, int32_t* failed) {
   int nfail = 0;
   for (int64_t c = 0; c < N; ++c) {
-    HostEnv env{anom + c, pitch, doy_ptr, doy_rows, w, std::vector<float>(Q, -1234.f), std::vector<uint8_t>(3 * w, 0)};
-    marex::ExactQueue<Q, HostEnv> lane(env, w, qf);
+    HostEnv env(anom + c, pitch, doy_ptr, doy_rows, w, Q, qf);
+    marex::ExactQueue<Q, HostEnv> lane(env, w);
     g_lane = c;
     g_day = 0;
     const bool ok = lane.run([&](int d, float v) {
@@ -90,4 +93,10 @@ extern "C" int xq_host(const float* anom, int64_t N, int64_t pitch, const int32_
   return r;
 }
 
-extern "C" int xq_kk_max_host(int rows, float percentile) { return marex::xq_kk_max<HostEnv>(rows, percentile / 100.0f); }
+extern "C" int xq_kk_max_host(int rows, float percentile) {
+  HostEnv env(nullptr, 0, nullptr, nullptr, 1, 1, percentile / 100.0f);
+  int r0, r1;
+  float g;
+  env.rank(rows < 1 ? 1 : rows, r0, r1, g);
+  return (rows < 1 ? 1 : rows) - r0;
+}
