@@ -11,6 +11,7 @@ run bench_full 900 python bench.py --steps 20 --warmup 3
 run bench_reference 600 python bench.py --impl reference --steps 2 --warmup 1
 W3=0.25deg_40yr_shifting_hobday_exact
 run bench_config3 600 python bench.py --steps 5 --warmup 3 --no-e2e --no-cpu --workload $W3
+run bench_icon 600 python bench.py --steps 5 --warmup 3 --no-e2e --no-cpu --workload icon_1Mi_cells_30yr_shifting_hobday_approx
 for c in 16 24; do run bench_e2e_chunks$c 600 python bench.py --steps 2 --warmup 3 --no-cpu --no-parity --e2e-chunks $c; done
 run ncu_queue 600 ncu --section SpeedOfLight --section Occupancy --section LaunchStats --section WarpStateStats --section SchedulerStats --section MemoryWorkloadAnalysis --section MemoryWorkloadAnalysis_Tables --section InstructionStats --section SourceCounters --import-source on --clock-control none -k regex:"hobday_exact_queue" -s 1 -c 1 -o "$out/prof_queue3" python bench.py --steps 1 --warmup 1 --no-e2e --no-cpu --no-parity --workload $W3
 grep -h '"metric"' "$out"/bench_*.log | cut -c1-300
