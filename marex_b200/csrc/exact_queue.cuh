@@ -76,7 +76,8 @@ constexpr int XQ_DEPTH = XQ_DEPTH_V;  // neighbours of the guess a selection pas
 constexpr int XQ_NDOY = 366;
 constexpr int XQ_PASSES = 24;  // bracketing passes before a lane gives up
 
-template <int Q, class Env>
+// WC: window_days_hobday as a compile-time constant (0 = run-time): slot arithmetic and the per-slot loops fold.
+template <int Q, class Env, int WC = 0>
 struct ExactQueue {
   Env& e;
   const int w, half;
@@ -85,7 +86,7 @@ struct ExactQueue {
   int h, m_gt, m_eq, n;
 
   XQ_HD ExactQueue(Env& env, int w_)
-      : e(env), w(w_), half(w_ / 2), pivot(-Env::inf()), x(-Env::inf()), scale(0.f), h(0), m_gt(0), m_eq(0), n(0) {}
+      : e(env), w(WC ? WC : w_), half((WC ? WC : w_) / 2), pivot(-Env::inf()), x(-Env::inf()), scale(0.f), h(0), m_gt(0), m_eq(0), n(0) {}
 
   static XQ_HD int wrap(int d) { return ((d % XQ_NDOY) + XQ_NDOY) % XQ_NDOY; }
 

@@ -68,7 +68,10 @@ __device__ __forceinline__ int pooled_row(const uint16_t* __restrict__ p, int la
 constexpr int BAND_INV = BIN_INV;  // bin code of an invalid sample (NaN or >= last edge)
 constexpr int BAND_PRE = 26;       // entering samples prefetched into registers per step
 
-template <int P, int K, int OY>
+// NYC: rows per day of year as a compile-time constant (0 = from the calendar table).  The day-of-year-major code array
+// has exactly NY slots per day of year, so for the record lengths the instantiations exist for (NY = 25: 40 years with a
+// 15-year baseline; NY = 15: 30 years) the per-sample guards and the tail loops of the scans compile away.
+template <int P, int K, int OY, int NYC = 0>
 __global__ void __launch_bounds__(OY * 32, (OY <= 16 && K <= 64) ? 2 : 1) hobday_band_kernel(const BandParams p) {
   constexpr int KB = K / 8;  // blocks in the band
   constexpr int TY = OY - 2 * P, TX = 32 - 2 * P, CS = OY * 32;
@@ -211,7 +214,7 @@ __global__ void __launch_bounds__(OY * 32, (OY <= 16 && K <= 64) ? 2 : 1) hobday
   auto prefetch = [&](int step) {
     if (!own_valid) return;
     const long long* oe = s_off + ((step & 1) * 2 + 1) * BAND_CAP;
-    const int ne = s_cnt[((step & 1) * 2 + 1) * 2 + 1] - s_cnt[((step & 1) * 2 + 1) * 2];
+    const int ne = NYC ? NYC : s_cnt[((step & 1) * 2 + 1) * 2 + 1] - s_cnt[((step & 1) * 2 + 1) * 2];
 #pragma unroll
     for (int u = 0; u < BAND_PRE; ++u) pre[u] = (u < ne) ? load_at(oe[u]) : -1;
   };
@@ -223,7 +226,8 @@ __global__ void __launch_bounds__(OY * 32, (OY <= 16 && K <= 64) ? 2 : 1) hobday
     const long long* ol = s_off + (par * 2 + 0) * BAND_CAP;
     const int bl0 = s_cnt[(par * 2 + 0) * 2], bl1 = s_cnt[(par * 2 + 0) * 2 + 1];
     const int be0 = s_cnt[(par * 2 + 1) * 2], be1 = s_cnt[(par * 2 + 1) * 2 + 1];
-    const int nl = bl1 - bl0, ne = be1 - be0;
+    const int nl = NYC ? NYC : bl1 - bl0, ne = NYC ? NYC : be1 - be0;
+    constexpr bool SHORT = NYC > 0 && NYC <= BAND_PRE;  // every row of a day fits the prefetch registers / the staged offsets
     // Event list: ev[n_ev] with n_ev a multiple of CS (32-bit index arithmetic, one slot per sample that
     // matters).  Entering and leaving samples are flushed separately, so a list carries one sign.
     int n_ev = 0;
@@ -243,7 +247,7 @@ __global__ void __launch_bounds__(OY * 32, (OY <= 16 && K <= 64) ? 2 : 1) hobday
       int all = BAND_INV;
 #pragma unroll
       for (int u = 0; u < BAND_PRE; ++u) all &= pre[u];  // missing slots are -1: neutral
-      for (int b = be0 + BAND_PRE; b < be1; ++b) all &= load_row(b);
+      if (!SHORT) for (int b = be0 + BAND_PRE; b < be1; ++b) all &= load_row(b);
       if (all == BAND_INV) return;
       dead = false;
       skip_leaving = true;  // every leaving sample is invalid: the valid count does not change
@@ -254,7 +258,7 @@ __global__ void __launch_bounds__(OY * 32, (OY <= 16 && K <= 64) ? 2 : 1) hobday
       if (u == 13 && n_ev > EV_FULL) flush(+1);
       if (u < ne) scan(pre[u]);  // warp-uniform guard
     }
-    for (int b = be0 + BAND_PRE; b < be1; ++b) { if (n_ev > EV_FULL) flush(+1); scan(load_row(b)); }
+    if (!SHORT) for (int b = be0 + BAND_PRE; b < be1; ++b) { if (n_ev > EV_FULL) flush(+1); scan(load_row(b)); }
     flush(+1);
     NT += ne;
     if (!skip_leaving) {
@@ -269,7 +273,7 @@ __global__ void __launch_bounds__(OY * 32, (OY <= 16 && K <= 64) ? 2 : 1) hobday
 #pragma unroll
         for (int u = 0; u < BATCH; ++u) if (u0 + u < nlc) scan(vl[u]);
       }
-      for (int a = bl0 + BAND_CAP; a < bl1; ++a) { if (n_ev > EV_FULL) flush(-1); scan(load_row(a)); }
+      if (!SHORT) for (int a = bl0 + BAND_CAP; a < bl1; ++a) { if (n_ev > EV_FULL) flush(-1); scan(load_row(a)); }
       flush(-1);
     }
     NTr[tid] = (uint16_t)NT;
@@ -985,7 +989,18 @@ extern "C" int marex_hobday_thresholds_pooled_bins(const uint16_t* bins, int64_t
     if (K == 64) { if (TY == 12) MAREX_BAND(PP, 64, 12); else MAREX_BAND(PP, 64, 3); }   \
     else { if (TY == 12) MAREX_BAND(PP, 128, 12); else MAREX_BAND(PP, 128, 3); }         \
   } while (0)
-    if (P == 1) MAREX_BAND_K(1); else if (P == 2) MAREX_BAND_K(2); else MAREX_BAND_K(3);
+#define MAREX_BAND_NY(NN)                                                                                      \
+  do {                                                                                                         \
+    cudaError_t e = cudaFuncSetAttribute(hobday_band_kernel<2, 64, 16, NN>,                                    \
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);              \
+    if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(hobday_band)");                            \
+    hobday_band_kernel<2, 64, 16, NN><<<grid, 16 * 32, smem, st>>>(bp);                                        \
+  } while (0)
+    const bool fold = P == 2 && K == 64 && TY == 12 && !tune_get("pool_generic", 0);
+    if (fold && NY == 25) MAREX_BAND_NY(25);
+    else if (fold && NY == 15) MAREX_BAND_NY(15);
+    else if (P == 1) MAREX_BAND_K(1); else if (P == 2) MAREX_BAND_K(2); else MAREX_BAND_K(3);
+#undef MAREX_BAND_NY
 #undef MAREX_BAND_K
 #undef MAREX_BAND
     MAREX_LAUNCH_CHECK("hobday_band_kernel");

@@ -123,14 +123,18 @@ constexpr int SD_MAX_YEARS = 1024;
 #define MAREX_SD_MINBLOCKS 2
 #endif
 
-template <int V, int R, int NST, int MODE, typename Acc, bool DIG>
+// SC / WC / DC: smooth_days_baseline, window_year_baseline and the strip length as compile-time constants (0 = taken from
+// the parameters).  The instantiation for the reference's defaults (S = 21, W = 15, hence D = 48) lets the compiler unroll
+// the window assembly and fold the ring and stage offsets; same arithmetic in the same order, bit-identical results.
+template <int V, int R, int NST, int MODE, typename Acc, bool DIG, int SC = 0, int WC = 0, int DC = 0>
 __global__ void __launch_bounds__(DIG ? 512 : MAREX_SD_MAXTHREADS, DIG ? 0 : MAREX_SD_MINBLOCKS)
     shift_daily_kernel(const __grid_constant__ CUtensorMap tmap,
                                                           const __grid_constant__ DailyParams p) {
   constexpr int CW = 32 * V;  // gridpoints per CTA
   extern __shared__ __align__(1024) unsigned char smem_raw[];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int D = p.D, W = p.W, S = p.S, off = p.S / 2, Tn = p.T;
+  const int D = DC ? DC : p.D, W = WC ? WC : p.W, S = SC ? SC : p.S, off = S / 2, Tn = p.T;
+  const int rows_box = (SC && DC) ? DC + SC - 1 : p.rows_box;
   // shared memory carve-up (all offsets multiples of 128 bytes)
   uint64_t* bar = reinterpret_cast<uint64_t*>(smem_raw);  // [NST]
   size_t o = 128;
@@ -141,10 +145,10 @@ __global__ void __launch_bounds__(DIG ? 512 : MAREX_SD_MAXTHREADS, DIG ? 0 : MAR
   float* s_edges = reinterpret_cast<float*>(smem_raw + o);
   if (DIG) o += (((size_t)p.n_edges * 4 + 127) / 128) * 128;
   float* xs = reinterpret_cast<float*>(smem_raw + o);     // [NST][rows_box][CW]
-  const int stage_elems = p.rows_box * CW;
+  const int stage_elems = rows_box * CW;
   float* ring = xs + (size_t)NST * stage_elems;           // [W][D][CW]
   Acc* bs = reinterpret_cast<Acc*>(ring + (size_t)W * D * CW);  // [n_blk][CW] sums of R box rows
-  const int n_blk = (p.rows_box + R - 1) / R;
+  const int n_blk = (rows_box + R - 1) / R;
 
   // strips of one gridpoint group are adjacent CTAs: they run at the same time and at the
   // same pace, so the S - 1 halo rows a strip shares with its neighbour are L2 hits
@@ -154,7 +158,7 @@ __global__ void __launch_bounds__(DIG ? 512 : MAREX_SD_MAXTHREADS, DIG ? 0 : MAR
   const bool live = c < p.N;  // N % 4 == 0 and V divides 4: a thread's V gridpoints are all live or all dead
   const int d0 = strip * D;
   const int rbase = warp * R;
-  const uint32_t box_bytes = (uint32_t)p.rows_box * CW * 4u;
+  const uint32_t box_bytes = (uint32_t)rows_box * CW * 4u;
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < NST; ++s) mbar_init(&bar[s], 1);
@@ -173,7 +177,7 @@ __global__ void __launch_bounds__(DIG ? 512 : MAREX_SD_MAXTHREADS, DIG ? 0 : MAR
   int issue_year = 0, issue_st = 0;
   auto issue = [&]() {  // a box that lies entirely outside the series is neither loaded nor waited for
     const int tb = ybase[issue_year] + d0 - off;
-    if (tb < Tn && tb + p.rows_box > 0) {
+    if (tb < Tn && tb + rows_box > 0) {
       mbar_expect_tx(&bar[issue_st], box_bytes);
       tma_load_2d(xs + (size_t)issue_st * stage_elems, &tmap, c0, tb, &bar[issue_st]);
     }
@@ -210,7 +214,7 @@ __global__ void __launch_bounds__(DIG ? 512 : MAREX_SD_MAXTHREADS, DIG ? 0 : MAR
     const bool target = i >= W;
     {
       const int tb = base + d0 - off;
-      if (tb < Tn && tb + p.rows_box > 0) {
+      if (tb < Tn && tb + rows_box > 0) {
         mbar_wait(&bar[st], (phase >> st) & 1u);
         phase ^= 1u << st;
       }
@@ -289,7 +293,7 @@ __global__ void __launch_bounds__(DIG ? 512 : MAREX_SD_MAXTHREADS, DIG ? 0 : MAR
         for (int v = 0; v < V; ++v) e.a[v] = 0;
 #pragma unroll
         for (int r = 0; r < R; ++r)
-          if (blk * R + r < p.rows_box) {
+          if (blk * R + r < rows_box) {
             const Pack<float, V> xr = ldp<float, V>(Xb + r * CW);
 #pragma unroll
             for (int v = 0; v < V; ++v) e.a[v] += (Acc)xr.a[v];
@@ -523,6 +527,8 @@ extern "C" int marex_shift_anomaly_daily_f32(const float* x, int64_t T, int64_t 
   const ShiftEnv env = shift_env();
   const size_t fixed = 128 + (((size_t)(W + 1) * 8 + 127) / 128) * 128 + (((size_t)(n_years + 1) * 4 + 127) / 128) * 128 +
                        (digit ? (((size_t)n_edges * 4 + 127) / 128) * 128 : 0);
+  constexpr int MAREX_OK_SPECIALISE = 1;
+  bool try_special = !env.v && !env.r && !env.nw && !env.f64 && !tune_get("shift_generic", 0);
   auto launch = [&](auto kern, int V, int R, int nst, int cps, int acc_bytes) -> int {
     const size_t row = (size_t)128 * V;
     auto smem_of = [&](int D) {
@@ -542,6 +548,10 @@ extern "C" int marex_shift_anomaly_daily_f32(const float* x, int64_t T, int64_t 
     p.D = R * NW;
     p.rows_box = p.D + S - 1;
     p.n_strips = n_strips;
+    if (try_special && V == 1 && R == 4 && nst == 2 && acc_bytes == 4 && !digit && S == 21 && W == 15 && p.D == 48) {
+      try_special = false;  // the caller launches the instantiation with these constants instead
+      return MAREX_OK_SPECIALISE;
+    }
     const size_t smem = smem_of(p.D);
     CUtensorMap tmap;
     int rc = make_tmap_2d(&tmap, x, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, T, N, pitch, p.rows_box, 32 * V);
@@ -571,6 +581,10 @@ extern "C" int marex_shift_anomaly_daily_f32(const float* x, int64_t T, int64_t 
     // (day, gridpoint) cap the resident threads, and fewer, fatter threads lose more to latency than they save in
     // instructions.
     rc = MAREX_SD(1, 4, 2);
+    if (rc == MAREX_OK_SPECIALISE) {  // the reference's default windows on the default shape: constants folded
+      rc = mode ? launch(shift_daily_kernel<1, 4, 2, 1, float, false, 21, 15, 48>, 1, 4, 2, 2, 4)
+                : launch(shift_daily_kernel<1, 4, 2, 0, float, false, 21, 15, 48>, 1, 4, 2, 2, 4);
+    }
     if (rc == MAREX_ERR_UNSUPPORTED) rc = MAREX_SD(2, 2, 2);
     if (rc == MAREX_ERR_UNSUPPORTED) rc = MAREX_SD(1, 4, 1);
     if (rc == MAREX_ERR_UNSUPPORTED) rc = MAREX_SD(1, 1, 1);

@@ -739,7 +739,7 @@ struct XqDevEnv {
 
 constexpr int XQ_WARPS = 4;
 
-template <int Q>
+template <int Q, int WC>
 __global__ void __launch_bounds__(XQ_WARPS * 32, 6) hobday_exact_queue_kernel(const float* __restrict__ anom, int64_t N, int64_t pitch,
                                                                           const int32_t* __restrict__ doy_ptr,
                                                                           const int32_t* __restrict__ doy_rows, int w, float qf,
@@ -755,7 +755,7 @@ __global__ void __launch_bounds__(XQ_WARPS * 32, 6) hobday_exact_queue_kernel(co
   unsigned char* base = smem_raw + wi * per_warp;
   XqDevEnv env{reinterpret_cast<const char*>(anom + (live ? c : N - 1)), (uint32_t)(pitch * 4), doy_ptr, doy_rows, reinterpret_cast<float*>(base) + lane,
                base + (size_t)Q * 128 + lane, w, qf};
-  ExactQueue<Q, XqDevEnv> lane_q(env, w);
+  ExactQueue<Q, XqDevEnv, WC> lane_q(env, w);
   bool ok = !(force_fail == 1 || (force_fail == 2 && (group & 1)));
   if (ok) ok = lane_q.run([&](int d, float v) { if (live) thr[(int64_t)d * N + c] = v; });
   if (!ok && lane == 0) fail_list[1 + atomicAdd(&fail_list[0], 1)] = (int32_t)group;
@@ -1198,15 +1198,16 @@ extern "C" int marex_hobday_thresholds_exact_f32(const float* anom, int64_t T, i
       MAREX_REQUIRE(e == cudaSuccess, "cudaMemsetAsync failed");
       const int ff = (int)tune_get("exact_force_fail", 0);
       const unsigned qgrid = (unsigned)((grid + XQ_WARPS - 1) / XQ_WARPS);
-      if (qcap == 64) {
-        rc = set_smem(hobday_exact_queue_kernel<64>, smem_q);
-        if (rc) return rc;
-        hobday_exact_queue_kernel<64><<<qgrid, XQ_WARPS * 32, smem_q, st>>>(anom, N, pitch, doy_ptr, doy_rows, w, qf, thr, fail_list, ff);
-      } else {
-        rc = set_smem(hobday_exact_queue_kernel<128>, smem_q);
-        if (rc) return rc;
-        hobday_exact_queue_kernel<128><<<qgrid, XQ_WARPS * 32, smem_q, st>>>(anom, N, pitch, doy_ptr, doy_rows, w, qf, thr, fail_list, ff);
-      }
+#define MAREX_XQ(QQ, WW)                                                                                              \
+  do {                                                                                                                \
+    rc = set_smem(hobday_exact_queue_kernel<QQ, WW>, smem_q);                                                         \
+    if (rc) return rc;                                                                                                \
+    hobday_exact_queue_kernel<QQ, WW><<<qgrid, XQ_WARPS * 32, smem_q, st>>>(anom, N, pitch, doy_ptr, doy_rows, w, qf, \
+                                                                            thr, fail_list, ff);                      \
+  } while (0)
+      if (qcap == 64) { if (w == 11) MAREX_XQ(64, 11); else MAREX_XQ(64, 0); }  // 11 days: the reference's default window
+      else MAREX_XQ(128, 0);
+#undef MAREX_XQ
       MAREX_LAUNCH_CHECK("hobday_exact_queue_kernel");
       hobday_exact_win_kernel<uint16_t><<<grid, 32, smem_win, st>>>(anom, T, N, pitch, doy_ptr, doy_rows, w, rowcap_day,
                                                                     qf, thr, nullptr, fail_list);

@@ -127,6 +127,8 @@ DAILY_SHAPES = [
     ("1990-03-17", "2002-11-05", 4, 64, 1, 1, {}),                           # W = 1, S = 1
     ("1990-01-01", "1999-02-11", 4, 64, 3, 6, {}),                           # even S
     ("1982-01-01", "2002-03-05", 8, 36, 15, 21, {}),                         # the benchmark's windows
+    ("1982-03-17", "2002-03-05", 4, 64, 15, 21, {}),                         # ... starting mid-year (constants-folded instantiation)
+    ("1982-01-01", "2002-03-05", 8, 36, 15, 21, {"shift_generic": 1}),       # ... through the instantiation with run-time windows
     ("1988-02-29", "2001-03-01", 8, 36, 2, 3, {}),                           # starts on a leap day, W = 2
     ("1990-01-01", "2001-07-01", 8, 36, 5, 11, {"shift_v": 1, "shift_r": 4}),
     ("1990-01-01", "2001-07-01", 8, 36, 5, 11, {"shift_v": 2, "shift_r": 4}),
@@ -158,6 +160,31 @@ def test_shifting_baseline_anomaly_daily_kernel(tune, T0, T1, ny, nx, W, S, knob
     if knobs.get("shift_f64"):  # float64 sums, one rounding: what the oracle does
         fin = np.isfinite(ref)
         assert _frac_bits_differ(got[fin], ref[fin]) < 1e-3
+
+
+@pytest.mark.parametrize("mode", ["anomaly", "climatology"])
+def test_constants_folded_instantiation_is_bit_identical(tune, mode):
+    """S = 21, W = 15 run an instantiation with the windows and the strip length as compile-time constants: same
+    arithmetic in the same order as the run-time instantiation (shift_generic = 1), bit for bit."""
+    mb = _cuda()
+    x, time = _field(T0="1982-01-01", T1="2003-05-09", ny=8, nx=36, seed=4)
+    f = x.reshape(len(time), -1)
+    f[:, 5] = np.nan
+    f[700:760, 8] = np.nan
+    cal = mb.detect.build_calendar(time)
+    xd, _space = mb.detect._to_device_field(x, "cuda")
+
+    def run():
+        if mode == "anomaly":
+            r = mb.compute_normalised_anomaly_arrays(xd, cal, "shifting_baseline", 15, 21, validate=False)
+            return r["dat_anomaly"].cpu().numpy()
+        return mb.rolling_climatology_arrays(xd, time, 15, 21).cpu().numpy()
+
+    a = run()
+    tune(shift_generic=1)
+    b = run()
+    np.testing.assert_array_equal(np.isnan(a), np.isnan(b))
+    np.testing.assert_array_equal(a[~np.isnan(a)].view(np.uint32), b[~np.isnan(b)].view(np.uint32))
 
 
 def test_shifting_baseline_falls_back_to_generic_kernel(tune):
@@ -622,6 +649,22 @@ def test_banded_pooled_kernel_bit_exact(tune, env, ws, w, p):
     np.testing.assert_array_equal(
         res["extreme_events"].cpu().numpy(), mo.compare_hobday(a.reshape(len(time), -1), doy, np.ascontiguousarray(ref.T))
     )
+
+
+@pytest.mark.parametrize("generic", [0, 1])
+def test_banded_kernel_with_rows_per_day_folded(tune, generic):
+    """15 rows per day of year select the band kernel instantiation with that count as a compile-time constant (no
+    per-sample guards); pool_generic = 1 runs the same field through the run-time instantiation."""
+    mb = _cuda()
+    tune(pool_generic=generic)
+    a, time, doy = _hetero_anoms(T1="2005-01-01", seed=12)
+    ny, nx = a.shape[1:]
+    a2 = a.reshape(len(time), -1)
+    ref = mo.hobday_thresholds_approx(a2, doy, 0.95, 11, 5, (ny, nx))
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        res = mb.identify_extremes_arrays(torch.from_numpy(a2).cuda(), doy, (ny, nx), "hobday_extreme", 95, 11, 5)
+    _ulp_equal(res["thresholds"].cpu().numpy().reshape(-1, 366), ref)
 
 
 def test_pooled_path_digitize_matches_numpy_digitize():
