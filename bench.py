@@ -79,9 +79,9 @@ def kernel_bytes_per_cell(T, T_out):
 
 
 STAGE_KERNELS = {
-    "marex_shift_anomaly_daily_f32": ["shift_daily_kernel"],
+    "marex_shift_anomaly_daily_f32": ["shift_daily_kernel<1, 4, 2, MODE, float, false, S = 21, W = 15, D = 48> (run-time windows otherwise)"],
     "marex_digitize_doy_f32": ["digitize_doy_kernel"],
-    "marex_hobday_thresholds_pooled_bins": ["init_band_kernel", "hobday_band_kernel<P, 64, 16>", "hobday_band_kernel<P, 128, 16> (retry list)", "hobday_pool_tile_kernel (fall-back list)"],
+    "marex_hobday_thresholds_pooled_bins": ["init_band_kernel", "hobday_band_kernel<P, 64, 16, NY> (NY = 15 / 25 folded, else run-time)", "hobday_band_kernel<P, 128, 16> (retry list)", "hobday_pool_tile_kernel (fall-back list)"],
     "marex_hobday_thresholds_exact_f32": ["hobday_exact_queue_kernel<64>", "hobday_exact_win_kernel (list fall-back)"],
     "marex_compare_hobday": ["compare_doy_kernel"],
     "marex_compare_hobday_bins": ["compare_bins_kernel"],
