@@ -64,6 +64,25 @@ def test_library_is_sm100a_with_tma():
     assert "UTMALDG.2D" in sass and "SYNCS.ARRIVE.TRANS64" in sass
 
 
+def test_library_holds_the_constants_folded_instantiations():
+    """The default windows run instantiations with S / W / strip length, rows per day of year and the day-of-year window
+    as compile-time constants; losing one silently would cost 10-14 % of its kernel's time."""
+    from marex_b200 import _build
+
+    path = _build.build(force=False)
+    out = subprocess.run(["cuobjdump", "--dump-elf-symbols", path], capture_output=True, text=True)
+    if out.returncode != 0:
+        pytest.skip("cuobjdump not available")
+    for mangled in (
+        "shift_daily_kernelILi1ELi4ELi2ELi0EfLb0ELi21ELi15ELi48E",  # anomaly, mode 0
+        "shift_daily_kernelILi1ELi4ELi2ELi1EfLb0ELi21ELi15ELi48E",  # climatology, mode 1
+        "hobday_band_kernelILi2ELi64ELi16ELi25E",
+        "hobday_band_kernelILi2ELi64ELi16ELi15E",
+        "hobday_exact_queue_kernelILi64ELi11E",
+    ):
+        assert mangled in out.stdout, mangled
+
+
 def test_no_product_import_of_the_oracle():
     """The product path must not route through the oracle (test infrastructure only)."""
     pkg = os.path.join(ROOT, "marex_b200")
